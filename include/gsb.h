@@ -1,0 +1,235 @@
+/*
+ * gsb.h -- C ABI of libgsb.so: the B200-native (sm_100a) differentiable 3D-Gaussian
+ * rasterizer that replaces GSORB-SLAM's libCudaRasterizer.so + simple_knn.
+ *
+ * Every entry point below is what the reference's C++ seam for this path binds today:
+ *
+ *   gsb_forward / gsb_forward_ws   <- CudaRasterizer::Rasterizer::forward
+ *                                     (Thirdparty/diff_gaussian_rasterization/cuda_rasterizer/rasterizer.h:31-53,
+ *                                      called from src/Rasterizer.cu:191)
+ *   gsb_backward                   <- CudaRasterizer::Rasterizer::backward  (rasterizer.h:55-83, src/Rasterizer.cu:265)
+ *   gsb_visible_filter             <- CudaRasterizer::Rasterizer::visible_filter (rasterizer.h:85-100, src/Rasterizer.cu:365)
+ *   gsb_mark_visible               <- CudaRasterizer::Rasterizer::markVisible (rasterizer.h:24-29, src/Rasterizer.cu:310)
+ *   gsb_knn_mean_dist2             <- SimpleKNN::knn (include/simple_knn.h:15-19, src/spatial.cu:24)
+ *
+ * plus fused extensions of the caller-side prologue/epilogue:
+ *
+ *   gsb_pose_grad                  <- autograd of the bmm at src/Render.cc:750-752 into Tcw
+ *   gsb_adam_step                  <- torch::optim::Adam step of src/Gaussian.cc:131-175
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers to contiguous fp32 / int32 arrays unless the
+ *     name ends in _host.  Optional inputs are NULL (the reference passes the null
+ *     data_ptr of an empty tensor: include/Rasterizer.cuh:320-334).
+ *   - Matrices are 16 floats read column-major (m[0]x + m[4]y + m[8]z + m[12]), exactly as
+ *     the reference kernels read them (auxiliary.h:58-77).
+ *   - Every call is asynchronous on `stream` (a cudaStream_t; NULL = legacy default stream)
+ *     except where noted; the library keeps no global mutable state, never calls
+ *     cudaMalloc/cudaFree on the hot path, and is re-entrant from multiple threads.
+ *   - Functions return GSB_OK (0) or a negative gsb_status; they never throw.
+ *     gsb_last_error() returns a thread-local description of the last failure.
+ *   - Gradient outputs are FULLY WRITTEN by gsb_backward (zero for invisible Gaussians);
+ *     the caller does not need to zero them (the reference requires zeroed buffers,
+ *     src/Rasterizer.cu:253-261; zeroed buffers remain valid input).
+ */
+#ifndef GSB_H_INCLUDED
+#define GSB_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSB_VERSION_MAJOR 0
+#define GSB_VERSION_MINOR 1
+
+typedef enum gsb_status {
+    GSB_OK = 0,
+    GSB_ERR_INVALID_ARGUMENT = -1,  /* reference: AT_ERROR / std::invalid_argument (Rasterizer.cu:158, Rasterizer.cuh:310-316) */
+    GSB_ERR_CUDA = -2,              /* a CUDA runtime call or launch failed */
+    GSB_ERR_WORKSPACE = -3,         /* caller-provided workspace too small / allocator returned NULL */
+    GSB_ERR_OVERFLOW = -4,          /* num_rendered exceeded the binning capacity given to gsb_forward_ws */
+    GSB_ERR_UNSUPPORTED = -5        /* e.g. NUM_CHANNELS != 3 without precomputed colours (impl.cu:245-248) */
+} gsb_status;
+
+typedef void* gsb_stream_t; /* cudaStream_t */
+
+/* Scratch allocator callback: return >= bytes of device memory (256-byte aligned), or
+ * NULL on failure.  Mirrors std::function<char*(size_t)> of rasterizer.h:32-34; unlike
+ * the reference's resizeFunctional (src/Rasterizer.cu:127-134) the memory need NOT be
+ * zeroed.  The returned block must stay alive until gsb_backward has consumed it. */
+typedef void* (*gsb_alloc_fn)(void* user, size_t bytes);
+
+/* Inputs of one rasterization (argument set of rasterizer.h:35-53). */
+typedef struct gsb_raster_args {
+    int P;                       /* number of Gaussians */
+    int D;                       /* active SH degree (0..3) */
+    int M;                       /* SH coefficients per Gaussian (0 if colours are precomputed) */
+    int width, height;
+    const float* background;     /* [3] */
+    const float* means3D;        /* [P,3] */
+    const float* shs;            /* [P,M,3] or NULL */
+    const float* colors_precomp; /* [P,3] or NULL (exactly one of shs / colors_precomp) */
+    const float* opacities;      /* [P] */
+    const float* scales;         /* [P,3] or NULL */
+    float scale_modifier;
+    const float* rotations;      /* [P,4] (w,x,y,z), used as given, NOT normalised (forward.cu:127) */
+    const float* cov3D_precomp;  /* [P,6] or NULL (exactly one of scales+rotations / cov3D_precomp) */
+    const float* viewmatrix;     /* [16] */
+    const float* projmatrix;     /* [16] */
+    const float* cam_pos;        /* [3] (only read on the SH path) */
+    float tan_fovx, tan_fovy;
+    int prefiltered;             /* reference traps if a culled point was declared prefiltered; here: ignored */
+} gsb_raster_args;
+
+/* Gradient outputs of rasterizer.h:74-83.  Any pointer may be NULL to skip that output. */
+typedef struct gsb_grad_outputs {
+    float* dL_dmean2D;   /* [P,3]  (x,y written, z = 0)                               */
+    float* dL_dconic;    /* [P,4]  (slots 0,1,3 written, slot 2 = 0; backward.cu:549-551) */
+    float* dL_dopacity;  /* [P]    */
+    float* dL_dcolor;    /* [P,3]  */
+    float* dL_dmean3D;   /* [P,3]  */
+    float* dL_dcov3D;    /* [P,6]  */
+    float* dL_dsh;       /* [P,M,3] (only when shs != NULL) */
+    float* dL_dscale;    /* [P,3]  */
+    float* dL_drot;      /* [P,4]  w.r.t. the quaternion as given (no normalisation Jacobian; backward.cu:340) */
+} gsb_grad_outputs;
+
+/* ---- library info ------------------------------------------------------------------- */
+int gsb_version(void);                  /* (major << 16) | minor */
+const char* gsb_last_error(void);       /* thread-local; "" if none */
+
+/* ---- workspace sizing ----------------------------------------------------------------
+ * Byte sizes of the three opaque state blobs (the analogue of required<GeometryState>(P),
+ * required<ImageState>(W*H), required<BinningState>(R), rasterizer_impl.h:67-73). */
+size_t gsb_geometry_bytes(int P);
+size_t gsb_image_bytes(int width, int height);
+size_t gsb_binning_bytes(long long max_rendered);
+/* Same three numbers through one call (out pointers may be NULL). */
+int gsb_workspace_query(int P, int width, int height, long long max_rendered,
+                        size_t* geometry_bytes, size_t* image_bytes, size_t* binning_bytes);
+
+/* ---- forward ------------------------------------------------------------------------
+ * Drop-in for Rasterizer::forward.  Allocates the three state blobs through the
+ * callbacks, performs ONE stream synchronisation to learn num_rendered (the reference
+ * does a blocking cudaMemcpy at rasterizer_impl.cu:285) and returns it (>= 0), or a
+ * negative gsb_status.  out_color [3,H,W], out_depth [1,H,W], radii [P] (may be NULL)
+ * are fully written. */
+int gsb_forward(const gsb_raster_args* args,
+                gsb_alloc_fn geometry_alloc, void* geometry_user,
+                gsb_alloc_fn binning_alloc, void* binning_user,
+                gsb_alloc_fn image_alloc, void* image_user,
+                float* out_color, float* out_depth, int* radii,
+                gsb_stream_t stream);
+
+/* Sync-free forward over caller-provided workspaces (sizes from gsb_*_bytes).  The
+ * binning blob is sized for `max_rendered` tile instances; if the frame needs more, the
+ * instance list is truncated on the device, an overflow flag is latched in the geometry
+ * blob and gsb_num_rendered() reports GSB_ERR_OVERFLOW.  Returns GSB_OK once everything
+ * is enqueued. */
+int gsb_forward_ws(const gsb_raster_args* args,
+                   void* geometry, size_t geometry_bytes,
+                   void* binning, size_t binning_bytes, long long max_rendered,
+                   void* image, size_t image_bytes,
+                   float* out_color, float* out_depth, int* radii,
+                   gsb_stream_t stream);
+
+/* Synchronises `stream` and returns the num_rendered recorded in a geometry blob
+ * (>= 0), or GSB_ERR_OVERFLOW. */
+long long gsb_num_rendered(const void* geometry, gsb_stream_t stream);
+
+/* ---- backward -----------------------------------------------------------------------
+ * Drop-in for Rasterizer::backward.  `R` is the value returned by gsb_forward (pass -1
+ * after gsb_forward_ws: the count is read from the geometry blob on the device).
+ * `radii` may be NULL (the blob keeps a copy).  dL_dpix is [3,H,W]; the gradient of the
+ * depth output is not propagated (include/Rasterizer.cuh:210). */
+int gsb_backward(const gsb_raster_args* args, long long R, const int* radii,
+                 const void* geometry, const void* binning, const void* image,
+                 const float* dL_dpix, const gsb_grad_outputs* grads,
+                 gsb_stream_t stream);
+
+/* ---- visibility helpers --------------------------------------------------------------*/
+/* Radii-only projection (Rasterizer::visible_filter): radii[P] fully written. */
+int gsb_visible_filter(const gsb_raster_args* args, int* radii, gsb_stream_t stream);
+/* present[i] = (view-space z > 0.2) (Rasterizer::markVisible / checkFrustum). */
+int gsb_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present, gsb_stream_t stream);
+
+/* ---- simple_knn -----------------------------------------------------------------------
+ * mean_dist2[i] = mean of the squared distances from points[i] to its 3 nearest
+ * neighbours (SimpleKNN::knn).  `workspace` must hold gsb_knn_workspace_bytes(P) bytes.
+ * Performs one stream synchronisation (the reference does two blocking copies of the
+ * bounding box, simple_knn.cu:193-200). */
+size_t gsb_knn_workspace_bytes(int P);
+int gsb_knn_mean_dist2(int P, const float* points, float* mean_dist2,
+                       void* workspace, size_t workspace_bytes, gsb_stream_t stream);
+
+/* ---- fused caller-side pieces (extensions) ------------------------------*/
+/* Prologue of Render::StartSplatting (src/Render.cc:750-759) in one pass:
+ *   means_cam = (Tcw * [mean;1]).xyz, opacities = sigmoid(logit), rot = normalize(q),
+ *   scales = exp(log_scale).  Tcw is [4,4] ROW-major (torch layout).  Any output may be NULL. */
+int gsb_prologue(int P, const float* Tcw, const float* means_world, const float* logit_opacities,
+                 const float* unnorm_quats, const float* log_scales,
+                 float* means_cam, float* opacities, float* rotations, float* scales,
+                 gsb_stream_t stream);
+/* Backward of that prologue: chain rule through sigmoid / normalize / exp / the rigid
+ * transform, plus dL/dTcw[0:3,:] = sum_i g_i [p_i;1]^T (the "camera-pose backward";
+ * src/Render.cc:750-752 differentiated by autograd in the reference).  dL_dTcw is 12 floats
+ * (rows 0..2 of the 4x4, row-major), fully written.  Any output may be NULL. */
+int gsb_prologue_backward(int P, const float* Tcw, const float* means_world,
+                          const float* logit_opacities, const float* unnorm_quats,
+                          const float* log_scales,
+                          const float* dL_dmeans_cam, const float* dL_dopacities,
+                          const float* dL_drotations, const float* dL_dscales,
+                          float* dL_dmeans_world, float* dL_dlogit_opacities,
+                          float* dL_dunnorm_quats, float* dL_dlog_scales, float* dL_dTcw,
+                          gsb_stream_t stream);
+/* dL/dTcw only (12 floats), from camera-frame mean gradients. */
+int gsb_pose_grad(int P, const float* means_world, const float* dL_dmeans_cam, float* dL_dTcw,
+                  gsb_stream_t stream);
+
+/* Fused multi-tensor Adam (torch::optim::Adam semantics: bias-corrected, eps outside the
+ * sqrt, no weight decay / amsgrad; src/Gaussian.cc:131-175).  One launch updates n
+ * contiguous fp32 values: p -= lr * mhat / (sqrt(vhat) + eps).  `step` is the 1-based step
+ * count AFTER this update. */
+int gsb_adam_step(long long n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                  float lr, float beta1, float beta2, float eps, long long step,
+                  gsb_stream_t stream);
+
+/* ---- host-buffer convenience (bench "e2e" leg and quick integration tests) -------------
+ * One forward + backward with every array in HOST memory (pinned recommended): copies the
+ * inputs H2D, runs gsb_forward_ws + gsb_backward, copies colour/depth/radii and the
+ * gradients back.  `device_scratch` must hold gsb_host_scratch_bytes(...) bytes of DEVICE
+ * memory.  Synchronises `stream` before returning.  Returns num_rendered or an error. */
+size_t gsb_host_scratch_bytes(int P, int M, int width, int height, long long max_rendered);
+long long gsb_forward_backward_host(const gsb_raster_args* host_args, long long max_rendered,
+                                    const float* dL_dpix_host,
+                                    float* out_color_host, float* out_depth_host, int* radii_host,
+                                    const gsb_grad_outputs* host_grads,
+                                    void* device_scratch, size_t device_scratch_bytes,
+                                    gsb_stream_t stream);
+
+/* ---- introspection for parity tests ----------------------------------------------------
+ * Copies of internal state into caller DEVICE buffers (any pointer may be NULL):
+ * final transmittance [H*W], n_contrib [H*W], tile ranges [tiles*2], sorted instance list
+ * [R], projected state per Gaussian (depths [P], means2D [P,2], conic_opacity [P,4],
+ * tiles_touched [P]). */
+int gsb_debug_image_state(const void* image, int width, int height,
+                          float* final_T, uint32_t* n_contrib, uint32_t* ranges,
+                          gsb_stream_t stream);
+int gsb_debug_binning_state(const void* geometry, const void* binning, long long R,
+                            uint32_t* point_list, gsb_stream_t stream);
+int gsb_debug_geometry_state(const void* geometry, int P, float* depths, float* means2D,
+                             float* conic_opacity, uint32_t* tiles_touched,
+                             gsb_stream_t stream);
+
+/* Number of kernels launched by this thread through the library since the last call
+ * (used by bench.py for its gpu_launches claim). */
+long long gsb_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSB_H_INCLUDED */

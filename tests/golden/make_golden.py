@@ -1,0 +1,236 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by RUNNING THE REFERENCE KERNELS.
+
+The reference ships no golden vectors, so parity is pinned on outputs
+of the reference's own CUDA code: oracle/_ref/libgsref.so = the unmodified
+Thirdparty/diff_gaussian_rasterization/cuda_rasterizer/*.cu + src/simple_knn.cu compiled for
+sm_100a (oracle/Makefile), executed on a B200:
+
+    gpurun -- python tests/golden/make_golden.py --out gpurun_out/golden
+    cp gpurun_out/golden/*.npz gpurun_out/golden/*.json tests/golden/
+
+Each small case stores its inputs (so the fixture does not depend on numpy's RNG stream) and
+every reference output the parity contract names.  Large cases store digests + strided
+samples only.  The script also compares the CPU oracle with the reference on the spot and
+writes the result to <out>/oracle_vs_reference.json (the "pinning" evidence).
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from gsorb_slam_b200.scene import make_scene  # noqa: E402
+
+
+def sha(a) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def small_cases():
+    """name -> (scene, extra kwargs for the frame)"""
+    rng = np.random.default_rng(1234)
+    cases = {}
+    sc = make_scene(256, "tiny", seed=0, scale_mul=4.0)
+    cases["tiny_default"] = (sc, {})
+    # non-zero background + a real view matrix (radius-filter mode of Render::StartSplatting)
+    sc = make_scene(384, "tiny", seed=1, scale_mul=3.0, background=0.3)
+    ang = 0.2
+    Tcw = np.eye(4, dtype=np.float32)
+    Tcw[:3, :3] = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]], np.float32)
+    Tcw[:3, 3] = [0.1, -0.05, 0.2]
+    sc.cam.set_pose(Tcw)
+    cases["tiny_view_bg"] = (sc, {})
+    # spherical harmonics colours, degree 2 of 3 (M = 16)
+    sc = make_scene(256, "tiny", seed=2, scale_mul=4.0)
+    shs = rng.normal(0, 0.5, (256, 16, 3)).astype(np.float32)
+    sc.cam.set_pose(Tcw)
+    cases["tiny_sh"] = (sc, dict(colors=None, shs=shs, sh_degree=2))
+    # precomputed 3D covariances
+    sc = make_scene(256, "tiny", seed=3, scale_mul=4.0)
+    A = rng.normal(0, 1, (256, 3, 3)).astype(np.float32) * sc.scales[:, None, :]
+    S = A @ A.transpose(0, 2, 1)
+    cov = np.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], 1).astype(np.float32)
+    cases["tiny_cov"] = (sc, dict(scales=None, rotations=None, cov3D=cov))
+    # ragged image (not a multiple of 16) with big and small splats mixed
+    sc = make_scene(2000, (100, 75, 90.0, 88.0), seed=4, scale_mul=2.0, scale_jitter=0.8)
+    cases["ragged_100x75"] = (sc, {})
+    return cases
+
+
+def frame_kwargs(sc, extra):
+    cam = sc.cam
+    kw = dict(width=cam.width, height=cam.height, means3D=sc.means3D, opacities=sc.opacities,
+              background=sc.background, viewmatrix=cam.viewmatrix, projmatrix=cam.projmatrix,
+              tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, colors=sc.colors, scales=sc.scales,
+              rotations=sc.rotations, campos=cam.campos)
+    kw.update(extra)
+    return kw
+
+
+def run_ref(kw, dL):
+    import torch
+    from oracle import gs_ref
+    fr = gs_ref.RefFrame(**kw)
+    g = fr.backward(dL)
+    torch.cuda.synchronize()
+    ims, bs, gs = fr.image_state(), fr.binning_state(), fr.geometry_state()
+    out = dict(color=fr.color, depth=fr.depth, radii=fr.radii, final_T=ims["final_T"], n_contrib=ims["n_contrib"],
+               ranges=ims["ranges"], point_list=bs["point_list"], depths=gs["depths"], means2D=gs["means2D"],
+               conic_opacity=gs["conic_opacity"], tiles_touched=gs["tiles_touched"], rgb=gs["rgb"], **g)
+    out = {k: v.detach().cpu().numpy().copy() for k, v in out.items()}
+    out["num_rendered"] = np.int64(fr.num_rendered)
+    return out
+
+
+def run_oracle(kw, dL):
+    from oracle import gs_oracle
+    fr = gs_oracle.OracleFrame(**kw)
+    g = fr.backward(dL)
+    ims, bs, gs = fr.image_state(), fr.binning(), fr.geometry()
+    out = dict(color=fr.color, depth=fr.depth, radii=fr.radii, final_T=ims["final_T"], n_contrib=ims["n_contrib"],
+               ranges=bs["ranges"], point_list=bs["point_list"], depths=gs["depths"], means2D=gs["means2D"],
+               conic_opacity=gs["conic_opacity"], tiles_touched=gs["tiles_touched"], rgb=gs["rgb"])
+    out.update({k: v for k, v in g.items() if v is not None})
+    out["num_rendered"] = np.int64(fr.num_rendered)
+    return out
+
+
+INT_KEYS = ["radii", "n_contrib", "ranges", "point_list", "tiles_touched", "num_rendered"]
+FLOAT_KEYS = ["color", "depth", "final_T", "depths", "means2D", "conic_opacity", "dL_dmean2D", "dL_dconic",
+              "dL_dopacity", "dL_dcolor", "dL_dmean3D", "dL_dcov3D", "dL_dscale", "dL_drot", "dL_dsh"]
+
+
+def compare(a, b):
+    """max abs / max rel-to-scale differences + exact-equality flags for the integer state."""
+    rep = {}
+    for k in INT_KEYS:
+        if k in a and k in b:
+            x, y = np.asarray(a[k]).astype(np.int64).ravel(), np.asarray(b[k]).astype(np.int64).ravel()
+            rep[k] = dict(equal=bool(x.shape == y.shape and np.array_equal(x, y)),
+                          mismatches=int((x != y).sum()) if x.shape == y.shape else -1)
+    for k in FLOAT_KEYS:
+        if k in a and k in b and a[k] is not None and b[k] is not None:
+            x, y = np.asarray(a[k], np.float64).ravel(), np.asarray(b[k], np.float64).ravel()
+            if x.shape != y.shape:
+                rep[k] = dict(shape_mismatch=True)
+                continue
+            d = np.abs(x - y)
+            scale = max(float(np.abs(y).max()), 1e-30)
+            rep[k] = dict(max_abs=float(d.max()) if d.size else 0.0, max_rel_to_scale=float(d.max() / scale) if d.size else 0.0,
+                          bit_equal=bool(np.array_equal(np.asarray(a[k], np.float32).ravel().view(np.uint32),
+                                                        np.asarray(b[k], np.float32).ravel().view(np.uint32))))
+    return rep
+
+
+def digest_large(out, W, H):
+    d = dict(num_rendered=int(out["num_rendered"]), visible=int((out["radii"] > 0).sum()),
+             radii_sha=sha(out["radii"].astype(np.int32)), point_list_sha=sha(out["point_list"].astype(np.uint32)),
+             ranges_sha=sha(out["ranges"].astype(np.uint32)), n_contrib_sha=sha(out["n_contrib"].astype(np.uint32)),
+             color_mean=[float(x) for x in out["color"].reshape(3, -1).mean(1)],
+             final_T_mean=float(out["final_T"].mean()))
+    return d
+
+
+def time_ref(kw, dL, iters=20, warm=5):
+    """fwd / bwd device time of the reference kernels (CUDA events), per call."""
+    import torch
+    from oracle import gs_ref
+    fr = gs_ref.RefFrame(run=False, **kw)
+    dLd = torch.from_numpy(dL).cuda()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    tf, tb = [], []
+    for it in range(warm + iters):
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        fr.forward()
+        e1.record()
+        fr.backward(dLd)
+        e2.record()
+        torch.cuda.synchronize()
+        if it >= warm:
+            tf.append(e0.elapsed_time(e1))
+            tb.append(e1.elapsed_time(e2))
+    return dict(fwd_ms=float(np.median(tf)), bwd_ms=float(np.median(tb)), fwd_min=float(min(tf)), bwd_min=float(min(tb)),
+                num_rendered=int(fr.num_rendered), visible=int((fr.radii > 0).sum().item()), iters=iters)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "golden"))
+    ap.add_argument("--large", default="100000,1000000")
+    ap.add_argument("--time", action="store_true", help="also time the reference kernels (fwd, bwd)")
+    args = ap.parse_args()
+    os.makedirs(args.out, exist_ok=True)
+    report = {}
+    for name, (sc, extra) in small_cases().items():
+        kw = frame_kwargs(sc, extra)
+        ref = run_ref(kw, sc.dL_dpix)
+        orc = run_oracle(kw, sc.dL_dpix)
+        report[name] = compare(orc, ref)
+        inputs = {("in_" + k): np.asarray(v) for k, v in kw.items() if v is not None}
+        inputs["in_dL_dpix"] = sc.dL_dpix
+        np.savez_compressed(os.path.join(args.out, f"{name}.npz"), **inputs, **{("ref_" + k): v for k, v in ref.items()})
+        print(name, "R", int(ref["num_rendered"]), json.dumps({k: v for k, v in report[name].items() if k in ("radii", "point_list", "color", "dL_dmean3D")}), flush=True)
+    # simple_knn fixture
+    from oracle import gs_ref, gs_oracle
+    pts = make_scene(5000, "tum", seed=7).means3D
+    knn_ref = gs_ref.knn_mean_dist2(pts).cpu().numpy()
+    knn_orc = gs_oracle.knn_mean_dist2(pts)
+    report["knn_5000"] = dict(max_abs=float(np.abs(knn_ref - knn_orc).max()), bit_equal=bool(np.array_equal(knn_ref, knn_orc)))
+    np.savez_compressed(os.path.join(args.out, "knn_5000.npz"), in_points=pts, ref_mean_dist2=knn_ref)
+    print("knn", report["knn_5000"], flush=True)
+    # visible_filter / mark_visible fixture (1.2x image, unchanged tanfov: src/Render.cc:784-831)
+    sc = make_scene(4000, "tum", seed=8)
+    vf = dict(width=int(sc.cam.width * 1.2), height=int(sc.cam.height * 1.2), means3D=sc.means3D, scales=sc.scales,
+              rotations=sc.rotations, viewmatrix=sc.cam.viewmatrix, projmatrix=sc.cam.projmatrix,
+              tanfovx=sc.cam.tanfovx, tanfovy=sc.cam.tanfovy)
+    r_ref = gs_ref.visible_filter(**vf).cpu().numpy()
+    r_orc = gs_oracle.visible_filter(**vf)
+    m_ref = gs_ref.mark_visible(sc.means3D, sc.cam.viewmatrix, sc.cam.projmatrix).cpu().numpy()
+    m_orc = gs_oracle.mark_visible(sc.means3D, sc.cam.viewmatrix, sc.cam.projmatrix)
+    report["visible_filter_4000"] = dict(radii_equal=bool(np.array_equal(r_ref, r_orc)), mark_equal=bool(np.array_equal(m_ref, m_orc)))
+    np.savez_compressed(os.path.join(args.out, "visible_4000.npz"), **{("in_" + k): np.asarray(v) for k, v in vf.items()},
+                        ref_radii=r_ref, ref_present=m_ref)
+    print("visible", report["visible_filter_4000"], flush=True)
+
+    digests, timing = {}, {}
+    for P in [int(x) for x in args.large.split(",") if x]:
+        sc = make_scene(P, "tum", seed=0)
+        kw = frame_kwargs(sc, {})
+        ref = run_ref(kw, sc.dL_dpix)
+        name = f"tum_{P}"
+        digests[name] = digest_large(ref, sc.cam.width, sc.cam.height)
+        sub = {k: ref[k][..., ::10, ::10].copy() for k in ("color", "depth")}
+        sub["final_T"] = ref["final_T"][::10, ::10].copy()
+        sub["n_contrib"] = ref["n_contrib"][::10, ::10].copy()
+        idx = np.arange(0, P, max(1, P // 4096))
+        for k in ("dL_dmean3D", "dL_dscale", "dL_drot", "dL_dopacity", "dL_dcolor", "dL_dmean2D", "dL_dconic", "radii"):
+            sub[k] = ref[k][idx].copy()
+        np.savez_compressed(os.path.join(args.out, f"{name}_sample.npz"), sample_idx=idx, **sub)
+        if P <= 200000:
+            t0 = time.time()
+            orc = run_oracle(kw, sc.dL_dpix)
+            report[name] = compare(orc, ref)
+            report[name]["oracle_seconds"] = time.time() - t0
+        print(name, json.dumps(digests[name]), flush=True)
+        if args.time:
+            timing[name] = time_ref(kw, sc.dL_dpix)
+            print("timing", name, json.dumps(timing[name]), flush=True)
+    json.dump(digests, open(os.path.join(args.out, "large_digests.json"), "w"), indent=1)
+    json.dump(report, open(os.path.join(args.out, "oracle_vs_reference.json"), "w"), indent=1)
+    if timing:
+        json.dump(timing, open(os.path.join(args.out, "reference_timing.json"), "w"), indent=1)
+    print("done")
+
+
+if __name__ == "__main__":
+    main()
