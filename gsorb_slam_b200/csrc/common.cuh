@@ -54,6 +54,7 @@ struct GeomHeader {            // first 256 bytes of the geometry blob (device m
     uint32_t visible;          // number of Gaussians with radii > 0 (diagnostics)
     uint32_t pad[64 - 15];
 };
+// The header is zeroed by the forward before the first kernel; the scan kernel fills it.
 static_assert(sizeof(GeomHeader) == 256, "header is 256 bytes");
 
 inline __host__ __device__ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -109,7 +110,9 @@ constexpr int SORT_RADIX = 1 << SORT_RADIX_BITS;
 constexpr int SORT_MAX_PASSES = 8;
 
 struct BinningLayout {
-    size_t keys0, keys1, vals0, vals1, hist, lookback, total;
+    // vals0 sits at offset 0: the radix passes are arranged so that the SORTED instance list
+    // always ends up there, whatever the capacity / pass count (gsb_backward relies on it).
+    size_t vals0, vals1, keys0, keys1, hist, lookback, total;
     long long capacity;
     int sort_tiles;
     __host__ __device__ static BinningLayout make(long long cap)
@@ -120,10 +123,10 @@ struct BinningLayout {
         if (cap < 1) cap = 1;
         L.capacity = cap;
         L.sort_tiles = (int)((cap + SORT_TILE - 1) / SORT_TILE);
+        L.vals0 = take((size_t)cap * 4 + 64);   // +64: 16-byte aligned over-fetch by the blend stagers
+        L.vals1 = take((size_t)cap * 4 + 64);
         L.keys0 = take((size_t)cap * 8);
         L.keys1 = take((size_t)cap * 8);
-        L.vals0 = take((size_t)cap * 4);
-        L.vals1 = take((size_t)cap * 4);
         L.hist = take((size_t)SORT_MAX_PASSES * SORT_RADIX * 4);
         L.lookback = take((size_t)SORT_MAX_PASSES * L.sort_tiles * SORT_RADIX * 4);
         L.total = off;

@@ -1,0 +1,328 @@
+// preprocess.cu -- per-Gaussian projection (K1), tile-count scan (K2), radii-only filter (K10)
+// and frustum mask (K11) for sm_100a.
+//
+// Replaces (reference file:line, behaviour only -- nothing is copied):
+//   FORWARD::preprocess / preprocessCUDA      forward.cu:155-256
+//   computeCov3D / computeCov2D               forward.cu:118-152 / :74-113
+//   in_frustum, getRect, ndc2Pix              auxiliary.h:139-163, :46-56, :41-44
+//   cub::DeviceScan::InclusiveSum + D2H copy  rasterizer_impl.cu:280-285
+//   preprocessfilterCUDA / visible_filter     forward.cu:404-473, rasterizer_impl.cu:348-401
+//   checkFrustum / markVisible                rasterizer_impl.cu:55-67, :142-154
+//
+// Layout: the reference scatters the projected state over seven SoA arrays (79 B/Gaussian);
+// here one 48-byte SplatRec per Gaussian carries everything the blend kernels gather, and
+// the AoS float3 inputs are staged through shared memory with 128-bit coalesced loads.
+#include "common.cuh"
+
+namespace gsb {
+
+constexpr int PRE_THREADS = 256;
+
+// Stage a block's [PRE_THREADS,3] slice of an AoS float3 array into shared memory with
+// LDG.128 (3072 B per block = 192 float4), falling back to scalar loads when the base
+// pointer is not 16-byte aligned or the slice is ragged.
+__device__ __forceinline__ void stage_float3(const float* __restrict__ g, float* s, int P, int base, bool aligned)
+{
+    const int n = min(PRE_THREADS, P - base) * 3;  // floats in this slice
+    const float* src = g + (size_t)base * 3;
+    if (aligned && n == PRE_THREADS * 3) {
+        if (threadIdx.x < PRE_THREADS * 3 / 4)
+            reinterpret_cast<float4*>(s)[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(src) + threadIdx.x);
+    } else {
+        for (int i = threadIdx.x; i < n; i += PRE_THREADS) s[i] = __ldg(src + i);
+    }
+}
+
+struct Projected {
+    bool visible;
+    float depth, px, py, conx, cony, conz;
+    float cov_xx, cov_yy;
+    int radius;
+    uint32_t minx, miny, maxx, maxy;
+};
+
+// forward.cu:155-256 up to the tile rectangle; op order as the reference compiles it.
+__device__ __forceinline__ Projected project_gaussian(const FwdParams& p, float mx, float my, float mz,
+                                                      const float* cov3D, int W, int H, int gx, int gy)
+{
+    Projected o;
+    o.visible = false;
+    o.radius = 0;
+    const float* V = p.viewmatrix;
+    const float* PM = p.projmatrix;
+    const float pvz = xform_row(V, 2, mx, my, mz);
+    if (!(pvz > 0.2f)) return o;  // auxiliary.h:154 (NaN also culls: "z <= 0.2" is false for NaN in the
+                                  // reference, but such a Gaussian dies at det/radius; keep it out)
+    const float hx = xform_row(PM, 0, mx, my, mz);
+    const float hy = xform_row(PM, 1, mx, my, mz);
+    const float hw = xform_row(PM, 3, mx, my, mz);
+    const float p_w = __fdiv_rn(1.0f, __fadd_rn(hw, 0.0000001f));
+    const float projx = __fmul_rn(hx, p_w), projy = __fmul_rn(hy, p_w);
+    float cov[3];
+    compute_cov2d(mx, my, mz, p.focal_x, p.focal_y, p.tan_fovx, p.tan_fovy, cov3D, V, cov, nullptr);
+    const float det = fmaf(cov[0], cov[2], -__fmul_rn(cov[1], cov[1]));
+    if (det == 0.0f) return o;
+    const float det_inv = __fdiv_rn(1.f, det);
+    o.conx = __fmul_rn(cov[2], det_inv);
+    o.cony = __fmul_rn(cov[1], -det_inv);
+    o.conz = __fmul_rn(cov[0], det_inv);
+    const float mid = __fmul_rn(__fadd_rn(cov[0], cov[2]), 0.5f);
+    const float disc = fmaxf(fmaf(mid, mid, -det), 0.1f);
+    const float sq = __fsqrt_rn(disc);
+    const float lambda1 = __fadd_rn(mid, sq), lambda2 = __fsub_rn(mid, sq);
+    const float my_radius = ceilf(__fmul_rn(__fsqrt_rn(fmaxf(lambda1, lambda2)), 3.f));
+    o.px = ndc2pix(projx, W);
+    o.py = ndc2pix(projy, H);
+    o.radius = (int)my_radius;
+    get_rect(o.px, o.py, o.radius, gx, gy, o.minx, o.miny, o.maxx, o.maxy);
+    if ((o.maxx - o.minx) * (o.maxy - o.miny) == 0) {
+        o.radius = 0;
+        return o;
+    }
+    o.depth = pvz;
+    o.cov_xx = cov[0];
+    o.cov_yy = cov[2];
+    o.visible = true;
+    return o;
+}
+
+// forward.cu:20-71 computeColorFromSH
+__device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh, float mx, float my, float mz,
+                                          const float* __restrict__ campos, float* rgb, uint32_t& clamped)
+{
+    float dx = mx - campos[0], dy = my - campos[1], dz = mz - campos[2];
+    const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float x = dx / len, y = dy / len, z = dz / len;
+    clamped = 0;
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        auto S = [&](int k) { return sh[k * 3 + ch]; };
+        float res = SH_C0 * S(0);
+        if (deg > 0) {
+            res = res - SH_C1 * y * S(1) + SH_C1 * z * S(2) - SH_C1 * x * S(3);
+            if (deg > 1) {
+                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                res = res + SH_C2[0] * xy * S(4) + SH_C2[1] * yz * S(5) + SH_C2[2] * (2.0f * zz - xx - yy) * S(6) +
+                      SH_C2[3] * xz * S(7) + SH_C2[4] * (xx - yy) * S(8);
+                if (deg > 2) {
+                    res = res + SH_C3[0] * y * (3.0f * xx - yy) * S(9) + SH_C3[1] * xy * z * S(10) +
+                          SH_C3[2] * y * (4.0f * zz - xx - yy) * S(11) +
+                          SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * S(12) +
+                          SH_C3[4] * x * (4.0f * zz - xx - yy) * S(13) + SH_C3[5] * z * (xx - yy) * S(14) +
+                          SH_C3[6] * x * (xx - 3.0f * yy) * S(15);
+                }
+            }
+        }
+        res += 0.5f;
+        if (res < 0.f) clamped |= 1u << ch;
+        rgb[ch] = fmaxf(res, 0.0f);
+    }
+}
+
+// One thread per Gaussian, 256 per CTA.  Emits the packed record, radii, tiles_touched and
+// the CTA's tile-count sum (first level of the two-level scan).
+__global__ void __launch_bounds__(PRE_THREADS)
+preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ radii_blob, int* __restrict__ radii_out,
+                  uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ block_sums,
+                  uint8_t* __restrict__ clamped_out, int aligned_means, int aligned_scales, int aligned_colors)
+{
+    __shared__ __align__(16) float s_mean[PRE_THREADS * 3];
+    __shared__ __align__(16) float s_scale[PRE_THREADS * 3];
+    __shared__ __align__(16) float s_col[PRE_THREADS * 3];
+    __shared__ uint32_t s_warp[PRE_THREADS / 32];
+    const int base = blockIdx.x * PRE_THREADS;
+    const int idx = base + threadIdx.x;
+    stage_float3(p.means3D, s_mean, p.P, base, aligned_means);
+    if (p.scales) stage_float3(p.scales, s_scale, p.P, base, aligned_scales);
+    if (p.colors_precomp) stage_float3(p.colors_precomp, s_col, p.P, base, aligned_colors);
+    __syncthreads();
+
+    uint32_t touched = 0;
+    if (idx < p.P) {
+        const float mx = s_mean[3 * threadIdx.x], my = s_mean[3 * threadIdx.x + 1], mz = s_mean[3 * threadIdx.x + 2];
+        float cov3D[6];
+        if (p.cov3D_precomp) {
+            const float2* c2 = reinterpret_cast<const float2*>(p.cov3D_precomp + 6 * (size_t)idx);
+            const float2 a = __ldg(c2), b = __ldg(c2 + 1), c = __ldg(c2 + 2);
+            cov3D[0] = a.x; cov3D[1] = a.y; cov3D[2] = b.x; cov3D[3] = b.y; cov3D[4] = c.x; cov3D[5] = c.y;
+        } else {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+            compute_cov3d(s_scale[3 * threadIdx.x], s_scale[3 * threadIdx.x + 1], s_scale[3 * threadIdx.x + 2],
+                          p.scale_modifier, q.x, q.y, q.z, q.w, cov3D);
+        }
+        const Projected o = project_gaussian(p, mx, my, mz, cov3D, p.W, p.H, p.tiles_x, p.tiles_y);
+        int radius = 0;
+        if (o.visible) {
+            radius = o.radius;
+            touched = (o.maxy - o.miny) * (o.maxx - o.minx);
+            float rgb[3];
+            uint32_t cl = 0;
+            if (p.colors_precomp) {
+                rgb[0] = s_col[3 * threadIdx.x]; rgb[1] = s_col[3 * threadIdx.x + 1]; rgb[2] = s_col[3 * threadIdx.x + 2];
+            } else {
+                sh_to_rgb(p.D, p.shs + (size_t)idx * p.M * 3, mx, my, mz, p.cam_pos, rgb, cl);
+                clamped_out[idx] = (uint8_t)cl;
+            }
+            const float opacity = __ldg(p.opacities + idx);
+            // Conservative cull data (never changes a result: the exact tests of forward.cu:346-356
+            // are still applied to everything that survives).
+            //   alpha >= 1/255 needs power >= -ln(255*opacity); keep a safety margin.
+            const float lim = logf(255.0f * opacity);             // > 0 iff the splat can ever contribute
+            float thr, ex, ey;
+            if (!(lim > 0.f)) {
+                thr = 1.0f;  // power <= 0 < thr always: never contributes
+                ex = ey = 0.f;
+            } else {
+                const float t2 = 2.0f * (lim * 1.002f + 0.01f);   // 2 * (-thr)
+                thr = -0.5f * t2;
+                // bbox of {d : d^T Q d <= t2} is sqrt(t2 * (Q^-1)_ii); Q^-1 = cov2D up to fp32 rounding
+                // of the conic, hence the 2 % + 0.05 px slack.
+                ex = sqrtf(t2 * o.cov_xx) * 1.02f + 0.05f;
+                ey = sqrtf(t2 * o.cov_yy) * 1.02f + 0.05f;
+                if (!(ex < 60000.f)) ex = 60000.f;  // also catches NaN
+                if (!(ey < 60000.f)) ey = 60000.f;
+            }
+            const __half2 ext = __halves2half2(__float2half_ru(ex), __float2half_ru(ey));
+            SplatRec r;
+            r.a = make_float4(o.px, o.py, o.conx, o.cony);
+            r.b = make_float4(o.conz, opacity, thr, o.depth);
+            r.c = make_float4(rgb[0], rgb[1], rgb[2], __uint_as_float(*reinterpret_cast<const uint32_t*>(&ext)));
+            rec[idx] = r;
+        }
+        radii_blob[idx] = radius;
+        if (radii_out) radii_out[idx] = radius;
+        tiles_touched[idx] = touched;
+    }
+    // CTA sum of tiles_touched
+    uint32_t v = touched;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane_id() == 0) s_warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int w = 0; w < PRE_THREADS / 32; w++) s += s_warp[w];
+        block_sums[blockIdx.x] = s;
+    }
+}
+
+// Second scan level: one CTA turns block_sums into exclusive block_offsets and fills the
+// header (num_rendered, clamp to the binning capacity, overflow flag).
+__global__ void __launch_bounds__(1024)
+scan_blocks_kernel(const uint32_t* __restrict__ block_sums, uint32_t* __restrict__ block_offsets, int num_blocks,
+                   GeomHeader* __restrict__ hdr, uint32_t capacity, int P)
+{
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < num_blocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t x = i < num_blocks ? block_sums[i] : 0u;
+        uint32_t v = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane_id() >= (uint32_t)o) v += t;
+        }
+        if (lane_id() == 31) s_warp[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = s_warp[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane_id() >= (uint32_t)o) w += t;
+            }
+            s_warp[threadIdx.x] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t warp_excl = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0u;
+        const uint32_t carry = s_carry;
+        if (i < num_blocks) block_offsets[i] = carry + warp_excl + v - x;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + warp_excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t total = s_carry;
+        hdr->magic = GEOM_MAGIC;
+        hdr->P = P;
+        hdr->num_rendered = total;
+        hdr->num_rendered_clamped = min(total, capacity);
+        hdr->overflow = total > capacity ? 1u : 0u;
+        hdr->capacity = capacity;
+    }
+}
+
+int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, int* radii_out, cudaStream_t s)
+{
+    if (p.P <= 0) return GSB_OK;
+    auto al = [](const void* q) { return q && (reinterpret_cast<uintptr_t>(q) & 15) == 0 ? 1 : 0; };
+    preprocess_kernel<<<GL.num_blocks, PRE_THREADS, 0, s>>>(
+        p, reinterpret_cast<SplatRec*>(geom + GL.rec), reinterpret_cast<int*>(geom + GL.radii), radii_out,
+        reinterpret_cast<uint32_t*>(geom + GL.tiles_touched), reinterpret_cast<uint32_t*>(geom + GL.block_sums),
+        reinterpret_cast<uint8_t*>(geom + GL.clamped), al(p.means3D), al(p.scales), al(p.colors_precomp));
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+
+int launch_scan_blocks(char* geom, const GeomLayout& GL, uint32_t capacity, int P, cudaStream_t s)
+{
+    scan_blocks_kernel<<<1, 1024, 0, s>>>(reinterpret_cast<const uint32_t*>(geom + GL.block_sums),
+                                          reinterpret_cast<uint32_t*>(geom + GL.block_offsets), GL.num_blocks,
+                                          reinterpret_cast<GeomHeader*>(geom + GL.header), capacity, P);
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+
+// ---- visible_filter: radii only (forward.cu:404-473) ---------------------------------------
+__global__ void __launch_bounds__(PRE_THREADS)
+visible_filter_kernel(FwdParams p, int* __restrict__ radii)
+{
+    const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
+    if (idx >= p.P) return;
+    const float mx = __ldg(p.means3D + 3 * (size_t)idx), my = __ldg(p.means3D + 3 * (size_t)idx + 1),
+                mz = __ldg(p.means3D + 3 * (size_t)idx + 2);
+    float cov3D[6];
+    if (p.cov3D_precomp) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) cov3D[k] = __ldg(p.cov3D_precomp + 6 * (size_t)idx + k);
+    } else {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+        compute_cov3d(__ldg(p.scales + 3 * (size_t)idx), __ldg(p.scales + 3 * (size_t)idx + 1),
+                      __ldg(p.scales + 3 * (size_t)idx + 2), p.scale_modifier, q.x, q.y, q.z, q.w, cov3D);
+    }
+    const Projected o = project_gaussian(p, mx, my, mz, cov3D, p.W, p.H, p.tiles_x, p.tiles_y);
+    radii[idx] = o.visible ? o.radius : 0;
+}
+
+int launch_visible_filter(const FwdParams& p, int* radii, cudaStream_t s)
+{
+    if (p.P <= 0) return GSB_OK;
+    visible_filter_kernel<<<(p.P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(p, radii);
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+
+// ---- mark_visible (rasterizer_impl.cu:55-67) ------------------------------------------------
+__global__ void __launch_bounds__(PRE_THREADS)
+mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view, uint8_t* __restrict__ present)
+{
+    const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
+    if (idx >= P) return;
+    const float z = xform_row(view, 2, __ldg(means3D + 3 * (size_t)idx), __ldg(means3D + 3 * (size_t)idx + 1),
+                              __ldg(means3D + 3 * (size_t)idx + 2));
+    present[idx] = z > 0.2f ? 1 : 0;
+}
+
+int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s)
+{
+    if (P <= 0) return GSB_OK;
+    mark_visible_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(P, means3D, viewmatrix, present);
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+
+}  // namespace gsb
