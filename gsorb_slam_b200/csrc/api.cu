@@ -1,0 +1,430 @@
+// api.cu -- the C ABI of libgsb.so (include/gsb.h): argument validation, workspace layout,
+// kernel orchestration.  No torch types, no global mutable state (error text and launch
+// counter are thread-local), no cudaMalloc/cudaFree on any path.
+//
+// Orchestration replaces CudaRasterizer::Rasterizer::{forward,backward,visible_filter,
+// markVisible} (rasterizer_impl.cu:199-345, :405-498, :348-401, :142-154).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "common.cuh"
+
+namespace gsb {
+
+static thread_local char g_err[512] = "";
+static thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// Mirrors the argument checks of the reference surface: means3D shape (src/Rasterizer.cu:158-160),
+// sh / colour and scale+rotation / cov3D exclusivity (include/Rasterizer.cuh:310-316), NUM_CHANNELS
+// (rasterizer_impl.cu:245-248).
+static int validate(const gsb_raster_args* a, bool need_colors)
+{
+    if (!a) return fail(GSB_ERR_INVALID_ARGUMENT, "args is NULL");
+    if (a->P < 0) return fail(GSB_ERR_INVALID_ARGUMENT, "P must be >= 0 (got %d)", a->P);
+    if (a->width <= 0 || a->height <= 0)
+        return fail(GSB_ERR_INVALID_ARGUMENT, "image size must be positive (got %dx%d)", a->width, a->height);
+    if (!(a->tan_fovx > 0.f) || !(a->tan_fovy > 0.f)) return fail(GSB_ERR_INVALID_ARGUMENT, "tan_fov must be positive");
+    if (!a->viewmatrix || !a->projmatrix) return fail(GSB_ERR_INVALID_ARGUMENT, "viewmatrix / projmatrix are required");
+    if (a->P > 0) {
+        if (!a->means3D) return fail(GSB_ERR_INVALID_ARGUMENT, "means3D must have dimensions (num_points, 3)");
+        const bool has_sr = a->scales && a->rotations;
+        if ((a->scales != nullptr) != (a->rotations != nullptr))
+            return fail(GSB_ERR_INVALID_ARGUMENT, "scales and rotations must be given together");
+        if (has_sr == (a->cov3D_precomp != nullptr))
+            return fail(GSB_ERR_INVALID_ARGUMENT, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+        if (need_colors) {
+            if (!a->opacities) return fail(GSB_ERR_INVALID_ARGUMENT, "opacities are required");
+            if ((a->shs != nullptr) == (a->colors_precomp != nullptr))
+                return fail(GSB_ERR_INVALID_ARGUMENT, "Please provide exactly one of either SHs or precomputed colors!");
+            if (a->shs) {
+                if (a->D < 0 || a->D > 3) return fail(GSB_ERR_INVALID_ARGUMENT, "SH degree must be 0..3 (got %d)", a->D);
+                if (a->M < (a->D + 1) * (a->D + 1))
+                    return fail(GSB_ERR_INVALID_ARGUMENT, "M = %d SH coefficients cannot hold degree %d", a->M, a->D);
+                if (!a->cam_pos) return fail(GSB_ERR_INVALID_ARGUMENT, "cam_pos is required with SHs");
+            }
+        }
+    }
+    if (need_colors && !a->background) return fail(GSB_ERR_INVALID_ARGUMENT, "background is required");
+    return GSB_OK;
+}
+
+static FwdParams make_params(const gsb_raster_args* a)
+{
+    FwdParams p;
+    p.P = a->P; p.D = a->D; p.M = a->shs ? a->M : 0; p.W = a->width; p.H = a->height;
+    p.tiles_x = (a->width + TILE_X - 1) / TILE_X;
+    p.tiles_y = (a->height + TILE_Y - 1) / TILE_Y;
+    p.background = a->background; p.means3D = a->means3D; p.shs = a->shs; p.colors_precomp = a->colors_precomp;
+    p.opacities = a->opacities; p.scales = a->scales; p.scale_modifier = a->scale_modifier; p.rotations = a->rotations;
+    p.cov3D_precomp = a->cov3D_precomp; p.viewmatrix = a->viewmatrix; p.projmatrix = a->projmatrix; p.cam_pos = a->cam_pos;
+    p.tan_fovx = a->tan_fovx; p.tan_fovy = a->tan_fovy;
+    p.focal_y = a->height / (2.0f * a->tan_fovy);  // rasterizer_impl.cu:224-225
+    p.focal_x = a->width / (2.0f * a->tan_fovx);
+    return p;
+}
+
+static int forward_stage1(const FwdParams& p, char* geom, const GeomLayout& GL, int* radii, uint32_t capacity, cudaStream_t s)
+{
+    GSB_CUDA_CHECK(cudaMemsetAsync(geom + GL.header, 0, sizeof(GeomHeader), s));
+    if (int rc = launch_preprocess(p, geom, GL, radii, s)) return rc;
+    return launch_scan_blocks(geom, GL, capacity, p.P, s);
+}
+
+static int forward_stage2(const FwdParams& p, char* geom, const GeomLayout& GL, char* binning, const BinningLayout& BL,
+                          char* image, const ImageLayout& IL, long long grid_instances, float* out_color, float* out_depth,
+                          cudaStream_t s)
+{
+    if (int rc = launch_binning(p, geom, GL, binning, BL, image, IL, grid_instances, s)) return rc;
+    return launch_blend_forward(p, geom, GL, reinterpret_cast<const uint32_t*>(binning + BL.vals0), image, IL, out_color,
+                                out_depth, s);
+}
+
+__global__ void unpack_geometry_kernel(int P, const SplatRec* __restrict__ rec, const int* __restrict__ radii,
+                                       const uint32_t* __restrict__ tiles_touched, float* depths, float* means2D,
+                                       float* conic_opacity, uint32_t* tt_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const bool vis = radii[i] > 0;
+    const SplatRec r = rec[i];
+    if (depths) depths[i] = vis ? r.b.w : 0.f;
+    if (means2D) { means2D[2 * i] = vis ? r.a.x : 0.f; means2D[2 * i + 1] = vis ? r.a.y : 0.f; }
+    if (conic_opacity) {
+        conic_opacity[4 * i] = vis ? r.a.z : 0.f; conic_opacity[4 * i + 1] = vis ? r.a.w : 0.f;
+        conic_opacity[4 * i + 2] = vis ? r.b.x : 0.f; conic_opacity[4 * i + 3] = vis ? r.b.y : 0.f;
+    }
+    if (tt_out) tt_out[i] = tiles_touched[i];
+}
+
+}  // namespace gsb
+
+using namespace gsb;
+
+extern "C" {
+
+int gsb_version(void) { return (GSB_VERSION_MAJOR << 16) | GSB_VERSION_MINOR; }
+const char* gsb_last_error(void) { return g_err; }
+long long gsb_launch_count_reset(void)
+{
+    const long long n = g_launches;
+    g_launches = 0;
+    return n;
+}
+
+size_t gsb_geometry_bytes(int P) { return GeomLayout::make(P).total; }
+size_t gsb_image_bytes(int width, int height) { return ImageLayout::make(width > 0 ? width : 1, height > 0 ? height : 1).total; }
+size_t gsb_binning_bytes(long long max_rendered) { return BinningLayout::make(max_rendered).total; }
+int gsb_workspace_query(int P, int width, int height, long long max_rendered, size_t* geometry_bytes, size_t* image_bytes,
+                        size_t* binning_bytes)
+{
+    if (P < 0 || width <= 0 || height <= 0 || max_rendered < 0)
+        return fail(GSB_ERR_INVALID_ARGUMENT, "workspace_query: bad sizes");
+    if (geometry_bytes) *geometry_bytes = gsb_geometry_bytes(P);
+    if (image_bytes) *image_bytes = gsb_image_bytes(width, height);
+    if (binning_bytes) *binning_bytes = gsb_binning_bytes(max_rendered);
+    return GSB_OK;
+}
+
+int gsb_forward(const gsb_raster_args* args, gsb_alloc_fn geometry_alloc, void* geometry_user, gsb_alloc_fn binning_alloc,
+                void* binning_user, gsb_alloc_fn image_alloc, void* image_user, float* out_color, float* out_depth,
+                int* radii, gsb_stream_t stream)
+{
+    if (int rc = validate(args, true)) return rc;
+    if (!geometry_alloc || !binning_alloc || !image_alloc) return fail(GSB_ERR_INVALID_ARGUMENT, "allocator callbacks are required");
+    if (!out_color || !out_depth) return fail(GSB_ERR_INVALID_ARGUMENT, "out_color / out_depth are required");
+    cudaStream_t s = (cudaStream_t)stream;
+    const FwdParams p = make_params(args);
+    const GeomLayout GL = GeomLayout::make(p.P);
+    const ImageLayout IL = ImageLayout::make(p.W, p.H);
+    char* geom = (char*)geometry_alloc(geometry_user, GL.total);
+    char* image = (char*)image_alloc(image_user, IL.total);
+    if (!geom || !image) return fail(GSB_ERR_WORKSPACE, "geometry / image allocator returned NULL");
+    if (int rc = forward_stage1(p, geom, GL, radii, 0xffffffffu, s)) return rc;
+    // the one synchronisation of the drop-in path (rasterizer_impl.cu:285 does a blocking cudaMemcpy)
+    GeomHeader h;
+    GSB_CUDA_CHECK(cudaMemcpyAsync(&h, geom + GL.header, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
+    GSB_CUDA_CHECK(cudaStreamSynchronize(s));
+    const long long R = h.num_rendered;
+    if (R >= (1ll << 30)) return fail(GSB_ERR_OVERFLOW, "num_rendered %lld exceeds the 2^30 instance limit", R);
+    const BinningLayout BL = BinningLayout::make(R);
+    char* binning = (char*)binning_alloc(binning_user, BL.total);
+    if (!binning) return fail(GSB_ERR_WORKSPACE, "binning allocator returned NULL");
+    if (int rc = forward_stage2(p, geom, GL, binning, BL, image, IL, R, out_color, out_depth, s)) return rc;
+    return (int)R;
+}
+
+int gsb_forward_ws(const gsb_raster_args* args, void* geometry, size_t geometry_bytes, void* binning, size_t binning_bytes,
+                   long long max_rendered, void* image, size_t image_bytes, float* out_color, float* out_depth, int* radii,
+                   gsb_stream_t stream)
+{
+    if (int rc = validate(args, true)) return rc;
+    if (!out_color || !out_depth) return fail(GSB_ERR_INVALID_ARGUMENT, "out_color / out_depth are required");
+    if (max_rendered < 0 || max_rendered >= (1ll << 30)) return fail(GSB_ERR_INVALID_ARGUMENT, "max_rendered out of range");
+    const FwdParams p = make_params(args);
+    const GeomLayout GL = GeomLayout::make(p.P);
+    const ImageLayout IL = ImageLayout::make(p.W, p.H);
+    const BinningLayout BL = BinningLayout::make(max_rendered);
+    if (!geometry || geometry_bytes < GL.total) return fail(GSB_ERR_WORKSPACE, "geometry workspace too small (%zu < %zu)", geometry_bytes, GL.total);
+    if (!image || image_bytes < IL.total) return fail(GSB_ERR_WORKSPACE, "image workspace too small (%zu < %zu)", image_bytes, IL.total);
+    if (!binning || binning_bytes < BL.total) return fail(GSB_ERR_WORKSPACE, "binning workspace too small (%zu < %zu)", binning_bytes, BL.total);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int rc = forward_stage1(p, (char*)geometry, GL, radii, (uint32_t)max_rendered, s)) return rc;
+    return forward_stage2(p, (char*)geometry, GL, (char*)binning, BL, (char*)image, IL, max_rendered, out_color, out_depth, s);
+}
+
+long long gsb_num_rendered(const void* geometry, gsb_stream_t stream)
+{
+    if (!geometry) return fail(GSB_ERR_INVALID_ARGUMENT, "geometry is NULL");
+    GeomHeader h;
+    cudaStream_t s = (cudaStream_t)stream;
+    GSB_CUDA_CHECK(cudaMemcpyAsync(&h, geometry, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
+    GSB_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (h.magic != GEOM_MAGIC) return fail(GSB_ERR_INVALID_ARGUMENT, "geometry blob has no valid header");
+    if (h.overflow) return fail(GSB_ERR_OVERFLOW, "num_rendered %u exceeded the binning capacity %u", h.num_rendered, h.capacity);
+    return (long long)h.num_rendered;
+}
+
+int gsb_backward(const gsb_raster_args* args, long long R, const int* radii, const void* geometry, const void* binning,
+                 const void* image, const float* dL_dpix, const gsb_grad_outputs* grads, gsb_stream_t stream)
+{
+    if (int rc = validate(args, true)) return rc;
+    if (!geometry || !binning || !image) return fail(GSB_ERR_INVALID_ARGUMENT, "forward state blobs are required");
+    if (!dL_dpix || !grads) return fail(GSB_ERR_INVALID_ARGUMENT, "dL_dpix / grads are required");
+    (void)R;  // tile ranges in the image blob already bound every list
+    cudaStream_t s = (cudaStream_t)stream;
+    const FwdParams p = make_params(args);
+    const GeomLayout GL = GeomLayout::make(p.P);
+    const ImageLayout IL = ImageLayout::make(p.W, p.H);
+    char* geom = (char*)const_cast<void*>(geometry);  // the packed accumulators live in the blob
+    if (int rc = launch_blend_backward(p, geom, GL, reinterpret_cast<const uint32_t*>(binning), (const char*)image, IL, dL_dpix, s))
+        return rc;
+    return launch_gauss_backward(p, geom, GL, radii, *grads, s);
+}
+
+int gsb_visible_filter(const gsb_raster_args* args, int* radii, gsb_stream_t stream)
+{
+    if (int rc = validate(args, false)) return rc;
+    if (!radii && args->P > 0) return fail(GSB_ERR_INVALID_ARGUMENT, "radii is required");
+    return launch_visible_filter(make_params(args), radii, (cudaStream_t)stream);
+}
+
+int gsb_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
+                     gsb_stream_t stream)
+{
+    (void)projmatrix;  // the reference's in_frustum only tests view-space z (auxiliary.h:139-163)
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return fail(GSB_ERR_INVALID_ARGUMENT, "mark_visible: bad arguments");
+    return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+size_t gsb_knn_workspace_bytes(int P) { return knn_workspace_bytes(P); }
+int gsb_knn_mean_dist2(int P, const float* points, float* mean_dist2, void* workspace, size_t workspace_bytes,
+                       gsb_stream_t stream)
+{
+    if (P < 0 || (P > 0 && (!points || !mean_dist2))) return fail(GSB_ERR_INVALID_ARGUMENT, "knn: bad arguments");
+    if (P == 0) return GSB_OK;
+    if (!workspace || workspace_bytes < knn_workspace_bytes(P)) return fail(GSB_ERR_WORKSPACE, "knn workspace too small");
+    return launch_knn(P, points, mean_dist2, (char*)workspace, (cudaStream_t)stream);
+}
+
+int gsb_prologue(int P, const float* Tcw, const float* means_world, const float* logit_opacities, const float* unnorm_quats,
+                 const float* log_scales, float* means_cam, float* opacities, float* rotations, float* scales,
+                 gsb_stream_t stream)
+{
+    if (P < 0) return fail(GSB_ERR_INVALID_ARGUMENT, "prologue: P < 0");
+    if (P > 0 && ((means_cam && (!Tcw || !means_world)) || (opacities && !logit_opacities) || (rotations && !unnorm_quats) ||
+                  (scales && !log_scales)))
+        return fail(GSB_ERR_INVALID_ARGUMENT, "prologue: an output was requested without its input");
+    return launch_prologue(P, Tcw, means_world, logit_opacities, unnorm_quats, log_scales, means_cam, opacities, rotations,
+                           scales, (cudaStream_t)stream);
+}
+
+int gsb_prologue_backward(int P, const float* Tcw, const float* means_world, const float* logit_opacities,
+                          const float* unnorm_quats, const float* log_scales, const float* dL_dmeans_cam,
+                          const float* dL_dopacities, const float* dL_drotations, const float* dL_dscales,
+                          float* dL_dmeans_world, float* dL_dlogit_opacities, float* dL_dunnorm_quats, float* dL_dlog_scales,
+                          float* dL_dTcw, gsb_stream_t stream)
+{
+    if (P < 0) return fail(GSB_ERR_INVALID_ARGUMENT, "prologue_backward: P < 0");
+    if (P > 0 && (((dL_dmeans_world || dL_dTcw) && (!dL_dmeans_cam || !Tcw || !means_world)) ||
+                  (dL_dlogit_opacities && (!dL_dopacities || !logit_opacities)) ||
+                  (dL_dunnorm_quats && (!dL_drotations || !unnorm_quats)) || (dL_dlog_scales && (!dL_dscales || !log_scales))))
+        return fail(GSB_ERR_INVALID_ARGUMENT, "prologue_backward: an output was requested without its inputs");
+    return launch_prologue_backward(P, Tcw, means_world, logit_opacities, unnorm_quats, log_scales, dL_dmeans_cam, dL_dopacities,
+                                    dL_drotations, dL_dscales, dL_dmeans_world, dL_dlogit_opacities, dL_dunnorm_quats,
+                                    dL_dlog_scales, dL_dTcw, (cudaStream_t)stream);
+}
+
+int gsb_pose_grad(int P, const float* means_world, const float* dL_dmeans_cam, float* dL_dTcw, gsb_stream_t stream)
+{
+    if (P < 0 || !dL_dTcw || (P > 0 && (!means_world || !dL_dmeans_cam))) return fail(GSB_ERR_INVALID_ARGUMENT, "pose_grad: bad arguments");
+    return launch_prologue_backward(P, nullptr, means_world, nullptr, nullptr, nullptr, dL_dmeans_cam, nullptr, nullptr, nullptr,
+                                    nullptr, nullptr, nullptr, nullptr, dL_dTcw, (cudaStream_t)stream);
+}
+
+int gsb_adam_step(long long n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
+                  float beta2, float eps, long long step, gsb_stream_t stream)
+{
+    if (n < 0 || step < 1 || (n > 0 && (!param || !grad || !exp_avg || !exp_avg_sq)))
+        return fail(GSB_ERR_INVALID_ARGUMENT, "adam_step: bad arguments");
+    return launch_adam(n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, (cudaStream_t)stream);
+}
+
+// ---- host-buffer convenience ----------------------------------------------------------------
+namespace {
+struct HostLayout {
+    size_t means, colors, shs, opac, scales, rots, cov, bg, view, proj, campos, dpix;
+    size_t out_color, out_depth, radii;
+    size_t g_mean2D, g_conic, g_opac, g_color, g_mean3D, g_cov3D, g_sh, g_scale, g_rot;
+    size_t geom, image, binning, total;
+    GeomLayout GL;
+    ImageLayout IL;
+    BinningLayout BL;
+    static HostLayout make(int P, int M, int W, int H, long long max_rendered)
+    {
+        HostLayout L;
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+        const size_t Pz = (size_t)(P > 0 ? P : 0), HW = (size_t)W * H, Mz = (size_t)(M > 0 ? M : 0);
+        L.means = take(Pz * 12); L.colors = take(Pz * 12); L.shs = take(Pz * Mz * 12); L.opac = take(Pz * 4);
+        L.scales = take(Pz * 12); L.rots = take(Pz * 16); L.cov = take(Pz * 24); L.bg = take(12); L.view = take(64);
+        L.proj = take(64); L.campos = take(12); L.dpix = take(HW * 12);
+        L.out_color = take(HW * 12); L.out_depth = take(HW * 4); L.radii = take(Pz * 4);
+        L.g_mean2D = take(Pz * 12); L.g_conic = take(Pz * 16); L.g_opac = take(Pz * 4); L.g_color = take(Pz * 12);
+        L.g_mean3D = take(Pz * 12); L.g_cov3D = take(Pz * 24); L.g_sh = take(Pz * Mz * 12); L.g_scale = take(Pz * 12);
+        L.g_rot = take(Pz * 16);
+        L.GL = GeomLayout::make(P); L.IL = ImageLayout::make(W, H); L.BL = BinningLayout::make(max_rendered);
+        L.geom = take(L.GL.total); L.image = take(L.IL.total); L.binning = take(L.BL.total);
+        L.total = off;
+        return L;
+    }
+};
+}  // namespace
+
+size_t gsb_host_scratch_bytes(int P, int M, int width, int height, long long max_rendered)
+{
+    if (width <= 0 || height <= 0) return 0;
+    return HostLayout::make(P, M, width, height, max_rendered).total;
+}
+
+long long gsb_forward_backward_host(const gsb_raster_args* host_args, long long max_rendered, const float* dL_dpix_host,
+                                    float* out_color_host, float* out_depth_host, int* radii_host,
+                                    const gsb_grad_outputs* host_grads, void* device_scratch, size_t device_scratch_bytes,
+                                    gsb_stream_t stream)
+{
+    if (int rc = validate(host_args, true)) return rc;
+    if (max_rendered < 0 || max_rendered >= (1ll << 30)) return fail(GSB_ERR_INVALID_ARGUMENT, "max_rendered out of range");
+    const gsb_raster_args& h = *host_args;
+    const int P = h.P, M = h.shs ? h.M : 0, W = h.width, H = h.height;
+    const HostLayout L = HostLayout::make(P, M, W, H, max_rendered);
+    if (!device_scratch || device_scratch_bytes < L.total)
+        return fail(GSB_ERR_WORKSPACE, "device scratch too small (%zu < %zu)", device_scratch_bytes, L.total);
+    cudaStream_t s = (cudaStream_t)stream;
+    char* d = (char*)device_scratch;
+    const size_t Pz = (size_t)P, HW = (size_t)W * H;
+    auto up = [&](size_t off, const void* src, size_t bytes) -> const float* {
+        if (!src || !bytes) return nullptr;
+        cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, s);
+        return reinterpret_cast<const float*>(d + off);
+    };
+    gsb_raster_args a = h;
+    a.means3D = up(L.means, h.means3D, Pz * 12);
+    a.colors_precomp = up(L.colors, h.colors_precomp, Pz * 12);
+    a.shs = up(L.shs, h.shs, Pz * M * 12);
+    a.opacities = up(L.opac, h.opacities, Pz * 4);
+    a.scales = up(L.scales, h.scales, Pz * 12);
+    a.rotations = up(L.rots, h.rotations, Pz * 16);
+    a.cov3D_precomp = up(L.cov, h.cov3D_precomp, Pz * 24);
+    a.background = up(L.bg, h.background, 12);
+    a.viewmatrix = up(L.view, h.viewmatrix, 64);
+    a.projmatrix = up(L.proj, h.projmatrix, 64);
+    a.cam_pos = up(L.campos, h.cam_pos, 12);
+    const float* dpix = dL_dpix_host ? up(L.dpix, dL_dpix_host, HW * 12) : nullptr;
+    GSB_CUDA_CHECK(cudaGetLastError());
+    float* oc = reinterpret_cast<float*>(d + L.out_color);
+    float* od = reinterpret_cast<float*>(d + L.out_depth);
+    int* rd = reinterpret_cast<int*>(d + L.radii);
+    if (int rc = gsb_forward_ws(&a, d + L.geom, L.GL.total, d + L.binning, L.BL.total, max_rendered, d + L.image, L.IL.total, oc,
+                                od, rd, stream))
+        return rc;
+    if (out_color_host) GSB_CUDA_CHECK(cudaMemcpyAsync(out_color_host, oc, HW * 12, cudaMemcpyDeviceToHost, s));
+    if (out_depth_host) GSB_CUDA_CHECK(cudaMemcpyAsync(out_depth_host, od, HW * 4, cudaMemcpyDeviceToHost, s));
+    if (radii_host && P) GSB_CUDA_CHECK(cudaMemcpyAsync(radii_host, rd, Pz * 4, cudaMemcpyDeviceToHost, s));
+    if (dpix && host_grads) {
+        gsb_grad_outputs g;
+        auto dev = [&](size_t off, const float* host) { return host ? reinterpret_cast<float*>(d + off) : nullptr; };
+        g.dL_dmean2D = dev(L.g_mean2D, host_grads->dL_dmean2D); g.dL_dconic = dev(L.g_conic, host_grads->dL_dconic);
+        g.dL_dopacity = dev(L.g_opac, host_grads->dL_dopacity); g.dL_dcolor = dev(L.g_color, host_grads->dL_dcolor);
+        g.dL_dmean3D = dev(L.g_mean3D, host_grads->dL_dmean3D); g.dL_dcov3D = dev(L.g_cov3D, host_grads->dL_dcov3D);
+        g.dL_dsh = M ? dev(L.g_sh, host_grads->dL_dsh) : nullptr; g.dL_dscale = a.scales ? dev(L.g_scale, host_grads->dL_dscale) : nullptr;
+        g.dL_drot = a.rotations ? dev(L.g_rot, host_grads->dL_drot) : nullptr;
+        if (int rc = gsb_backward(&a, -1, rd, d + L.geom, d + L.binning, d + L.image, dpix, &g, stream)) return rc;
+        auto down = [&](float* host, const float* devp, size_t bytes) {
+            if (host && devp && bytes) cudaMemcpyAsync(host, devp, bytes, cudaMemcpyDeviceToHost, s);
+        };
+        down(host_grads->dL_dmean2D, g.dL_dmean2D, Pz * 12); down(host_grads->dL_dconic, g.dL_dconic, Pz * 16);
+        down(host_grads->dL_dopacity, g.dL_dopacity, Pz * 4); down(host_grads->dL_dcolor, g.dL_dcolor, Pz * 12);
+        down(host_grads->dL_dmean3D, g.dL_dmean3D, Pz * 12); down(host_grads->dL_dcov3D, g.dL_dcov3D, Pz * 24);
+        down(host_grads->dL_dsh, g.dL_dsh, Pz * M * 12); down(host_grads->dL_dscale, g.dL_dscale, Pz * 12);
+        down(host_grads->dL_drot, g.dL_drot, Pz * 16);
+        GSB_CUDA_CHECK(cudaGetLastError());
+    }
+    return gsb_num_rendered(d + L.geom, stream);
+}
+
+// ---- introspection ----------------------------------------------------------------------------
+int gsb_debug_image_state(const void* image, int width, int height, float* final_T, uint32_t* n_contrib, uint32_t* ranges,
+                          gsb_stream_t stream)
+{
+    if (!image || width <= 0 || height <= 0) return fail(GSB_ERR_INVALID_ARGUMENT, "debug_image_state: bad arguments");
+    const ImageLayout IL = ImageLayout::make(width, height);
+    cudaStream_t s = (cudaStream_t)stream;
+    const char* im = (const char*)image;
+    const size_t HW = (size_t)width * height, T = (size_t)IL.tiles_x * IL.tiles_y;
+    if (final_T) GSB_CUDA_CHECK(cudaMemcpyAsync(final_T, im + IL.final_T, HW * 4, cudaMemcpyDeviceToDevice, s));
+    if (n_contrib) GSB_CUDA_CHECK(cudaMemcpyAsync(n_contrib, im + IL.n_contrib, HW * 4, cudaMemcpyDeviceToDevice, s));
+    if (ranges) GSB_CUDA_CHECK(cudaMemcpyAsync(ranges, im + IL.ranges, T * 8, cudaMemcpyDeviceToDevice, s));
+    return GSB_OK;
+}
+
+int gsb_debug_binning_state(const void* geometry, const void* binning, long long R, uint32_t* point_list, gsb_stream_t stream)
+{
+    (void)geometry;
+    if (!binning || R < 0) return fail(GSB_ERR_INVALID_ARGUMENT, "debug_binning_state: bad arguments");
+    if (point_list && R)
+        GSB_CUDA_CHECK(cudaMemcpyAsync(point_list, binning, (size_t)R * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return GSB_OK;
+}
+
+int gsb_debug_geometry_state(const void* geometry, int P, float* depths, float* means2D, float* conic_opacity,
+                             uint32_t* tiles_touched, gsb_stream_t stream)
+{
+    if (!geometry || P < 0) return fail(GSB_ERR_INVALID_ARGUMENT, "debug_geometry_state: bad arguments");
+    if (P == 0) return GSB_OK;
+    const GeomLayout GL = GeomLayout::make(P);
+    const char* g = (const char*)geometry;
+    unpack_geometry_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        P, reinterpret_cast<const SplatRec*>(g + GL.rec), reinterpret_cast<const int*>(g + GL.radii),
+        reinterpret_cast<const uint32_t*>(g + GL.tiles_touched), depths, means2D, conic_opacity, tiles_touched);
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+
+}  // extern "C"

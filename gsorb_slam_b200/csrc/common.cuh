@@ -1,12 +1,15 @@
 // common.cuh -- shared device/host helpers of libgsb (sm_100a only).
 //
-// Floating-point contract: this library is compiled with -fmad=false; every fused
-// multiply-add is an explicit fmaf().  The forward geometry follows, op for op, the fp32
-// sequence nvcc emits for the reference sources (forward.cu:74-152,155-256; auxiliary.h)
-// so that radii / tile rectangles / sort keys / conics are bit-identical to the
-// reference kernels -- see DESIGN.md "Arithmetic contract".
+// Floating-point contract: every operation that feeds a DECISION (cull, ceil, trunc, == 0,
+// alpha / transmittance thresholds) is written with explicit __fmul_rn / __fadd_rn / fmaf
+// intrinsics, which nvcc never re-associates or contracts, in the exact fp32 sequence the
+// reference sources compile to (forward.cu:74-152,155-256,261-401; auxiliary.h).  Radii,
+// tile rectangles, sort keys, conics, n_contrib and the blended image are therefore
+// bit-identical to the reference kernels -- see DESIGN.md "Arithmetic contract".  Gradient
+// arithmetic uses ordinary expressions (tolerance 1e-3, tests/).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stddef.h>
 #include "../../include/gsb.h"
@@ -310,20 +313,33 @@ struct FwdParams {
 };
 
 int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, int* radii_out, cudaStream_t s);
+int launch_scan_blocks(char* geom, const GeomLayout& GL, uint32_t capacity, int P, cudaStream_t s);
 int launch_visible_filter(const FwdParams& p, int* radii, cudaStream_t s);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s);
-int launch_binning(const FwdParams& p, char* geom, const GeomLayout& GL, char* binning,
-                   const BinningLayout& BL, char* image, const ImageLayout& IL,
-                   const uint32_t** point_list_out, cudaStream_t s);
-int launch_scan_blocks(char* geom, const GeomLayout& GL, uint32_t capacity, cudaStream_t s);
-const uint32_t* sorted_point_list(const FwdParams& p, const char* binning, const BinningLayout& BL);
-int launch_blend_forward(const FwdParams& p, const char* geom, const GeomLayout& GL,
-                         const uint32_t* point_list, char* image, const ImageLayout& IL,
-                         float* out_color, float* out_depth, cudaStream_t s);
-int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL,
-                          const uint32_t* point_list, const char* image, const ImageLayout& IL,
-                          const float* dL_dpix, cudaStream_t s);
+int sort_passes_for(int tiles);
+int launch_sort_pairs(GeomHeader* hdr, uint64_t* const kbuf[2], uint32_t* const vbuf[2], int start, int passes,
+                      uint32_t* hist, uint32_t* lookback, int sort_tiles, cudaStream_t s);
+// grid_instances: host-side upper bound on the instance count used to size the sort grid
+// (the exact count lives in the header on the device).
+int launch_binning(const FwdParams& p, char* geom, const GeomLayout& GL, char* binning, const BinningLayout& BL,
+                   char* image, const ImageLayout& IL, long long grid_instances, cudaStream_t s);
+int launch_blend_forward(const FwdParams& p, const char* geom, const GeomLayout& GL, const uint32_t* point_list,
+                         char* image, const ImageLayout& IL, float* out_color, float* out_depth, cudaStream_t s);
+int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, const uint32_t* point_list,
+                          const char* image, const ImageLayout& IL, const float* dL_dpix, cudaStream_t s);
 int launch_gauss_backward(const FwdParams& p, const char* geom, const GeomLayout& GL, const int* radii,
                           const gsb_grad_outputs& g, cudaStream_t s);
+int launch_prologue(int P, const float* Tcw, const float* means_world, const float* logit, const float* quats,
+                    const float* log_scales, float* means_cam, float* opac, float* rot, float* scales, cudaStream_t s);
+int launch_prologue_backward(int P, const float* Tcw, const float* means_world, const float* logit, const float* quats,
+                             const float* log_scales, const float* g_means, const float* g_opac, const float* g_rot,
+                             const float* g_scales, float* d_means, float* d_logit, float* d_quats, float* d_log_scales,
+                             float* dTcw, cudaStream_t s);
+int launch_adam(long long n, float* param, const float* grad, float* m, float* v, float lr, float beta1, float beta2,
+                float eps, long long step, cudaStream_t s);
+size_t knn_workspace_bytes(int P);
+int launch_knn(int P, const float* points, float* mean_dist2, char* ws, cudaStream_t s);
+int launch_unpack_geometry(int P, const SplatRec* rec, const uint32_t* tiles_touched, float* depths, float* means2D,
+                           float* conic_opacity, uint32_t* tt_out, cudaStream_t s);
 
 }  // namespace gsb

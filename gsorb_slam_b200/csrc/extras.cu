@@ -1,0 +1,169 @@
+// extras.cu -- fused caller-side pieces around the rasterizer, sm_100a.
+//
+//   prologue           Render::StartSplatting's torch prologue, src/Render.cc:750-759
+//                      (Tcw.repeat(N,1,1).bmm([mean;1]), sigmoid, normalize, exp) in ONE pass
+//                      with no N x 4 x 4 intermediate.
+//   prologue_backward  what autograd does for that prologue, plus the camera-pose gradient
+//                      dL/dTcw[0:3,:] = sum_i g_i [p_i;1]^T reduced on chip.
+//   pose_grad          that reduction alone.
+//   adam_step          torch::optim::Adam step of src/Gaussian.cc:131-175 over a flat block.
+#include "common.cuh"
+
+namespace gsb {
+
+constexpr int EX_THREADS = 256;
+
+__global__ void __launch_bounds__(EX_THREADS)
+prologue_kernel(int P, const float* __restrict__ Tcw, const float* __restrict__ means_world,
+                const float* __restrict__ logit, const float* __restrict__ quats, const float* __restrict__ log_scales,
+                float* __restrict__ means_cam, float* __restrict__ opac, float* __restrict__ rot, float* __restrict__ scales)
+{
+    const int idx = blockIdx.x * EX_THREADS + threadIdx.x;
+    if (idx >= P) return;
+    const size_t i = (size_t)idx;
+    if (means_cam) {
+        const float x = means_world[3 * i], y = means_world[3 * i + 1], z = means_world[3 * i + 2];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            means_cam[3 * i + r] = fmaf(Tcw[4 * r + 2], z, fmaf(Tcw[4 * r + 1], y, Tcw[4 * r] * x)) + Tcw[4 * r + 3];
+    }
+    if (opac) opac[i] = 1.0f / (1.0f + expf(-logit[i]));
+    if (rot) {
+        const float a = quats[4 * i], b = quats[4 * i + 1], c = quats[4 * i + 2], d = quats[4 * i + 3];
+        const float nrm = fmaxf(sqrtf(a * a + b * b + c * c + d * d), 1e-12f);  // F::normalize eps
+        rot[4 * i] = a / nrm; rot[4 * i + 1] = b / nrm; rot[4 * i + 2] = c / nrm; rot[4 * i + 3] = d / nrm;
+    }
+    if (scales) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) scales[3 * i + k] = expf(log_scales[3 * i + k]);
+    }
+}
+
+// Block-reduce 12 partial sums and add them to out[12] with one atomic per value per CTA.
+__device__ __forceinline__ void reduce12_and_add(float* v, float* __restrict__ out)
+{
+    __shared__ float s_part[EX_THREADS / 32][12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        float x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane_id() == 0) s_part[threadIdx.x >> 5][k] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        float x = 0.f;
+#pragma unroll
+        for (int w = 0; w < EX_THREADS / 32; w++) x += s_part[w][threadIdx.x];
+        atomicAdd(out + threadIdx.x, x);
+    }
+}
+
+__global__ void __launch_bounds__(EX_THREADS)
+prologue_backward_kernel(int P, const float* __restrict__ Tcw, const float* __restrict__ means_world,
+                         const float* __restrict__ logit, const float* __restrict__ quats,
+                         const float* __restrict__ log_scales, const float* __restrict__ g_means,
+                         const float* __restrict__ g_opac, const float* __restrict__ g_rot, const float* __restrict__ g_scales,
+                         float* __restrict__ d_means, float* __restrict__ d_logit, float* __restrict__ d_quats,
+                         float* __restrict__ d_log_scales, float* __restrict__ dTcw)
+{
+    float part[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) part[k] = 0.f;
+    for (int idx = blockIdx.x * EX_THREADS + threadIdx.x; idx < P; idx += gridDim.x * EX_THREADS) {
+        const size_t i = (size_t)idx;
+        if (g_means) {
+            const float g0 = g_means[3 * i], g1 = g_means[3 * i + 1], g2 = g_means[3 * i + 2];
+            if (d_means) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) d_means[3 * i + c] = Tcw[c] * g0 + Tcw[4 + c] * g1 + Tcw[8 + c] * g2;
+            }
+            if (dTcw) {
+                const float x = means_world[3 * i], y = means_world[3 * i + 1], z = means_world[3 * i + 2];
+                part[0] += g0 * x; part[1] += g0 * y; part[2] += g0 * z; part[3] += g0;
+                part[4] += g1 * x; part[5] += g1 * y; part[6] += g1 * z; part[7] += g1;
+                part[8] += g2 * x; part[9] += g2 * y; part[10] += g2 * z; part[11] += g2;
+            }
+        }
+        if (d_logit && g_opac) {
+            const float s = 1.0f / (1.0f + expf(-logit[i]));
+            d_logit[i] = g_opac[i] * s * (1.0f - s);
+        }
+        if (d_quats && g_rot) {
+            const float a = quats[4 * i], b = quats[4 * i + 1], c = quats[4 * i + 2], d = quats[4 * i + 3];
+            const float nrm = fmaxf(sqrtf(a * a + b * b + c * c + d * d), 1e-12f);
+            const float na = a / nrm, nb = b / nrm, nc = c / nrm, nd = d / nrm;
+            const float ga = g_rot[4 * i], gb = g_rot[4 * i + 1], gc = g_rot[4 * i + 2], gd = g_rot[4 * i + 3];
+            const float dot = na * ga + nb * gb + nc * gc + nd * gd;
+            d_quats[4 * i] = (ga - na * dot) / nrm;
+            d_quats[4 * i + 1] = (gb - nb * dot) / nrm;
+            d_quats[4 * i + 2] = (gc - nc * dot) / nrm;
+            d_quats[4 * i + 3] = (gd - nd * dot) / nrm;
+        }
+        if (d_log_scales && g_scales) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) d_log_scales[3 * i + k] = g_scales[3 * i + k] * expf(log_scales[3 * i + k]);
+        }
+    }
+    if (dTcw) reduce12_and_add(part, dTcw);
+}
+
+__global__ void __launch_bounds__(EX_THREADS)
+adam_kernel(long long n, float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
+            float* __restrict__ v, float beta1, float beta2, float eps, float step_size, float inv_sqrt_bc2)
+{
+    for (long long i = (long long)blockIdx.x * EX_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * EX_THREADS) {
+        const float g = grad[i];
+        const float mi = m[i] + (g - m[i]) * (1.0f - beta1);            // exp_avg.lerp_(grad, 1 - beta1)
+        const float vi = v[i] * beta2 + (1.0f - beta2) * g * g;         // mul_(beta2).addcmul_(g, g, 1 - beta2)
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;             // (sqrt(v) / sqrt(bc2)).add_(eps)
+        param[i] = param[i] - step_size * (mi / denom);                 // addcdiv_(m, denom, -step_size)
+    }
+}
+
+static int grid_for(long long n)
+{
+    long long g = (n + EX_THREADS - 1) / EX_THREADS;
+    const long long cap = (long long)NUM_SMS * 16;
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+int launch_prologue(int P, const float* Tcw, const float* means_world, const float* logit, const float* quats,
+                    const float* log_scales, float* means_cam, float* opac, float* rot, float* scales, cudaStream_t s)
+{
+    if (P <= 0) return GSB_OK;
+    prologue_kernel<<<(P + EX_THREADS - 1) / EX_THREADS, EX_THREADS, 0, s>>>(P, Tcw, means_world, logit, quats, log_scales,
+                                                                             means_cam, opac, rot, scales);
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+
+int launch_prologue_backward(int P, const float* Tcw, const float* means_world, const float* logit, const float* quats,
+                             const float* log_scales, const float* g_means, const float* g_opac, const float* g_rot,
+                             const float* g_scales, float* d_means, float* d_logit, float* d_quats, float* d_log_scales,
+                             float* dTcw, cudaStream_t s)
+{
+    if (dTcw) GSB_CUDA_CHECK(cudaMemsetAsync(dTcw, 0, 12 * sizeof(float), s));
+    if (P <= 0) return GSB_OK;
+    prologue_backward_kernel<<<grid_for(P), EX_THREADS, 0, s>>>(P, Tcw, means_world, logit, quats, log_scales, g_means, g_opac,
+                                                                g_rot, g_scales, d_means, d_logit, d_quats, d_log_scales, dTcw);
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+
+int launch_adam(long long n, float* param, const float* grad, float* m, float* v, float lr, float beta1, float beta2,
+                float eps, long long step, cudaStream_t s)
+{
+    if (n <= 0) return GSB_OK;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    const float step_size = (float)((double)lr / bc1);
+    const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    adam_kernel<<<grid_for(n), EX_THREADS, 0, s>>>(n, param, grad, m, v, beta1, beta2, eps, step_size, inv_sqrt_bc2);
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+
+}  // namespace gsb

@@ -36,7 +36,7 @@ __device__ __forceinline__ void stage_float3(const float* __restrict__ g, float*
 struct Projected {
     bool visible;
     float depth, px, py, conx, cony, conz;
-    float cov_xx, cov_yy;
+    float cov_xx, cov_yy, det;
     int radius;
     uint32_t minx, miny, maxx, maxy;
 };
@@ -82,6 +82,7 @@ __device__ __forceinline__ Projected project_gaussian(const FwdParams& p, float 
     o.depth = pvz;
     o.cov_xx = cov[0];
     o.cov_yy = cov[2];
+    o.det = det;
     o.visible = true;
     return o;
 }
@@ -179,8 +180,13 @@ preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ rad
                 // of the conic, hence the 2 % + 0.05 px slack.
                 ex = sqrtf(t2 * o.cov_xx) * 1.02f + 0.05f;
                 ey = sqrtf(t2 * o.cov_yy) * 1.02f + 0.05f;
-                if (!(ex < 60000.f)) ex = 60000.f;  // also catches NaN
-                if (!(ey < 60000.f)) ey = 60000.f;
+                // No culling for anything numerically suspicious: a non-positive-definite 2D
+                // covariance (possible with caller-supplied cov3D) has an unbounded footprint, and
+                // for splats with sigma > 100 px in both axes the fp32 determinant (hence the conic)
+                // can be off by more than the slack.
+                const bool sane = o.det > 0.f && o.cov_xx > 0.f && o.cov_yy > 0.f && fminf(o.cov_xx, o.cov_yy) < 1.0e4f;
+                if (!sane || !(ex < 60000.f)) ex = 60000.f;  // also catches NaN
+                if (!sane || !(ey < 60000.f)) ey = 60000.f;
             }
             const __half2 ext = __halves2half2(__float2half_ru(ex), __float2half_ru(ey));
             SplatRec r;

@@ -42,6 +42,10 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
 #define GSB_VERSION_MAJOR 0
 #define GSB_VERSION_MINOR 1
 
@@ -229,6 +233,9 @@ int gsb_debug_geometry_state(const void* geometry, int P, float* depths, float* 
  * (used by bench.py for its gpu_launches claim). */
 long long gsb_launch_count_reset(void);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

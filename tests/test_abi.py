@@ -1,0 +1,83 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/gsb.h declares; the pure
+host-side entry points (sizes, validation, error text) behave.  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "gsb.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gsb_[a-z0-9_]+)\s*\(", src)) - {"gsb_alloc_fn"})
+
+
+def test_library_exports_every_declared_symbol():
+    from gsorb_slam_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "libgsb.so not built (make -C gsorb_slam_b200/csrc)"
+    L = C.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 24
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in gsb.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes signature table out of sync with gsb.h"
+
+
+def test_version_and_sizes():
+    from gsorb_slam_b200 import _lib
+    L = _lib.lib()
+    assert L.gsb_version() == (0 << 16) | 1
+    g, i, b = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    assert L.gsb_workspace_query(1000, 640, 480, 5000, C.byref(g), C.byref(i), C.byref(b)) == 0
+    assert g.value == L.gsb_geometry_bytes(1000) and g.value >= 1000 * 48
+    assert i.value == L.gsb_image_bytes(640, 480) and i.value >= 640 * 480 * 8
+    assert b.value == L.gsb_binning_bytes(5000) and b.value >= 5000 * 24
+    assert L.gsb_geometry_bytes(0) > 0
+    assert L.gsb_workspace_query(-1, 640, 480, 0, None, None, None) == -1
+    assert b"bad sizes" in L.gsb_last_error()
+
+
+def test_validation_errors_match_reference_messages():
+    """Argument checks happen before any CUDA call, so they can be exercised without a GPU."""
+    from gsorb_slam_b200 import _lib
+    L = _lib.lib()
+    a = _lib.RasterArgs()
+    a.P, a.width, a.height, a.tan_fovx, a.tan_fovy = 4, 64, 64, 0.5, 0.5
+    dummy = C.c_void_p(256)   # never dereferenced: validation fails first
+    a.viewmatrix = a.projmatrix = a.background = a.means3D = a.opacities = dummy
+    a.scales = a.rotations = dummy
+    # neither SHs nor colours
+    rc = L.gsb_forward_ws(C.byref(a), dummy, 1 << 30, dummy, 1 << 30, 100, dummy, 1 << 30, dummy, dummy, None, None)
+    assert rc == -1 and b"exactly one of either SHs or precomputed colors" in L.gsb_last_error()
+    a.colors_precomp = dummy
+    a.cov3D_precomp = dummy   # both scale/rotation and cov3D
+    rc = L.gsb_forward_ws(C.byref(a), dummy, 1 << 30, dummy, 1 << 30, 100, dummy, 1 << 30, dummy, dummy, None, None)
+    assert rc == -1 and b"scale/rotation pair or precomputed 3D covariance" in L.gsb_last_error()
+    a.cov3D_precomp = None
+    a.width = 0
+    rc = L.gsb_forward_ws(C.byref(a), dummy, 1 << 30, dummy, 1 << 30, 100, dummy, 1 << 30, dummy, dummy, None, None)
+    assert rc == -1
+    a.width = 64
+    rc = L.gsb_forward_ws(C.byref(a), dummy, 16, dummy, 1 << 30, 100, dummy, 1 << 30, dummy, dummy, None, None)
+    assert rc == -3 and b"geometry workspace too small" in L.gsb_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(-1)
+
+
+def test_operator_surface_mirrors_reference_names():
+    from gsorb_slam_b200 import rasterizer as R
+    for n in ("GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "_RasterizeGaussians", "distCUDA2"):
+        assert hasattr(R, n)
+    for n in ("forward", "Visable", "mark_visible"):
+        assert hasattr(R.GaussianRasterizer, n)
+    import torch
+    rs = R.GaussianRasterizationSettings(64, 64, 0.5, 0.5, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 0, torch.zeros(3), False)
+    r = R.GaussianRasterizer(rs)
+    m = torch.zeros(4, 3)
+    with pytest.raises(ValueError, match="exactly one of either SHs or precomputed colors"):
+        r.forward(m, m, torch.zeros(4, 1), scales=m, rotations=torch.zeros(4, 4))
+    with pytest.raises(ValueError, match="scale/rotation pair or precomputed 3D covariance"):
+        r.forward(m, m, torch.zeros(4, 1), colors_precomp=m)

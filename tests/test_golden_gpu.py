@@ -1,0 +1,64 @@
+"""-m gpu: libgsb (through the C ABI) against the golden outputs of the reference kernels.
+
+Bar: integer / index state bit-exact (radii, tiles_touched, sorted instance list, tile ranges,
+n_contrib), projected geometry bit-exact, images within 1e-4 and gradients within 1e-3 relative
+(tests/helpers.py)."""
+import numpy as np
+import pytest
+
+from helpers import GEOM_KEYS, GRAD_KEYS, IMAGE_KEYS, SMALL_CASES, TOL_GRAD, TOL_IMAGE, load_case, rel_to_scale, to_np
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gsb(kw, dL, **extra):
+    from gsorb_slam_b200.lowlevel import Frame
+    fr = Frame(**kw, **extra)
+    g = fr.backward(dL)
+    out = dict(color=fr.color, depth=fr.depth, radii=fr.radii, num_rendered=fr.rendered())
+    out.update(fr.image_state())
+    out.update(fr.binning_state())
+    out.update(fr.geometry_state())
+    out.update({k: v for k, v in g.items() if v is not None})
+    return {k: to_np(v) for k, v in out.items()}
+
+
+@pytest.mark.parametrize("sync_free", [False, True])
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_small_case_matches_reference(name, sync_free):
+    kw, dL, ref = load_case(name)
+    out = run_gsb(kw, dL, sync_free=sync_free, max_rendered=1 << 16)
+    assert int(out["num_rendered"]) == int(ref["num_rendered"])
+    for k in ("radii", "tiles_touched", "point_list", "ranges", "n_contrib"):
+        np.testing.assert_array_equal(out[k].astype(np.int64).ravel(), ref[k].astype(np.int64).ravel(), err_msg=k)
+    vis = ref["radii"] > 0
+    for k in GEOM_KEYS:   # bit-exact for every rendered Gaussian
+        a, b = out[k].reshape(len(vis), -1)[vis], ref[k].reshape(len(vis), -1)[vis]
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32), err_msg=k)
+    for k in IMAGE_KEYS:
+        assert rel_to_scale(out[k], ref[k]) <= TOL_IMAGE, k
+    for k in GRAD_KEYS:
+        if k in out and k in ref and ref[k].size and k != "dL_dsh" or (k == "dL_dsh" and "shs" in kw):
+            assert rel_to_scale(out[k], ref[k].reshape(out[k].shape)) <= TOL_GRAD, k
+
+
+def test_image_is_bit_exact_on_tiny_default():
+    """Same op order and the same expf: the forward image is expected to match the reference bit for bit."""
+    kw, dL, ref = load_case("tiny_default")
+    out = run_gsb(kw, dL)
+    for k in IMAGE_KEYS:
+        np.testing.assert_array_equal(out[k].ravel().view(np.uint32), ref[k].ravel().view(np.uint32), err_msg=k)
+
+
+def test_sync_free_overflow_is_reported_not_corrupting():
+    """gsb_forward_ws with a too-small binning capacity: truncated list, latched overflow flag, GSB_ERR_OVERFLOW."""
+    from gsorb_slam_b200 import _lib
+    from gsorb_slam_b200.lowlevel import Frame
+    kw, dL, ref = load_case("tiny_cov")
+    fr = Frame(**kw, sync_free=True, max_rendered=1000)
+    with pytest.raises(_lib.GsbError) as e:
+        fr.rendered()
+    assert e.value.code == -4
+    fr2 = Frame(**kw, sync_free=True, max_rendered=int(ref["num_rendered"]))   # exactly enough
+    assert fr2.rendered() == int(ref["num_rendered"])
+    np.testing.assert_array_equal(to_np(fr2.color).view(np.uint32), ref["color"].view(np.uint32))
