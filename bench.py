@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd frames/s of the rasterizer hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one rasterizer forward + backward of the RGB pass (3 channels, bg = 0, dL/dpixel
+supplied) over one synthetic frame per rank.  Default workload: the headline configuration,
+1 M Gaussians at 640x480 (gsorb_slam_b200/scene.py CONFIGS["headline_1m"], seed 0).
+
+* ``value``   : whole-job frames/s with every input resident in HBM (gsb_forward_ws + gsb_backward,
+                sync-free), timed with CUDA events around each step, L2 flushed between steps.
+* ``e2e``     : same metric through the host-buffer C-ABI call (gsb_forward_backward_host): pinned host
+                inputs copied H2D and image + gradients copied D2H inside the timed region.
+* ``roofline``: dominant kernel's algorithmic bytes / its CUDA-event duration (gsb_profile_*), against
+                MEASURED_PEAKS.json (fallback 6650 GB/s, B200_PROFILING.md).
+* ``cpu_baseline``: the oracle's naive per-pixel C++ loop (oracle/gs_oracle.cpp, OpenMP) on the box's
+                host cores, a bounded sample of the same workload (rank 0, N = 1 only).
+* N > 1       : keyframe-batch shard -- every rank rasterizes a different camera over replicated
+                Gaussians, then ONE NCCL all-reduce of the packed per-Gaussian gradient block [14, P]
+                (SURVEY.md 8e); weak scaling, value = N frames / max-over-ranks step time.
+* ``--impl reference``: the UNMODIFIED reference CUDA kernels (oracle/_ref/libgsref.so, built from
+                /root/reference by oracle/Makefile) driven as src/Rasterizer.cu drives them, same workload.
+                (The reference's implementation of this path is CUDA, not CPU, so this arm runs on the
+                GPU; without the prebuilt library it falls back to the CPU oracle port.)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fwd+bwd frames/sec @1M Gaussians 640x480"
+UNIT = "frames/s"
+
+
+# ---------------------------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self._stop, self._t = gpu_index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_rank_scene(workload: str, rank: int):
+    """Replicated Gaussians (seed 0); every rank looks at them from its own keyframe pose."""
+    from gsorb_slam_b200.scene import make_config
+    sc = make_config(workload, seed=0)
+    if rank > 0:
+        ang = 0.01 * rank
+        Tcw = np.eye(4, dtype=np.float32)
+        Tcw[:3, :3] = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]], np.float32)
+        Tcw[:3, 3] = [0.02 * rank, -0.01 * rank, 0.01 * rank]
+        # default mode of Render::StartSplatting: means pre-transformed, identity view (src/Render.cc:748-754)
+        m = sc.means3D @ Tcw[:3, :3].T + Tcw[:3, 3]
+        sc.means3D = m.astype(np.float32)
+        rng = np.random.default_rng(1000 + rank)
+        sc.dL_dpix = (rng.normal(0, 1, sc.dL_dpix.shape) / (sc.cam.width * sc.cam.height)).astype(np.float32)
+    return sc
+
+
+def algorithmic_bytes(P, V, R, HW):
+    """SURVEY.md 8(d) / BASELINE.md 3.4, per launch."""
+    return {
+        "frame": 272 * P + 124 * R + 44 * HW,
+        "blend_forward": 44 * R + 24 * HW,
+        "blend_backward": 44 * R + 20 * HW + 36 * V,
+        "sort_passes": None,  # filled by caller: passes * 24 * R
+        "preprocess": 56 * P + 48 * V + 8 * P,
+        "gauss_backward": 48 * V + 44 * P + 108 * P,
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from gsorb_slam_b200 import _lib
+    from gsorb_slam_b200.lowlevel import Frame, frame_from_scene
+
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libgsb has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    sc = make_rank_scene(args.workload, rank)
+    P, W, H = sc.P, sc.cam.width, sc.cam.height
+    HW = W * H
+    max_rendered = 4 * P + 4096
+    fr = frame_from_scene(sc, device=dev, sync_free=True, max_rendered=max_rendered)
+    R = fr.rendered()
+    V = int((fr.radii > 0).sum().item())
+    dL = torch.from_numpy(sc.dL_dpix).to(dev)
+    # packed gradient block [14, P]: means3D 3 | colour 3 | opacity 1 | scale 3 | rotation 4 -- the block the
+    # all-reduce (and Adam) consume; the remaining reference outputs go to side buffers.
+    block = torch.empty(14 * P, dtype=torch.float32, device=dev)
+    side = torch.empty(13 * P, dtype=torch.float32, device=dev)
+    g = _lib.GradOutputs()
+    bp, sp = block.data_ptr(), side.data_ptr()
+    g.dL_dmean3D, g.dL_dcolor, g.dL_dopacity, g.dL_dscale, g.dL_drot = bp, bp + 12 * P, bp + 24 * P, bp + 28 * P, bp + 40 * P
+    g.dL_dmean2D, g.dL_dconic, g.dL_dcov3D, g.dL_dsh = sp, sp + 12 * P, sp + 28 * P, None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        _lib.check(L.gsb_forward_ws(C.byref(fr._args), fr.geom.data_ptr(), fr.geom.numel(), fr.binning.data_ptr(),
+                                    fr.binning.numel(), max_rendered, fr.img.data_ptr(), fr.img.numel(), fr.color.data_ptr(),
+                                    fr.depth.data_ptr(), fr.radii.data_ptr(), stream))
+        _lib.check(L.gsb_backward(C.byref(fr._args), -1, fr.radii.data_ptr(), fr.geom.data_ptr(), fr.binning.data_ptr(),
+                                  fr.img.data_ptr(), dL.data_ptr(), C.byref(g), stream))
+        if world > 1:
+            dist.all_reduce(block)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    with ClockSampler(local) as clk:
+        L.gsb_launch_count_reset()
+        ms_total = timed(step, args.steps, args.warmup)
+        launches = int(L.gsb_launch_count_reset())
+        launches_timed = launches * args.steps // (args.steps + args.warmup)
+    ms_per_step = ms_total / args.steps
+    value = world * 1000.0 / ms_per_step
+
+    # ---- e2e: host buffers through gsb_forward_backward_host ----
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h = dict(means=pin(sc.means3D), colors=pin(sc.colors), opac=pin(sc.opacities), scales=pin(sc.scales), rots=pin(sc.rotations),
+             bg=pin(sc.background), view=pin(sc.cam.viewmatrix), proj=pin(sc.cam.projmatrix), campos=pin(sc.cam.campos), dL=pin(sc.dL_dpix))
+    ha = _lib.RasterArgs()
+    ha.P, ha.D, ha.M, ha.width, ha.height = P, 0, 0, W, H
+    ha.background, ha.means3D, ha.colors_precomp, ha.opacities = h["bg"].data_ptr(), h["means"].data_ptr(), h["colors"].data_ptr(), h["opac"].data_ptr()
+    ha.scales, ha.scale_modifier, ha.rotations = h["scales"].data_ptr(), 1.0, h["rots"].data_ptr()
+    ha.viewmatrix, ha.projmatrix, ha.cam_pos = h["view"].data_ptr(), h["proj"].data_ptr(), h["campos"].data_ptr()
+    ha.tan_fovx, ha.tan_fovy = float(sc.cam.tanfovx), float(sc.cam.tanfovy)
+    ho = dict(color=torch.empty((3, H, W)).pin_memory(), depth=torch.empty((1, H, W)).pin_memory(),
+              radii=torch.empty(P, dtype=torch.int32).pin_memory(), block=torch.empty(14 * P).pin_memory())
+    hg = _lib.GradOutputs()
+    hb = ho["block"].data_ptr()
+    hg.dL_dmean3D, hg.dL_dcolor, hg.dL_dopacity, hg.dL_dscale, hg.dL_drot = hb, hb + 12 * P, hb + 24 * P, hb + 28 * P, hb + 40 * P
+    nscratch = int(L.gsb_host_scratch_bytes(P, 0, W, H, max_rendered))
+    scratch = torch.empty(nscratch, dtype=torch.uint8, device=dev)
+    h2d = sum(h[k].numel() * 4 for k in h)
+    d2h = (3 * HW + HW + P + 14 * P) * 4
+
+    def step_e2e():
+        rc = L.gsb_forward_backward_host(C.byref(ha), max_rendered, h["dL"].data_ptr(), ho["color"].data_ptr(), ho["depth"].data_ptr(),
+                                         ho["radii"].data_ptr(), C.byref(hg), scratch.data_ptr(), nscratch, stream)
+        _lib.check(rc)
+        if world > 1:   # the exchange step of the sharded loop, on the device copy of the block is not available here:
+            pass        # e2e at N > 1 = N independent host-fed replicas (documented in DESIGN.md)
+
+    e2e_steps = max(3, min(args.steps, 20))
+    ms_e2e = timed(step_e2e, e2e_steps, 3) / e2e_steps
+    e2e_value = world * 1000.0 / ms_e2e
+    e2e_ok = bool(np.isfinite(ho["color"].numpy()).all())
+
+    # ---- roofline: per-stage device time over the same number of steps ----
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    L.gsb_profile_begin()
+    for _ in range(args.steps):
+        flush.zero_()
+        step()
+    ns = L.gsb_num_stages()
+    sms, scn = (C.c_float * ns)(), (C.c_int * ns)()
+    L.gsb_profile_end(sms, scn)
+    stages = {L.gsb_stage_name(i).decode(): {"ms_per_step": sms[i] / args.steps, "launches_per_step": scn[i] / args.steps}
+              for i in range(ns) if scn[i]}
+    peak, peak_src = load_peaks()
+    ab = algorithmic_bytes(P, V, R, HW)
+    passes = round(stages.get("sort_passes", {}).get("launches_per_step", 6))
+    ab["sort_passes"] = passes * 24 * R
+    dom = max((k for k in stages if ab.get(k)), key=lambda k: stages[k]["ms_per_step"])
+    dom_ms = stages[dom]["ms_per_step"] / max(1.0, stages[dom]["launches_per_step"] if dom != "sort_passes" else 1.0)
+    achieved = ab[dom] / (dom_ms * 1e-3) / 1e9
+    for k in stages:
+        if ab.get(k):
+            stages[k]["alg_GBps"] = ab[k] / (stages[k]["ms_per_step"] * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": ab[dom], "kernel_ms": dom_ms,
+                "frame_alg_bytes": ab["frame"], "frame_frac_of_peak": ab["frame"] / (ms_per_step * 1e-3) / 1e9 / peak,
+                "stages": stages}
+
+    # ---- cpu baseline (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args.workload)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {P} Gaussians {W}x{H}, RGB pass fwd+bwd, seed 0 (SLAM-like init, scene.py)",
+                           "frames_per_step_per_gpu": 1, "num_rendered": R, "visible": V,
+                           "l2": "flushed between steps (512 MiB memset, outside the event brackets)",
+                           "parallelism": "single GPU" if world == 1 else f"keyframe-batch shard x{world} + NCCL all-reduce of the [14,P] gradient block"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+                        "steps": e2e_steps, "finite": e2e_ok,
+                        "api": "gsb_forward_backward_host (pinned host buffers)"},
+                "gpu_launches": launches_timed, "clocks": clk.summary(), "roofline": roofline}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(workload: str, budget_s: float = 20.0):
+    """The oracle's per-pixel C++ loop on the host cores: whole frames of the same workload until ~budget_s."""
+    from gsorb_slam_b200.scene import make_config
+    from oracle import gs_oracle
+    sc = make_config(workload, seed=0)
+    gs_oracle.lib()
+    t0 = time.time()
+    n = 0
+    while True:
+        fr = gs_oracle.frame_from_scene(sc)
+        fr.backward(sc.dL_dpix)
+        n += 1
+        el = time.time() - t0
+        if el > budget_s or n >= 8:
+            break
+    return {"value": n / el, "unit": UNIT, "cores": gs_oracle.num_threads(), "kind": "port",
+            "sample": f"{n} full frame(s) fwd+bwd of {workload} through oracle/gs_oracle.cpp (OpenMP, pre-binned tile lists) in {el:.1f} s"}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if rank != 0:
+        return
+    from oracle import gs_ref
+    sc = make_rank_scene(args.workload, 0)
+    P, W, H = sc.P, sc.cam.width, sc.cam.height
+    base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    cfg = {"workload": f"{args.workload}: {P} Gaussians {W}x{H}, RGB pass fwd+bwd, seed 0 (SLAM-like init, scene.py)"}
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if gs_ref.available() and has_gpu:
+        import torch
+        torch.cuda.set_device(local)
+        fr = gs_ref.frame_from_scene(sc, run=False)
+        dL = torch.from_numpy(sc.dL_dpix).cuda()
+        flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+        def step():
+            fr.forward()          # RasterizeGaussiansCUDA: fresh outputs + scratch, blocking num_rendered copy
+            fr.backward(dL)       # RasterizeGaussiansBackwardCUDA: 9 zero-filled gradient tensors
+
+        def timed(fn, steps, warmup):
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize()
+            evs = []
+            for _ in range(steps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                evs.append((a, b))
+            torch.cuda.synchronize()
+            return sum(a.elapsed_time(b) for a, b in evs) / steps
+
+        with ClockSampler(local) as clk:
+            ms = timed(step, args.steps, args.warmup)
+        # e2e: same tensors from pinned host memory, outputs + the consumer-visible gradients back to the host
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        hin = {k: pin(getattr(sc, k)) for k in ("means3D", "colors", "opacities", "scales", "rotations", "dL_dpix")}
+        hout = dict(color=torch.empty((3, H, W)).pin_memory(), depth=torch.empty((1, H, W)).pin_memory(),
+                    radii=torch.empty(P, dtype=torch.int32).pin_memory(), block=torch.empty(14 * P).pin_memory())
+
+        def step_e2e():
+            fr.means3D = hin["means3D"].cuda(non_blocking=True)
+            fr.colors = hin["colors"].cuda(non_blocking=True)
+            fr.opacities = hin["opacities"].cuda(non_blocking=True)
+            fr.scales = hin["scales"].cuda(non_blocking=True)
+            fr.rotations = hin["rotations"].cuda(non_blocking=True)
+            d = hin["dL_dpix"].cuda(non_blocking=True)
+            fr.forward()
+            g = fr.backward(d)
+            hout["color"].copy_(fr.color, non_blocking=True)
+            hout["depth"].copy_(fr.depth, non_blocking=True)
+            hout["radii"].copy_(fr.radii, non_blocking=True)
+            blk = torch.cat([g["dL_dmean3D"].reshape(-1), g["dL_dcolor"].reshape(-1), g["dL_dopacity"].reshape(-1),
+                             g["dL_dscale"].reshape(-1), g["dL_drot"].reshape(-1)])
+            hout["block"].copy_(blk, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_steps = max(3, min(args.steps, 20))
+        ms_e2e = timed(step_e2e, e2e_steps, 3)
+        h2d = sum(v.numel() * 4 for v in hin.values())
+        d2h = (3 * H * W + H * W + P + 14 * P) * 4
+        line = dict(base, value=1000.0 / ms, ms_per_step=ms, config=dict(cfg, num_rendered=int(fr.num_rendered),
+                    l2="flushed between steps (512 MiB memset, outside the event brackets)",
+                    parallelism="single GPU (the reference has no multi-GPU path; rank 0 only)"),
+                    e2e={"value": 1000.0 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+                    clocks=clk.summary(),
+                    cpu_baseline={"value": 1000.0 / ms, "unit": UNIT, "cores": 1, "kind": "reference",
+                                  "sample": "unmodified reference CUDA kernels (oracle/_ref/libgsref.so, sm_100a build) on the same GPU, "
+                                            "driven like src/Rasterizer.cu:136-297; 1 host thread"})
+        print(json.dumps(line), flush=True)
+        return
+    # no prebuilt reference library or no GPU: the CPU oracle port, bounded sample
+    from oracle import gs_oracle
+    gs_oracle.lib()
+    ts = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.time()
+        f = gs_oracle.frame_from_scene(sc)
+        f.backward(sc.dL_dpix)
+        if it >= args.warmup:
+            ts.append(time.time() - t0)
+        if sum(ts) > 120:
+            break
+    v = len(ts) / sum(ts)
+    line = dict(base, value=v, ms_per_step=1000.0 / v, steps=len(ts), config=cfg,
+                e2e={"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                cpu_baseline={"value": v, "unit": UNIT, "cores": gs_oracle.num_threads(), "kind": "port",
+                              "sample": f"{len(ts)} full frame(s) of {args.workload} through oracle/gs_oracle.cpp (OpenMP)"})
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="headline_1m")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

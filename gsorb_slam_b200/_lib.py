@@ -57,6 +57,10 @@ SIGNATURES = {
     "gsb_debug_binning_state": (_i, [_vp, _vp, _ll, _vp, _vp]),
     "gsb_debug_geometry_state": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "gsb_launch_count_reset": (_ll, []),
+    "gsb_num_stages": (_i, []),
+    "gsb_stage_name": (C.c_char_p, [_i]),
+    "gsb_profile_begin": (_i, []),
+    "gsb_profile_end": (_i, [C.POINTER(_f), C.POINTER(_i)]),
 }
 
 _lib = None

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 #include "common.cuh"
 
 namespace gsb {
@@ -22,6 +23,26 @@ void set_error(const char* fmt, ...)
     va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+
+struct ProfEvent { int stage; cudaEvent_t a, b; };
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfEvent>* g_prof = nullptr;
+
+StageTimer::StageTimer(int st, cudaStream_t str) : stage(st), s(str), ev(nullptr)
+{
+    if (!g_prof_on) return;
+    ProfEvent e;
+    e.stage = st;
+    if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+    cudaEventRecord(e.a, s);
+    g_prof->push_back(e);
+    ev = reinterpret_cast<void*>(g_prof->size());  // index + 1
+}
+StageTimer::~StageTimer()
+{
+    if (!ev) return;
+    cudaEventRecord((*g_prof)[reinterpret_cast<size_t>(ev) - 1].b, s);
+}
 
 static int fail(int code, const char* fmt, ...)
 {
@@ -127,6 +148,40 @@ long long gsb_launch_count_reset(void)
     const long long n = g_launches;
     g_launches = 0;
     return n;
+}
+
+static const char* kStageNames[ST_COUNT] = {"memset", "preprocess", "scan", "duplicate", "sort_histogram", "sort_passes",
+                                            "tile_ranges", "blend_forward", "blend_backward", "gauss_backward", "other"};
+int gsb_num_stages(void) { return ST_COUNT; }
+const char* gsb_stage_name(int stage) { return stage >= 0 && stage < ST_COUNT ? kStageNames[stage] : ""; }
+int gsb_profile_begin(void)
+{
+    if (!g_prof) g_prof = new std::vector<ProfEvent>();
+    for (auto& e : *g_prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    g_prof->clear();
+    g_prof_on = true;
+    return GSB_OK;
+}
+int gsb_profile_end(float* stage_ms, int* stage_count)
+{
+    g_prof_on = false;
+    if (stage_ms) for (int i = 0; i < ST_COUNT; i++) stage_ms[i] = 0.f;
+    if (stage_count) for (int i = 0; i < ST_COUNT; i++) stage_count[i] = 0;
+    if (!g_prof) return GSB_OK;
+    int rc = GSB_OK;
+    for (auto& e : *g_prof) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(e.b) != cudaSuccess || cudaEventElapsedTime(&ms, e.a, e.b) != cudaSuccess) {
+            rc = fail(GSB_ERR_CUDA, "profile_end: event query failed");
+        } else {
+            if (stage_ms) stage_ms[e.stage] += ms;
+            if (stage_count) stage_count[e.stage] += 1;
+        }
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    g_prof->clear();
+    return rc;
 }
 
 size_t gsb_geometry_bytes(int P) { return GeomLayout::make(P).total; }

@@ -261,15 +261,21 @@ int launch_sort_pairs(GeomHeader* hdr, uint64_t* const kbuf[2], uint32_t* const 
 {
     int cur = start;
     const int hist_grid = sort_tiles < NUM_SMS * 4 ? sort_tiles : NUM_SMS * 4;
-    sort_histogram_kernel<<<hist_grid, SORT_THREADS, 0, s>>>(kbuf[cur], hdr, hist, passes);
-    GSB_LAUNCH_CHECK();
+    {
+        StageTimer _t(ST_SORT_HIST, s);
+        sort_histogram_kernel<<<hist_grid, SORT_THREADS, 0, s>>>(kbuf[cur], hdr, hist, passes);
+        GSB_LAUNCH_CHECK();
+    }
     GSB_CUDA_CHECK(cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(SortSmem)));
     for (int pass = 0; pass < passes; pass++) {
-        onesweep_pass_kernel<<<sort_tiles, SORT_THREADS, sizeof(SortSmem), s>>>(
-            kbuf[cur], kbuf[cur ^ 1], vbuf[cur], vbuf[cur ^ 1], hdr, hist + pass * SORT_RADIX,
-            lookback + (size_t)pass * sort_tiles * SORT_RADIX, pass, pass * SORT_RADIX_BITS);
-        GSB_LAUNCH_CHECK();
+        {
+            StageTimer _t(ST_SORT_PASS, s);
+            onesweep_pass_kernel<<<sort_tiles, SORT_THREADS, sizeof(SortSmem), s>>>(
+                kbuf[cur], kbuf[cur ^ 1], vbuf[cur], vbuf[cur ^ 1], hdr, hist + pass * SORT_RADIX,
+                lookback + (size_t)pass * sort_tiles * SORT_RADIX, pass, pass * SORT_RADIX_BITS);
+            GSB_LAUNCH_CHECK();
+        }
         cur ^= 1;
     }
     return GSB_OK;
@@ -301,16 +307,25 @@ int launch_binning(const FwdParams& p, char* geom, const GeomLayout& GL, char* b
     // hist and lookback are adjacent in the blob: one memset
     GSB_CUDA_CHECK(cudaMemsetAsync(hist, 0, BL.lookback - BL.hist + (size_t)passes * sort_tiles * SORT_RADIX * 4, s));
 
-    duplicate_kernel<<<GL.num_blocks, DUP_THREADS, 0, s>>>(
-        p.P, reinterpret_cast<const SplatRec*>(geom + GL.rec), reinterpret_cast<const int*>(geom + GL.radii),
-        reinterpret_cast<const uint32_t*>(geom + GL.tiles_touched), reinterpret_cast<const uint32_t*>(geom + GL.block_offsets),
-        hdr, kbuf[cur], vbuf[cur], p.tiles_x, p.tiles_y);
-    GSB_LAUNCH_CHECK();
+    {
+
+        StageTimer _t(ST_DUPLICATE, s);
+
+        duplicate_kernel<<<GL.num_blocks, DUP_THREADS, 0, s>>>(
+            p.P, reinterpret_cast<const SplatRec*>(geom + GL.rec), reinterpret_cast<const int*>(geom + GL.radii),
+            reinterpret_cast<const uint32_t*>(geom + GL.tiles_touched), reinterpret_cast<const uint32_t*>(geom + GL.block_offsets),
+            hdr, kbuf[cur], vbuf[cur], p.tiles_x, p.tiles_y);
+        GSB_LAUNCH_CHECK();
+
+    }
     if (int rc = launch_sort_pairs(hdr, kbuf, vbuf, cur, passes, hist, lookback, sort_tiles, s)) return rc;
     // cur == 0 here
     const int rg = sort_tiles * (SORT_TILE / 256) < NUM_SMS * 8 ? sort_tiles * (SORT_TILE / 256) : NUM_SMS * 8;
-    tile_ranges_kernel<<<rg, 256, 0, s>>>(kbuf[0], hdr, ranges);
-    GSB_LAUNCH_CHECK();
+    {
+        StageTimer _t(ST_RANGES, s);
+        tile_ranges_kernel<<<rg, 256, 0, s>>>(kbuf[0], hdr, ranges);
+        GSB_LAUNCH_CHECK();
+    }
     return GSB_OK;
 }
 

@@ -190,12 +190,15 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
     if (p.W <= 0 || p.H <= 0 || p.P <= 0) return GSB_OK;
     GSB_CUDA_CHECK(cudaMemsetAsync(geom + GL.acc, 0, (size_t)p.P * sizeof(GradAcc), s));
     dim3 grid(IL.tiles_x, IL.tiles_y);
-    blend_backward_kernel<<<grid, BLEND_THREADS, 0, s>>>(
-        reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec),
-        p.W, p.H, p.background, reinterpret_cast<const float*>(image + IL.final_T),
-        reinterpret_cast<const uint32_t*>(image + IL.n_contrib), reinterpret_cast<const uint32_t*>(image + IL.tile_max_contrib),
-        dL_dpix, reinterpret_cast<float*>(geom + GL.acc));
-    GSB_LAUNCH_CHECK();
+    {
+        StageTimer _t(ST_BLEND_BWD, s);
+        blend_backward_kernel<<<grid, BLEND_THREADS, 0, s>>>(
+            reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec),
+            p.W, p.H, p.background, reinterpret_cast<const float*>(image + IL.final_T),
+            reinterpret_cast<const uint32_t*>(image + IL.n_contrib), reinterpret_cast<const uint32_t*>(image + IL.tile_max_contrib),
+            dL_dpix, reinterpret_cast<float*>(geom + GL.acc));
+        GSB_LAUNCH_CHECK();
+    }
     return GSB_OK;
 }
 

@@ -130,11 +130,14 @@ int launch_blend_forward(const FwdParams& p, const char* geom, const GeomLayout&
 {
     if (p.W <= 0 || p.H <= 0) return GSB_OK;
     dim3 grid(IL.tiles_x, IL.tiles_y);
-    blend_forward_kernel<<<grid, BLEND_THREADS, 0, s>>>(
-        reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec),
-        p.W, p.H, p.background, out_color, out_depth, reinterpret_cast<float*>(image + IL.final_T),
-        reinterpret_cast<uint32_t*>(image + IL.n_contrib), reinterpret_cast<uint32_t*>(image + IL.tile_max_contrib));
-    GSB_LAUNCH_CHECK();
+    {
+        StageTimer _t(ST_BLEND_FWD, s);
+        blend_forward_kernel<<<grid, BLEND_THREADS, 0, s>>>(
+            reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec),
+            p.W, p.H, p.background, out_color, out_depth, reinterpret_cast<float*>(image + IL.final_T),
+            reinterpret_cast<uint32_t*>(image + IL.n_contrib), reinterpret_cast<uint32_t*>(image + IL.tile_max_contrib));
+        GSB_LAUNCH_CHECK();
+    }
     return GSB_OK;
 }
 

@@ -275,6 +275,21 @@ __device__ const float SH_C3[] = {-0.5900435899266435f, 2.890611442640554f, -0.4
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// ---- per-stage device timing (gsb_profile_begin / gsb_profile_end) -------------------------
+enum Stage {
+    ST_MEMSET = 0, ST_PREPROCESS, ST_SCAN, ST_DUPLICATE, ST_SORT_HIST, ST_SORT_PASS, ST_RANGES, ST_BLEND_FWD,
+    ST_BLEND_BWD, ST_GAUSS_BWD, ST_OTHER, ST_COUNT
+};
+// Scoped: when profiling is enabled on this thread, records a CUDA event on `s` before and
+// after the enclosed launches (events on the launching stream, so they bracket exactly them).
+struct StageTimer {
+    int stage;
+    cudaStream_t s;
+    void* ev;
+    StageTimer(int stage, cudaStream_t s);
+    ~StageTimer();
+};
+
 #define GSB_CUDA_CHECK(expr)                                                              \
     do {                                                                                  \
         cudaError_t _e = (expr);                                                          \

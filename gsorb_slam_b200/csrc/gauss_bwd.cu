@@ -250,8 +250,11 @@ int launch_gauss_backward(const FwdParams& p, const char* geom, const GeomLayout
     q.acc = reinterpret_cast<const float*>(geom + GL.acc);
     q.clamped = reinterpret_cast<const uint8_t*>(geom + GL.clamped);
     q.g = g;
-    gauss_backward_kernel<<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(q);
-    GSB_LAUNCH_CHECK();
+    {
+        StageTimer _t(ST_GAUSS_BWD, s);
+        gauss_backward_kernel<<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(q);
+        GSB_LAUNCH_CHECK();
+    }
     return GSB_OK;
 }
 

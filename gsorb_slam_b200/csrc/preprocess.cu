@@ -266,20 +266,26 @@ int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, int*
 {
     if (p.P <= 0) return GSB_OK;
     auto al = [](const void* q) { return q && (reinterpret_cast<uintptr_t>(q) & 15) == 0 ? 1 : 0; };
-    preprocess_kernel<<<GL.num_blocks, PRE_THREADS, 0, s>>>(
-        p, reinterpret_cast<SplatRec*>(geom + GL.rec), reinterpret_cast<int*>(geom + GL.radii), radii_out,
-        reinterpret_cast<uint32_t*>(geom + GL.tiles_touched), reinterpret_cast<uint32_t*>(geom + GL.block_sums),
-        reinterpret_cast<uint8_t*>(geom + GL.clamped), al(p.means3D), al(p.scales), al(p.colors_precomp));
-    GSB_LAUNCH_CHECK();
+    {
+        StageTimer _t(ST_PREPROCESS, s);
+        preprocess_kernel<<<GL.num_blocks, PRE_THREADS, 0, s>>>(
+            p, reinterpret_cast<SplatRec*>(geom + GL.rec), reinterpret_cast<int*>(geom + GL.radii), radii_out,
+            reinterpret_cast<uint32_t*>(geom + GL.tiles_touched), reinterpret_cast<uint32_t*>(geom + GL.block_sums),
+            reinterpret_cast<uint8_t*>(geom + GL.clamped), al(p.means3D), al(p.scales), al(p.colors_precomp));
+        GSB_LAUNCH_CHECK();
+    }
     return GSB_OK;
 }
 
 int launch_scan_blocks(char* geom, const GeomLayout& GL, uint32_t capacity, int P, cudaStream_t s)
 {
-    scan_blocks_kernel<<<1, 1024, 0, s>>>(reinterpret_cast<const uint32_t*>(geom + GL.block_sums),
-                                          reinterpret_cast<uint32_t*>(geom + GL.block_offsets), GL.num_blocks,
-                                          reinterpret_cast<GeomHeader*>(geom + GL.header), capacity, P);
-    GSB_LAUNCH_CHECK();
+    {
+        StageTimer _t(ST_SCAN, s);
+        scan_blocks_kernel<<<1, 1024, 0, s>>>(reinterpret_cast<const uint32_t*>(geom + GL.block_sums),
+                                              reinterpret_cast<uint32_t*>(geom + GL.block_offsets), GL.num_blocks,
+                                              reinterpret_cast<GeomHeader*>(geom + GL.header), capacity, P);
+        GSB_LAUNCH_CHECK();
+    }
     return GSB_OK;
 }
 
@@ -307,8 +313,11 @@ visible_filter_kernel(FwdParams p, int* __restrict__ radii)
 int launch_visible_filter(const FwdParams& p, int* radii, cudaStream_t s)
 {
     if (p.P <= 0) return GSB_OK;
-    visible_filter_kernel<<<(p.P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(p, radii);
-    GSB_LAUNCH_CHECK();
+    {
+        StageTimer _t(ST_OTHER, s);
+        visible_filter_kernel<<<(p.P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(p, radii);
+        GSB_LAUNCH_CHECK();
+    }
     return GSB_OK;
 }
 
@@ -326,8 +335,11 @@ mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __res
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s)
 {
     if (P <= 0) return GSB_OK;
-    mark_visible_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(P, means3D, viewmatrix, present);
-    GSB_LAUNCH_CHECK();
+    {
+        StageTimer _t(ST_OTHER, s);
+        mark_visible_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(P, means3D, viewmatrix, present);
+        GSB_LAUNCH_CHECK();
+    }
     return GSB_OK;
 }
 

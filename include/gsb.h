@@ -233,6 +233,16 @@ int gsb_debug_geometry_state(const void* geometry, int P, float* depths, float* 
  * (used by bench.py for its gpu_launches claim). */
 long long gsb_launch_count_reset(void);
 
+/* Per-stage device timing for bench.py's roofline line.  Between gsb_profile_begin() and
+ * gsb_profile_end() every kernel launched by this thread through the library is bracketed by
+ * CUDA events on its own stream.  gsb_profile_end synchronises those events and returns, per
+ * stage, the summed milliseconds and the number of timed launches (arrays of gsb_num_stages()
+ * entries, either may be NULL). */
+int gsb_num_stages(void);
+const char* gsb_stage_name(int stage);
+int gsb_profile_begin(void);
+int gsb_profile_end(float* stage_ms, int* stage_count);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
