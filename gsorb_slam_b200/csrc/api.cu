@@ -102,11 +102,13 @@ static FwdParams make_params(const gsb_raster_args* a)
     return p;
 }
 
-static int forward_stage1(const FwdParams& p, char* geom, const GeomLayout& GL, int* radii, uint32_t capacity, cudaStream_t s)
+static int forward_stage1(const FwdParams& p, char* geom, const GeomLayout& GL, char* image, const ImageLayout& IL, int* radii,
+                          uint32_t capacity, cudaStream_t s)
 {
     GSB_CUDA_CHECK(cudaMemsetAsync(geom + GL.header, 0, sizeof(GeomHeader), s));
-    if (int rc = launch_preprocess(p, geom, GL, radii, s)) return rc;
-    return launch_scan_blocks(geom, GL, capacity, p.P, s);
+    GSB_CUDA_CHECK(cudaMemsetAsync(image + IL.tile_count, 0, (size_t)IL.tiles_x * IL.tiles_y * 4 * TILE_CTR_STRIDE, s));
+    if (int rc = launch_preprocess(p, geom, GL, image, IL, radii, s)) return rc;
+    return launch_tile_scan(geom, GL, image, IL, capacity, p.P, s);
 }
 
 static int forward_stage2(const FwdParams& p, char* geom, const GeomLayout& GL, char* binning, const BinningLayout& BL,
@@ -114,7 +116,7 @@ static int forward_stage2(const FwdParams& p, char* geom, const GeomLayout& GL, 
                           cudaStream_t s)
 {
     if (int rc = launch_binning(p, geom, GL, binning, BL, image, IL, grid_instances, s)) return rc;
-    return launch_blend_forward(p, geom, GL, reinterpret_cast<const uint32_t*>(binning + BL.vals0), image, IL, out_color,
+    return launch_blend_forward(p, geom, GL, reinterpret_cast<const uint32_t*>(binning + BL.point_list), image, IL, out_color,
                                 out_depth, s);
 }
 
@@ -126,11 +128,11 @@ __global__ void unpack_geometry_kernel(int P, const SplatRec* __restrict__ rec, 
     if (i >= P) return;
     const bool vis = radii[i] > 0;
     const SplatRec r = rec[i];
-    if (depths) depths[i] = vis ? r.b.w : 0.f;
+    if (depths) depths[i] = vis ? r.c.w : 0.f;
     if (means2D) { means2D[2 * i] = vis ? r.a.x : 0.f; means2D[2 * i + 1] = vis ? r.a.y : 0.f; }
     if (conic_opacity) {
-        conic_opacity[4 * i] = vis ? r.a.z : 0.f; conic_opacity[4 * i + 1] = vis ? r.a.w : 0.f;
-        conic_opacity[4 * i + 2] = vis ? r.b.x : 0.f; conic_opacity[4 * i + 3] = vis ? r.b.y : 0.f;
+        conic_opacity[4 * i] = vis ? r.b.x : 0.f; conic_opacity[4 * i + 1] = vis ? r.b.y : 0.f;
+        conic_opacity[4 * i + 2] = vis ? r.b.z : 0.f; conic_opacity[4 * i + 3] = vis ? r.b.w : 0.f;
     }
     if (tt_out) tt_out[i] = tiles_touched[i];
 }
@@ -151,7 +153,7 @@ long long gsb_launch_count_reset(void)
 }
 
 static const char* kStageNames[ST_COUNT] = {"memset", "preprocess", "scan", "duplicate", "sort_histogram", "sort_passes",
-                                            "tile_ranges", "blend_forward", "blend_backward", "gauss_backward", "other"};
+                                            "tile_sort", "blend_forward", "blend_backward", "gauss_backward", "other"};
 int gsb_num_stages(void) { return ST_COUNT; }
 const char* gsb_stage_name(int stage) { return stage >= 0 && stage < ST_COUNT ? kStageNames[stage] : ""; }
 int gsb_profile_begin(void)
@@ -212,7 +214,7 @@ int gsb_forward(const gsb_raster_args* args, gsb_alloc_fn geometry_alloc, void* 
     char* geom = (char*)geometry_alloc(geometry_user, GL.total);
     char* image = (char*)image_alloc(image_user, IL.total);
     if (!geom || !image) return fail(GSB_ERR_WORKSPACE, "geometry / image allocator returned NULL");
-    if (int rc = forward_stage1(p, geom, GL, radii, 0xffffffffu, s)) return rc;
+    if (int rc = forward_stage1(p, geom, GL, image, IL, radii, 0xffffffffu, s)) return rc;
     // the one synchronisation of the drop-in path (rasterizer_impl.cu:285 does a blocking cudaMemcpy)
     GeomHeader h;
     GSB_CUDA_CHECK(cudaMemcpyAsync(&h, geom + GL.header, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
@@ -241,7 +243,7 @@ int gsb_forward_ws(const gsb_raster_args* args, void* geometry, size_t geometry_
     if (!image || image_bytes < IL.total) return fail(GSB_ERR_WORKSPACE, "image workspace too small (%zu < %zu)", image_bytes, IL.total);
     if (!binning || binning_bytes < BL.total) return fail(GSB_ERR_WORKSPACE, "binning workspace too small (%zu < %zu)", binning_bytes, BL.total);
     cudaStream_t s = (cudaStream_t)stream;
-    if (int rc = forward_stage1(p, (char*)geometry, GL, radii, (uint32_t)max_rendered, s)) return rc;
+    if (int rc = forward_stage1(p, (char*)geometry, GL, (char*)image, IL, radii, (uint32_t)max_rendered, s)) return rc;
     return forward_stage2(p, (char*)geometry, GL, (char*)binning, BL, (char*)image, IL, max_rendered, out_color, out_depth, s);
 }
 

@@ -1,62 +1,309 @@
-// binning.cu -- tile-instance emission (K3), cub-free onesweep radix sort (K4) and tile
-// ranges (K5) for sm_100a.
+// binning.cu -- tile binning and depth ordering (K2-K5) for sm_100a, plus the library's
+// stand-alone onesweep radix sort (used by knn.cu).
 //
 // Replaces (reference file:line, behaviour only):
-//   duplicateWithKeys                       rasterizer_impl.cu:71-112
-//   cub::DeviceRadixSort::SortPairs         rasterizer_impl.cu:307-315   (stable LSD sort of
-//                                           (tile << 32 | depth bits, gaussian id) pairs)
-//   identifyTileRanges (+ memset)           rasterizer_impl.cu:117-139, :317
+//   cub::DeviceScan::InclusiveSum + D2H copy  rasterizer_impl.cu:280-285
+//   duplicateWithKeys                         rasterizer_impl.cu:71-112
+//   cub::DeviceRadixSort::SortPairs           rasterizer_impl.cu:307-315  (6 global passes over
+//                                             (tile << 32 | depth bits, id) pairs at 640x480)
+//   identifyTileRanges (+ memset)             rasterizer_impl.cu:117-139, :317
 //
-// The sort is a hand-written "onesweep" least-significant-digit radix sort: one histogram
-// kernel for all digit positions, then one kernel per 8-bit digit that ranks a 4096-key tile
-// in shared memory (warp match_any ranking, stable), resolves its global offsets with a
-// decoupled look-back over the preceding tiles and scatters keys + values -- each pass reads
-// and writes every pair exactly once.  Stability is part of the contract: equal keys keep
-// ascending Gaussian order, which is how the reference resolves depth ties.
+// B200 design: the reference sorts ONE global list by a 43-45 bit key (six read+write passes
+// over 24 B per instance).  Here the tile is known when an instance is created, so
+//   1. preprocess counts instances per tile (atomics on T counters),
+//   2. one CTA scans the T counts -> every tile's [start, end) segment = the tile ranges
+//      (identifyTileRanges disappears) and num_rendered,
+//   3. duplicate claims slots in the segments with per-tile cursors and writes
+//      (depth bits << 32 | id) records -- bucketed by tile, arbitrary order inside a tile,
+//   4. one CTA per tile sorts its segment in SHARED memory (a tile's list fits: up to 4096
+//      entries in 32 KB, up to 16384 in 128 KB of the 227 KB an sm_100 CTA can own) with a
+//      bitonic network on the full 64-bit record and writes the ids out.
+// Ordering by (depth bits, id) is exactly the order the reference's stable radix sort
+// produces (instances are emitted in ascending id, so ties keep id order), hence the sorted
+// list is bit-identical -- while every instance is written twice and read twice instead of
+// seven times.  Tiles longer than 16384 entries fall back to a global-memory network.
 #include "common.cuh"
 
 namespace gsb {
 
 constexpr int DUP_THREADS = 256;
 
-// ---- K3: one thread per Gaussian writes its (key, id) run -----------------------------------
-__global__ void __launch_bounds__(DUP_THREADS)
-duplicate_kernel(int P, const SplatRec* __restrict__ rec, const int* __restrict__ radii,
-                 const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ block_offsets,
-                 const GeomHeader* __restrict__ hdr, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                 int tiles_x, int tiles_y)
+// ---- K2: one CTA scans the per-tile counts into segments ---------------------------------------
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges, uint32_t* __restrict__ cursor,
+                 int tiles, GeomHeader* __restrict__ hdr, uint32_t capacity, int P)
 {
-    __shared__ uint32_t s_warp[DUP_THREADS / 32];
-    const int idx = blockIdx.x * DUP_THREADS + threadIdx.x;
-    const uint32_t touched = idx < P ? tiles_touched[idx] : 0u;
-    uint32_t v = touched;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane_id() >= (uint32_t)o) v += t;
-    }
-    if (lane_id() == 31) s_warp[threadIdx.x >> 5] = v;
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-    uint32_t warp_excl = 0;
+    for (int base = 0; base < tiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t x = i < tiles ? tile_count[(size_t)i * TILE_CTR_STRIDE] : 0u;
+        uint32_t v = x;
 #pragma unroll
-    for (int w = 0; w < DUP_THREADS / 32; w++)
-        if (w < (int)(threadIdx.x >> 5)) warp_excl += s_warp[w];
-    if (touched == 0) return;
-    uint32_t off = block_offsets[blockIdx.x] + warp_excl + v - touched;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane_id() >= (uint32_t)o) v += t;
+        }
+        if (lane_id() == 31) s_warp[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = s_warp[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane_id() >= (uint32_t)o) w += t;
+            }
+            s_warp[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const uint32_t warp_excl = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0u;
+        const uint32_t carry = s_carry;
+        if (i < tiles) {
+            const uint32_t start = carry + warp_excl + v - x;
+            // a too-small binning capacity truncates the tail of the tile-major list (overflow is latched below)
+            ranges[i] = make_uint2(min(start, capacity), min(start + x, capacity));
+            cursor[(size_t)i * TILE_CTR_STRIDE] = start;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + warp_excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t total = s_carry;
+        hdr->magic = GEOM_MAGIC;
+        hdr->P = P;
+        hdr->num_rendered = total;
+        hdr->num_rendered_clamped = min(total, capacity);
+        hdr->overflow = total > capacity ? 1u : 0u;
+        hdr->capacity = capacity;
+    }
+}
+
+// ---- K3: one thread per Gaussian claims a slot in every tile segment it touches -----------------
+__global__ void __launch_bounds__(DUP_THREADS)
+duplicate_kernel(int P, const SplatRec* __restrict__ rec, const int* __restrict__ radii, uint32_t* __restrict__ cursor,
+                 const GeomHeader* __restrict__ hdr, uint64_t* __restrict__ pairs, int tiles_x, int tiles_y)
+{
+    const int idx = blockIdx.x * DUP_THREADS + threadIdx.x;
+    if (idx >= P) return;
+    const int radius = radii[idx];
+    if (radius <= 0) return;
     const uint32_t cap = hdr->num_rendered_clamped;
     const float4 a = rec[idx].a;
-    const float depth = rec[idx].b.w;
+    const uint64_t record = ((uint64_t)__float_as_uint(rec[idx].c.w) << 32) | (uint32_t)idx;
     uint32_t minx, miny, maxx, maxy;
-    get_rect(a.x, a.y, radii[idx], tiles_x, tiles_y, minx, miny, maxx, maxy);
-    const uint64_t dbits = (uint64_t)__float_as_uint(depth);
+    get_rect(a.x, a.y, radius, tiles_x, tiles_y, minx, miny, maxx, maxy);
     for (uint32_t y = miny; y < maxy; y++)
         for (uint32_t x = minx; x < maxx; x++) {
-            if (off < cap) {
-                keys[off] = ((uint64_t)(y * (uint32_t)tiles_x + x) << 32) | dbits;
-                vals[off] = (uint32_t)idx;
-            }
-            off++;
+            const uint32_t pos = atomicAdd(&cursor[(size_t)(y * (uint32_t)tiles_x + x) * TILE_CTR_STRIDE], 1u);
+            if (pos < cap) pairs[pos] = record;
         }
+}
+
+// ---- K4: per-tile sort -----------------------------------------------------------------------------
+// Bitonic network with every comparator pointing the same way (first step of each merge is a
+// "flip", i ^ (k-1)), so a virtual +inf padding above n needs no storage: comparators whose
+// upper element is >= n are skipped.
+template <typename F>
+__device__ __forceinline__ void bitonic_network(uint32_t n, uint32_t npow2, uint32_t nthreads, F cmpxchg_and_sync)
+{
+    for (uint32_t k = 2; k <= npow2; k <<= 1) {
+        const uint32_t half = k >> 1;
+        // flip step: element i of the lower half of each k-block meets base + (k-1-i)
+        for (uint32_t p = threadIdx.x; p < (npow2 >> 1); p += nthreads) {
+            const uint32_t blk = p / half, off = p % half;
+            const uint32_t i = blk * k + off, l = blk * k + (k - 1 - off);
+            if (l < n) cmpxchg_and_sync(i, l, false);
+        }
+        cmpxchg_and_sync(0, 0, true);
+        for (uint32_t j = half >> 1; j > 0; j >>= 1) {
+            for (uint32_t p = threadIdx.x; p < (npow2 >> 1); p += nthreads) {
+                const uint32_t i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), l = i | j;
+                if (l < n) cmpxchg_and_sync(i, l, false);
+            }
+            cmpxchg_and_sync(0, 0, true);
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t next_pow2(uint32_t n)
+{
+    return n <= 1 ? 1u : 1u << (32 - __clz(n - 1));
+}
+
+constexpr int TSORT_SMALL = 4096;    // entries, 32 KB
+constexpr int TSORT_MID = 16384;     // entries, 128 KB
+constexpr int TSORT_THREADS = 256;
+
+// Register-resident bitonic sort of E * 256 records by one 256-thread CTA (blocked layout:
+// thread t owns elements t*E .. t*E+E-1).  Of the log2(n)(log2(n)+1)/2 comparator stages only
+// those that cross warps (stride >= 32 E) go through shared memory; strides inside a warp are
+// 64-bit shuffles and strides inside a thread are register compare-exchanges.
+__device__ __forceinline__ void cx(uint64_t& lo, uint64_t& hi)
+{
+    const uint64_t a = lo, b = hi;
+    const bool sw = a > b;
+    lo = sw ? b : a;
+    hi = sw ? a : b;
+}
+
+template <int E>
+__device__ __forceinline__ void tile_sort_regs(uint64_t* __restrict__ s /* smem, E*256 records, padded with ~0 */)
+{
+    constexpr uint32_t N = E * TSORT_THREADS;
+    const uint32_t t = threadIdx.x, lane = t & 31;
+    uint64_t a[E];
+#pragma unroll
+    for (int r = 0; r < E; r++) a[r] = s[t * E + r];
+#pragma unroll
+    for (uint32_t k = 2; k <= N; k <<= 1) {
+        // ---- flip step of the merge of size k ----
+        if (k <= (uint32_t)E) {
+#pragma unroll
+            for (int b0 = 0; b0 < E; b0 += (int)k)
+#pragma unroll
+                for (int o = 0; o < (int)k / 2; o++) cx(a[b0 + o], a[b0 + (int)k - 1 - o]);
+        } else if (k <= 32u * E) {
+            const uint32_t m = k / E;  // 2..32 threads per k-block
+            uint64_t other[E];
+#pragma unroll
+            for (int r = 0; r < E; r++) other[r] = __shfl_xor_sync(0xffffffffu, a[E - 1 - r], m - 1);
+            const bool lower = (lane & (m >> 1)) == 0;
+#pragma unroll
+            for (int r = 0; r < E; r++) a[r] = lower ? (a[r] < other[r] ? a[r] : other[r]) : (a[r] > other[r] ? a[r] : other[r]);
+        }
+        uint32_t j = k >> 2;  // first stride of the half-cleaners
+        if (k > 32u * E) {
+            // cross-warp part of this merge in shared memory: flip, then strides >= 32 E
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < E; r++) s[t * E + r] = a[r];
+            __syncthreads();
+            const uint32_t half = k >> 1;
+            for (uint32_t p = t; p < N / 2; p += TSORT_THREADS) {
+                const uint32_t blk = p / half, off = p % half;
+                const uint32_t i = blk * k + off, l = blk * k + (k - 1 - off);
+                const uint64_t x = s[i], y = s[l];
+                if (x > y) { s[i] = y; s[l] = x; }
+            }
+            __syncthreads();
+            for (; j >= 32u * E; j >>= 1) {
+                for (uint32_t p = t; p < N / 2; p += TSORT_THREADS) {
+                    const uint32_t i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), l = i | j;
+                    const uint64_t x = s[i], y = s[l];
+                    if (x > y) { s[i] = y; s[l] = x; }
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int r = 0; r < E; r++) a[r] = s[t * E + r];
+        }
+        // ---- half-cleaners inside a warp (shuffles) ----
+#pragma unroll
+        for (uint32_t jj = 16u * E; jj >= (uint32_t)E; jj >>= 1) {
+            if (jj <= j && jj >= 1) {
+                const uint32_t m = jj / E;
+                const bool lower = (lane & m) == 0;
+#pragma unroll
+                for (int r = 0; r < E; r++) {
+                    const uint64_t o = __shfl_xor_sync(0xffffffffu, a[r], m);
+                    a[r] = lower ? (a[r] < o ? a[r] : o) : (a[r] > o ? a[r] : o);
+                }
+            }
+        }
+        // ---- half-cleaners inside a thread (registers) ----
+#pragma unroll
+        for (int jj = E / 2; jj >= 1; jj >>= 1) {
+            if ((uint32_t)jj <= j) {
+#pragma unroll
+                for (int r = 0; r < E; r++)
+                    if ((r & jj) == 0) cx(a[r], a[r | jj]);
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < E; r++) s[t * E + r] = a[r];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(TSORT_THREADS)
+tile_sort_small_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list)
+{
+    __shared__ __align__(16) uint64_t s[TSORT_SMALL];
+    const uint2 r = ranges[blockIdx.x];
+    const uint32_t n = r.y - r.x;
+    if (n == 0 || n > (uint32_t)TSORT_SMALL) return;   // longer lists: the 128 KB / global classes
+    const uint32_t npad = n <= 256 ? 256u : next_pow2(n);
+    for (uint32_t i = threadIdx.x; i < npad; i += TSORT_THREADS) s[i] = i < n ? pairs[r.x + i] : ~0ull;
+    __syncthreads();
+    switch (npad) {
+        case 256: tile_sort_regs<1>(s); break;
+        case 512: tile_sort_regs<2>(s); break;
+        case 1024: tile_sort_regs<4>(s); break;
+        case 2048: tile_sort_regs<8>(s); break;
+        default: tile_sort_regs<16>(s); break;
+    }
+    for (uint32_t i = threadIdx.x; i < n; i += TSORT_THREADS) point_list[r.x + i] = (uint32_t)s[i];
+}
+
+template <int CAP, int THREADS, bool DYNAMIC>
+__global__ void __launch_bounds__(THREADS)
+tile_sort_smem_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list,
+                      int tiles, uint32_t lo_excl, uint32_t hi_incl)
+{
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ __align__(16) uint64_t stat_smem[DYNAMIC ? 1 : CAP];
+    uint64_t* s = DYNAMIC ? reinterpret_cast<uint64_t*>(dyn_smem) : stat_smem;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint2 r = ranges[tile];
+        const uint32_t n = r.y - r.x;
+        if (n <= lo_excl || n > hi_incl) continue;   // another size class handles this tile
+        __syncthreads();                              // previous tile's readers are done with s[]
+        for (uint32_t i = threadIdx.x; i < n; i += THREADS) s[i] = pairs[r.x + i];
+        __syncthreads();
+        bitonic_network(n, next_pow2(n), THREADS, [&](uint32_t i, uint32_t l, bool sync) {
+            if (sync) {
+                __syncthreads();
+                return;
+            }
+            const uint64_t a = s[i], b = s[l];
+            if (a > b) {
+                s[i] = b;
+                s[l] = a;
+            }
+        });
+        for (uint32_t i = threadIdx.x; i < n; i += THREADS) point_list[r.x + i] = (uint32_t)s[i];
+    }
+}
+
+// Fallback for tiles with more than TSORT_MID entries: the same network on global memory, one
+// 1024-thread CTA per such tile (correct for any length; pathological inputs only).
+__global__ void __launch_bounds__(1024)
+tile_sort_global_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list,
+                        int tiles, uint32_t lo_excl)
+{
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint2 r = ranges[tile];
+        const uint32_t n = r.y - r.x;
+        if (n <= lo_excl) continue;
+        uint64_t* s = pairs + r.x;
+        bitonic_network(n, next_pow2(n), 1024, [&](uint32_t i, uint32_t l, bool sync) {
+            if (sync) {
+                __threadfence_block();
+                __syncthreads();
+                return;
+            }
+            const uint64_t a = s[i], b = s[l];
+            if (a > b) {
+                s[i] = b;
+                s[l] = a;
+            }
+        });
+        for (uint32_t i = threadIdx.x; i < n; i += 1024) point_list[r.x + i] = (uint32_t)s[i];
+    }
 }
 
 // ---- K4: onesweep radix sort ------------------------------------------------------------------
@@ -233,26 +480,6 @@ onesweep_pass_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict_
     }
 }
 
-// ---- K5: tile ranges ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-tile_ranges_kernel(const uint64_t* __restrict__ keys, const GeomHeader* __restrict__ hdr, uint2* __restrict__ ranges)
-{
-    const uint32_t R = hdr->num_rendered_clamped;
-    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < R; i += gridDim.x * 256) {
-        const uint32_t cur = (uint32_t)(keys[i] >> 32);
-        if (i == 0) {
-            ranges[cur].x = 0;
-        } else {
-            const uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
-            if (cur != prev) {
-                ranges[prev].y = i;
-                ranges[cur].x = i;
-            }
-        }
-        if (i == R - 1) ranges[cur].y = R;
-    }
-}
-
 // Sort hdr->num_rendered_clamped (u64 key, u32 value) pairs, stable, on the low passes*8 key
 // bits.  Input in kbuf/vbuf[start]; output in kbuf/vbuf[start ^ (passes & 1)].  `hist` and
 // `lookback` must be zeroed, as must hdr->sort_tile_counter[0..passes).
@@ -281,50 +508,51 @@ int launch_sort_pairs(GeomHeader* hdr, uint64_t* const kbuf[2], uint32_t* const 
     return GSB_OK;
 }
 
-int sort_passes_for(int tiles)
+int launch_tile_scan(char* geom, const GeomLayout& GL, char* image, const ImageLayout& IL, uint32_t capacity, int P,
+                     cudaStream_t s)
 {
-    int bits = 0;
-    while ((1 << bits) < tiles) bits++;
-    const int key_bits = 32 + (bits > 0 ? bits : 1);
-    return (key_bits + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS;
+    StageTimer _t(ST_SCAN, s);
+    tile_scan_kernel<<<1, 1024, 0, s>>>(reinterpret_cast<const uint32_t*>(image + IL.tile_count),
+                                        reinterpret_cast<uint2*>(image + IL.ranges),
+                                        reinterpret_cast<uint32_t*>(image + IL.tile_cursor), IL.tiles_x * IL.tiles_y,
+                                        reinterpret_cast<GeomHeader*>(geom + GL.header), capacity, P);
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
 }
 
 int launch_binning(const FwdParams& p, char* geom, const GeomLayout& GL, char* binning, const BinningLayout& BL,
                    char* image, const ImageLayout& IL, long long grid_instances, cudaStream_t s)
 {
-    GeomHeader* hdr = reinterpret_cast<GeomHeader*>(geom + GL.header);
-    uint64_t* kbuf[2] = {reinterpret_cast<uint64_t*>(binning + BL.keys0), reinterpret_cast<uint64_t*>(binning + BL.keys1)};
-    uint32_t* vbuf[2] = {reinterpret_cast<uint32_t*>(binning + BL.vals0), reinterpret_cast<uint32_t*>(binning + BL.vals1)};
-    uint32_t* hist = reinterpret_cast<uint32_t*>(binning + BL.hist);
-    uint32_t* lookback = reinterpret_cast<uint32_t*>(binning + BL.lookback);
-    uint2* ranges = reinterpret_cast<uint2*>(image + IL.ranges);
-    const int tiles = p.tiles_x * p.tiles_y;
-    const int passes = sort_passes_for(tiles);
-    int cur = passes & 1;  // an even number of ping-pong passes ends in buffer 0
-    GSB_CUDA_CHECK(cudaMemsetAsync(ranges, 0, (size_t)tiles * sizeof(uint2), s));
     if (grid_instances <= 0 || p.P <= 0) return GSB_OK;
-    const int sort_tiles = (int)((grid_instances + SORT_TILE - 1) / SORT_TILE);
-    // hist and lookback are adjacent in the blob: one memset
-    GSB_CUDA_CHECK(cudaMemsetAsync(hist, 0, BL.lookback - BL.hist + (size_t)passes * sort_tiles * SORT_RADIX * 4, s));
-
+    const GeomHeader* hdr = reinterpret_cast<const GeomHeader*>(geom + GL.header);
+    uint64_t* pairs = reinterpret_cast<uint64_t*>(binning + BL.pairs);
+    uint32_t* point_list = reinterpret_cast<uint32_t*>(binning + BL.point_list);
+    const uint2* ranges = reinterpret_cast<const uint2*>(image + IL.ranges);
+    const int tiles = p.tiles_x * p.tiles_y;
     {
-
         StageTimer _t(ST_DUPLICATE, s);
-
         duplicate_kernel<<<GL.num_blocks, DUP_THREADS, 0, s>>>(
             p.P, reinterpret_cast<const SplatRec*>(geom + GL.rec), reinterpret_cast<const int*>(geom + GL.radii),
-            reinterpret_cast<const uint32_t*>(geom + GL.tiles_touched), reinterpret_cast<const uint32_t*>(geom + GL.block_offsets),
-            hdr, kbuf[cur], vbuf[cur], p.tiles_x, p.tiles_y);
+            reinterpret_cast<uint32_t*>(image + IL.tile_cursor), hdr, pairs, p.tiles_x, p.tiles_y);
         GSB_LAUNCH_CHECK();
-
     }
-    if (int rc = launch_sort_pairs(hdr, kbuf, vbuf, cur, passes, hist, lookback, sort_tiles, s)) return rc;
-    // cur == 0 here
-    const int rg = sort_tiles * (SORT_TILE / 256) < NUM_SMS * 8 ? sort_tiles * (SORT_TILE / 256) : NUM_SMS * 8;
     {
-        StageTimer _t(ST_RANGES, s);
-        tile_ranges_kernel<<<rg, 256, 0, s>>>(kbuf[0], hdr, ranges);
+        StageTimer _t(ST_TILE_SORT, s);
+        tile_sort_small_kernel<<<tiles, TSORT_THREADS, 0, s>>>(ranges, pairs, point_list);
         GSB_LAUNCH_CHECK();
+        if (grid_instances > TSORT_SMALL) {   // a longer tile list is only possible then
+            GSB_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_smem_kernel<TSORT_MID, 1024, true>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, TSORT_MID * 8));
+            const int g = tiles < NUM_SMS ? tiles : NUM_SMS;
+            tile_sort_smem_kernel<TSORT_MID, 1024, true><<<g, 1024, TSORT_MID * 8, s>>>(ranges, pairs, point_list, tiles,
+                                                                                       (uint32_t)TSORT_SMALL, (uint32_t)TSORT_MID);
+            GSB_LAUNCH_CHECK();
+        }
+        if (grid_instances > TSORT_MID) {
+            const int g = tiles < NUM_SMS ? tiles : NUM_SMS;
+            tile_sort_global_kernel<<<g, 1024, 0, s>>>(ranges, pairs, point_list, tiles, (uint32_t)TSORT_MID);
+            GSB_LAUNCH_CHECK();
+        }
     }
     return GSB_OK;
 }

@@ -8,13 +8,14 @@
 //
 // What is different (design, not results):
 //   * the reference issues 9 global atomicAdds per contributing (pixel, splat) pair; here a
-//     warp owns an 8x4 pixel block, reduces the 9 partial sums of a splat across its lanes
-//     with a shuffle reduce-scatter (14 SHFL instead of 45) and issues ONE predicated
-//     RED.ADD.F32 instruction (9 lanes, one 48-byte packed accumulator per Gaussian), and only
-//     for splats that touched at least one pixel of the block;
+//     QUARTER-WARP owns a 4x2 pixel block, reduces the 9 partial sums of a splat across its 8
+//     lanes with a shuffle reduce-scatter (10 SHFL) and issues two RED.ADD.F32 instructions
+//     into one 48-byte packed accumulator per Gaussian, and only for splats that touched at
+//     least one pixel of the block; the four quarters of a warp work on four different splats
+//     at once;
 //   * the walk starts at the tile's highest n_contrib (recorded by the forward pass), not at
-//     the end of the tile's list, and each warp culls staged splats against its pixel block
-//     and its own highest n_contrib with one ballot per 32 splats;
+//     the end of the tile's list, and each warp culls staged splats against its four pixel
+//     blocks and their highest n_contrib with four ballots per 32 splats;
 //   * records are gathered with cp.async into double-buffered shared memory (stage.cuh).
 #include "common.cuh"
 #include "stage.cuh"
@@ -36,11 +37,13 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const int batches = (n + BLEND_BATCH - 1) / BLEND_BATCH;
     if (batches == 0) return;
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t q = lane >> 3, l8 = lane & 7, qshift = q * 8;
     const int bx0 = blockIdx.x * TILE_X + (warp & 1) * 8, by0 = blockIdx.y * TILE_Y + (warp >> 1) * 4;
-    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+    const int px = bx0 + (q & 1) * 4 + (l8 & 3), py = by0 + (q >> 1) * 2 + (l8 >> 2);
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
-    const float fx0 = (float)bx0, fx1 = (float)(bx0 + 7), fy0 = (float)by0, fy1 = (float)(by0 + 3);
+    const float xa0 = (float)bx0, xa1 = (float)(bx0 + 3), xb0 = (float)(bx0 + 4), xb1 = (float)(bx0 + 7);
+    const float ya0 = (float)by0, ya1 = (float)(by0 + 1), yb0 = (float)(by0 + 2), yb1 = (float)(by0 + 3);
     const size_t HW = (size_t)W * H, pix = (size_t)py * W + px;
 
     const float T_final = inside ? final_T[pix] : 0.f;
@@ -55,9 +58,13 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const float bg_dot_dpixel = __ldg(bg) * d0 + __ldg(bg + 1) * d1 + __ldg(bg + 2) * d2;
     float ar0 = 0.f, ar1 = 0.f, ar2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-    int warp_max = last_contributor;
+    // highest n_contrib of each quarter-warp (the cull pass needs all four) and of the warp
+    int qmax = last_contributor;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) warp_max = max(warp_max, __shfl_xor_sync(0xffffffffu, warp_max, o));
+    for (int o = 4; o > 0; o >>= 1) qmax = max(qmax, __shfl_xor_sync(0xffffffffu, qmax, o));
+    const int qm0 = __shfl_sync(0xffffffffu, qmax, 0), qm1 = __shfl_sync(0xffffffffu, qmax, 8);
+    const int qm2 = __shfl_sync(0xffffffffu, qmax, 16), qm3 = __shfl_sync(0xffffffffu, qmax, 24);
+    const int warp_max = max(max(qm0, qm1), max(qm2, qm3));
 
     // slot t of batch k holds list entry (n - 1 - k*256 - t): slots run back to front
     const uint32_t* ids = point_list + range.x;
@@ -85,30 +92,41 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         const int cnt = min(BLEND_BATCH, first_pos);
         if (first_pos - cnt < warp_max) {  // some slot of this batch has pos <= warp_max
             for (int c0 = 0; c0 < cnt; c0 += 32) {
+                // ---- cull pass ----
                 const int j = c0 + (int)lane;
-                bool hit = false;
-                if (j < cnt && first_pos - j <= warp_max) {
-                    const float2 c = *reinterpret_cast<const float2*>(&S.a[buf][j]);
-                    const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&S.c[buf][j].w));
-                    hit = !(c.x + e.x < fx0 || c.x - e.x > fx1 || c.y + e.y < fy0 || c.y - e.y > fy1);
+                const int posj = first_pos - j;
+                bool hxa = false, hxb = false, hya = false, hyb = false;
+                if (j < cnt && posj <= warp_max) {
+                    const float4 A = S.a[buf][j];
+                    const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&A.z));
+                    const float lox = A.x - e.x, hix = A.x + e.x, loy = A.y - e.y, hiy = A.y + e.y;
+                    hxa = !(hix < xa0 || lox > xa1);
+                    hxb = !(hix < xb0 || lox > xb1);
+                    hya = !(hiy < ya0 || loy > ya1);
+                    hyb = !(hiy < yb0 || loy > yb1);
                 }
-                uint32_t mask = __ballot_sync(0xffffffffu, hit);
-                while (mask) {
-                    const int jj = __ffs(mask) - 1;
+                const uint32_t m0 = __ballot_sync(0xffffffffu, hxa && hya && posj <= qm0);
+                const uint32_t m1 = __ballot_sync(0xffffffffu, hxb && hya && posj <= qm1);
+                const uint32_t m2 = __ballot_sync(0xffffffffu, hxa && hyb && posj <= qm2);
+                const uint32_t m3 = __ballot_sync(0xffffffffu, hxb && hyb && posj <= qm3);
+                uint32_t mask = q == 0 ? m0 : q == 1 ? m1 : q == 2 ? m2 : m3;
+                // ---- gradient pass: every quarter-warp walks its survivors back to front ----
+                while (__any_sync(0xffffffffu, mask != 0)) {
+                    const bool act = mask != 0;
+                    const int e = c0 + (act ? __ffs(mask) - 1 : 0);
                     mask &= mask - 1;
-                    const int e = c0 + jj;
                     const int pos = first_pos - e;
                     const float4 A = S.a[buf][e];
                     const float4 B = S.b[buf][e];
                     const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
-                    const float power = splat_power(dx, dy, A.z, A.w, B.x);
+                    const float power = splat_power(dx, dy, B.x, B.y, B.z);
                     float v[8], v8 = 0.f;
 #pragma unroll
                     for (int k = 0; k < 8; k++) v[k] = 0.f;
                     bool contrib = false;
-                    if (pos <= last_contributor && !(power > 0.0f) && !(power < B.z)) {
+                    if (act && pos <= last_contributor && !(power > 0.0f) && !(power < A.w)) {
                         const float G = expf(power);
-                        const float alpha = fminf(0.99f, __fmul_rn(B.y, G));
+                        const float alpha = fminf(0.99f, __fmul_rn(B.w, G));
                         if (!(alpha < 1.0f / 255.0f)) {
                             contrib = true;
                             const float4 Cc = S.c[buf][e];
@@ -122,10 +140,10 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                             dL_dalpha *= T;
                             last_alpha = alpha;
                             dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-                            const float dL_dG = B.y * dL_dalpha;
+                            const float dL_dG = B.w * dL_dalpha;
                             const float gdx = G * dx, gdy = G * dy;
-                            const float dG_ddelx = -gdx * A.z - gdy * A.w;
-                            const float dG_ddely = -gdy * B.x - gdx * A.w;
+                            const float dG_ddelx = -gdx * B.x - gdy * B.y;
+                            const float dG_ddely = -gdy * B.z - gdx * B.y;
                             v[0] = dL_dG * dG_ddelx * ddelx_dx;
                             v[1] = dL_dG * dG_ddely * ddely_dy;
                             v[2] = -0.5f * gdx * dx * dL_dG;
@@ -137,44 +155,41 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                             v8 = dchannel_dcolor * d2;
                         }
                     }
-                    if (!__any_sync(0xffffffffu, contrib)) continue;
-                    // reduce-scatter 8 values over the warp: 4 + 2 + 1 + 1 + 1 shuffles
+                    const uint32_t cb = __ballot_sync(0xffffffffu, contrib);
+                    if (cb == 0) continue;
+                    // reduce-scatter the 8 sums over the quarter-warp's 8 lanes: 4 + 2 + 1 shuffles,
+                    // after which lane l8 holds sum number (bit2, bit1, bit0 of l8) complete
                     {
-                        const bool hi = lane & 16;
+                        const bool hi = l8 & 4;
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
                             const float send = hi ? v[k] : v[k + 4];
                             const float keep = hi ? v[k + 4] : v[k];
-                            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
                         }
                     }
                     {
-                        const bool hi = lane & 8;
+                        const bool hi = l8 & 2;
 #pragma unroll
                         for (int k = 0; k < 2; k++) {
                             const float send = hi ? v[k] : v[k + 2];
                             const float keep = hi ? v[k + 2] : v[k];
-                            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
                         }
                     }
                     {
-                        const bool hi = lane & 4;
+                        const bool hi = l8 & 1;
                         const float send = hi ? v[0] : v[1];
                         const float keep = hi ? v[1] : v[0];
-                        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
                     }
-                    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
-                    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v8 += __shfl_xor_sync(0xffffffffu, v8, o);
-                    // lanes 0,4,...,28 hold sums 0..7 (index = bits 4,3,2 of the lane); lane 1 adds sum 8
-                    const uint32_t id = s_ids[buf][e];
-                    float* dst = acc + (size_t)id * 12;
-                    if ((lane & 3) == 0) {
-                        const int k = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                    for (int o = 4; o > 0; o >>= 1) v8 += __shfl_xor_sync(0xffffffffu, v8, o);
+                    if ((cb >> qshift) & 0xffu) {  // this quarter touched the splat
+                        float* dst = acc + (size_t)s_ids[buf][e] * 12;
+                        const int k = ((l8 >> 2) & 1) * 4 + ((l8 >> 1) & 1) * 2 + (l8 & 1);
                         atomicAdd(dst + k, v[0]);
-                    } else if (lane == 1) {
-                        atomicAdd(dst + 8, v8);
+                        if (l8 == 0) atomicAdd(dst + 8, v8);
                     }
                 }
             }

@@ -7,11 +7,12 @@
 // last blended splat, colour = C + T * bg, planar CHW output.
 //
 // What is different from the reference kernel (design, not results):
-//   * one CTA per 16x16 tile as before, but each WARP owns an 8x4 pixel block and culls the
-//     staged splats against that block with one ballot per 32 splats (conservative
-//     footprint boxes computed in preprocess), so a pixel evaluates only the few splats
-//     that can reach its block instead of every splat binned to the tile;
-//   * a warp retires as soon as its 32 pixels are saturated;
+//   * one CTA per 16x16 tile as before, but each QUARTER-WARP owns a 4x2 pixel block: per 32
+//     staged splats a warp runs one cull pass (lane j tests splat j's conservative footprint
+//     box, computed in preprocess, against the warp's four blocks -> four ballots), then every
+//     quarter-warp walks only ITS survivors, so a pixel evaluates the few splats that can
+//     reach its block instead of every splat binned to the tile;
+//   * a quarter / warp retires as soon as its pixels are saturated;
 //   * splat records are one 48-byte gather (3 x 16-byte cp.async straight into shared
 //     memory, double buffered, ids prefetched two batches ahead) instead of four separate
 //     arrays plus a per-pair colour read from global memory;
@@ -34,12 +35,16 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     const int n = (int)(range.y - range.x);
     const int batches = (n + BLEND_BATCH - 1) / BLEND_BATCH;
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    // warp -> 8x4 pixel block of the tile
+    // warp -> 8x4 pixel block of the tile; quarter-warp q -> 4x2 sub-block; lane -> pixel
+    const uint32_t q = lane >> 3, l8 = lane & 7, qshift = q * 8;
     const int bx0 = blockIdx.x * TILE_X + (warp & 1) * 8, by0 = blockIdx.y * TILE_Y + (warp >> 1) * 4;
-    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+    const int px = bx0 + (q & 1) * 4 + (l8 & 3), py = by0 + (q >> 1) * 2 + (l8 >> 2);
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
-    const float fx0 = (float)bx0, fx1 = (float)(bx0 + 7), fy0 = (float)by0, fy1 = (float)(by0 + 3);
+    // sub-block extents used by the cull pass (pixel centres): x halves [bx0, bx0+3], [bx0+4, bx0+7];
+    // y halves [by0, by0+1], [by0+2, by0+3]
+    const float xa0 = (float)bx0, xa1 = (float)(bx0 + 3), xb0 = (float)(bx0 + 4), xb1 = (float)(bx0 + 7);
+    const float ya0 = (float)by0, ya1 = (float)(by0 + 1), yb0 = (float)(by0 + 2), yb1 = (float)(by0 + 3);
     if (threadIdx.x == 0) s_max = 0;
 
     bool done = !inside;
@@ -53,7 +58,8 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
         stage_issue(S, 0, rec, id0);
         if (batches > 1) id_next = BLEND_BATCH + (int)threadIdx.x < n ? __ldg(ids + BLEND_BATCH + threadIdx.x) : 0xffffffffu;
     }
-    bool warp_done = __all_sync(0xffffffffu, done);
+    uint32_t done_bits = __ballot_sync(0xffffffffu, done);
+    bool warp_done = done_bits == 0xffffffffu;
     for (int b = 0; b < batches; b++) {
         const int buf = b & 1;
         if (b + 1 < batches) stage_issue(S, buf ^ 1, rec, id_next);
@@ -67,24 +73,33 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
         if (!warp_done) {
             const int cnt = min(BLEND_BATCH, n - b * BLEND_BATCH);
             for (int c0 = 0; c0 < cnt; c0 += 32) {
+                // ---- cull pass: lane j tests staged splat c0+j against the four 4x2 sub-blocks ----
                 const int j = c0 + (int)lane;
-                bool hit = false;
+                bool hxa = false, hxb = false, hya = false, hyb = false;
                 if (j < cnt) {
-                    const float2 c = *reinterpret_cast<const float2*>(&S.a[buf][j]);
-                    const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&S.c[buf][j].w));
-                    hit = !(c.x + e.x < fx0 || c.x - e.x > fx1 || c.y + e.y < fy0 || c.y - e.y > fy1);
+                    const float4 A = S.a[buf][j];
+                    const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&A.z));
+                    const float lox = A.x - e.x, hix = A.x + e.x, loy = A.y - e.y, hiy = A.y + e.y;
+                    hxa = !(hix < xa0 || lox > xa1);
+                    hxb = !(hix < xb0 || lox > xb1);
+                    hya = !(hiy < ya0 || loy > ya1);
+                    hyb = !(hiy < yb0 || loy > yb1);
                 }
-                uint32_t mask = __ballot_sync(0xffffffffu, hit);
-                while (mask) {
-                    const int jj = __ffs(mask) - 1;
+                const uint32_t m0 = __ballot_sync(0xffffffffu, hxa && hya), m1 = __ballot_sync(0xffffffffu, hxb && hya);
+                const uint32_t m2 = __ballot_sync(0xffffffffu, hxa && hyb), m3 = __ballot_sync(0xffffffffu, hxb && hyb);
+                uint32_t mask = q == 0 ? m0 : q == 1 ? m1 : q == 2 ? m2 : m3;
+                if (((done_bits >> qshift) & 0xffu) == 0xffu) mask = 0;  // this quarter is saturated
+                // ---- blend pass: every quarter-warp walks ITS survivors, in list order ----
+                while (__any_sync(0xffffffffu, mask != 0)) {
+                    const bool act = mask != 0;
+                    const int e = c0 + (act ? __ffs(mask) - 1 : 0);
                     mask &= mask - 1;
-                    const int e = c0 + jj;
                     const float4 A = S.a[buf][e];
                     const float4 B = S.b[buf][e];
                     const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
-                    const float power = splat_power(dx, dy, A.z, A.w, B.x);
-                    if (done || power > 0.0f || power < B.z) continue;
-                    const float alpha = fminf(0.99f, __fmul_rn(B.y, expf(power)));
+                    const float power = splat_power(dx, dy, B.x, B.y, B.z);
+                    if (!act || done || power > 0.0f || power < A.w) continue;
+                    const float alpha = fminf(0.99f, __fmul_rn(B.w, expf(power)));
                     if (alpha < 1.0f / 255.0f) continue;
                     const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
                     if (test_T < 0.0001f) {
@@ -95,11 +110,12 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                     C0 = fmaf(__fmul_rn(Cc.x, alpha), T, C0);
                     C1 = fmaf(__fmul_rn(Cc.y, alpha), T, C1);
                     C2 = fmaf(__fmul_rn(Cc.z, alpha), T, C2);
-                    if (T > 0.5f) D = B.w;
+                    if (T > 0.5f) D = Cc.w;
                     T = test_T;
                     last = (uint32_t)(b * BLEND_BATCH + e + 1);
                 }
-                if (__all_sync(0xffffffffu, done)) {
+                done_bits = __ballot_sync(0xffffffffu, done);
+                if (done_bits == 0xffffffffu) {
                     warp_done = true;
                     break;
                 }

@@ -19,16 +19,17 @@ namespace gsb {
 constexpr int TILE_X = 16;   // config.h:16 (tile-rect membership is part of the semantics)
 constexpr int TILE_Y = 16;   // config.h:17
 constexpr int NUM_SMS = 148; // B200
+constexpr int TILE_CTR_STRIDE = 64;  // words between per-tile atomic counters (256 B)
 
 // ---------------------------------------------------------------------------------------
 // Packed per-Gaussian splat record: 48 bytes, 16-byte aligned, gathered by the blend
-// kernels with 3 x 128-bit (cp.async / LDG.128) accesses.
-//   a = { x_pix, y_pix, conic.x, conic.y }
-//   b = { conic.z, opacity, power_threshold, depth }
-//   c = { r, g, b, half2(extent_x, extent_y) }
+// kernels with 3 x 16-byte asynchronous copies.
+//   a = { x_pix, y_pix, half2(extent_x, extent_y), power_threshold }   <- all the cull pass reads
+//   b = { conic.x, conic.y, conic.z, opacity }
+//   c = { r, g, b, depth }
 // power_threshold: conservative lower bound on `power` below which alpha < 1/255 is
 // certain (the exact test is still applied to everything that passes).
-// extent_x/y: conservative half-extents (pixels) of the alpha >= 1/255 ellipse's bbox.
+// extent_x/y: conservative half-extents (pixels) of the alpha >= 1/255 footprint's bbox.
 // ---------------------------------------------------------------------------------------
 struct alignas(16) SplatRec {
     float4 a, b, c;
@@ -63,7 +64,7 @@ static_assert(sizeof(GeomHeader) == 256, "header is 256 bytes");
 inline __host__ __device__ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct GeomLayout {            // offsets inside the geometry blob
-    size_t header, rec, radii, tiles_touched, block_sums, block_offsets, clamped, acc, total;
+    size_t header, rec, radii, tiles_touched, clamped, acc, total;
     int num_blocks;            // preprocess blocks of 256 Gaussians
     __host__ __device__ static GeomLayout make(int P)
     {
@@ -76,8 +77,6 @@ struct GeomLayout {            // offsets inside the geometry blob
         L.rec = take(Pz * sizeof(SplatRec));
         L.radii = take(Pz * 4);
         L.tiles_touched = take(Pz * 4);
-        L.block_sums = take((size_t)L.num_blocks * 4 + 4);
-        L.block_offsets = take((size_t)L.num_blocks * 4 + 4);
         L.clamped = take(Pz);
         L.acc = take(Pz * sizeof(GradAcc));
         L.total = off;
@@ -86,7 +85,7 @@ struct GeomLayout {            // offsets inside the geometry blob
 };
 
 struct ImageLayout {
-    size_t final_T, n_contrib, ranges, tile_max_contrib, total;
+    size_t final_T, n_contrib, ranges, tile_max_contrib, tile_count, tile_cursor, total;
     int tiles_x, tiles_y;
     __host__ __device__ static ImageLayout make(int W, int H)
     {
@@ -100,6 +99,10 @@ struct ImageLayout {
         L.n_contrib = take(HW * 4);
         L.ranges = take(T * 8);
         L.tile_max_contrib = take(T * 4);
+        // one counter per TILE_CTR_STRIDE words: adjacent tiles land in different L2 slices, so the
+        // ~2 M atomics of a frame are not funnelled through the few slices a dense array maps to
+        L.tile_count = take(T * 4 * TILE_CTR_STRIDE);    // instances per tile (atomics in preprocess)
+        L.tile_cursor = take(T * 4 * TILE_CTR_STRIDE);   // next free slot of each tile's segment (duplicate)
         L.total = off;
         return L;
     }
@@ -113,11 +116,11 @@ constexpr int SORT_RADIX = 1 << SORT_RADIX_BITS;
 constexpr int SORT_MAX_PASSES = 8;
 
 struct BinningLayout {
-    // vals0 sits at offset 0: the radix passes are arranged so that the SORTED instance list
-    // always ends up there, whatever the capacity / pass count (gsb_backward relies on it).
-    size_t vals0, vals1, keys0, keys1, hist, lookback, total;
+    // point_list sits at offset 0 whatever the capacity (gsb_backward relies on it): the
+    // depth-sorted Gaussian ids, tile after tile.  `pairs` holds the unsorted
+    // (depth bits << 32 | id) records bucketed by tile.
+    size_t point_list, pairs, total;
     long long capacity;
-    int sort_tiles;
     __host__ __device__ static BinningLayout make(long long cap)
     {
         BinningLayout L;
@@ -125,13 +128,8 @@ struct BinningLayout {
         auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
         if (cap < 1) cap = 1;
         L.capacity = cap;
-        L.sort_tiles = (int)((cap + SORT_TILE - 1) / SORT_TILE);
-        L.vals0 = take((size_t)cap * 4 + 64);   // +64: 16-byte aligned over-fetch by the blend stagers
-        L.vals1 = take((size_t)cap * 4 + 64);
-        L.keys0 = take((size_t)cap * 8);
-        L.keys1 = take((size_t)cap * 8);
-        L.hist = take((size_t)SORT_MAX_PASSES * SORT_RADIX * 4);
-        L.lookback = take((size_t)SORT_MAX_PASSES * L.sort_tiles * SORT_RADIX * 4);
+        L.point_list = take((size_t)cap * 4 + 64);
+        L.pairs = take((size_t)cap * 8);
         L.total = off;
         return L;
     }
@@ -277,7 +275,7 @@ void count_launch(int n = 1);
 
 // ---- per-stage device timing (gsb_profile_begin / gsb_profile_end) -------------------------
 enum Stage {
-    ST_MEMSET = 0, ST_PREPROCESS, ST_SCAN, ST_DUPLICATE, ST_SORT_HIST, ST_SORT_PASS, ST_RANGES, ST_BLEND_FWD,
+    ST_MEMSET = 0, ST_PREPROCESS, ST_SCAN, ST_DUPLICATE, ST_SORT_HIST, ST_SORT_PASS, ST_TILE_SORT, ST_BLEND_FWD,
     ST_BLEND_BWD, ST_GAUSS_BWD, ST_OTHER, ST_COUNT
 };
 // Scoped: when profiling is enabled on this thread, records a CUDA event on `s` before and
@@ -327,8 +325,10 @@ struct FwdParams {
     float tan_fovx, tan_fovy, focal_x, focal_y;
 };
 
-int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, int* radii_out, cudaStream_t s);
-int launch_scan_blocks(char* geom, const GeomLayout& GL, uint32_t capacity, int P, cudaStream_t s);
+int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, char* image, const ImageLayout& IL,
+                      int* radii_out, cudaStream_t s);
+int launch_tile_scan(char* geom, const GeomLayout& GL, char* image, const ImageLayout& IL, uint32_t capacity, int P,
+                     cudaStream_t s);
 int launch_visible_filter(const FwdParams& p, int* radii, cudaStream_t s);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s);
 int sort_passes_for(int tiles);

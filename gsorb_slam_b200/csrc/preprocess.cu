@@ -124,13 +124,12 @@ __device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh,
 // the CTA's tile-count sum (first level of the two-level scan).
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ radii_blob, int* __restrict__ radii_out,
-                  uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ block_sums,
+                  uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ tile_count,
                   uint8_t* __restrict__ clamped_out, int aligned_means, int aligned_scales, int aligned_colors)
 {
     __shared__ __align__(16) float s_mean[PRE_THREADS * 3];
     __shared__ __align__(16) float s_scale[PRE_THREADS * 3];
     __shared__ __align__(16) float s_col[PRE_THREADS * 3];
-    __shared__ uint32_t s_warp[PRE_THREADS / 32];
     const int base = blockIdx.x * PRE_THREADS;
     const int idx = base + threadIdx.x;
     stage_float3(p.means3D, s_mean, p.P, base, aligned_means);
@@ -156,6 +155,8 @@ preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ rad
         if (o.visible) {
             radius = o.radius;
             touched = (o.maxy - o.miny) * (o.maxx - o.minx);
+            for (uint32_t ty = o.miny; ty < o.maxy; ty++)   // per-tile instance counts (first half of the binning)
+                for (uint32_t tx = o.minx; tx < o.maxx; tx++) atomicAdd(&tile_count[(size_t)(ty * (uint32_t)p.tiles_x + tx) * TILE_CTR_STRIDE], 1u);
             float rgb[3];
             uint32_t cl = 0;
             if (p.colors_precomp) {
@@ -190,79 +191,19 @@ preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ rad
             }
             const __half2 ext = __halves2half2(__float2half_ru(ex), __float2half_ru(ey));
             SplatRec r;
-            r.a = make_float4(o.px, o.py, o.conx, o.cony);
-            r.b = make_float4(o.conz, opacity, thr, o.depth);
-            r.c = make_float4(rgb[0], rgb[1], rgb[2], __uint_as_float(*reinterpret_cast<const uint32_t*>(&ext)));
+            r.a = make_float4(o.px, o.py, __uint_as_float(*reinterpret_cast<const uint32_t*>(&ext)), thr);
+            r.b = make_float4(o.conx, o.cony, o.conz, opacity);
+            r.c = make_float4(rgb[0], rgb[1], rgb[2], o.depth);
             rec[idx] = r;
         }
         radii_blob[idx] = radius;
         if (radii_out) radii_out[idx] = radius;
         tiles_touched[idx] = touched;
     }
-    // CTA sum of tiles_touched
-    uint32_t v = touched;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane_id() == 0) s_warp[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t s = 0;
-#pragma unroll
-        for (int w = 0; w < PRE_THREADS / 32; w++) s += s_warp[w];
-        block_sums[blockIdx.x] = s;
-    }
 }
 
-// Second scan level: one CTA turns block_sums into exclusive block_offsets and fills the
-// header (num_rendered, clamp to the binning capacity, overflow flag).
-__global__ void __launch_bounds__(1024)
-scan_blocks_kernel(const uint32_t* __restrict__ block_sums, uint32_t* __restrict__ block_offsets, int num_blocks,
-                   GeomHeader* __restrict__ hdr, uint32_t capacity, int P)
-{
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < num_blocks; base += 1024) {
-        const int i = base + threadIdx.x;
-        const uint32_t x = i < num_blocks ? block_sums[i] : 0u;
-        uint32_t v = x;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-            if (lane_id() >= (uint32_t)o) v += t;
-        }
-        if (lane_id() == 31) s_warp[threadIdx.x >> 5] = v;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            uint32_t w = s_warp[threadIdx.x];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane_id() >= (uint32_t)o) w += t;
-            }
-            s_warp[threadIdx.x] = w;  // inclusive over warps
-        }
-        __syncthreads();
-        const uint32_t warp_excl = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0u;
-        const uint32_t carry = s_carry;
-        if (i < num_blocks) block_offsets[i] = carry + warp_excl + v - x;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = carry + warp_excl + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        const uint32_t total = s_carry;
-        hdr->magic = GEOM_MAGIC;
-        hdr->P = P;
-        hdr->num_rendered = total;
-        hdr->num_rendered_clamped = min(total, capacity);
-        hdr->overflow = total > capacity ? 1u : 0u;
-        hdr->capacity = capacity;
-    }
-}
-
-int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, int* radii_out, cudaStream_t s)
+int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, char* image, const ImageLayout& IL,
+                      int* radii_out, cudaStream_t s)
 {
     if (p.P <= 0) return GSB_OK;
     auto al = [](const void* q) { return q && (reinterpret_cast<uintptr_t>(q) & 15) == 0 ? 1 : 0; };
@@ -270,20 +211,8 @@ int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, int*
         StageTimer _t(ST_PREPROCESS, s);
         preprocess_kernel<<<GL.num_blocks, PRE_THREADS, 0, s>>>(
             p, reinterpret_cast<SplatRec*>(geom + GL.rec), reinterpret_cast<int*>(geom + GL.radii), radii_out,
-            reinterpret_cast<uint32_t*>(geom + GL.tiles_touched), reinterpret_cast<uint32_t*>(geom + GL.block_sums),
+            reinterpret_cast<uint32_t*>(geom + GL.tiles_touched), reinterpret_cast<uint32_t*>(image + IL.tile_count),
             reinterpret_cast<uint8_t*>(geom + GL.clamped), al(p.means3D), al(p.scales), al(p.colors_precomp));
-        GSB_LAUNCH_CHECK();
-    }
-    return GSB_OK;
-}
-
-int launch_scan_blocks(char* geom, const GeomLayout& GL, uint32_t capacity, int P, cudaStream_t s)
-{
-    {
-        StageTimer _t(ST_SCAN, s);
-        scan_blocks_kernel<<<1, 1024, 0, s>>>(reinterpret_cast<const uint32_t*>(geom + GL.block_sums),
-                                              reinterpret_cast<uint32_t*>(geom + GL.block_offsets), GL.num_blocks,
-                                              reinterpret_cast<GeomHeader*>(geom + GL.header), capacity, P);
         GSB_LAUNCH_CHECK();
     }
     return GSB_OK;

@@ -34,7 +34,7 @@ def test_version_and_sizes():
     assert L.gsb_workspace_query(1000, 640, 480, 5000, C.byref(g), C.byref(i), C.byref(b)) == 0
     assert g.value == L.gsb_geometry_bytes(1000) and g.value >= 1000 * 48
     assert i.value == L.gsb_image_bytes(640, 480) and i.value >= 640 * 480 * 8
-    assert b.value == L.gsb_binning_bytes(5000) and b.value >= 5000 * 24
+    assert b.value == L.gsb_binning_bytes(5000) and b.value >= 5000 * 12
     assert L.gsb_geometry_bytes(0) > 0
     assert L.gsb_workspace_query(-1, 640, 480, 0, None, None, None) == -1
     assert b"bad sizes" in L.gsb_last_error()

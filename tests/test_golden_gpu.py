@@ -62,3 +62,25 @@ def test_sync_free_overflow_is_reported_not_corrupting():
     fr2 = Frame(**kw, sync_free=True, max_rendered=int(ref["num_rendered"]))   # exactly enough
     assert fr2.rendered() == int(ref["num_rendered"])
     np.testing.assert_array_equal(to_np(fr2.color).view(np.uint32), ref["color"].view(np.uint32))
+
+
+@pytest.mark.parametrize("P,intr", [(60_000, (64, 64, 64.0, 64.0)), (300_000, (48, 48, 48.0, 48.0))])
+def test_long_tile_lists_match_oracle(P, intr):
+    """Per-tile shared-memory sort size classes: > 4096 entries per tile (128 KB class) and > 16384 (global-memory
+    fallback).  Checked against the CPU oracle: identical instance list, ranges and n_contrib; image within 1e-4."""
+    from gsorb_slam_b200.lowlevel import frame_from_scene
+    from gsorb_slam_b200.scene import make_scene
+    from oracle import gs_oracle
+    sc = make_scene(P, intr, seed=11, cull_frac=0.0)
+    sc.opacities *= 0.05   # keep pixels unsaturated so deep list positions matter
+    fr = frame_from_scene(sc)
+    orc = gs_oracle.frame_from_scene(sc)
+    ob = orc.binning()
+    per_tile = (ob["ranges"][:, 1].astype(np.int64) - ob["ranges"][:, 0]).max()
+    assert per_tile > (16384 if P > 100_000 else 4096), per_tile
+    assert fr.rendered() == orc.num_rendered
+    np.testing.assert_array_equal(to_np(fr.binning_state()["point_list"]).astype(np.uint32), ob["point_list"])
+    ims = fr.image_state()
+    np.testing.assert_array_equal(to_np(ims["ranges"]).astype(np.uint32), ob["ranges"])
+    np.testing.assert_array_equal(to_np(ims["n_contrib"]).astype(np.uint32), orc.image_state()["n_contrib"])
+    assert rel_to_scale(to_np(fr.color), orc.color) <= TOL_IMAGE
