@@ -56,7 +56,7 @@ static int fail(int code, const char* fmt, ...)
 // Mirrors the argument checks of the reference surface: means3D shape (src/Rasterizer.cu:158-160),
 // sh / colour and scale+rotation / cov3D exclusivity (include/Rasterizer.cuh:310-316), NUM_CHANNELS
 // (rasterizer_impl.cu:245-248).
-static int validate(const gsb_raster_args* a, bool need_colors)
+static int validate(const gsb_raster_args* a, bool need_colors, bool need_opacity = true)
 {
     if (!a) return fail(GSB_ERR_INVALID_ARGUMENT, "args is NULL");
     if (a->P < 0) return fail(GSB_ERR_INVALID_ARGUMENT, "P must be >= 0 (got %d)", a->P);
@@ -72,7 +72,7 @@ static int validate(const gsb_raster_args* a, bool need_colors)
         if (has_sr == (a->cov3D_precomp != nullptr))
             return fail(GSB_ERR_INVALID_ARGUMENT, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
         if (need_colors) {
-            if (!a->opacities) return fail(GSB_ERR_INVALID_ARGUMENT, "opacities are required");
+            if (need_opacity && !a->opacities) return fail(GSB_ERR_INVALID_ARGUMENT, "opacities are required");
             if ((a->shs != nullptr) == (a->colors_precomp != nullptr))
                 return fail(GSB_ERR_INVALID_ARGUMENT, "Please provide exactly one of either SHs or precomputed colors!");
             if (a->shs) {
@@ -262,7 +262,7 @@ long long gsb_num_rendered(const void* geometry, gsb_stream_t stream)
 int gsb_backward(const gsb_raster_args* args, long long R, const int* radii, const void* geometry, const void* binning,
                  const void* image, const float* dL_dpix, const gsb_grad_outputs* grads, gsb_stream_t stream)
 {
-    if (int rc = validate(args, true)) return rc;
+    if (int rc = validate(args, true, false)) return rc;  // opacities are not an input of the backward (rasterizer.h:55-83)
     if (!geometry || !binning || !image) return fail(GSB_ERR_INVALID_ARGUMENT, "forward state blobs are required");
     if (!dL_dpix || !grads) return fail(GSB_ERR_INVALID_ARGUMENT, "dL_dpix / grads are required");
     (void)R;  // tile ranges in the image blob already bound every list

@@ -5,6 +5,10 @@
 // position of the last blended splat, walk the tile's list backwards, T <- T / (1 - alpha),
 // running "colour behind" accumulator, background term, gradients w.r.t. colour, 2D mean
 // (in NDC units: x 0.5 W, x 0.5 H), conic (slots x, y, w) and opacity.  No depth gradient.
+// Per pair only u = G dL/dalpha and its first / second moments in (dx, dy) are formed; the
+// linear maps from those 6 sums to d(mean2D), d(conic), d(opacity) use per-Gaussian constants
+// and are applied once per Gaussian in gauss_bwd.cu (packed accumulator layout:
+// {S u dx, S u dy, S u dx^2, S u dx dy, S u dy^2, S u, S wc d_r, S wc d_g, S wc d_b}).
 //
 // What is different (design, not results):
 //   * the reference issues 9 global atomicAdds per contributing (pixel, splat) pair; here a
@@ -57,7 +61,6 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     }
     const float bg_dot_dpixel = __ldg(bg) * d0 + __ldg(bg + 1) * d1 + __ldg(bg + 2) * d2;
     float ar0 = 0.f, ar1 = 0.f, ar2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
-    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
     // highest n_contrib of each quarter-warp (the cull pass needs all four) and of the warp
     int qmax = last_contributor;
 #pragma unroll
@@ -130,29 +133,29 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                         if (!(alpha < 1.0f / 255.0f)) {
                             contrib = true;
                             const float4 Cc = S.c[buf][e];
-                            T = __fdiv_rn(T, __fsub_rn(1.f, alpha));
-                            const float dchannel_dcolor = alpha * T;
-                            ar0 = last_alpha * lc0 + (1.f - last_alpha) * ar0;
-                            ar1 = last_alpha * lc1 + (1.f - last_alpha) * ar1;
-                            ar2 = last_alpha * lc2 + (1.f - last_alpha) * ar2;
+                            const float inv = __fdividef(1.0f, 1.0f - alpha);   // 1 / (1 - alpha), MUFU.RCP
+                            T *= inv;                                           // T_before = T_after / (1 - alpha)
+                            const float wc = alpha * T;                         // d colour_out / d colour_splat
+                            const float om = 1.f - last_alpha;
+                            ar0 = fmaf(last_alpha, lc0, om * ar0);              // colour accumulated behind this splat
+                            ar1 = fmaf(last_alpha, lc1, om * ar1);
+                            ar2 = fmaf(last_alpha, lc2, om * ar2);
                             lc0 = Cc.x; lc1 = Cc.y; lc2 = Cc.z;
-                            float dL_dalpha = (Cc.x - ar0) * d0 + (Cc.y - ar1) * d1 + (Cc.z - ar2) * d2;
-                            dL_dalpha *= T;
                             last_alpha = alpha;
-                            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-                            const float dL_dG = B.w * dL_dalpha;
-                            const float gdx = G * dx, gdy = G * dy;
-                            const float dG_ddelx = -gdx * B.x - gdy * B.y;
-                            const float dG_ddely = -gdy * B.z - gdx * B.y;
-                            v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                            v[1] = dL_dG * dG_ddely * ddely_dy;
-                            v[2] = -0.5f * gdx * dx * dL_dG;
-                            v[3] = -0.5f * gdx * dy * dL_dG;
-                            v[4] = -0.5f * gdy * dy * dL_dG;
-                            v[5] = G * dL_dalpha;
-                            v[6] = dchannel_dcolor * d0;
-                            v[7] = dchannel_dcolor * d1;
-                            v8 = dchannel_dcolor * d2;
+                            float dL_dalpha = T * fmaf(Cc.x - ar0, d0, fmaf(Cc.y - ar1, d1, (Cc.z - ar2) * d2));
+                            dL_dalpha = fmaf(-T_final * inv, bg_dot_dpixel, dL_dalpha);
+                            // raw moments of u = G * dL/dalpha; the conic / opacity / 0.5 W factors are
+                            // per-Gaussian constants and are applied once, in gauss_bwd.cu
+                            const float u = G * dL_dalpha, ux = u * dx, uy = u * dy;
+                            v[0] = ux;
+                            v[1] = uy;
+                            v[2] = ux * dx;
+                            v[3] = ux * dy;
+                            v[4] = uy * dy;
+                            v[5] = u;
+                            v[6] = wc * d0;
+                            v[7] = wc * d1;
+                            v8 = wc * d2;
                         }
                     }
                     const uint32_t cb = __ballot_sync(0xffffffffu, contrib);

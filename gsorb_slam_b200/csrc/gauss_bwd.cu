@@ -15,7 +15,8 @@ constexpr int GB_THREADS = 256;
 struct GaussBwdParams {
     FwdParams f;
     const int* radii;
-    const float* acc;          // [P][12] packed blend-backward sums
+    const float* acc;          // [P][12] packed blend-backward sums (raw moments, see blend_bwd.cu)
+    const SplatRec* rec;       // conic + opacity for the moment -> gradient maps
     const uint8_t* clamped;    // SH clamp bits
     gsb_grad_outputs g;
 };
@@ -87,21 +88,28 @@ gauss_backward_kernel(GaussBwdParams q)
     const size_t i = (size_t)idx;
     const gsb_grad_outputs& g = q.g;
     const bool rendered = q.radii[idx] > 0;
-    // packed sums from the blend backward (zero for Gaussians that were never blended)
+    // packed sums from the blend backward -> reference-layout 2D gradients (backward.cu:536-554):
+    //   dL/dmean2D = -0.5 W o (A X + B Y), -0.5 H o (C Y + B X);  dL/dconic = -0.5 o (XX, XY, YY);  dL/dopacity = U
     float a[9];
     if (rendered) {
         const float4* ap = reinterpret_cast<const float4*>(q.acc + i * 12);
         const float4 a0 = ap[0], a1 = ap[1];
-        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+        const float4 cb = q.rec[i].b;  // conic.x, conic.y, conic.z, opacity
+        const float X = a0.x, Y = a0.y, XX = a0.z, XY = a0.w, YY = a1.x, U = a1.y;
+        a[0] = -0.5f * p.W * cb.w * (cb.x * X + cb.y * Y);
+        a[1] = -0.5f * p.H * cb.w * (cb.z * Y + cb.y * X);
+        a[2] = -0.5f * cb.w * XX;
+        a[3] = -0.5f * cb.w * XY;
+        a[4] = -0.5f * cb.w * YY;
+        a[5] = U;
+        a[6] = a1.z; a[7] = a1.w;
         a[8] = q.acc[i * 12 + 8];
     } else {
 #pragma unroll
         for (int k = 0; k < 9; k++) a[k] = 0.f;
     }
     if (g.dL_dmean2D) { g.dL_dmean2D[3 * i] = a[0]; g.dL_dmean2D[3 * i + 1] = a[1]; g.dL_dmean2D[3 * i + 2] = 0.f; }
-    if (g.dL_dconic) {
-        reinterpret_cast<float4*>(g.dL_dconic)[i] = make_float4(a[2], a[3], 0.f, a[4]);
-    }
+    if (g.dL_dconic) { g.dL_dconic[4 * i] = a[2]; g.dL_dconic[4 * i + 1] = a[3]; g.dL_dconic[4 * i + 2] = 0.f; g.dL_dconic[4 * i + 3] = a[4]; }
     if (g.dL_dopacity) g.dL_dopacity[i] = a[5];
     if (g.dL_dcolor) { g.dL_dcolor[3 * i] = a[6]; g.dL_dcolor[3 * i + 1] = a[7]; g.dL_dcolor[3 * i + 2] = a[8]; }
 
@@ -248,6 +256,7 @@ int launch_gauss_backward(const FwdParams& p, const char* geom, const GeomLayout
     q.f = p;
     q.radii = radii ? radii : reinterpret_cast<const int*>(geom + GL.radii);
     q.acc = reinterpret_cast<const float*>(geom + GL.acc);
+    q.rec = reinterpret_cast<const SplatRec*>(geom + GL.rec);
     q.clamped = reinterpret_cast<const uint8_t*>(geom + GL.clamped);
     q.g = g;
     {

@@ -1,0 +1,117 @@
+"""Multi-GPU plumbing of the render-optimise loop: one process per GPU,
+``torch.distributed`` (NCCL over NVLink on the B200 box, gloo in the CPU tests).
+
+The reference is single-GPU (every call site passes device 0, src/Render.cc:775,824).  The loop
+shards two ways, both with ONE exchange step -- a sum all-reduce of the packed per-Gaussian
+gradient block -- placed between ``loss.backward()`` and ``Gaussian::StepUpdataForGaussian``
+(src/Render.cc:471-475):
+
+* keyframe-batch shard: rank r renders keyframes ``keyframes[r::world]`` of the candidate list
+  (``Render::RenderForFrame`` draws one random keyframe per Adam step, src/Render.cc:423) over
+  replicated Gaussians;
+* tile-row shard: rank r owns a contiguous band of tile rows of the same keyframe
+  (``tile_row_bands``).
+
+The gradient block is ``[14, P]`` fp32, group-major so every group is a contiguous view that
+``gsb_backward`` / ``gsb_prologue_backward`` write in place and ``gsb_adam_step`` reads in
+place -- no pack / unpack copy around the collective:
+
+    rows 0-2  d(mean)   rows 3-5  d(rgb)   row 6  d(logit opacity)   rows 7-9  d(log scale)
+    rows 10-13  d(unnormalised quaternion)
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+GROUPS: Tuple[Tuple[str, int], ...] = (("means", 3), ("rgb", 3), ("opacity", 1), ("scales", 3), ("quats", 4))
+BLOCK_ROWS = sum(w for _, w in GROUPS)  # 14
+
+
+class GradBlock:
+    """One contiguous ``[14 * P]`` fp32 buffer with a ``[P, w]`` view per parameter group."""
+
+    def __init__(self, P: int, device, dtype=torch.float32):
+        self.P = int(P)
+        self.flat = torch.zeros(BLOCK_ROWS * self.P, dtype=dtype, device=device)
+        self.views: Dict[str, torch.Tensor] = {}
+        off = 0
+        for name, w in GROUPS:
+            self.views[name] = self.flat[off:off + w * self.P].view(self.P, w)
+            off += w * self.P
+
+    def __getitem__(self, name: str) -> torch.Tensor:
+        return self.views[name]
+
+    def ptr(self, name: str) -> int:
+        return self.views[name].data_ptr()
+
+
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def allreduce_gradients(block: GradBlock, average: bool = False, group=None, async_op: bool = False):
+    """The exchange step: ONE sum all-reduce over the whole block (56 B per Gaussian).  With
+    ``average`` the sum is divided by the world size (mini-batch mean over keyframes)."""
+    rank, n = world()
+    if n == 1:
+        return None
+    work = dist.all_reduce(block.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    if average and not async_op:
+        block.flat.mul_(1.0 / n)
+    return work
+
+
+def shard_keyframes(keyframes: List, rank: Optional[int] = None, world_size: Optional[int] = None) -> List:
+    """Round-robin assignment of a candidate keyframe list to ranks (rank r takes r, r+n, ...)."""
+    r, n = world()
+    rank = r if rank is None else rank
+    world_size = n if world_size is None else world_size
+    return list(keyframes[rank::world_size])
+
+
+def tile_row_bands(tiles_y: int, world_size: int, weights: Optional[List[float]] = None) -> List[Tuple[int, int]]:
+    """Contiguous bands ``[begin, end)`` of tile rows, one per rank, covering ``[0, tiles_y)``.
+    ``weights`` (per tile row, e.g. instance counts of the previous frame) balances the bands by
+    load instead of by height; bands may be empty when there are more ranks than rows."""
+    if world_size <= 0:
+        raise ValueError("world_size must be positive")
+    if weights is None:
+        weights = [1.0] * tiles_y
+    if len(weights) != tiles_y:
+        raise ValueError("one weight per tile row")
+    total = float(sum(weights))
+    cum = [0.0]
+    for w in weights:
+        cum.append(cum[-1] + float(w))
+    bands, begin = [], 0
+    for r in range(world_size):
+        if r == world_size - 1:
+            end = tiles_y
+        else:
+            target = total * (r + 1) / world_size   # cut where the cumulative load is closest to r+1 equal shares
+            end = min(range(begin, tiles_y + 1), key=lambda e: (abs(cum[e] - target), e))
+        bands.append((begin, end))
+        begin = end
+    return bands
+
+
+def broadcast_densification(new_rows: Optional[torch.Tensor], src: int = 0, group=None) -> torch.Tensor:
+    """Densify / prune decisions must be identical on every rank (replicated Gaussians): rank ``src``
+    decides, everyone else receives.  ``new_rows`` is a ``[K, 14]`` tensor of raw parameters on ``src``."""
+    rank, n = world()
+    if n == 1:
+        return new_rows
+    dev = new_rows.device if new_rows is not None else torch.device("cpu")
+    count = torch.tensor([0 if new_rows is None else new_rows.shape[0]], dtype=torch.int64, device=dev)
+    dist.broadcast(count, src=src, group=group)
+    k = int(count.item())
+    buf = new_rows if rank == src else torch.empty((k, BLOCK_ROWS), dtype=torch.float32, device=dev)
+    if k:
+        dist.broadcast(buf, src=src, group=group)
+    return buf

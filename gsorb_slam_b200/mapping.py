@@ -1,0 +1,122 @@
+"""Fused render-optimise step over the C ABI: the hot loop of ``Render::RenderForFrame``
+(src/Render.cc:402-493) with the Gaussian parameters, their Adam state and the gradient block
+resident on the GPU in packed ``[14, P]`` form.
+
+One ``step()`` = prologue (pose transform + sigmoid / normalize / exp, src/Render.cc:750-759)
+-> rasterizer forward -> caller-supplied dL/dpixel -> rasterizer backward -> prologue backward
+(+ camera-pose gradient dL/dTcw) -> all-reduce of the gradient block over the
+ranks (distributed.py) -> Adam (``torch::optim::Adam`` semantics of src/Gaussian.cc:131-175:
+betas (0.9, 0.999), eps 1e-15, per-group learning rates of Examples/RGB-D/replica.yaml:95-99).
+With world size 1 the step is the reference's single-view step.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GradOutputs, RasterArgs
+from .distributed import GROUPS, GradBlock, allreduce_gradients
+
+# Examples/RGB-D/replica.yaml:95-99 (Mapping.lrs*)
+DEFAULT_LR = {"means": 1e-4, "rgb": 2.5e-3, "quats": 1e-3, "opacity": 0.05, "scales": 1e-3}
+
+
+class MapOptimizer:
+    def __init__(self, means, rgb, logit_opacities, log_scales, unnorm_quats, *, width, height, tanfovx, tanfovy,
+                 projmatrix, background=None, lr: Optional[Dict[str, float]] = None, betas=(0.9, 0.999), eps=1e-15,
+                 device="cuda:0", max_rendered: Optional[int] = None):
+        self.L = _lib.lib()
+        self.dev = torch.device(device)
+        d = self.dev
+        t = lambda a: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(d, torch.float32)
+        self.P = int(t(means).shape[0])
+        P = self.P
+        self.params = GradBlock(P, d)   # same packed layout as the gradient block
+        self.params["means"].copy_(t(means)); self.params["rgb"].copy_(t(rgb))
+        self.params["opacity"].copy_(t(logit_opacities).reshape(P, 1)); self.params["scales"].copy_(t(log_scales))
+        self.params["quats"].copy_(t(unnorm_quats))
+        self.grads = GradBlock(P, d)
+        self.exp_avg, self.exp_avg_sq = GradBlock(P, d), GradBlock(P, d)
+        self.lr = dict(DEFAULT_LR if lr is None else lr)
+        self.betas, self.eps, self.t = betas, float(eps), 0
+        self.W, self.H = int(width), int(height)
+        self.tanfovx, self.tanfovy = float(tanfovx), float(tanfovy)
+        self.proj = t(projmatrix).reshape(16).contiguous()
+        # default mode of Render::StartSplatting: identity view, means pre-transformed (src/Render.cc:748-754)
+        self.view = torch.eye(4, device=d).reshape(16).contiguous()
+        self.campos = torch.zeros(3, device=d)
+        self.bg = t(background if background is not None else np.zeros(3, np.float32))
+        # activated temporaries + their gradients
+        e = lambda *s: torch.empty(s, dtype=torch.float32, device=d)
+        self.means_cam, self.opac, self.rot, self.scales = e(P, 3), e(P), e(P, 4), e(P, 3)
+        self.g_means_cam, self.g_opac, self.g_rot, self.g_scales = e(P, 3), e(P), e(P, 4), e(P, 3)
+        self.g_side = e(P, 13)   # mean2D 3 | conic 4 | cov3D 6: reference outputs nobody consumes here
+        self.dTcw = e(3, 4)
+        self.color, self.depth = e(3, self.H, self.W), e(1, self.H, self.W)
+        self.radii = torch.empty(P, dtype=torch.int32, device=d)
+        self.max_rendered = int(max_rendered) if max_rendered else 4 * P + 4096
+        L = self.L
+        u8 = lambda n: torch.empty(int(n), dtype=torch.uint8, device=d)
+        self.geom, self.img = u8(L.gsb_geometry_bytes(P)), u8(L.gsb_image_bytes(self.W, self.H))
+        self.binning = u8(L.gsb_binning_bytes(self.max_rendered))
+        a = RasterArgs()
+        a.P, a.D, a.M, a.width, a.height = P, 0, 0, self.W, self.H
+        a.background, a.means3D, a.colors_precomp = self.bg.data_ptr(), self.means_cam.data_ptr(), self.params.ptr("rgb")
+        a.opacities, a.scales, a.scale_modifier, a.rotations = self.opac.data_ptr(), self.scales.data_ptr(), 1.0, self.rot.data_ptr()
+        a.viewmatrix, a.projmatrix, a.cam_pos = self.view.data_ptr(), self.proj.data_ptr(), self.campos.data_ptr()
+        a.tan_fovx, a.tan_fovy = self.tanfovx, self.tanfovy
+        self.args = a
+        sp = self.g_side.data_ptr()
+        self.gout = GradOutputs(dL_dmean2D=sp, dL_dconic=sp + 12 * P, dL_dcov3D=sp + 28 * P, dL_dopacity=self.g_opac.data_ptr(),
+                                dL_dcolor=self.grads.ptr("rgb"), dL_dmean3D=self.g_means_cam.data_ptr(), dL_dsh=None,
+                                dL_dscale=self.g_scales.data_ptr(), dL_drot=self.g_rot.data_ptr())
+
+    def _s(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def render(self, Tcw: torch.Tensor):
+        """Forward only: prologue + rasterizer.  Returns (color [3,H,W], depth [1,H,W], radii [P])."""
+        L, p, s = self.L, self.params, self._s()
+        self._Tcw = Tcw.to(self.dev, torch.float32).contiguous()
+        with torch.cuda.device(self.dev):
+            _lib.check(L.gsb_prologue(self.P, self._Tcw.data_ptr(), p.ptr("means"), p.ptr("opacity"), p.ptr("quats"), p.ptr("scales"),
+                                      self.means_cam.data_ptr(), self.opac.data_ptr(), self.rot.data_ptr(), self.scales.data_ptr(), s))
+            _lib.check(L.gsb_forward_ws(C.byref(self.args), self.geom.data_ptr(), self.geom.numel(), self.binning.data_ptr(),
+                                        self.binning.numel(), self.max_rendered, self.img.data_ptr(), self.img.numel(),
+                                        self.color.data_ptr(), self.depth.data_ptr(), self.radii.data_ptr(), s))
+        return self.color, self.depth, self.radii
+
+    def backward(self, dL_dpix: torch.Tensor):
+        """Rasterizer backward + prologue backward into the packed gradient block (and dL/dTcw)."""
+        L, p, g, s = self.L, self.params, self.grads, self._s()
+        dL = dL_dpix.to(self.dev, torch.float32).contiguous()
+        with torch.cuda.device(self.dev):
+            _lib.check(L.gsb_backward(C.byref(self.args), -1, self.radii.data_ptr(), self.geom.data_ptr(), self.binning.data_ptr(),
+                                      self.img.data_ptr(), dL.data_ptr(), C.byref(self.gout), s))
+            _lib.check(L.gsb_prologue_backward(self.P, self._Tcw.data_ptr(), p.ptr("means"), p.ptr("opacity"), p.ptr("quats"),
+                                               p.ptr("scales"), self.g_means_cam.data_ptr(), self.g_opac.data_ptr(),
+                                               self.g_rot.data_ptr(), self.g_scales.data_ptr(), g.ptr("means"), g.ptr("opacity"),
+                                               g.ptr("quats"), g.ptr("scales"), self.dTcw.data_ptr(), s))
+        return g
+
+    def adam(self):
+        """torch::optim::Adam step on every group, reading the (all-reduced) gradient block in place."""
+        self.t += 1
+        L, s = self.L, self._s()
+        with torch.cuda.device(self.dev):
+            for name, w in GROUPS:
+                _lib.check(L.gsb_adam_step(w * self.P, self.params.ptr(name), self.grads.ptr(name), self.exp_avg.ptr(name),
+                                           self.exp_avg_sq.ptr(name), float(self.lr[name]), float(self.betas[0]), float(self.betas[1]),
+                                           self.eps, self.t, s))
+
+    def step(self, Tcw: torch.Tensor, loss_grad: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], average: bool = False):
+        """One optimisation step on this rank's keyframe.  ``loss_grad(color, depth) -> dL/dcolor``."""
+        color, depth, _ = self.render(Tcw)
+        self.backward(loss_grad(color, depth))
+        allreduce_gradients(self.grads, average=average)
+        self.adam()
+        return color

@@ -1,0 +1,79 @@
+"""CPU suite, world_size 2 over gloo: the host-side logic of the multi-GPU path."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, P):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gsorb_slam_b200.distributed import BLOCK_ROWS, GradBlock, allreduce_gradients, broadcast_densification, shard_keyframes
+    try:
+        blk = GradBlock(P, "cpu")
+        g = torch.Generator().manual_seed(100 + rank)
+        for name in ("means", "rgb", "opacity", "scales", "quats"):
+            blk[name].copy_(torch.randn(blk[name].shape, generator=g))
+        mine = blk.flat.clone()
+        allreduce_gradients(blk)
+        # expected: sum over ranks of the per-rank blocks (regenerate the other rank's block)
+        exp = torch.zeros_like(mine)
+        for r in range(world):
+            gr = torch.Generator().manual_seed(100 + r)
+            b2 = GradBlock(P, "cpu")
+            for name in ("means", "rgb", "opacity", "scales", "quats"):
+                b2[name].copy_(torch.randn(b2[name].shape, generator=gr))
+            exp += b2.flat
+        assert torch.allclose(blk.flat, exp, atol=1e-6), "all-reduce of the packed block != sum of rank blocks"
+        # views alias the flat buffer (no pack / unpack around the collective)
+        assert blk["quats"].data_ptr() == blk.flat.data_ptr() + 10 * P * 4
+        assert blk.flat.numel() == BLOCK_ROWS * P
+        # average mode
+        blk2 = GradBlock(P, "cpu")
+        blk2.flat.fill_(float(rank + 1))
+        allreduce_gradients(blk2, average=True)
+        assert torch.allclose(blk2.flat, torch.full_like(blk2.flat, sum(range(1, world + 1)) / world))
+        # keyframe sharding: disjoint cover
+        kfs = list(range(7))
+        mine_kf = shard_keyframes(kfs)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine_kf)
+        assert sorted(sum(gathered, [])) == kfs
+        # densification broadcast: everyone ends with rank 0's rows
+        rows = torch.arange(3 * BLOCK_ROWS, dtype=torch.float32).reshape(3, BLOCK_ROWS) if rank == 0 else None
+        out = broadcast_densification(rows)
+        assert out.shape == (3, BLOCK_ROWS) and float(out[2, 13]) == 3 * BLOCK_ROWS - 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_exchange_step():
+    mp.spawn(_worker, args=(2, _free_port(), 1000), nprocs=2, join=True)
+
+
+def test_tile_row_bands_cover_and_balance():
+    from gsorb_slam_b200.distributed import tile_row_bands
+    for tiles_y, world in [(61, 2), (61, 4), (61, 8), (30, 8), (3, 8), (43, 1)]:
+        b = tile_row_bands(tiles_y, world)
+        assert len(b) == world and b[0][0] == 0 and b[-1][1] == tiles_y
+        assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+        assert all(e >= s for s, e in b)
+        if tiles_y >= world:
+            h = [e - s for s, e in b]
+            assert max(h) - min(h) <= 2
+    # load-balanced: a heavy first row gets a band of its own
+    b = tile_row_bands(8, 2, weights=[10, 1, 1, 1, 1, 1, 1, 1])
+    assert b == [(0, 1), (1, 8)]
+    with pytest.raises(ValueError):
+        tile_row_bands(4, 0)

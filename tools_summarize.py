@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Summaries of ncu outputs (launch list csv / raw page csv) for profiles/*.md."""
+import csv, collections, sys
+
+def launches(path):
+    rows = list(csv.reader(open(path)))
+    h = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
+    hdr = rows[h]; ki = hdr.index('Kernel Name'); vi = hdr.index('Metric Value')
+    agg = collections.OrderedDict()
+    for r in rows[h + 2:]:
+        if len(r) <= vi: continue
+        n = r[ki].split('(')[0][:70]
+        agg.setdefault(n, []).append(float(r[vi].replace(',', '')))
+    tot = sum(sum(v) for v in agg.values())
+    out = []
+    for n, v in agg.items():
+        out.append(f"{n:70s} n={len(v):3d} avg={sum(v)/len(v)/1000:8.1f} us share={sum(v)/tot*100:5.1f}%")
+    return "\n".join(out)
+
+def raw(path, keys=None):
+    rows = list(csv.reader(open(path)))
+    hdr = rows[0]; idx = {h: i for i, h in enumerate(hdr)}
+    keys = keys or ['gpu__time_duration.sum', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+                    'sm__warps_active.avg.pct_of_peak_sustained_active', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+                    'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'launch__registers_per_thread',
+                    'lts__t_sectors_op_red.sum', 'lts__t_sectors_op_atom.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']
+    out = []
+    for r in rows[2:]:
+        out.append(r[idx['Kernel Name']].split('(')[0])
+        for k in keys:
+            if k in idx: out.append(f"    {k:70s} {r[idx[k]]} {rows[1][idx[k]]}")
+    return "\n".join(out)
+
+if __name__ == '__main__':
+    print(launches(sys.argv[2]) if sys.argv[1] == 'launches' else raw(sys.argv[2]))
