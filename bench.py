@@ -205,6 +205,22 @@ def run_ours(args):
     ms_per_step = ms_total / args.steps
     value = world * 1000.0 / ms_per_step
 
+    if args.quick:
+        L.gsb_profile_begin()
+        for _ in range(args.steps):
+            flush.zero_()
+            step()
+        ns = L.gsb_num_stages()
+        sms, scn = (C.c_float * ns)(), (C.c_int * ns)()
+        L.gsb_profile_end(sms, scn)
+        if rank == 0:
+            st = {L.gsb_stage_name(i).decode(): round(sms[i] / args.steps * 1000, 1) for i in range(ns) if scn[i]}
+            print(json.dumps({"quick": True, "value": value, "ms_per_step": ms_per_step, "stages_us": st,
+                              "env": {k: v for k, v in os.environ.items() if k.startswith("GSB_")}}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- e2e: host buffers through gsb_forward_backward_host ----
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h = dict(means=pin(sc.means3D), colors=pin(sc.colors), opac=pin(sc.opacities), scales=pin(sc.scales), rots=pin(sc.rotations),
@@ -422,6 +438,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline_1m")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="developer mode: value + per-stage times only (no e2e / cpu legs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -21,12 +21,14 @@
 //     the end of the tile's list, and each warp culls staged splats against its four pixel
 //     blocks and their highest n_contrib with four ballots per 32 splats;
 //   * records are gathered with cp.async into double-buffered shared memory (stage.cuh).
+#include <cstdlib>
 #include "common.cuh"
 #include "stage.cuh"
 
 namespace gsb {
 
-__global__ void __launch_bounds__(BLEND_THREADS)
+template <int MINB>
+__global__ void __launch_bounds__(BLEND_THREADS, MINB)
 blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                       const SplatRec* __restrict__ rec, int W, int H, const float* __restrict__ bg,
                       const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
@@ -207,14 +209,29 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
 {
     if (p.W <= 0 || p.H <= 0 || p.P <= 0) return GSB_OK;
     GSB_CUDA_CHECK(cudaMemsetAsync(geom + GL.acc, 0, (size_t)p.P * sizeof(GradAcc), s));
+    // tuning knob (resident CTAs per SM the compiler must allow, i.e. the register budget)
+    static const int minb = [] { const char* e = getenv("GSB_BLEND_BWD_MINB"); return e ? atoi(e) : 4; }();
     dim3 grid(IL.tiles_x, IL.tiles_y);
     {
         StageTimer _t(ST_BLEND_BWD, s);
-        blend_backward_kernel<<<grid, BLEND_THREADS, 0, s>>>(
-            reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec),
+        switch (minb) {
+            case 3: blend_backward_kernel<3><<<grid, BLEND_THREADS, 0, s>>>(reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec),
             p.W, p.H, p.background, reinterpret_cast<const float*>(image + IL.final_T),
             reinterpret_cast<const uint32_t*>(image + IL.n_contrib), reinterpret_cast<const uint32_t*>(image + IL.tile_max_contrib),
-            dL_dpix, reinterpret_cast<float*>(geom + GL.acc));
+            dL_dpix, reinterpret_cast<float*>(geom + GL.acc)); break;
+            case 5: blend_backward_kernel<5><<<grid, BLEND_THREADS, 0, s>>>(reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec),
+            p.W, p.H, p.background, reinterpret_cast<const float*>(image + IL.final_T),
+            reinterpret_cast<const uint32_t*>(image + IL.n_contrib), reinterpret_cast<const uint32_t*>(image + IL.tile_max_contrib),
+            dL_dpix, reinterpret_cast<float*>(geom + GL.acc)); break;
+            case 6: blend_backward_kernel<6><<<grid, BLEND_THREADS, 0, s>>>(reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec),
+            p.W, p.H, p.background, reinterpret_cast<const float*>(image + IL.final_T),
+            reinterpret_cast<const uint32_t*>(image + IL.n_contrib), reinterpret_cast<const uint32_t*>(image + IL.tile_max_contrib),
+            dL_dpix, reinterpret_cast<float*>(geom + GL.acc)); break;
+            default: blend_backward_kernel<4><<<grid, BLEND_THREADS, 0, s>>>(reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec),
+            p.W, p.H, p.background, reinterpret_cast<const float*>(image + IL.final_T),
+            reinterpret_cast<const uint32_t*>(image + IL.n_contrib), reinterpret_cast<const uint32_t*>(image + IL.tile_max_contrib),
+            dL_dpix, reinterpret_cast<float*>(geom + GL.acc)); break;
+        }
         GSB_LAUNCH_CHECK();
     }
     return GSB_OK;

@@ -17,12 +17,14 @@
 //     memory, double buffered, ids prefetched two batches ahead) instead of four separate
 //     arrays plus a per-pair colour read from global memory;
 //   * the tile's highest n_contrib is recorded for the backward pass.
+#include <cstdlib>
 #include "common.cuh"
 #include "stage.cuh"
 
 namespace gsb {
 
-__global__ void __launch_bounds__(BLEND_THREADS)
+template <int MINB>
+__global__ void __launch_bounds__(BLEND_THREADS, MINB)
 blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                      const SplatRec* __restrict__ rec, int W, int H, const float* __restrict__ bg,
                      float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ final_T,
@@ -145,13 +147,22 @@ int launch_blend_forward(const FwdParams& p, const char* geom, const GeomLayout&
                          char* image, const ImageLayout& IL, float* out_color, float* out_depth, cudaStream_t s)
 {
     if (p.W <= 0 || p.H <= 0) return GSB_OK;
+    // tuning knob (resident CTAs per SM the compiler must allow, i.e. the register budget)
+    static const int minb = [] { const char* e = getenv("GSB_BLEND_FWD_MINB"); return e ? atoi(e) : 6; }();
     dim3 grid(IL.tiles_x, IL.tiles_y);
     {
         StageTimer _t(ST_BLEND_FWD, s);
-        blend_forward_kernel<<<grid, BLEND_THREADS, 0, s>>>(
-            reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec),
+        switch (minb) {
+            case 4: blend_forward_kernel<4><<<grid, BLEND_THREADS, 0, s>>>(reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec),
             p.W, p.H, p.background, out_color, out_depth, reinterpret_cast<float*>(image + IL.final_T),
-            reinterpret_cast<uint32_t*>(image + IL.n_contrib), reinterpret_cast<uint32_t*>(image + IL.tile_max_contrib));
+            reinterpret_cast<uint32_t*>(image + IL.n_contrib), reinterpret_cast<uint32_t*>(image + IL.tile_max_contrib)); break;
+            case 8: blend_forward_kernel<8><<<grid, BLEND_THREADS, 0, s>>>(reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec),
+            p.W, p.H, p.background, out_color, out_depth, reinterpret_cast<float*>(image + IL.final_T),
+            reinterpret_cast<uint32_t*>(image + IL.n_contrib), reinterpret_cast<uint32_t*>(image + IL.tile_max_contrib)); break;
+            default: blend_forward_kernel<6><<<grid, BLEND_THREADS, 0, s>>>(reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec),
+            p.W, p.H, p.background, out_color, out_depth, reinterpret_cast<float*>(image + IL.final_T),
+            reinterpret_cast<uint32_t*>(image + IL.n_contrib), reinterpret_cast<uint32_t*>(image + IL.tile_max_contrib)); break;
+        }
         GSB_LAUNCH_CHECK();
     }
     return GSB_OK;

@@ -1,0 +1,189 @@
+"""-m gpu: the rest of the exported surface against reference goldens / torch, plus full-size properties."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, TOL_GRAD, TOL_IMAGE, load_case, rel_to_scale, to_np
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def test_knn_matches_reference_bit_exact():
+    import torch
+    from gsorb_slam_b200.rasterizer import distCUDA2
+    z = np.load(os.path.join(GOLDEN, "knn_5000.npz"))
+    out = distCUDA2(torch.from_numpy(z["in_points"]).cuda()).cpu().numpy()
+    np.testing.assert_array_equal(out.view(np.uint32), z["ref_mean_dist2"].view(np.uint32))
+
+
+def test_visible_filter_and_mark_visible_match_reference():
+    import torch
+    from gsorb_slam_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+    z = np.load(os.path.join(GOLDEN, "visible_4000.npz"))
+    t = lambda k: torch.from_numpy(np.ascontiguousarray(z[k])).cuda()
+    rs = GaussianRasterizationSettings(int(z["in_height"]), int(z["in_width"]), float(z["in_tanfovx"]), float(z["in_tanfovy"]),
+                                       torch.zeros(3).cuda(), 1.0, t("in_viewmatrix"), t("in_projmatrix"), 0, torch.zeros(3).cuda(), False)
+    r = GaussianRasterizer(rs)
+    (radii,) = r.Visable(t("in_means3D"), None, t("in_scales"), t("in_rotations"))
+    np.testing.assert_array_equal(radii.cpu().numpy(), z["ref_radii"])
+    np.testing.assert_array_equal(r.mark_visible(t("in_means3D")).cpu().numpy().astype(np.uint8), z["ref_present"])
+
+
+@pytest.mark.parametrize("name", ["tiny_default", "tiny_sh", "tiny_cov"])
+def test_autograd_operator_matches_reference(name):
+    """GaussianRasterizer.forward + loss.backward() (the call Render.cc makes) against the reference gradients."""
+    import torch
+    from gsorb_slam_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+    kw, dL, ref = load_case(name)
+    t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    rs = GaussianRasterizationSettings(kw["height"], kw["width"], kw["tanfovx"], kw["tanfovy"], t(kw["background"]),
+                                       float(kw.get("scale_modifier", 1.0)), t(kw["viewmatrix"]), t(kw["projmatrix"]),
+                                       int(kw.get("sh_degree", 0)), t(kw["campos"]), False)
+    leaf = lambda a: None if a is None else t(a).requires_grad_(True)
+    means, opac = leaf(kw["means3D"]), leaf(kw["opacities"].reshape(-1, 1))
+    shs, cols = leaf(kw.get("shs")), leaf(kw.get("colors"))
+    scales, rots, cov = leaf(kw.get("scales")), leaf(kw.get("rotations")), leaf(kw.get("cov3D"))
+    means2D = torch.zeros_like(means, requires_grad=True)
+    color, radii, depth = GaussianRasterizer(rs).forward(means, means2D, opac, shs, cols, scales, rots, cov)
+    assert rel_to_scale(to_np(color), ref["color"]) <= TOL_IMAGE
+    np.testing.assert_array_equal(to_np(radii), ref["radii"])
+    (color * t(dL)).sum().backward()
+    pairs = [(means, "dL_dmean3D"), (opac, "dL_dopacity"), (means2D, "dL_dmean2D"), (cols, "dL_dcolor"), (shs, "dL_dsh"),
+             (scales, "dL_dscale"), (rots, "dL_drot"), (cov, "dL_dcov3D")]
+    for leaf_t, key in pairs:
+        if leaf_t is not None:
+            assert rel_to_scale(to_np(leaf_t.grad), ref[key].reshape(leaf_t.shape)) <= TOL_GRAD, key
+
+
+def test_mapping_step_matches_torch_prologue_and_adam():
+    """Fused prologue / prologue-backward / pose gradient / Adam against torch autograd + torch.optim.Adam
+    (the libtorch pieces of Render.cc:750-759 and Gaussian.cc:131-175, pinned on the installed torch)."""
+    import torch
+    import torch.nn.functional as F
+    from gsorb_slam_b200.mapping import DEFAULT_LR, MapOptimizer
+    from gsorb_slam_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+    from gsorb_slam_b200.scene import make_scene
+    sc = make_scene(2000, (128, 96, 110.0, 108.0), seed=21, scale_mul=2.0)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    ang = 0.15
+    Tcw = torch.eye(4, device=dev)
+    Tcw[:3, :3] = t(np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]], np.float32))
+    Tcw[:3, 3] = t(np.array([0.05, -0.02, 0.1], np.float32))
+    world_means = (t(sc.means3D) - Tcw[:3, 3]) @ Tcw[:3, :3]          # so that Tcw maps them back into view
+    dL = t(sc.dL_dpix) * 1e3
+    opt = MapOptimizer(world_means, sc.colors, sc.logit_opacities, sc.log_scales, sc.unnorm_quats, width=sc.cam.width,
+                       height=sc.cam.height, tanfovx=sc.cam.tanfovx, tanfovy=sc.cam.tanfovy, projmatrix=sc.cam.projmatrix, device=dev)
+    # torch twin
+    p = dict(means=world_means.clone().requires_grad_(True), rgb=t(sc.colors).requires_grad_(True),
+             opacity=t(sc.logit_opacities).reshape(-1, 1).requires_grad_(True), scales=t(sc.log_scales).requires_grad_(True),
+             quats=t(sc.unnorm_quats).requires_grad_(True))
+    Tcw_t = Tcw.clone().requires_grad_(True)
+    adam = torch.optim.Adam([{"params": [p[k]], "lr": DEFAULT_LR[k]} for k in p], eps=1e-15)
+    rs = GaussianRasterizationSettings(sc.cam.height, sc.cam.width, float(sc.cam.tanfovx), float(sc.cam.tanfovy), torch.zeros(3, device=dev),
+                                       1.0, torch.eye(4, device=dev), t(sc.cam.projmatrix).reshape(4, 4), 0, torch.zeros(3, device=dev), False)
+    rast = GaussianRasterizer(rs)
+    for it in range(3):
+        N = p["means"].shape[0]
+        hom = torch.cat([p["means"], torch.ones(N, 1, device=dev)], 1).unsqueeze(-1)
+        mc = Tcw_t.repeat(N, 1, 1).bmm(hom)[:, :3, 0]                                  # Render.cc:750-752
+        color, _, _ = rast.forward(mc, torch.zeros_like(mc), torch.sigmoid(p["opacity"]), colors_precomp=p["rgb"],
+                                   scales=torch.exp(p["scales"]), rotations=F.normalize(p["quats"]))
+        adam.zero_grad()
+        Tcw_t.grad = None
+        (color * dL).sum().backward()
+        c2 = opt.step(Tcw, lambda c, d: dL)
+        assert rel_to_scale(to_np(c2), to_np(color)) <= TOL_IMAGE
+        for k in p:   # raw-parameter gradients through the fused prologue backward
+            assert rel_to_scale(to_np(opt.grads[k]), to_np(p[k].grad)) <= TOL_GRAD, (it, k)
+        assert rel_to_scale(to_np(opt.dTcw), to_np(Tcw_t.grad[:3])) <= TOL_GRAD, "camera-pose gradient"
+        adam.step()
+        for k in p:
+            assert rel_to_scale(to_np(opt.params[k]), to_np(p[k])) <= 1e-5, (it, k)
+
+
+def test_host_buffer_entry_point_equals_device_path():
+    from gsorb_slam_b200 import _lib
+    from gsorb_slam_b200.lowlevel import Frame
+    import torch
+    kw, dL, ref = load_case("ragged_100x75")
+    L = _lib.lib()
+    P, W, H = kw["means3D"].shape[0], kw["width"], kw["height"]
+    h = {k: np.ascontiguousarray(kw[k], np.float32) for k in ("background", "means3D", "colors", "opacities", "scales", "rotations",
+                                                               "viewmatrix", "projmatrix", "campos")}
+    a = _lib.RasterArgs()
+    a.P, a.D, a.M, a.width, a.height = P, 0, 0, W, H
+    a.background, a.means3D, a.colors_precomp, a.opacities = (h[k].ctypes.data for k in ("background", "means3D", "colors", "opacities"))
+    a.scales, a.scale_modifier, a.rotations = h["scales"].ctypes.data, 1.0, h["rotations"].ctypes.data
+    a.viewmatrix, a.projmatrix, a.cam_pos = h["viewmatrix"].ctypes.data, h["projmatrix"].ctypes.data, h["campos"].ctypes.data
+    a.tan_fovx, a.tan_fovy = kw["tanfovx"], kw["tanfovy"]
+    color, depth, radii = np.zeros((3, H, W), np.float32), np.zeros((1, H, W), np.float32), np.zeros(P, np.int32)
+    g = {k: np.zeros(s, np.float32) for k, s in dict(dL_dmean2D=(P, 3), dL_dconic=(P, 4), dL_dopacity=(P,), dL_dcolor=(P, 3),
+                                                      dL_dmean3D=(P, 3), dL_dcov3D=(P, 6), dL_dscale=(P, 3), dL_drot=(P, 4)).items()}
+    go = _lib.GradOutputs(**{k: v.ctypes.data for k, v in g.items()})
+    cap = 1 << 16
+    n = int(L.gsb_host_scratch_bytes(P, 0, W, H, cap))
+    scratch = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dLc = np.ascontiguousarray(dL, np.float32)
+    R = L.gsb_forward_backward_host(C.byref(a), cap, dLc.ctypes.data, color.ctypes.data, depth.ctypes.data, radii.ctypes.data,
+                                    C.byref(go), scratch.data_ptr(), n, None)
+    assert R == int(ref["num_rendered"])
+    np.testing.assert_array_equal(radii, ref["radii"])
+    np.testing.assert_array_equal(color.view(np.uint32), ref["color"].view(np.uint32))
+    fr = Frame(**kw)
+    gd = fr.backward(dL)
+    for k in g:
+        assert rel_to_scale(g[k], to_np(gd[k]).reshape(g[k].shape)) <= 1e-5, k   # atomics order only
+
+
+@pytest.mark.parametrize("P", [100_000, 1_000_000])
+def test_full_size_digests_match_reference(P):
+    """BASELINE.json sizes (100 k and the 1 M headline at 640x480): SHA-256 digests of every integer output and strided
+    samples of the images / gradients against what the reference kernels produced on the same seeded scene."""
+    from gsorb_slam_b200.lowlevel import frame_from_scene
+    from gsorb_slam_b200.scene import make_scene
+    dig = json.load(open(os.path.join(GOLDEN, "large_digests.json")))[f"tum_{P}"]
+    smp = np.load(os.path.join(GOLDEN, f"tum_{P}_sample.npz"))
+    sc = make_scene(P, "tum", seed=0)
+    fr = frame_from_scene(sc)
+    g = fr.backward(sc.dL_dpix)
+    assert fr.rendered() == dig["num_rendered"]
+    radii = to_np(fr.radii)
+    assert int((radii > 0).sum()) == dig["visible"]
+    assert sha(radii.astype(np.int32)) == dig["radii_sha"]
+    pl = to_np(fr.binning_state()["point_list"]).astype(np.uint32)
+    assert sha(pl) == dig["point_list_sha"]
+    ims = fr.image_state()
+    assert sha(to_np(ims["ranges"]).astype(np.uint32)) == dig["ranges_sha"]
+    assert sha(to_np(ims["n_contrib"]).astype(np.uint32)) == dig["n_contrib_sha"]
+    color, depth = to_np(fr.color), to_np(fr.depth)
+    np.testing.assert_array_equal(color[..., ::10, ::10].view(np.uint32), smp["color"].view(np.uint32))
+    np.testing.assert_array_equal(depth[..., ::10, ::10].view(np.uint32), smp["depth"].view(np.uint32))
+    np.testing.assert_array_equal(to_np(ims["final_T"])[::10, ::10].view(np.uint32), smp["final_T"].view(np.uint32))
+    idx = smp["sample_idx"]
+    for k in ("dL_dmean3D", "dL_dscale", "dL_drot", "dL_dopacity", "dL_dcolor", "dL_dmean2D", "dL_dconic"):
+        ours = to_np(g[k])[idx].reshape(smp[k].shape)
+        scale = max(np.abs(to_np(g[k])).max(), 1e-30)
+        assert np.abs(ours - smp[k]).max() / scale <= TOL_GRAD, k
+    # properties that do not need the reference: sortedness of every tile list, idempotence, linearity of the backward
+    rg = to_np(ims["ranges"]).astype(np.int64)
+    depths = to_np(fr.geometry_state()["depths"])
+    dd = depths[pl.astype(np.int64)]
+    tile_of = np.repeat(np.arange(rg.shape[0]), rg[:, 1] - rg[:, 0])
+    same = tile_of[1:] == tile_of[:-1]
+    assert (dd[1:][same] >= dd[:-1][same]).all(), "tile lists are depth sorted"
+    tie = same & (dd[1:] == dd[:-1])
+    assert (pl[1:][tie] > pl[:-1][tie]).all(), "depth ties keep ascending Gaussian id"
+    c0 = color.copy()
+    fr.forward()
+    np.testing.assert_array_equal(to_np(fr.color).view(np.uint32), c0.view(np.uint32))
+    g2 = fr.backward(2.0 * sc.dL_dpix)
+    assert rel_to_scale(to_np(g2["dL_dmean3D"]), 2.0 * to_np(g["dL_dmean3D"])) <= 1e-4
