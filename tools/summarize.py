@@ -31,5 +31,23 @@ def raw(path, keys=None):
             if k in idx: out.append(f"    {k:70s} {r[idx[k]]} {rows[1][idx[k]]}")
     return "\n".join(out)
 
+def traffic(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, keyed by bench.py's stage names -> profiles/dram_traffic.json"""
+    import json
+    rows = list(csv.reader(open(path)))
+    hdr = rows[0]; idx = {h: i for i, h in enumerate(hdr)}
+    unit = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    stage = {'preprocess_kernel': 'preprocess', 'duplicate_kernel': 'duplicate', 'tile_sort_small_kernel': 'tile_sort',
+             'blend_forward_kernel': 'blend_forward', 'blend_backward_kernel': 'blend_backward',
+             'gauss_backward_kernel': 'gauss_backward', 'tile_scan_kernel': 'scan'}
+    agg = {}
+    for r in rows[2:]:
+        n = r[idx['Kernel Name']].split('(')[0].replace('void ', '').replace('gsb::', '').split('<')[0]
+        if n not in stage: continue
+        b = sum(float(r[idx[k]].replace(',', '')) * unit[rows[1][idx[k]]] for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+        agg.setdefault(stage[n], []).append(b)
+    return json.dumps({k: sum(v) / len(v) for k, v in agg.items()}, indent=1)
+
 if __name__ == '__main__':
-    print(launches(sys.argv[2]) if sys.argv[1] == 'launches' else raw(sys.argv[2]))
+    cmd = sys.argv[1]
+    print(launches(sys.argv[2]) if cmd == 'launches' else traffic(sys.argv[2]) if cmd == 'traffic' else raw(sys.argv[2]))
