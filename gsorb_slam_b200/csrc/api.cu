@@ -116,8 +116,7 @@ static int forward_stage2(const FwdParams& p, char* geom, const GeomLayout& GL, 
                           cudaStream_t s)
 {
     if (int rc = launch_binning(p, geom, GL, binning, BL, image, IL, grid_instances, s)) return rc;
-    return launch_blend_forward(p, geom, GL, reinterpret_cast<const uint32_t*>(binning + BL.point_list), image, IL, out_color,
-                                out_depth, s);
+    return launch_blend_forward(p, geom, GL, binning, BL, image, IL, out_color, out_depth, s);
 }
 
 __global__ void unpack_geometry_kernel(int P, const SplatRec* __restrict__ rec, const int* __restrict__ radii,
@@ -271,7 +270,7 @@ int gsb_backward(const gsb_raster_args* args, long long R, const int* radii, con
     const GeomLayout GL = GeomLayout::make(p.P);
     const ImageLayout IL = ImageLayout::make(p.W, p.H);
     char* geom = (char*)const_cast<void*>(geometry);  // the packed accumulators live in the blob
-    if (int rc = launch_blend_backward(p, geom, GL, reinterpret_cast<const uint32_t*>(binning), (const char*)image, IL, dL_dpix, s))
+    if (int rc = launch_blend_backward(p, geom, GL, (const char*)binning, (const char*)image, IL, dL_dpix, s))
         return rc;
     return launch_gauss_backward(p, geom, GL, radii, *grads, s);
 }

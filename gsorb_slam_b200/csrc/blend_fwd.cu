@@ -23,14 +23,16 @@
 
 namespace gsb {
 
-template <int MINB>
+template <int MINB, int NS>
 __global__ void __launch_bounds__(BLEND_THREADS, MINB)
 blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                      const SplatRec* __restrict__ rec, int W, int H, const float* __restrict__ bg,
                      float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ final_T,
-                     uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ tile_max_contrib)
+                     uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ tile_max_contrib,
+                     uint32_t* __restrict__ hits_full, uint32_t* __restrict__ hits_tail,
+                     GeomHeader* __restrict__ hdr, uint32_t layout_capacity)
 {
-    __shared__ StageBuf S;
+    __shared__ StageBuf<NS> S;
     __shared__ uint32_t s_max;
     const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
     const uint2 range = ranges[tile];
@@ -47,31 +49,40 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     // y halves [by0, by0+1], [by0+2, by0+3]
     const float xa0 = (float)bx0, xa1 = (float)(bx0 + 3), xb0 = (float)(bx0 + 4), xb1 = (float)(bx0 + 7);
     const float ya0 = (float)by0, ya1 = (float)(by0 + 1), yb0 = (float)(by0 + 2), yb1 = (float)(by0 + 3);
-    if (threadIdx.x == 0) s_max = 0;
+    if (threadIdx.x == 0) {
+        s_max = 0;
+        if (tile == 0) hdr->layout_capacity = layout_capacity;  // the backward pass locates the hit words with it
+    }
 
     bool done = !inside;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
     uint32_t last = 0;
 
     const uint32_t* ids = point_list + range.x;
-    uint32_t id_next = 0;
-    if (batches > 0) {
-        const uint32_t id0 = (int)threadIdx.x < n ? __ldg(ids + threadIdx.x) : 0xffffffffu;
-        stage_issue(S, 0, rec, id0);
-        if (batches > 1) id_next = BLEND_BATCH + (int)threadIdx.x < n ? __ldg(ids + BLEND_BATCH + threadIdx.x) : 0xffffffffu;
+    auto load_id = [&](int b) -> uint32_t {
+        const int e = b * BLEND_BATCH + (int)threadIdx.x;
+        return e < n ? __ldg(ids + e) : 0xffffffffu;
+    };
+    // prologue: batches 0 .. NS-2 in flight, ids of batch NS-1 in a register
+#pragma unroll
+    for (int i = 0; i < NS - 1; i++) {
+        if (i < batches) stage_issue(S, i, rec, load_id(i));
+        cp_async_commit();
     }
+    uint32_t id_next = NS - 1 < batches ? load_id(NS - 1) : 0xffffffffu;
     uint32_t done_bits = __ballot_sync(0xffffffffu, done);
     bool warp_done = done_bits == 0xffffffffu;
+    int buf = 0;
     for (int b = 0; b < batches; b++) {
-        const int buf = b & 1;
-        if (b + 1 < batches) stage_issue(S, buf ^ 1, rec, id_next);
-        else cp_async_commit();
-        if (b + 2 < batches) {
-            const int e = (b + 2) * BLEND_BATCH + (int)threadIdx.x;
-            id_next = e < n ? __ldg(ids + e) : 0xffffffffu;
-        }
-        cp_async_wait<1>();
+        cp_async_wait<NS - 2>();  // this thread's copies of batch b have landed
+        // one barrier per batch: publishes batch b, and everyone is finished with batch b-1 (whose buffer is reused below)
         if (__syncthreads_count(warp_done) == BLEND_THREADS) break;  // every pixel of the tile is saturated
+        {
+            const int nbuf = buf == 0 ? NS - 1 : buf - 1;  // (b + NS - 1) % NS
+            if (b + NS - 1 < batches) stage_issue(S, nbuf, rec, id_next);
+            cp_async_commit();
+            if (b + NS < batches) id_next = load_id(b + NS);
+        }
         if (!warp_done) {
             const int cnt = min(BLEND_BATCH, n - b * BLEND_BATCH);
             for (int c0 = 0; c0 < cnt; c0 += 32) {
@@ -91,11 +102,13 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                 const uint32_t m2 = __ballot_sync(0xffffffffu, hxa && hyb), m3 = __ballot_sync(0xffffffffu, hxb && hyb);
                 uint32_t mask = q == 0 ? m0 : q == 1 ? m1 : q == 2 ? m2 : m3;
                 if (((done_bits >> qshift) & 0xffu) == 0xffu) mask = 0;  // this quarter is saturated
+                uint32_t lane_hits = 0;  // entries of this window blended into THIS pixel
                 // ---- blend pass: every quarter-warp walks ITS survivors, in list order ----
                 while (__any_sync(0xffffffffu, mask != 0)) {
                     const bool act = mask != 0;
                     const int e = c0 + (act ? __ffs(mask) - 1 : 0);
-                    mask &= mask - 1;
+                    const uint32_t bit = mask & (0u - mask);
+                    mask ^= bit;
                     const float4 A = S.a[buf][e];
                     const float4 B = S.b[buf][e];
                     const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
@@ -115,7 +128,15 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                     if (T > 0.5f) D = Cc.w;
                     T = test_T;
                     last = (uint32_t)(b * BLEND_BATCH + e + 1);
+                    lane_hits |= bit;
                 }
+                // hit word of (window, 4x2 block): OR over the quarter's 8 lanes
+                lane_hits |= __shfl_xor_sync(0xffffffffu, lane_hits, 4);
+                lane_hits |= __shfl_xor_sync(0xffffffffu, lane_hits, 2);
+                lane_hits |= __shfl_xor_sync(0xffffffffu, lane_hits, 1);
+                if (l8 == 0)
+                    *hit_word(hits_full, hits_tail, tile, range.x, (uint32_t)n, (uint32_t)(b * (BLEND_BATCH / 32) + (c0 >> 5)),
+                              warp * 4 + q) = lane_hits;
                 done_bits = __ballot_sync(0xffffffffu, done);
                 if (done_bits == 0xffffffffu) {
                     warp_done = true;
@@ -123,7 +144,7 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                 }
             }
         }
-        __syncthreads();  // everyone is finished with `buf` before batch b+2 is staged into it
+        buf = buf == NS - 1 ? 0 : buf + 1;
     }
     cp_async_wait<0>();
     if (inside) {
@@ -143,26 +164,37 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     if (threadIdx.x == 0) tile_max_contrib[tile] = s_max;
 }
 
-int launch_blend_forward(const FwdParams& p, const char* geom, const GeomLayout& GL, const uint32_t* point_list,
+int launch_blend_forward(const FwdParams& p, char* geom, const GeomLayout& GL, char* binning, const BinningLayout& BL,
                          char* image, const ImageLayout& IL, float* out_color, float* out_depth, cudaStream_t s)
 {
+    const uint32_t* point_list = reinterpret_cast<const uint32_t*>(binning + BL.point_list);
     if (p.W <= 0 || p.H <= 0) return GSB_OK;
-    // tuning knob (resident CTAs per SM the compiler must allow, i.e. the register budget)
+    // tuning knobs: resident CTAs per SM the compiler must allow (the register budget) and the depth of the staging ring
     static const int minb = [] { const char* e = getenv("GSB_BLEND_FWD_MINB"); return e ? atoi(e) : 6; }();
+    static const int stages = [] { const char* e = getenv("GSB_BLEND_FWD_STAGES"); return e ? atoi(e) : 2; }();
     dim3 grid(IL.tiles_x, IL.tiles_y);
     {
         StageTimer _t(ST_BLEND_FWD, s);
-        switch (minb) {
-            case 4: blend_forward_kernel<4><<<grid, BLEND_THREADS, 0, s>>>(reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec),
-            p.W, p.H, p.background, out_color, out_depth, reinterpret_cast<float*>(image + IL.final_T),
-            reinterpret_cast<uint32_t*>(image + IL.n_contrib), reinterpret_cast<uint32_t*>(image + IL.tile_max_contrib)); break;
-            case 8: blend_forward_kernel<8><<<grid, BLEND_THREADS, 0, s>>>(reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec),
-            p.W, p.H, p.background, out_color, out_depth, reinterpret_cast<float*>(image + IL.final_T),
-            reinterpret_cast<uint32_t*>(image + IL.n_contrib), reinterpret_cast<uint32_t*>(image + IL.tile_max_contrib)); break;
-            default: blend_forward_kernel<6><<<grid, BLEND_THREADS, 0, s>>>(reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec),
-            p.W, p.H, p.background, out_color, out_depth, reinterpret_cast<float*>(image + IL.final_T),
-            reinterpret_cast<uint32_t*>(image + IL.n_contrib), reinterpret_cast<uint32_t*>(image + IL.tile_max_contrib)); break;
+#define GSB_FWD_LAUNCH(MB, NS)                                                                                          \
+    do {                                                                                                                \
+        static const bool attr_set = [] {  /* several resident CTAs x 24-37 KB: ask for the largest carve-out */      \
+            cudaFuncSetAttribute(blend_forward_kernel<MB, NS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);    \
+            return true;                                                                                                \
+        }();                                                                                                            \
+        (void)attr_set;                                                                                                 \
+        blend_forward_kernel<MB, NS><<<grid, BLEND_THREADS, 0, s>>>(                                                    \
+            reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec), \
+            p.W, p.H, p.background, out_color, out_depth, reinterpret_cast<float*>(image + IL.final_T),                 \
+            reinterpret_cast<uint32_t*>(image + IL.n_contrib), reinterpret_cast<uint32_t*>(image + IL.tile_max_contrib), \
+            reinterpret_cast<uint32_t*>(binning + BL.hits), reinterpret_cast<uint32_t*>(image + IL.hits_tail),          \
+            reinterpret_cast<GeomHeader*>(geom + GL.header), (uint32_t)BL.capacity);                                    \
+    } while (0)
+        if (stages == 3) {
+            if (minb == 4) GSB_FWD_LAUNCH(4, 3); else GSB_FWD_LAUNCH(6, 3);
+        } else {
+            if (minb == 4) GSB_FWD_LAUNCH(4, 2); else if (minb == 6) GSB_FWD_LAUNCH(6, 2); else GSB_FWD_LAUNCH(8, 2);
         }
+#undef GSB_FWD_LAUNCH
         GSB_LAUNCH_CHECK();
     }
     return GSB_OK;

@@ -20,6 +20,8 @@ constexpr int TILE_X = 16;   // config.h:16 (tile-rect membership is part of the
 constexpr int TILE_Y = 16;   // config.h:17
 constexpr int NUM_SMS = 148; // B200
 constexpr int TILE_CTR_STRIDE = 64;  // words between per-tile atomic counters (256 B)
+constexpr int HIT_BLOCKS = 32;       // 4x2-pixel blocks per 16x16 tile (one quarter-warp each)
+constexpr int HIT_WINDOW = 32;       // list entries covered by one hit word
 
 // ---------------------------------------------------------------------------------------
 // Packed per-Gaussian splat record: 48 bytes, 16-byte aligned, gathered by the blend
@@ -56,7 +58,8 @@ struct GeomHeader {            // first 256 bytes of the geometry blob (device m
     uint32_t capacity;         // binning capacity in instances
     uint32_t sort_tile_counter[8];  // dynamic tile ids, one per radix pass
     uint32_t visible;          // number of Gaussians with radii > 0 (diagnostics)
-    uint32_t pad[64 - 15];
+    uint32_t layout_capacity;  // capacity the binning blob was laid out for (BinningLayout::make argument)
+    uint32_t pad[64 - 16];
 };
 // The header is zeroed by the forward before the first kernel; the scan kernel fills it.
 static_assert(sizeof(GeomHeader) == 256, "header is 256 bytes");
@@ -85,7 +88,7 @@ struct GeomLayout {            // offsets inside the geometry blob
 };
 
 struct ImageLayout {
-    size_t final_T, n_contrib, ranges, tile_max_contrib, tile_count, tile_cursor, total;
+    size_t final_T, n_contrib, ranges, tile_max_contrib, tile_count, tile_cursor, hits_tail, total;
     int tiles_x, tiles_y;
     __host__ __device__ static ImageLayout make(int W, int H)
     {
@@ -103,6 +106,7 @@ struct ImageLayout {
         // ~2 M atomics of a frame are not funnelled through the few slices a dense array maps to
         L.tile_count = take(T * 4 * TILE_CTR_STRIDE);    // instances per tile (atomics in preprocess)
         L.tile_cursor = take(T * 4 * TILE_CTR_STRIDE);   // next free slot of each tile's segment (duplicate)
+        L.hits_tail = take(T * HIT_BLOCKS * 4);          // hit words of each tile's last, partial window (blend kernels)
         L.total = off;
         return L;
     }
@@ -118,8 +122,13 @@ constexpr int SORT_MAX_PASSES = 8;
 struct BinningLayout {
     // point_list sits at offset 0 whatever the capacity (gsb_backward relies on it): the
     // depth-sorted Gaussian ids, tile after tile.  `pairs` holds the unsorted
-    // (depth bits << 32 | id) records bucketed by tile.
-    size_t point_list, pairs, total;
+    // (depth bits << 32 | id) records bucketed by tile.  `hits` holds, per full 32-entry window
+    // of a tile's list and per 4x2-pixel block, the bit mask of the entries that were blended
+    // into at least one pixel of the block (written by the forward blend, consumed by the
+    // backward blend).  Window w of a tile whose list starts at s lives at index (s >> 5) + w,
+    // which never collides with the next tile's windows; each tile's last, partial window is
+    // kept in the image blob (ImageLayout::hits_tail).
+    size_t point_list, hits, pairs, total;
     long long capacity;
     __host__ __device__ static BinningLayout make(long long cap)
     {
@@ -129,6 +138,7 @@ struct BinningLayout {
         if (cap < 1) cap = 1;
         L.capacity = cap;
         L.point_list = take((size_t)cap * 4 + 64);
+        L.hits = take(((size_t)cap / HIT_WINDOW + 1) * HIT_BLOCKS * 4);
         L.pairs = take((size_t)cap * 8);
         L.total = off;
         return L;
@@ -338,9 +348,9 @@ int launch_sort_pairs(GeomHeader* hdr, uint64_t* const kbuf[2], uint32_t* const 
 // (the exact count lives in the header on the device).
 int launch_binning(const FwdParams& p, char* geom, const GeomLayout& GL, char* binning, const BinningLayout& BL,
                    char* image, const ImageLayout& IL, long long grid_instances, cudaStream_t s);
-int launch_blend_forward(const FwdParams& p, const char* geom, const GeomLayout& GL, const uint32_t* point_list,
+int launch_blend_forward(const FwdParams& p, char* geom, const GeomLayout& GL, char* binning, const BinningLayout& BL,
                          char* image, const ImageLayout& IL, float* out_color, float* out_depth, cudaStream_t s);
-int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, const uint32_t* point_list,
+int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, const char* binning,
                           const char* image, const ImageLayout& IL, const float* dL_dpix, cudaStream_t s);
 int launch_gauss_backward(const FwdParams& p, const char* geom, const GeomLayout& GL, const int* radii,
                           const gsb_grad_outputs& g, cudaStream_t s);
