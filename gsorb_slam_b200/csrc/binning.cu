@@ -34,12 +34,18 @@ tile_scan_kernel(const uint32_t* __restrict__ tile_count, uint2* __restrict__ ra
                  int tiles, GeomHeader* __restrict__ hdr, uint32_t capacity, int P)
 {
     __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
+    __shared__ uint32_t s_carry, s_maxlen;
+    if (threadIdx.x == 0) {
+        s_carry = 0;
+        s_maxlen = 0;
+    }
     __syncthreads();
+    uint32_t maxlen = 0;
     for (int base = 0; base < tiles; base += 1024) {
         const int i = base + threadIdx.x;
-        const uint32_t x = i < tiles ? tile_count[(size_t)i * TILE_CTR_STRIDE] : 0u;
+        const uint2 cnt = i < tiles ? *reinterpret_cast<const uint2*>(tile_count + (size_t)i * TILE_CTR_STRIDE) : make_uint2(0u, 0u);
+        const uint32_t x = cnt.x + cnt.y;   // instances of small (slot known) + large (slot claimed later) Gaussians
+        maxlen = max(maxlen, x);
         uint32_t v = x;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -64,14 +70,18 @@ tile_scan_kernel(const uint32_t* __restrict__ tile_count, uint2* __restrict__ ra
             const uint32_t start = carry + warp_excl + v - x;
             // a too-small binning capacity truncates the tail of the tile-major list (overflow is latched below)
             ranges[i] = make_uint2(min(start, capacity), min(start + x, capacity));
-            cursor[(size_t)i * TILE_CTR_STRIDE] = start;
+            cursor[(size_t)i * TILE_CTR_STRIDE] = start + cnt.x;   // large Gaussians fill the tail of the segment
         }
         __syncthreads();
         if (threadIdx.x == 1023) s_carry = carry + warp_excl + v;
         __syncthreads();
     }
+    maxlen = __reduce_max_sync(0xffffffffu, maxlen);
+    if (lane_id() == 0) atomicMax(&s_maxlen, maxlen);
+    __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t total = s_carry;
+        hdr->max_tile_len = s_maxlen;
         hdr->magic = GEOM_MAGIC;
         hdr->P = P;
         hdr->num_rendered = total;
@@ -81,10 +91,13 @@ tile_scan_kernel(const uint32_t* __restrict__ tile_count, uint2* __restrict__ ra
     }
 }
 
-// ---- K3: one thread per Gaussian claims a slot in every tile segment it touches -----------------
+// ---- K3: one thread per Gaussian writes its instances into the tile segments ---------------------
+// Slots of Gaussians touching <= 4 tiles were fixed by the counting atomics of preprocess
+// (GeomLayout::ranks): no atomics here.  Larger Gaussians claim slots in the tail of each segment.
 __global__ void __launch_bounds__(DUP_THREADS)
-duplicate_kernel(int P, const SplatRec* __restrict__ rec, const int* __restrict__ radii, uint32_t* __restrict__ cursor,
-                 const GeomHeader* __restrict__ hdr, uint64_t* __restrict__ pairs, int tiles_x, int tiles_y)
+duplicate_kernel(int P, const SplatRec* __restrict__ rec, const int* __restrict__ radii, const uint4* __restrict__ ranks,
+                 const uint2* __restrict__ ranges, uint32_t* __restrict__ cursor, const GeomHeader* __restrict__ hdr,
+                 uint64_t* __restrict__ pairs, int tiles_x, int tiles_y)
 {
     const int idx = blockIdx.x * DUP_THREADS + threadIdx.x;
     if (idx >= P) return;
@@ -95,11 +108,26 @@ duplicate_kernel(int P, const SplatRec* __restrict__ rec, const int* __restrict_
     const uint64_t record = ((uint64_t)__float_as_uint(rec[idx].c.w) << 32) | (uint32_t)idx;
     uint32_t minx, miny, maxx, maxy;
     get_rect(a.x, a.y, radius, tiles_x, tiles_y, minx, miny, maxx, maxy);
-    for (uint32_t y = miny; y < maxy; y++)
-        for (uint32_t x = minx; x < maxx; x++) {
-            const uint32_t pos = atomicAdd(&cursor[(size_t)(y * (uint32_t)tiles_x + x) * TILE_CTR_STRIDE], 1u);
-            if (pos < cap) pairs[pos] = record;
+    const uint32_t touched = (maxx - minx) * (maxy - miny);
+    if (touched <= 4) {
+        const uint4 rk4 = ranks[idx];
+        const uint32_t rk[4] = {rk4.x, rk4.y, rk4.z, rk4.w};
+        uint32_t tx = minx, ty = miny;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if ((uint32_t)k < touched) {
+                const uint32_t pos = ranges[ty * (uint32_t)tiles_x + tx].x + rk[k];
+                if (pos < cap) pairs[pos] = record;
+                if (++tx == maxx) { tx = minx; ty++; }
+            }
         }
+    } else {
+        for (uint32_t y = miny; y < maxy; y++)
+            for (uint32_t x = minx; x < maxx; x++) {
+                const uint32_t pos = atomicAdd(&cursor[(size_t)(y * (uint32_t)tiles_x + x) * TILE_CTR_STRIDE], 1u);
+                if (pos < cap) pairs[pos] = record;
+            }
+    }
 }
 
 // ---- K4: per-tile sort -----------------------------------------------------------------------------
@@ -229,31 +257,199 @@ __device__ __forceinline__ void tile_sort_regs(uint64_t* __restrict__ s /* smem,
     __syncthreads();
 }
 
+// ---- 32-bit keyed variant (the common size classes, n <= 4096) ----------------------------------
+// A tile's records are (depth bits << 32 | id).  Sorting 64-bit records costs a two-instruction
+// compare, four selects and two shuffles per comparator.  Here every record is replaced by ONE
+// 32-bit key: the depth, rebased to the tile's minimum and shifted so that the tile's depth range
+// fits in 32 - log2(npad) bits, above the record's index in the unsorted segment.  The key order
+// is the (depth, id) order except between records whose quantised depths collide (about two pairs
+// per 2000-entry tile); those are put right afterwards by an odd-even transposition on the exact
+// 64-bit records, restricted to neighbours with equal quantised depth.  A comparator is then one
+// VIMNMX pair, a shuffle stage one SHFL + one VIMNMX per element.
+template <int E>
+__device__ __forceinline__ void tile_sort_regs32(uint32_t* __restrict__ s, uint32_t (&a)[E])
+{
+    constexpr uint32_t N = E * TSORT_THREADS;
+    const uint32_t t = threadIdx.x, lane = t & 31;
+#pragma unroll
+    for (uint32_t k = 2; k <= N; k <<= 1) {
+        // ---- flip step of the merge of size k ----
+        if (k <= (uint32_t)E) {
+#pragma unroll
+            for (int b0 = 0; b0 < E; b0 += (int)k)
+#pragma unroll
+                for (int o = 0; o < (int)k / 2; o++) {
+                    const uint32_t x = a[b0 + o], y = a[b0 + (int)k - 1 - o];
+                    a[b0 + o] = min(x, y);
+                    a[b0 + (int)k - 1 - o] = max(x, y);
+                }
+        } else if (k <= 32u * E) {
+            const uint32_t m = k / E;  // 2..32 threads per k-block
+            uint32_t other[E];
+#pragma unroll
+            for (int r = 0; r < E; r++) other[r] = __shfl_xor_sync(0xffffffffu, a[E - 1 - r], m - 1);
+            const bool lower = (lane & (m >> 1)) == 0;
+#pragma unroll
+            for (int r = 0; r < E; r++) a[r] = lower ? min(a[r], other[r]) : max(a[r], other[r]);
+        }
+        uint32_t j = k >> 2;  // first stride of the half-cleaners
+        if (k > 32u * E) {
+            // cross-warp part of this merge in shared memory: flip, then strides >= 32 E
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < E; r++) s[t * E + r] = a[r];
+            __syncthreads();
+            const uint32_t half = k >> 1;
+            for (uint32_t p = t; p < N / 2; p += TSORT_THREADS) {
+                const uint32_t blk = p / half, off = p % half;
+                const uint32_t i = blk * k + off, l = blk * k + (k - 1 - off);
+                const uint32_t x = s[i], y = s[l];
+                s[i] = min(x, y);
+                s[l] = max(x, y);
+            }
+            __syncthreads();
+            for (; j >= 32u * E; j >>= 1) {
+                for (uint32_t p = t; p < N / 2; p += TSORT_THREADS) {
+                    const uint32_t i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), l = i | j;
+                    const uint32_t x = s[i], y = s[l];
+                    s[i] = min(x, y);
+                    s[l] = max(x, y);
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int r = 0; r < E; r++) a[r] = s[t * E + r];
+        }
+        // ---- half-cleaners inside a warp (shuffles) ----
+#pragma unroll
+        for (uint32_t jj = 16u * E; jj >= (uint32_t)E; jj >>= 1) {
+            if (jj <= j && jj >= 1) {
+                const uint32_t m = jj / E;
+                const bool lower = (lane & m) == 0;
+#pragma unroll
+                for (int r = 0; r < E; r++) {
+                    const uint32_t o = __shfl_xor_sync(0xffffffffu, a[r], m);
+                    a[r] = lower ? min(a[r], o) : max(a[r], o);
+                }
+            }
+        }
+        // ---- half-cleaners inside a thread (registers) ----
+#pragma unroll
+        for (int jj = E / 2; jj >= 1; jj >>= 1) {
+            if ((uint32_t)jj <= j) {
+#pragma unroll
+                for (int r = 0; r < E; r++)
+                    if ((r & jj) == 0) {
+                        const uint32_t x = a[r], y = a[r | jj];
+                        a[r] = min(x, y);
+                        a[r | jj] = max(x, y);
+                    }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < E; r++) s[t * E + r] = a[r];
+    __syncthreads();
+}
+
+template <int E>
+__device__ __forceinline__ void tile_sort_class32(const uint2 r, const uint64_t* __restrict__ pairs,
+                                                  uint32_t* __restrict__ point_list, uint32_t* __restrict__ s,
+                                                  uint32_t* __restrict__ s_red)
+{
+    constexpr int LOG_E = E == 1 ? 0 : E == 2 ? 1 : E == 4 ? 2 : E == 8 ? 3 : 4;
+    constexpr int IDX_BITS = 8 + LOG_E, DEPTH_BITS = 32 - IDX_BITS;
+    constexpr uint32_t IDX_MASK = (1u << IDX_BITS) - 1u;
+    const uint32_t n = r.y - r.x, t = threadIdx.x;
+    const uint64_t* seg = pairs + r.x;
+    // depth bits of this thread's E consecutive records, tile-wide minimum and maximum
+    uint32_t dep[E];
+    uint32_t mn = 0xffffffffu, mx = 0u;
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+        const uint32_t i = t * E + k;
+        dep[k] = i < n ? (uint32_t)(seg[i] >> 32) : 0u;
+        if (i < n) {
+            mn = min(mn, dep[k]);
+            mx = max(mx, dep[k]);
+        }
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((t & 31) == 0) {
+        s_red[t >> 5] = mn;
+        s_red[8 + (t >> 5)] = mx;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < TSORT_THREADS / 32; w++) {
+        mn = min(mn, s_red[w]);
+        mx = max(mx, s_red[8 + w]);
+    }
+    // largest quantised depth must stay below 2^DEPTH_BITS - 1 (the padding key is all ones)
+    const int need = 32 - __clz(mx - mn + 1u);
+    const int shift = need > DEPTH_BITS ? need - DEPTH_BITS : 0;
+    uint32_t a[E];
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+        const uint32_t i = t * E + k;
+        a[k] = i < n ? (((dep[k] - mn) >> shift) << IDX_BITS) | i : 0xffffffffu;
+    }
+    tile_sort_regs32<E>(s, a);
+    // exact order between neighbours whose quantised depths collide: odd-even transposition on the
+    // 64-bit records, until a whole round swaps nothing (runs are 2-3 entries long in practice)
+    bool tie = false;
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+        const uint32_t i = t * E + k;
+        if (i + 1 < n) tie |= (s[i] >> IDX_BITS) == (s[i + 1] >> IDX_BITS);
+    }
+    if (__syncthreads_or(tie)) {
+        while (true) {
+            bool swapped = false;
+#pragma unroll 1
+            for (uint32_t phase = 0; phase < 2; phase++) {
+                for (uint32_t i = 2 * t + phase; i + 1 < n; i += 2 * TSORT_THREADS) {
+                    const uint32_t x = s[i], y = s[i + 1];
+                    if ((x >> IDX_BITS) == (y >> IDX_BITS) && seg[x & IDX_MASK] > seg[y & IDX_MASK]) {
+                        s[i] = y;
+                        s[i + 1] = x;
+                        swapped = true;
+                    }
+                }
+                __syncthreads();
+            }
+            if (!__syncthreads_or(swapped)) break;
+        }
+    }
+    for (uint32_t i = t; i < n; i += TSORT_THREADS) point_list[r.x + i] = (uint32_t)seg[s[i] & IDX_MASK];
+}
+
 __global__ void __launch_bounds__(TSORT_THREADS)
 tile_sort_small_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list)
 {
-    __shared__ __align__(16) uint64_t s[TSORT_SMALL];
+    __shared__ __align__(16) uint32_t s[TSORT_SMALL];
+    __shared__ uint32_t s_red[16];
     const uint2 r = ranges[blockIdx.x];
     const uint32_t n = r.y - r.x;
     if (n == 0 || n > (uint32_t)TSORT_SMALL) return;   // longer lists: the 128 KB / global classes
     const uint32_t npad = n <= 256 ? 256u : next_pow2(n);
-    for (uint32_t i = threadIdx.x; i < npad; i += TSORT_THREADS) s[i] = i < n ? pairs[r.x + i] : ~0ull;
-    __syncthreads();
     switch (npad) {
-        case 256: tile_sort_regs<1>(s); break;
-        case 512: tile_sort_regs<2>(s); break;
-        case 1024: tile_sort_regs<4>(s); break;
-        case 2048: tile_sort_regs<8>(s); break;
-        default: tile_sort_regs<16>(s); break;
+        case 256: tile_sort_class32<1>(r, pairs, point_list, s, s_red); break;
+        case 512: tile_sort_class32<2>(r, pairs, point_list, s, s_red); break;
+        case 1024: tile_sort_class32<4>(r, pairs, point_list, s, s_red); break;
+        case 2048: tile_sort_class32<8>(r, pairs, point_list, s, s_red); break;
+        default: tile_sort_class32<16>(r, pairs, point_list, s, s_red); break;
     }
-    for (uint32_t i = threadIdx.x; i < n; i += TSORT_THREADS) point_list[r.x + i] = (uint32_t)s[i];
 }
 
 template <int CAP, int THREADS, bool DYNAMIC>
 __global__ void __launch_bounds__(THREADS)
 tile_sort_smem_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list,
-                      int tiles, uint32_t lo_excl, uint32_t hi_incl)
+                      int tiles, uint32_t lo_excl, uint32_t hi_incl, const GeomHeader* __restrict__ hdr)
 {
+    if (hdr->max_tile_len <= lo_excl) return;   // no tile of this size class in the frame
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ __align__(16) uint64_t stat_smem[DYNAMIC ? 1 : CAP];
     uint64_t* s = DYNAMIC ? reinterpret_cast<uint64_t*>(dyn_smem) : stat_smem;
@@ -283,8 +479,9 @@ tile_sort_smem_kernel(const uint2* __restrict__ ranges, const uint64_t* __restri
 // 1024-thread CTA per such tile (correct for any length; pathological inputs only).
 __global__ void __launch_bounds__(1024)
 tile_sort_global_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list,
-                        int tiles, uint32_t lo_excl)
+                        int tiles, uint32_t lo_excl, const GeomHeader* __restrict__ hdr)
 {
+    if (hdr->max_tile_len <= lo_excl) return;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const uint2 r = ranges[tile];
         const uint32_t n = r.y - r.x;
@@ -533,7 +730,8 @@ int launch_binning(const FwdParams& p, char* geom, const GeomLayout& GL, char* b
         StageTimer _t(ST_DUPLICATE, s);
         duplicate_kernel<<<GL.num_blocks, DUP_THREADS, 0, s>>>(
             p.P, reinterpret_cast<const SplatRec*>(geom + GL.rec), reinterpret_cast<const int*>(geom + GL.radii),
-            reinterpret_cast<uint32_t*>(image + IL.tile_cursor), hdr, pairs, p.tiles_x, p.tiles_y);
+            reinterpret_cast<const uint4*>(geom + GL.ranks), ranges, reinterpret_cast<uint32_t*>(image + IL.tile_cursor), hdr,
+            pairs, p.tiles_x, p.tiles_y);
         GSB_LAUNCH_CHECK();
     }
     {
@@ -545,12 +743,12 @@ int launch_binning(const FwdParams& p, char* geom, const GeomLayout& GL, char* b
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, TSORT_MID * 8));
             const int g = tiles < NUM_SMS ? tiles : NUM_SMS;
             tile_sort_smem_kernel<TSORT_MID, 1024, true><<<g, 1024, TSORT_MID * 8, s>>>(ranges, pairs, point_list, tiles,
-                                                                                       (uint32_t)TSORT_SMALL, (uint32_t)TSORT_MID);
+                                                                                       (uint32_t)TSORT_SMALL, (uint32_t)TSORT_MID, hdr);
             GSB_LAUNCH_CHECK();
         }
         if (grid_instances > TSORT_MID) {
             const int g = tiles < NUM_SMS ? tiles : NUM_SMS;
-            tile_sort_global_kernel<<<g, 1024, 0, s>>>(ranges, pairs, point_list, tiles, (uint32_t)TSORT_MID);
+            tile_sort_global_kernel<<<g, 1024, 0, s>>>(ranges, pairs, point_list, tiles, (uint32_t)TSORT_MID, hdr);
             GSB_LAUNCH_CHECK();
         }
     }

@@ -33,8 +33,8 @@
 
 namespace gsb {
 
-template <int MINB, int NS>
-__global__ void __launch_bounds__(BLEND_THREADS, MINB)
+template <int MINB, int NS, int HALVES>
+__global__ void __launch_bounds__(256 / HALVES, MINB)
 blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__ binning,
                       const SplatRec* __restrict__ rec, int W, int H, const float* __restrict__ bg,
                       const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
@@ -42,21 +42,25 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
                       float* __restrict__ acc /* [P][12] */, const uint32_t* __restrict__ hits_tail,
                       const GeomHeader* __restrict__ hdr)
 {
-    __shared__ StageBuf<NS> S;
+    constexpr int BLEND_THREADS = 256 / HALVES, BLEND_BATCH = BLEND_THREADS, BLOCKS = HIT_BLOCKS / HALVES;
+    __shared__ StageBuf<NS, BLEND_BATCH> S;
     __shared__ uint32_t s_ids[NS][BLEND_BATCH];
-    __shared__ uint32_t s_hits[NS][BLEND_BATCH];  // [window of the batch][4x2 block]
-    const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
+    __shared__ uint32_t s_hits[NS][(BLEND_BATCH / 32) * BLOCKS];  // [window of the batch][4x2 block of this CTA]
+    const uint32_t tile_y = blockIdx.y / HALVES, half = blockIdx.y % HALVES;
+    const uint32_t tile = tile_y * gridDim.x + blockIdx.x;
     const uint2 range = ranges[tile];
     const uint32_t len = range.y - range.x;
-    const int n = min((int)len, (int)tile_max_contrib[tile]);  // entries [0, n) can matter
+    // entries [0, n) can matter: n = highest n_contrib over this CTA's pixels (recorded per half tile by the forward)
+    const uint32_t tmax = HALVES == 2 ? tile_max_contrib[2 * tile + half] : max(tile_max_contrib[2 * tile], tile_max_contrib[2 * tile + 1]);
+    const int n = min((int)len, (int)tmax);
     const int batches = (n + BLEND_BATCH - 1) / BLEND_BATCH;
     if (batches == 0) return;
     const BinningLayout BL = BinningLayout::make((long long)hdr->layout_capacity);
     const uint32_t* point_list = reinterpret_cast<const uint32_t*>(binning + BL.point_list);
     const uint32_t* hits_full = reinterpret_cast<const uint32_t*>(binning + BL.hits);
-    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t lwarp = threadIdx.x >> 5, warp = half * (8 / HALVES) + lwarp, lane = lane_id();   // warp: 0..7 over the tile
     const uint32_t q = lane >> 3, l8 = lane & 7, qshift = q * 8;
-    const int bx0 = blockIdx.x * TILE_X + (warp & 1) * 8, by0 = blockIdx.y * TILE_Y + (warp >> 1) * 4;
+    const int bx0 = blockIdx.x * TILE_X + (warp & 1) * 8, by0 = tile_y * TILE_Y + (warp >> 1) * 4;
     const int px = bx0 + (q & 1) * 4 + (l8 & 3), py = by0 + (q >> 1) * 2 + (l8 >> 2);
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
@@ -72,6 +76,9 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
         d2 = dL_dpix[2 * HW + pix];
     }
     const float bg_dot_dpixel = __ldg(bg) * d0 + __ldg(bg + 1) * d1 + __ldg(bg + 2) * d2;
+    const float dk = (l8 & 4) ? d1 : d0, ds = (l8 & 4) ? d0 : d1;   // stage-1 keep / send factors of the colour sums
+    // accumulator slot of the sum lane l8 ends up with (GradAcc layout: {Su dx, Su dy, Su dx^2, Su dxdy, Su dy^2, Su, Sw dr, Sw dg, Sw db})
+    const int acc_slot = l8 == 0 ? 0 : l8 == 1 ? 2 : l8 == 2 ? 3 : l8 == 3 ? 6 : l8 == 4 ? 1 : l8 == 5 ? 4 : l8 == 6 ? 5 : 7;
     float ar0 = 0.f, ar1 = 0.f, ar2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
     // last window (of 32 list entries) in which this quarter-warp's 4x2 block blended anything: the forward
     // pass wrote hit words for every window up to it
@@ -89,10 +96,11 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
     auto stage = [&](int k, int buf, uint32_t id) {
         s_ids[buf][threadIdx.x] = id;
         stage_issue(S, buf, rec, id);
-        const uint32_t w = (uint32_t)(batches - 1 - k) * (BLEND_BATCH / 32) + (threadIdx.x >> 5);
-        if ((int)(w * 32) < n)
+        // hit words of the batch: (BLEND_BATCH / 32) windows x BLOCKS blocks, one 4-byte copy per thread
+        const uint32_t w = (uint32_t)(batches - 1 - k) * (BLEND_BATCH / 32) + threadIdx.x / BLOCKS;
+        if (threadIdx.x < (BLEND_BATCH / 32) * BLOCKS && (int)(w * 32) < n)
             cp_async4(&s_hits[buf][threadIdx.x], hit_word(const_cast<uint32_t*>(hits_full), const_cast<uint32_t*>(hits_tail), tile,
-                                                          range.x, len, w, threadIdx.x & 31));
+                                                          range.x, len, w, half * BLOCKS + threadIdx.x % BLOCKS));
     };
 #pragma unroll
     for (int i = 0; i < NS - 1; i++) {
@@ -116,7 +124,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
         for (int wi = BLEND_BATCH / 32 - 1; wi >= 0; wi--) {
             const int w = kb * (BLEND_BATCH / 32) + wi;
             if (w * 32 >= n) continue;
-            uint32_t mask = w <= wq_last ? s_hits[buf][wi * 32 + warp * 4 + q] : 0u;
+            uint32_t mask = w <= wq_last ? s_hits[buf][wi * BLOCKS + lwarp * 4 + q] : 0u;
             // ---- gradient pass: every quarter-warp walks the entries that hit ITS block, back to front ----
             while (__any_sync(0xffffffffu, mask != 0)) {
                 const bool act = mask != 0;
@@ -126,77 +134,71 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
                 const int pos = kb * BLEND_BATCH + e + 1;  // 1-based list position
                 const float4 A = S.a[buf][e];
                 const float4 B = S.b[buf][e];
+                const float4 Cc = S.c[buf][e];
                 const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
                 const float power = splat_power(dx, dy, B.x, B.y, B.z);
-                float v[8], v8 = 0.f;
-#pragma unroll
-                for (int kk = 0; kk < 8; kk++) v[kk] = 0.f;
-                bool contrib = false;
-                if (act && pos <= last_contributor && !(power > 0.0f) && !(power < A.w)) {
-                    const float G = expf(power);
-                    const float alpha = fminf(0.99f, __fmul_rn(B.w, G));
-                    if (!(alpha < 1.0f / 255.0f)) {
-                        contrib = true;
-                        const float4 Cc = S.c[buf][e];
-                        const float inv = __fdividef(1.0f, 1.0f - alpha);   // 1 / (1 - alpha), MUFU.RCP
-                        T *= inv;                                           // T_before = T_after / (1 - alpha)
-                        const float wc = alpha * T;                         // d colour_out / d colour_splat
-                        const float om = 1.f - last_alpha;
-                        ar0 = fmaf(last_alpha, lc0, om * ar0);              // colour accumulated behind this splat
-                        ar1 = fmaf(last_alpha, lc1, om * ar1);
-                        ar2 = fmaf(last_alpha, lc2, om * ar2);
-                        lc0 = Cc.x; lc1 = Cc.y; lc2 = Cc.z;
-                        last_alpha = alpha;
-                        float dL_dalpha = T * fmaf(Cc.x - ar0, d0, fmaf(Cc.y - ar1, d1, (Cc.z - ar2) * d2));
-                        dL_dalpha = fmaf(-T_final * inv, bg_dot_dpixel, dL_dalpha);
-                        // raw moments of u = G * dL/dalpha; the conic / opacity / 0.5 W factors are
-                        // per-Gaussian constants and are applied once, in gauss_bwd.cu
-                        const float u = G * dL_dalpha, ux = u * dx, uy = u * dy;
-                        v[0] = ux;
-                        v[1] = uy;
-                        v[2] = ux * dx;
-                        v[3] = ux * dy;
-                        v[4] = uy * dy;
-                        v[5] = u;
-                        v[6] = wc * d0;
-                        v[7] = wc * d1;
-                        v8 = wc * d2;
-                    }
+                // Branch-free body: a lane that does not contribute carries u = wc = 0 through the sums and
+                // leaves its recurrences untouched (with exact hit words nearly every visit has contributors,
+                // so skipping the arithmetic for an all-idle warp is not worth the divergence bookkeeping).
+                const float G = expf(fminf(power, 0.0f));
+                const float alpha = fminf(0.99f, __fmul_rn(B.w, G));
+                const bool contrib = act && pos <= last_contributor && !(power > 0.0f) && !(power < A.w) && !(alpha < 1.0f / 255.0f);
+                const float inv = rcp_approx(1.0f - alpha);                 // 1 / (1 - alpha), one MUFU.RCP
+                const float Tn = T * inv;                                   // T_before = T_after / (1 - alpha)
+                const float om = 1.f - last_alpha;
+                const float a0 = fmaf(last_alpha, lc0, om * ar0);           // colour accumulated behind this splat
+                const float a1 = fmaf(last_alpha, lc1, om * ar1);
+                const float a2 = fmaf(last_alpha, lc2, om * ar2);
+                float dL_dalpha = Tn * fmaf(Cc.x - a0, d0, fmaf(Cc.y - a1, d1, (Cc.z - a2) * d2));
+                dL_dalpha = fmaf(-T_final * inv, bg_dot_dpixel, dL_dalpha);
+                // raw moments of u = G * dL/dalpha; the conic / opacity / 0.5 W factors are per-Gaussian
+                // constants and are applied once, in gauss_bwd.cu
+                const float u = contrib ? G * dL_dalpha : 0.f;
+                const float wc = contrib ? alpha * Tn : 0.f;                // d colour_out / d colour_splat
+                if (contrib) {
+                    T = Tn;
+                    ar0 = a0; ar1 = a1; ar2 = a2;
+                    lc0 = Cc.x; lc1 = Cc.y; lc2 = Cc.z;
+                    last_alpha = alpha;
                 }
                 const uint32_t cb = __ballot_sync(0xffffffffu, contrib);
                 if (cb == 0) continue;
-                // reduce-scatter the 8 sums over the quarter-warp's 8 lanes: 4 + 2 + 1 shuffles,
-                // after which lane l8 holds sum number (bit2, bit1, bit0 of l8) complete
+                // Reduce-scatter of the 8 sums {S u dx, S u dx^2, S u dx dy, S w d_r | S u dy, S u dy^2, S u, S w d_g}
+                // over the quarter-warp's 8 lanes.  Stage 1 (lane bit 2) pairs sums whose summands differ only in a
+                // lane-selectable factor, so "keep" and "send" are formed directly (4 selects instead of 8):
+                //   m_k = hi ? dy : dx, m_s = hi ? dx : dy:  keep {u m_k, u m_k^2}, send {u m_s, u m_s^2}
+                const bool hi4 = l8 & 4;
+                const float mk = hi4 ? dy : dx, ms = hi4 ? dx : dy;
+                const float k0 = u * mk, s0 = u * ms;
+                const float k1 = k0 * mk, s1 = s0 * ms;
+                const float uxy = k0 * ms;                                  // u dx dy (symmetric)
+                const float k2 = hi4 ? u : uxy, s2 = hi4 ? uxy : u;
+                const float k3 = wc * dk, s3 = wc * ds;                     // dk / ds: d_r, d_g pre-swapped per lane
+                float r0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 4);
+                float r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 4);
+                float r2 = k2 + __shfl_xor_sync(0xffffffffu, s2, 4);
+                float r3 = k3 + __shfl_xor_sync(0xffffffffu, s3, 4);
+                float v8 = wc * d2;
+                v8 += __shfl_xor_sync(0xffffffffu, v8, 4);
                 {
-                    const bool hi = l8 & 4;
-#pragma unroll
-                    for (int kk = 0; kk < 4; kk++) {
-                        const float send = hi ? v[kk] : v[kk + 4];
-                        const float keep = hi ? v[kk + 4] : v[kk];
-                        v[kk] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                    }
-                }
-                {
-                    const bool hi = l8 & 2;
-#pragma unroll
-                    for (int kk = 0; kk < 2; kk++) {
-                        const float send = hi ? v[kk] : v[kk + 2];
-                        const float keep = hi ? v[kk + 2] : v[kk];
-                        v[kk] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                    }
+                    const bool hi = l8 & 2;  // keep (r0, r1) on the low pair, (r2, r3) on the high pair
+                    const float sa = hi ? r0 : r2, ka = hi ? r2 : r0;
+                    const float sb = hi ? r1 : r3, kb2 = hi ? r3 : r1;
+                    r0 = ka + __shfl_xor_sync(0xffffffffu, sa, 2);
+                    r1 = kb2 + __shfl_xor_sync(0xffffffffu, sb, 2);
+                    v8 += __shfl_xor_sync(0xffffffffu, v8, 2);
                 }
                 {
                     const bool hi = l8 & 1;
-                    const float send = hi ? v[0] : v[1];
-                    const float keep = hi ? v[1] : v[0];
-                    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+                    const float sa = hi ? r0 : r1, ka = hi ? r1 : r0;
+                    r0 = ka + __shfl_xor_sync(0xffffffffu, sa, 1);
+                    v8 += __shfl_xor_sync(0xffffffffu, v8, 1);
                 }
-#pragma unroll
-                for (int o = 4; o > 0; o >>= 1) v8 += __shfl_xor_sync(0xffffffffu, v8, o);
+                // lane l8 = (b2 b1 b0) now holds: b2 selects the {dx.. | dy..} family, b1 the pair, b0 the member:
+                //   000 S u dx   001 S u dx^2   010 S u dxdy   011 S w d_r   100 S u dy   101 S u dy^2   110 S u   111 S w d_g
                 if ((cb >> qshift) & 0xffu) {  // this quarter touched the splat
                     float* dst = acc + (size_t)s_ids[buf][e] * 12;
-                    const int kk = ((l8 >> 2) & 1) * 4 + ((l8 >> 1) & 1) * 2 + (l8 & 1);
-                    atomicAdd(dst + kk, v[0]);
+                    atomicAdd(dst + acc_slot, r0);
                     if (l8 == 0) atomicAdd(dst + 8, v8);
                 }
             }
@@ -211,30 +213,33 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
 {
     if (p.W <= 0 || p.H <= 0 || p.P <= 0) return GSB_OK;
     GSB_CUDA_CHECK(cudaMemsetAsync(geom + GL.acc, 0, (size_t)p.P * sizeof(GradAcc), s));
-    // tuning knobs: resident CTAs per SM the compiler must allow (the register budget) and the depth of the staging ring
-    static const int minb = [] { const char* e = getenv("GSB_BLEND_BWD_MINB"); return e ? atoi(e) : 3; }();
+    // tuning knobs: CTA shape (whole tile / half tile), resident CTAs per SM the compiler must allow (the register
+    // budget), depth of the staging ring
+    static const int halves = [] { const char* e = getenv("GSB_BLEND_BWD_HALVES"); return e ? atoi(e) : 1; }();
+    static const int minb = [] { const char* e = getenv("GSB_BLEND_BWD_MINB"); return e ? atoi(e) : 0; }();
     static const int stages = [] { const char* e = getenv("GSB_BLEND_BWD_STAGES"); return e ? atoi(e) : 3; }();
-    dim3 grid(IL.tiles_x, IL.tiles_y);
     {
         StageTimer _t(ST_BLEND_BWD, s);
-#define GSB_BWD_LAUNCH(MB, NS)                                                                                              \
+#define GSB_BWD_LAUNCH(MB, NS, HV)                                                                                          \
     do {                                                                                                                    \
         static const bool attr_set = [] {                                                                                   \
-            cudaFuncSetAttribute(blend_backward_kernel<MB, NS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);       \
+            cudaFuncSetAttribute(blend_backward_kernel<MB, NS, HV>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   \
             return true;                                                                                                    \
         }();                                                                                                                \
         (void)attr_set;                                                                                                     \
-        blend_backward_kernel<MB, NS><<<grid, BLEND_THREADS, 0, s>>>(                                                       \
+        blend_backward_kernel<MB, NS, HV><<<dim3(IL.tiles_x, IL.tiles_y * HV), 256 / HV, 0, s>>>(                           \
             reinterpret_cast<const uint2*>(image + IL.ranges), binning, reinterpret_cast<const SplatRec*>(geom + GL.rec), p.W, \
             p.H, p.background, reinterpret_cast<const float*>(image + IL.final_T),                                          \
             reinterpret_cast<const uint32_t*>(image + IL.n_contrib), reinterpret_cast<const uint32_t*>(image + IL.tile_max_contrib), \
             dL_dpix, reinterpret_cast<float*>(geom + GL.acc), reinterpret_cast<const uint32_t*>(image + IL.hits_tail),      \
             reinterpret_cast<const GeomHeader*>(geom + GL.header));                                                         \
     } while (0)
-        if (stages == 2) {
-            if (minb == 3) GSB_BWD_LAUNCH(3, 2); else if (minb == 5) GSB_BWD_LAUNCH(5, 2); else GSB_BWD_LAUNCH(4, 2);
+        if (halves == 2) {
+            if (stages == 2) { if (minb == 8) GSB_BWD_LAUNCH(8, 2, 2); else if (minb == 10) GSB_BWD_LAUNCH(10, 2, 2); else GSB_BWD_LAUNCH(6, 2, 2); }
+            else { if (minb == 8) GSB_BWD_LAUNCH(8, 3, 2); else if (minb == 10) GSB_BWD_LAUNCH(10, 3, 2); else GSB_BWD_LAUNCH(6, 3, 2); }
         } else {
-            if (minb == 3) GSB_BWD_LAUNCH(3, 3); else if (minb == 5) GSB_BWD_LAUNCH(5, 3); else GSB_BWD_LAUNCH(4, 3);
+            if (stages == 2) { if (minb == 3) GSB_BWD_LAUNCH(3, 2, 1); else GSB_BWD_LAUNCH(4, 2, 1); }
+            else { if (minb == 3) GSB_BWD_LAUNCH(3, 3, 1); else GSB_BWD_LAUNCH(4, 3, 1); }
         }
 #undef GSB_BWD_LAUNCH
         GSB_LAUNCH_CHECK();

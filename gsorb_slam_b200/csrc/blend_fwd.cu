@@ -23,8 +23,8 @@
 
 namespace gsb {
 
-template <int MINB, int NS>
-__global__ void __launch_bounds__(BLEND_THREADS, MINB)
+template <int MINB, int NS, int HALVES>
+__global__ void __launch_bounds__(256 / HALVES, MINB)
 blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                      const SplatRec* __restrict__ rec, int W, int H, const float* __restrict__ bg,
                      float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ final_T,
@@ -32,16 +32,18 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                      uint32_t* __restrict__ hits_full, uint32_t* __restrict__ hits_tail,
                      GeomHeader* __restrict__ hdr, uint32_t layout_capacity)
 {
-    __shared__ StageBuf<NS> S;
-    __shared__ uint32_t s_max;
-    const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
+    constexpr int BLEND_THREADS = 256 / HALVES, BLEND_BATCH = BLEND_THREADS;
+    __shared__ StageBuf<NS, BLEND_BATCH> S;
+    __shared__ uint32_t s_max[2];
+    const uint32_t tile_y = blockIdx.y / HALVES, half = blockIdx.y % HALVES;
+    const uint32_t tile = tile_y * gridDim.x + blockIdx.x;
     const uint2 range = ranges[tile];
     const int n = (int)(range.y - range.x);
     const int batches = (n + BLEND_BATCH - 1) / BLEND_BATCH;
-    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    // warp -> 8x4 pixel block of the tile; quarter-warp q -> 4x2 sub-block; lane -> pixel
+    // warp (numbered 0..7 over the whole tile) -> 8x4 pixel block of the tile; quarter-warp q -> 4x2 sub-block; lane -> pixel
+    const uint32_t warp = half * (8 / HALVES) + (threadIdx.x >> 5), lane = lane_id();
     const uint32_t q = lane >> 3, l8 = lane & 7, qshift = q * 8;
-    const int bx0 = blockIdx.x * TILE_X + (warp & 1) * 8, by0 = blockIdx.y * TILE_Y + (warp >> 1) * 4;
+    const int bx0 = blockIdx.x * TILE_X + (warp & 1) * 8, by0 = tile_y * TILE_Y + (warp >> 1) * 4;
     const int px = bx0 + (q & 1) * 4 + (l8 & 3), py = by0 + (q >> 1) * 2 + (l8 >> 2);
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
@@ -50,8 +52,8 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     const float xa0 = (float)bx0, xa1 = (float)(bx0 + 3), xb0 = (float)(bx0 + 4), xb1 = (float)(bx0 + 7);
     const float ya0 = (float)by0, ya1 = (float)(by0 + 1), yb0 = (float)(by0 + 2), yb1 = (float)(by0 + 3);
     if (threadIdx.x == 0) {
-        s_max = 0;
-        if (tile == 0) hdr->layout_capacity = layout_capacity;  // the backward pass locates the hit words with it
+        s_max[0] = s_max[1] = 0;
+        if (tile == 0 && half == 0) hdr->layout_capacity = layout_capacity;  // the backward pass locates the hit words with it
     }
 
     bool done = !inside;
@@ -159,9 +161,14 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     uint32_t m = last;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0 && m) atomicMax(&s_max, m);
+    if (lane == 0 && m) atomicMax(&s_max[warp >> 2], m);
     __syncthreads();
-    if (threadIdx.x == 0) tile_max_contrib[tile] = s_max;
+    // highest n_contrib of the upper and of the lower half of the tile (the backward pass starts there)
+    if (HALVES == 2) {
+        if (threadIdx.x == 0) tile_max_contrib[2 * tile + half] = s_max[half];
+    } else {
+        if (threadIdx.x < 2) tile_max_contrib[2 * tile + threadIdx.x] = s_max[threadIdx.x];
+    }
 }
 
 int launch_blend_forward(const FwdParams& p, char* geom, const GeomLayout& GL, char* binning, const BinningLayout& BL,
@@ -169,30 +176,33 @@ int launch_blend_forward(const FwdParams& p, char* geom, const GeomLayout& GL, c
 {
     const uint32_t* point_list = reinterpret_cast<const uint32_t*>(binning + BL.point_list);
     if (p.W <= 0 || p.H <= 0) return GSB_OK;
-    // tuning knobs: resident CTAs per SM the compiler must allow (the register budget) and the depth of the staging ring
-    static const int minb = [] { const char* e = getenv("GSB_BLEND_FWD_MINB"); return e ? atoi(e) : 6; }();
+    // tuning knobs: CTA shape (whole tile / half tile), resident CTAs per SM the compiler must allow (the register
+    // budget), depth of the staging ring
+    static const int halves = [] { const char* e = getenv("GSB_BLEND_FWD_HALVES"); return e ? atoi(e) : 1; }();
+    static const int minb = [] { const char* e = getenv("GSB_BLEND_FWD_MINB"); return e ? atoi(e) : 0; }();
     static const int stages = [] { const char* e = getenv("GSB_BLEND_FWD_STAGES"); return e ? atoi(e) : 2; }();
-    dim3 grid(IL.tiles_x, IL.tiles_y);
     {
         StageTimer _t(ST_BLEND_FWD, s);
-#define GSB_FWD_LAUNCH(MB, NS)                                                                                          \
+#define GSB_FWD_LAUNCH(MB, NS, HV)                                                                                      \
     do {                                                                                                                \
-        static const bool attr_set = [] {  /* several resident CTAs x 24-37 KB: ask for the largest carve-out */      \
-            cudaFuncSetAttribute(blend_forward_kernel<MB, NS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);    \
+        static const bool attr_set = [] {  /* many resident CTAs x 12-37 KB: ask for the largest carve-out */          \
+            cudaFuncSetAttribute(blend_forward_kernel<MB, NS, HV>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
             return true;                                                                                                \
         }();                                                                                                            \
         (void)attr_set;                                                                                                 \
-        blend_forward_kernel<MB, NS><<<grid, BLEND_THREADS, 0, s>>>(                                                    \
+        blend_forward_kernel<MB, NS, HV><<<dim3(IL.tiles_x, IL.tiles_y * HV), 256 / HV, 0, s>>>(                        \
             reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec), \
             p.W, p.H, p.background, out_color, out_depth, reinterpret_cast<float*>(image + IL.final_T),                 \
             reinterpret_cast<uint32_t*>(image + IL.n_contrib), reinterpret_cast<uint32_t*>(image + IL.tile_max_contrib), \
             reinterpret_cast<uint32_t*>(binning + BL.hits), reinterpret_cast<uint32_t*>(image + IL.hits_tail),          \
             reinterpret_cast<GeomHeader*>(geom + GL.header), (uint32_t)BL.capacity);                                    \
     } while (0)
-        if (stages == 3) {
-            if (minb == 4) GSB_FWD_LAUNCH(4, 3); else GSB_FWD_LAUNCH(6, 3);
+        if (halves == 2) {
+            if (stages == 3) { if (minb == 12) GSB_FWD_LAUNCH(12, 3, 2); else GSB_FWD_LAUNCH(16, 3, 2); }
+            else { if (minb == 12) GSB_FWD_LAUNCH(12, 2, 2); else GSB_FWD_LAUNCH(16, 2, 2); }
         } else {
-            if (minb == 4) GSB_FWD_LAUNCH(4, 2); else if (minb == 6) GSB_FWD_LAUNCH(6, 2); else GSB_FWD_LAUNCH(8, 2);
+            if (stages == 3) GSB_FWD_LAUNCH(6, 3, 1);
+            else { if (minb == 8) GSB_FWD_LAUNCH(8, 2, 1); else GSB_FWD_LAUNCH(6, 2, 1); }
         }
 #undef GSB_FWD_LAUNCH
         GSB_LAUNCH_CHECK();

@@ -59,7 +59,8 @@ struct GeomHeader {            // first 256 bytes of the geometry blob (device m
     uint32_t sort_tile_counter[8];  // dynamic tile ids, one per radix pass
     uint32_t visible;          // number of Gaussians with radii > 0 (diagnostics)
     uint32_t layout_capacity;  // capacity the binning blob was laid out for (BinningLayout::make argument)
-    uint32_t pad[64 - 16];
+    uint32_t max_tile_len;     // longest tile list (selects the tile-sort size classes that have work)
+    uint32_t pad[64 - 17];
 };
 // The header is zeroed by the forward before the first kernel; the scan kernel fills it.
 static_assert(sizeof(GeomHeader) == 256, "header is 256 bytes");
@@ -67,7 +68,7 @@ static_assert(sizeof(GeomHeader) == 256, "header is 256 bytes");
 inline __host__ __device__ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct GeomLayout {            // offsets inside the geometry blob
-    size_t header, rec, radii, tiles_touched, clamped, acc, total;
+    size_t header, rec, radii, tiles_touched, ranks, clamped, acc, total;
     int num_blocks;            // preprocess blocks of 256 Gaussians
     __host__ __device__ static GeomLayout make(int P)
     {
@@ -80,6 +81,7 @@ struct GeomLayout {            // offsets inside the geometry blob
         L.rec = take(Pz * sizeof(SplatRec));
         L.radii = take(Pz * 4);
         L.tiles_touched = take(Pz * 4);
+        L.ranks = take(Pz * 16);   // slot of the Gaussian inside each of the (at most 4) tile segments it joins
         L.clamped = take(Pz);
         L.acc = take(Pz * sizeof(GradAcc));
         L.total = off;
@@ -101,11 +103,13 @@ struct ImageLayout {
         L.final_T = take(HW * 4);
         L.n_contrib = take(HW * 4);
         L.ranges = take(T * 8);
-        L.tile_max_contrib = take(T * 4);
+        L.tile_max_contrib = take(T * 8);   // highest n_contrib of the upper / lower half of each tile
         // one counter per TILE_CTR_STRIDE words: adjacent tiles land in different L2 slices, so the
         // ~2 M atomics of a frame are not funnelled through the few slices a dense array maps to
-        L.tile_count = take(T * 4 * TILE_CTR_STRIDE);    // instances per tile (atomics in preprocess)
-        L.tile_cursor = take(T * 4 * TILE_CTR_STRIDE);   // next free slot of each tile's segment (duplicate)
+        // word 0: instances of Gaussians touching <= 4 tiles (their atomics return the slot, kept in GeomLayout::ranks);
+        // word 1: instances of larger Gaussians (slots claimed by `duplicate` through tile_cursor)
+        L.tile_count = take(T * 4 * TILE_CTR_STRIDE);
+        L.tile_cursor = take(T * 4 * TILE_CTR_STRIDE);   // next free slot for the larger Gaussians of each tile
         L.hits_tail = take(T * HIT_BLOCKS * 4);          // hit words of each tile's last, partial window (blend kernels)
         L.total = off;
         return L;

@@ -124,7 +124,7 @@ __device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh,
 // the CTA's tile-count sum (first level of the two-level scan).
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ radii_blob, int* __restrict__ radii_out,
-                  uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ tile_count,
+                  uint32_t* __restrict__ tiles_touched, uint4* __restrict__ ranks, uint32_t* __restrict__ tile_count,
                   uint8_t* __restrict__ clamped_out, int aligned_means, int aligned_scales, int aligned_colors)
 {
     __shared__ __align__(16) float s_mean[PRE_THREADS * 3];
@@ -155,8 +155,25 @@ preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ rad
         if (o.visible) {
             radius = o.radius;
             touched = (o.maxy - o.miny) * (o.maxx - o.minx);
-            for (uint32_t ty = o.miny; ty < o.maxy; ty++)   // per-tile instance counts (first half of the binning)
-                for (uint32_t tx = o.minx; tx < o.maxx; tx++) atomicAdd(&tile_count[(size_t)(ty * (uint32_t)p.tiles_x + tx) * TILE_CTR_STRIDE], 1u);
+            // First half of the binning: per-tile instance counts.  A Gaussian that joins at most four tile
+            // lists (nearly all of them at SLAM splat sizes) keeps the slot each atomic returns, so `duplicate`
+            // places its instances without a second round of atomics; larger ones are only counted here.
+            if (touched <= 4) {
+                uint32_t rk[4] = {0u, 0u, 0u, 0u};
+                uint32_t tx = o.minx, ty = o.miny;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if ((uint32_t)k < touched) {
+                        rk[k] = atomicAdd(&tile_count[(size_t)(ty * (uint32_t)p.tiles_x + tx) * TILE_CTR_STRIDE], 1u);
+                        if (++tx == o.maxx) { tx = o.minx; ty++; }
+                    }
+                }
+                ranks[idx] = make_uint4(rk[0], rk[1], rk[2], rk[3]);
+            } else {
+                for (uint32_t ty = o.miny; ty < o.maxy; ty++)
+                    for (uint32_t tx = o.minx; tx < o.maxx; tx++)
+                        atomicAdd(&tile_count[(size_t)(ty * (uint32_t)p.tiles_x + tx) * TILE_CTR_STRIDE + 1], 1u);
+            }
             float rgb[3];
             uint32_t cl = 0;
             if (p.colors_precomp) {
@@ -211,7 +228,8 @@ int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, char
         StageTimer _t(ST_PREPROCESS, s);
         preprocess_kernel<<<GL.num_blocks, PRE_THREADS, 0, s>>>(
             p, reinterpret_cast<SplatRec*>(geom + GL.rec), reinterpret_cast<int*>(geom + GL.radii), radii_out,
-            reinterpret_cast<uint32_t*>(geom + GL.tiles_touched), reinterpret_cast<uint32_t*>(image + IL.tile_count),
+            reinterpret_cast<uint32_t*>(geom + GL.tiles_touched), reinterpret_cast<uint4*>(geom + GL.ranks),
+            reinterpret_cast<uint32_t*>(image + IL.tile_count),
             reinterpret_cast<uint8_t*>(geom + GL.clamped), al(p.means3D), al(p.scales), al(p.colors_precomp));
         GSB_LAUNCH_CHECK();
     }

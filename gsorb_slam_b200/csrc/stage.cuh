@@ -1,6 +1,6 @@
 // stage.cuh -- shared-memory staging of a tile's splat records for the blend kernels.
 //
-// The blend kernels walk a tile's depth-sorted id list in batches of 256.  For every batch
+// The blend kernels walk a tile's depth-sorted id list in batches of one entry per thread.  For every batch
 // each thread gathers ONE 48-byte SplatRec (three 16-byte asynchronous global->shared
 // copies, LDGSTS, no register staging) into an NS-deep ring of SoA-of-float4 buffers:
 // a[] = {x, y, half2 footprint, power threshold}, b[] = {conic.x, conic.y, conic.z, opacity},
@@ -14,15 +14,15 @@
 
 namespace gsb {
 
-constexpr int BLEND_THREADS = 256;
-constexpr int BLEND_BATCH = 256;
-
-template <int NS>
+// A blend CTA covers a whole 16x16 tile (HALVES = 1: 256 threads) or its upper / lower half
+// (HALVES = 2: 128 threads, twice as many CTAs: finer load balance over the 148 SMs and a
+// barrier that couples 4 warps instead of 8).  The batch size equals the CTA size.
+template <int NS, int BATCH>
 struct StageBuf {
-    float4 a[NS][BLEND_BATCH];
-    float4 b[NS][BLEND_BATCH];
-    float4 c[NS][BLEND_BATCH];
-};  // 12 KB per stage
+    float4 a[NS][BATCH];
+    float4 b[NS][BATCH];
+    float4 c[NS][BATCH];
+};  // 48 B per entry and stage
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 {
@@ -44,8 +44,8 @@ __device__ __forceinline__ void cp_async_wait()
 // Issue this thread's gather for one batch (id == 0xffffffff: nothing to fetch).  The caller
 // commits the group -- every thread commits exactly one group per batch so wait_group counts
 // line up.
-template <int NS>
-__device__ __forceinline__ void stage_issue(StageBuf<NS>& S, int buf, const SplatRec* __restrict__ rec, uint32_t id)
+template <int NS, int BATCH>
+__device__ __forceinline__ void stage_issue(StageBuf<NS, BATCH>& S, int buf, const SplatRec* __restrict__ rec, uint32_t id)
 {
     if (id != 0xffffffffu) {
         const SplatRec* r = rec + id;
@@ -53,6 +53,13 @@ __device__ __forceinline__ void stage_issue(StageBuf<NS>& S, int buf, const Spla
         cp_async16(&S.b[buf][threadIdx.x], &r->b);
         cp_async16(&S.c[buf][threadIdx.x], &r->c);
     }
+}
+
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 // Address of the hit word of (window w, block) of a tile whose list is [start, start + len)

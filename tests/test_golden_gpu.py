@@ -84,3 +84,32 @@ def test_long_tile_lists_match_oracle(P, intr):
     np.testing.assert_array_equal(to_np(ims["ranges"]).astype(np.uint32), ob["ranges"])
     np.testing.assert_array_equal(to_np(ims["n_contrib"]).astype(np.uint32), orc.image_state()["n_contrib"])
     assert rel_to_scale(to_np(fr.color), orc.color) <= TOL_IMAGE
+
+
+@pytest.mark.parametrize("P,scale_mul", [(6_000, 1.0), (40_000, 1.0), (3_000, 6.0)])
+def test_depth_ties_and_large_splats_keep_reference_order(P, scale_mul):
+    """Every mean appears three times (exactly equal depths -> the sort's tie rule: ascending Gaussian id) and, with
+    scale_mul 6, most Gaussians touch more than four tiles (the cursor-claimed tail of the tile segments).  The
+    sorted instance list, ranges and n_contrib must equal the CPU oracle's (= the reference's stable radix order)."""
+    from gsorb_slam_b200.lowlevel import frame_from_scene
+    from gsorb_slam_b200.scene import make_scene
+    from oracle import gs_oracle
+    sc = make_scene(P, (160, 120, 130.0, 128.0), seed=3, scale_mul=scale_mul)
+    third = P // 3
+    for k in (1, 2):   # same position, different shape / colour / opacity
+        sc.means3D[k * third:(k + 1) * third] = sc.means3D[:third]
+    # a coarse depth grid on top: many different Gaussians share a depth inside one tile
+    sc.means3D[:, 2] = np.where(sc.means3D[:, 2] > 0.2, np.round(sc.means3D[:, 2] * 8) / 8 + 0.25, sc.means3D[:, 2]).astype(np.float32)
+    fr = frame_from_scene(sc)
+    g = fr.backward(sc.dL_dpix)
+    orc = gs_oracle.frame_from_scene(sc)
+    go = orc.backward(sc.dL_dpix)
+    ob = orc.binning()
+    assert fr.rendered() == orc.num_rendered
+    np.testing.assert_array_equal(to_np(fr.binning_state()["point_list"]).astype(np.uint32), ob["point_list"])
+    ims = fr.image_state()
+    np.testing.assert_array_equal(to_np(ims["ranges"]).astype(np.uint32), ob["ranges"])
+    np.testing.assert_array_equal(to_np(ims["n_contrib"]).astype(np.uint32), orc.image_state()["n_contrib"])
+    assert rel_to_scale(to_np(fr.color), orc.color) <= TOL_IMAGE
+    for k in ("dL_dmean3D", "dL_dscale", "dL_drot", "dL_dopacity", "dL_dcolor"):
+        assert rel_to_scale(to_np(g[k]), go[k].reshape(to_np(g[k]).shape)) <= TOL_GRAD, k
