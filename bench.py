@@ -153,7 +153,20 @@ def run_ours(args):
     dL = torch.from_numpy(sc.dL_dpix).to(dev)
     # packed gradient block [14, P]: means3D 3 | colour 3 | opacity 1 | scale 3 | rotation 4 -- the block the
     # all-reduce (and Adam) consume; the remaining reference outputs go to side buffers.
-    block = torch.empty(14 * P, dtype=torch.float32, device=dev)
+    # N > 1: the block lives in a symmetric (peer-mapped) allocation and the exchange step is ONE libgsb kernel
+    # (csrc/exchange.cu: NVSwitch multicast reduce for >= 4 ranks, peer loads/stores for 2); NCCL only as a fallback.
+    xch, xch_kind, use_mc = None, "none", False
+    if world > 1 and args.exchange != "nccl":
+        try:
+            from gsorb_slam_b200.distributed import SymmetricExchange
+            xch = SymmetricExchange(14 * P, dev)
+            use_mc = bool(xch.multicast_ptr) and (args.exchange == "multimem" or (args.exchange == "auto" and world >= 4))
+            xch_kind = "libgsb multimem (NVSwitch in-switch reduce)" if use_mc else "libgsb P2P (peer loads/stores over NVLink)"
+        except Exception as e:   # no symmetric memory on this box
+            xch, xch_kind = None, f"NCCL all-reduce (symmetric memory unavailable: {type(e).__name__})"
+    elif world > 1:
+        xch_kind = "NCCL all-reduce"
+    block = xch.alloc(14 * P) if xch is not None else torch.empty(14 * P, dtype=torch.float32, device=dev)
     side = torch.empty(13 * P, dtype=torch.float32, device=dev)
     g = _lib.GradOutputs()
     bp, sp = block.data_ptr(), side.data_ptr()
@@ -169,7 +182,10 @@ def run_ours(args):
         _lib.check(L.gsb_backward(C.byref(fr._args), -1, fr.radii.data_ptr(), fr.geom.data_ptr(), fr.binning.data_ptr(),
                                   fr.img.data_ptr(), dL.data_ptr(), C.byref(g), stream))
         if world > 1:
-            dist.all_reduce(block)
+            if xch is not None:
+                xch.allreduce(block, use_multicast=use_mc)
+            else:
+                dist.all_reduce(block)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -215,7 +231,7 @@ def run_ours(args):
         L.gsb_profile_end(sms, scn)
         if rank == 0:
             st = {L.gsb_stage_name(i).decode(): round(sms[i] / args.steps * 1000, 1) for i in range(ns) if scn[i]}
-            print(json.dumps({"quick": True, "value": value, "ms_per_step": ms_per_step, "stages_us": st,
+            print(json.dumps({"quick": True, "n_gpus": world, "exchange": xch_kind, "value": value, "ms_per_step": ms_per_step, "stages_us": st,
                               "env": {k: v for k, v in os.environ.items() if k.startswith("GSB_")}}), flush=True)
         if world > 1:
             dist.destroy_process_group()
@@ -300,7 +316,7 @@ def run_ours(args):
                 "config": {"workload": f"{args.workload}: {P} Gaussians {W}x{H}, RGB pass fwd+bwd, seed 0 (SLAM-like init, scene.py)",
                            "frames_per_step_per_gpu": 1, "num_rendered": R, "visible": V,
                            "l2": "flushed between steps (512 MiB memset, outside the event brackets)",
-                           "parallelism": "single GPU" if world == 1 else f"keyframe-batch shard x{world} + NCCL all-reduce of the [14,P] gradient block"},
+                           "parallelism": "single GPU" if world == 1 else f"keyframe-batch shard x{world} + one sum all-reduce of the [14,P] gradient block: {xch_kind}"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
                         "steps": e2e_steps, "finite": e2e_ok,
                         "api": "gsb_forward_backward_host (pinned host buffers)"},
@@ -437,6 +453,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline_1m")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "p2p", "multimem"], help="N > 1: how the gradient block is all-reduced")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="developer mode: value + per-stage times only (no e2e / cpu legs)")
     args = ap.parse_args()

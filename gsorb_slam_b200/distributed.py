@@ -31,11 +31,16 @@ BLOCK_ROWS = sum(w for _, w in GROUPS)  # 14
 
 
 class GradBlock:
-    """One contiguous ``[14 * P]`` fp32 buffer with a ``[P, w]`` view per parameter group."""
+    """One contiguous ``[14 * P]`` fp32 buffer with a ``[P, w]`` view per parameter group.
+    ``storage`` lets the caller place it in a symmetric allocation (``SymmetricExchange.alloc``)."""
 
-    def __init__(self, P: int, device, dtype=torch.float32):
+    def __init__(self, P: int, device, dtype=torch.float32, storage: Optional[torch.Tensor] = None):
         self.P = int(P)
-        self.flat = torch.zeros(BLOCK_ROWS * self.P, dtype=dtype, device=device)
+        if storage is None:
+            storage = torch.zeros(BLOCK_ROWS * self.P, dtype=dtype, device=device)
+        if storage.numel() < BLOCK_ROWS * self.P or storage.dtype != dtype:
+            raise ValueError("storage too small for the gradient block")
+        self.flat = storage[:BLOCK_ROWS * self.P]
         self.views: Dict[str, torch.Tensor] = {}
         off = 0
         for name, w in GROUPS:
@@ -53,6 +58,61 @@ def world() -> Tuple[int, int]:
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
+
+
+class SymmetricExchange:
+    """The exchange step as ONE libgsb kernel over NVLink / NVSwitch peer memory
+    (``gsb_exchange_allreduce``, csrc/exchange.cu) instead of an NCCL call.
+
+    ``alloc(n)`` returns an fp32 tensor inside a symmetric allocation (same offset on every rank,
+    peer-mapped by ``torch.distributed._symmetric_memory``; the NVSwitch multicast mapping is used
+    when the box offers one); ``allreduce(t)`` sums it in place across the ranks on the current
+    stream.  All ranks must create the object and call its methods in the same order.
+    Raises if symmetric memory is unavailable -- callers fall back to ``allreduce_gradients``."""
+
+    def __init__(self, capacity_floats: int, device, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._C, self._lib, self.L = C, _lib, _lib.lib()
+        self.rank, self.world = world()
+        if self.world < 2:
+            raise RuntimeError("SymmetricExchange needs an initialised process group with world size >= 2")
+        self.group = group if group is not None else dist.group.WORLD
+        self.dev = torch.device(device)
+        self.capacity = (int(capacity_floats) + 3) // 4 * 4
+        sync_words = int(self.L.gsb_exchange_sync_bytes(self.world)) // 4
+        # one symmetric allocation: [data | handshake scratch]
+        self.buf = symm_mem.empty(self.capacity + sync_words, dtype=torch.float32, device=self.dev)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group=self.group)
+        base = [int(p) for p in self.hdl.buffer_ptrs]
+        self._peer = (C.c_void_p * self.world)(*base)
+        self._sync = (C.c_void_p * self.world)(*[p + 4 * self.capacity for p in base])
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        self.multicast_ptr = mc
+        self._used = 0
+        torch.cuda.synchronize(self.dev)
+        dist.barrier(group=self.group)   # every rank's scratch is zeroed before anyone handshakes
+
+    def alloc(self, n: int) -> torch.Tensor:
+        n4 = (int(n) + 3) // 4 * 4
+        if self._used + n4 > self.capacity:
+            raise RuntimeError("symmetric allocation exhausted")
+        t = self.buf[self._used:self._used + int(n)]
+        self._used += n4
+        return t
+
+    def allreduce(self, t: torch.Tensor, use_multicast: bool = True):
+        """In-place sum over the ranks of a tensor obtained from ``alloc`` (numel % 4 == 0)."""
+        C = self._C
+        off = t.data_ptr() - self.buf.data_ptr()
+        if off < 0 or off + t.numel() * 4 > self.capacity * 4 or t.numel() % 4:
+            raise ValueError("tensor is not a 16-byte-granular slice of the symmetric allocation")
+        peer = (C.c_void_p * self.world)(*[int(p) + off for p in self.hdl.buffer_ptrs])
+        mc = self.multicast_ptr + off if (self.multicast_ptr and use_multicast) else None
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        self._lib.check(self.L.gsb_exchange_allreduce(mc, peer, self._sync, t.numel(), self.rank, self.world, stream))
 
 
 def allreduce_gradients(block: GradBlock, average: bool = False, group=None, async_op: bool = False):

@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from ._lib import GradOutputs, RasterArgs
-from .distributed import GROUPS, GradBlock, allreduce_gradients
+from .distributed import BLOCK_ROWS, GROUPS, GradBlock, SymmetricExchange, allreduce_gradients, world
 
 # Examples/RGB-D/replica.yaml:95-99 (Mapping.lrs*)
 DEFAULT_LR = {"means": 1e-4, "rgb": 2.5e-3, "quats": 1e-3, "opacity": 0.05, "scales": 1e-3}
@@ -39,7 +39,15 @@ class MapOptimizer:
         self.params["means"].copy_(t(means)); self.params["rgb"].copy_(t(rgb))
         self.params["opacity"].copy_(t(logit_opacities).reshape(P, 1)); self.params["scales"].copy_(t(log_scales))
         self.params["quats"].copy_(t(unnorm_quats))
-        self.grads = GradBlock(P, d)
+        # world size > 1: the gradient block lives in a symmetric allocation and is all-reduced by ONE libgsb kernel
+        # over NVLink (distributed.SymmetricExchange); NCCL only if peer mapping is unavailable
+        self.exchange = None
+        if world()[1] > 1 and self.dev.type == "cuda":
+            try:
+                self.exchange = SymmetricExchange(BLOCK_ROWS * P, d)
+            except Exception:
+                self.exchange = None
+        self.grads = GradBlock(P, d, storage=self.exchange.alloc(BLOCK_ROWS * P) if self.exchange else None)
         self.exp_avg, self.exp_avg_sq = GradBlock(P, d), GradBlock(P, d)
         self.lr = dict(DEFAULT_LR if lr is None else lr)
         self.betas, self.eps, self.t = betas, float(eps), 0
@@ -117,6 +125,11 @@ class MapOptimizer:
         """One optimisation step on this rank's keyframe.  ``loss_grad(color, depth) -> dL/dcolor``."""
         color, depth, _ = self.render(Tcw)
         self.backward(loss_grad(color, depth))
-        allreduce_gradients(self.grads, average=average)
+        if self.exchange is not None:
+            self.exchange.allreduce(self.grads.flat, use_multicast=world()[1] >= 4)
+            if average:
+                self.grads.flat.mul_(1.0 / world()[1])
+        else:
+            allreduce_gradients(self.grads, average=average)
         self.adam()
         return color

@@ -202,6 +202,24 @@ int gsb_adam_step(long long n, float* param, const float* grad, float* exp_avg, 
                   float lr, float beta1, float beta2, float eps, long long step,
                   gsb_stream_t stream);
 
+/* ---- multi-GPU exchange step (the reference is single-GPU) ----------------------
+ * In-place SUM all-reduce of n fp32 values (n % 4 == 0) that live at the same offset of a
+ * symmetric, peer-mapped allocation on every rank of one NVLink / NVSwitch box -- the packed
+ * [14, P] gradient block between loss.backward() and the Adam step (src/Render.cc:471-475).
+ * ONE kernel per rank: pairwise cross-rank barrier, reduce this rank's 1/world slice
+ * (multimem.ld_reduce through the NVSwitch multicast mapping when multicast_ptr != NULL, else
+ * 128-bit peer loads in rank order), publish it to every rank (multimem.st / peer stores), system
+ * fence, barrier.  All ranks end up bit-identical.  Every rank must call it in the same order.
+ *   peer_ptrs: HOST array of `world` DEVICE pointers -- this rank's mapping of every rank's buffer
+ *              (its own at index `rank`), each 16-byte aligned;
+ *   sync_ptrs: HOST array of `world` DEVICE pointers to a symmetric scratch of
+ *              gsb_exchange_sync_bytes(world) bytes per rank, zeroed ONCE when it is allocated.
+ * world == 1 is a no-op.  The mappings come from the caller (CUDA VMM / IPC; the Python host side
+ * uses torch.distributed._symmetric_memory). */
+size_t gsb_exchange_sync_bytes(int world);
+int gsb_exchange_allreduce(void* multicast_ptr, void* const* peer_ptrs, void* const* sync_ptrs,
+                           long long n, int rank, int world, gsb_stream_t stream);
+
 /* ---- host-buffer convenience (bench "e2e" leg and quick integration tests) -------------
  * One forward + backward with every array in HOST memory (pinned recommended): copies the
  * inputs H2D, runs gsb_forward_ws + gsb_backward, copies colour/depth/radii and the

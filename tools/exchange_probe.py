@@ -1,0 +1,37 @@
+"""torchrun probe: gsb_exchange_allreduce (multimem and P2P variants) vs NCCL all_reduce -- values and device time."""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gsorb_slam_b200.distributed import SymmetricExchange
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local); dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+n = 14 * 1_000_000
+X = SymmetricExchange(n, dev)
+blk = X.alloc(n)
+g = torch.Generator(device=dev); g.manual_seed(100 + rank)
+src = torch.randn(n, device=dev, generator=g)
+ref = src.clone(); dist.all_reduce(ref)
+out = {}
+for name, mc in (("multimem", True), ("p2p", False)):
+    if mc and not X.multicast_ptr:
+        if rank == 0: print("no multicast mapping on this box")
+        continue
+    blk.copy_(src); X.allreduce(blk, use_multicast=mc); torch.cuda.synchronize()
+    err = float((blk - ref).abs().max()); same = torch.empty(1, device=dev); 
+    chk = blk.double().sum().reshape(1); lst = [torch.empty_like(chk) for _ in range(world)]; dist.all_gather(lst, chk)
+    ident = all(float(x) == float(lst[0]) for x in lst)
+    ts = []
+    for it in range(15):
+        blk.copy_(src); a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); X.allreduce(blk, use_multicast=mc); b.record(); torch.cuda.synchronize()
+        if it >= 5: ts.append(a.elapsed_time(b))
+    t = torch.tensor([sum(ts) / len(ts)], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0: print(f"{name}: max|err| vs NCCL {err:.3e}, identical across ranks {ident}, {float(t)*1000:.1f} us (max over ranks)")
+ts = []
+for it in range(15):
+    ref.copy_(src); a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); dist.all_reduce(ref); b.record(); torch.cuda.synchronize()
+    if it >= 5: ts.append(a.elapsed_time(b))
+t = torch.tensor([sum(ts) / len(ts)], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+if rank == 0: print(f"nccl: {float(t)*1000:.1f} us")
+dist.destroy_process_group()
