@@ -393,13 +393,25 @@ long long gsb_forward_backward_host(const gsb_raster_args* host_args, long long 
     if (!device_scratch || device_scratch_bytes < L.total)
         return fail(GSB_ERR_WORKSPACE, "device scratch too small (%zu < %zu)", device_scratch_bytes, L.total);
     cudaStream_t s = (cudaStream_t)stream;
+    // A second, per-thread cached stream carries the transfers that can overlap kernels: the upload of dL/dpixel
+    // (needed only by the backward) runs under the forward pass, the download of image / depth / radii under the
+    // backward pass.  PCIe is full duplex and the two directions use different copy engines.
+    static thread_local cudaStream_t s2 = nullptr;
+    static thread_local cudaEvent_t ev_dl = nullptr, ev_fwd = nullptr, ev_img = nullptr;
+    if (!s2) {
+        GSB_CUDA_CHECK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+        GSB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_dl, cudaEventDisableTiming));
+        GSB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fwd, cudaEventDisableTiming));
+        GSB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_img, cudaEventDisableTiming));
+    }
     char* d = (char*)device_scratch;
     const size_t Pz = (size_t)P, HW = (size_t)W * H;
-    auto up = [&](size_t off, const void* src, size_t bytes) -> const float* {
+    auto up_on = [&](cudaStream_t st, size_t off, const void* src, size_t bytes) -> const float* {
         if (!src || !bytes) return nullptr;
-        cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, st);
         return reinterpret_cast<const float*>(d + off);
     };
+    auto up = [&](size_t off, const void* src, size_t bytes) { return up_on(s, off, src, bytes); };
     gsb_raster_args a = h;
     a.means3D = up(L.means, h.means3D, Pz * 12);
     a.colors_precomp = up(L.colors, h.colors_precomp, Pz * 12);
@@ -412,7 +424,10 @@ long long gsb_forward_backward_host(const gsb_raster_args* host_args, long long 
     a.viewmatrix = up(L.view, h.viewmatrix, 64);
     a.projmatrix = up(L.proj, h.projmatrix, 64);
     a.cam_pos = up(L.campos, h.cam_pos, 12);
-    const float* dpix = dL_dpix_host ? up(L.dpix, dL_dpix_host, HW * 12) : nullptr;
+    GSB_CUDA_CHECK(cudaEventRecord(ev_fwd, s));       // s2 must not start before earlier work on `stream` (scratch reuse)
+    GSB_CUDA_CHECK(cudaStreamWaitEvent(s2, ev_fwd, 0));
+    const float* dpix = dL_dpix_host ? up_on(s2, L.dpix, dL_dpix_host, HW * 12) : nullptr;
+    GSB_CUDA_CHECK(cudaEventRecord(ev_dl, s2));
     GSB_CUDA_CHECK(cudaGetLastError());
     float* oc = reinterpret_cast<float*>(d + L.out_color);
     float* od = reinterpret_cast<float*>(d + L.out_depth);
@@ -420,9 +435,12 @@ long long gsb_forward_backward_host(const gsb_raster_args* host_args, long long 
     if (int rc = gsb_forward_ws(&a, d + L.geom, L.GL.total, d + L.binning, L.BL.total, max_rendered, d + L.image, L.IL.total, oc,
                                 od, rd, stream))
         return rc;
-    if (out_color_host) GSB_CUDA_CHECK(cudaMemcpyAsync(out_color_host, oc, HW * 12, cudaMemcpyDeviceToHost, s));
-    if (out_depth_host) GSB_CUDA_CHECK(cudaMemcpyAsync(out_depth_host, od, HW * 4, cudaMemcpyDeviceToHost, s));
-    if (radii_host && P) GSB_CUDA_CHECK(cudaMemcpyAsync(radii_host, rd, Pz * 4, cudaMemcpyDeviceToHost, s));
+    GSB_CUDA_CHECK(cudaEventRecord(ev_fwd, s));
+    GSB_CUDA_CHECK(cudaStreamWaitEvent(s2, ev_fwd, 0));
+    if (out_color_host) GSB_CUDA_CHECK(cudaMemcpyAsync(out_color_host, oc, HW * 12, cudaMemcpyDeviceToHost, s2));
+    if (out_depth_host) GSB_CUDA_CHECK(cudaMemcpyAsync(out_depth_host, od, HW * 4, cudaMemcpyDeviceToHost, s2));
+    if (radii_host && P) GSB_CUDA_CHECK(cudaMemcpyAsync(radii_host, rd, Pz * 4, cudaMemcpyDeviceToHost, s2));
+    GSB_CUDA_CHECK(cudaEventRecord(ev_img, s2));
     if (dpix && host_grads) {
         gsb_grad_outputs g;
         auto dev = [&](size_t off, const float* host) { return host ? reinterpret_cast<float*>(d + off) : nullptr; };
@@ -431,6 +449,7 @@ long long gsb_forward_backward_host(const gsb_raster_args* host_args, long long 
         g.dL_dmean3D = dev(L.g_mean3D, host_grads->dL_dmean3D); g.dL_dcov3D = dev(L.g_cov3D, host_grads->dL_dcov3D);
         g.dL_dsh = M ? dev(L.g_sh, host_grads->dL_dsh) : nullptr; g.dL_dscale = a.scales ? dev(L.g_scale, host_grads->dL_dscale) : nullptr;
         g.dL_drot = a.rotations ? dev(L.g_rot, host_grads->dL_drot) : nullptr;
+        GSB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_dl, 0));
         if (int rc = gsb_backward(&a, -1, rd, d + L.geom, d + L.binning, d + L.image, dpix, &g, stream)) return rc;
         auto down = [&](float* host, const float* devp, size_t bytes) {
             if (host && devp && bytes) cudaMemcpyAsync(host, devp, bytes, cudaMemcpyDeviceToHost, s);
@@ -442,6 +461,7 @@ long long gsb_forward_backward_host(const gsb_raster_args* host_args, long long 
         down(host_grads->dL_drot, g.dL_drot, Pz * 16);
         GSB_CUDA_CHECK(cudaGetLastError());
     }
+    GSB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_img, 0));   // `stream` completes only after the side stream's downloads
     return gsb_num_rendered(d + L.geom, stream);
 }
 
