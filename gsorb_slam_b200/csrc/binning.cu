@@ -101,16 +101,19 @@ duplicate_kernel(int P, const SplatRec* __restrict__ rec, const int* __restrict_
 {
     const int idx = blockIdx.x * DUP_THREADS + threadIdx.x;
     if (idx >= P) return;
+    // every load that depends only on idx is issued before the first use (the kernel is one long latency chain otherwise);
+    // records / ranks of culled Gaussians are stale bytes inside the blob: harmless to read, never used
     const int radius = radii[idx];
-    if (radius <= 0) return;
-    const uint32_t cap = hdr->num_rendered_clamped;
     const float4 a = rec[idx].a;
-    const uint64_t record = ((uint64_t)__float_as_uint(rec[idx].c.w) << 32) | (uint32_t)idx;
+    const float depth = rec[idx].c.w;
+    const uint4 rk4 = ranks[idx];
+    const uint32_t cap = hdr->num_rendered_clamped;
+    if (radius <= 0) return;
+    const uint64_t record = ((uint64_t)__float_as_uint(depth) << 32) | (uint32_t)idx;
     uint32_t minx, miny, maxx, maxy;
     get_rect(a.x, a.y, radius, tiles_x, tiles_y, minx, miny, maxx, maxy);
     const uint32_t touched = (maxx - minx) * (maxy - miny);
     if (touched <= 4) {
-        const uint4 rk4 = ranks[idx];
         const uint32_t rk[4] = {rk4.x, rk4.y, rk4.z, rk4.w};
         uint32_t tx = minx, ty = miny;
 #pragma unroll

@@ -6,6 +6,7 @@
 // being stored by the forward pass (24 B/Gaussian less state), and every gradient array is
 // fully written (zeros for Gaussians that were not rendered), so the caller does not have
 // to zero-fill 108 B/Gaussian first (src/Rasterizer.cu:253-261).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace gsb {
@@ -79,7 +80,8 @@ __device__ __forceinline__ void sh_backward(int deg, int M, const float* __restr
     dmz += (-ox * oz * ddir[0] - oy * oz * ddir[1] + (sum2 - oz * oz) * ddir[2]) * invsum32;
 }
 
-__global__ void __launch_bounds__(GB_THREADS)
+template <int MINB>
+__global__ void __launch_bounds__(GB_THREADS, MINB)
 gauss_backward_kernel(GaussBwdParams q)
 {
     const int idx = blockIdx.x * GB_THREADS + threadIdx.x;
@@ -87,23 +89,34 @@ gauss_backward_kernel(GaussBwdParams q)
     if (idx >= p.P) return;
     const size_t i = (size_t)idx;
     const gsb_grad_outputs& g = q.g;
-    const bool rendered = q.radii[idx] > 0;
+    // every load that depends only on idx is issued up front, whether or not the Gaussian was rendered: the
+    // kernel is bound by memory latency, and a dependent chain radii -> accumulators -> parameters triples it
+    const int radius_ld = q.radii[idx];
+    const float4* ap = reinterpret_cast<const float4*>(q.acc + i * 12);
+    const float4 a0 = ap[0], a1 = ap[1];
+    const float a8 = q.acc[i * 12 + 8];
+    const float4 rb = q.rec[i].b;  // conic.x, conic.y, conic.z, opacity (stale bytes when not rendered: never used then)
+    const float mx = p.means3D[3 * i], my = p.means3D[3 * i + 1], mz = p.means3D[3 * i + 2];
+    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    if (!p.cov3D_precomp) {
+        qv = *reinterpret_cast<const float4*>(p.rotations + 4 * i);
+        s0 = p.scales[3 * i]; s1 = p.scales[3 * i + 1]; s2 = p.scales[3 * i + 2];
+    }
+    const bool rendered = radius_ld > 0;
     // packed sums from the blend backward -> reference-layout 2D gradients (backward.cu:536-554):
     //   dL/dmean2D = -0.5 W o (A X + B Y), -0.5 H o (C Y + B X);  dL/dconic = -0.5 o (XX, XY, YY);  dL/dopacity = U
     float a[9];
     if (rendered) {
-        const float4* ap = reinterpret_cast<const float4*>(q.acc + i * 12);
-        const float4 a0 = ap[0], a1 = ap[1];
-        const float4 cb = q.rec[i].b;  // conic.x, conic.y, conic.z, opacity
         const float X = a0.x, Y = a0.y, XX = a0.z, XY = a0.w, YY = a1.x, U = a1.y;
-        a[0] = -0.5f * p.W * cb.w * (cb.x * X + cb.y * Y);
-        a[1] = -0.5f * p.H * cb.w * (cb.z * Y + cb.y * X);
-        a[2] = -0.5f * cb.w * XX;
-        a[3] = -0.5f * cb.w * XY;
-        a[4] = -0.5f * cb.w * YY;
+        a[0] = -0.5f * p.W * rb.w * (rb.x * X + rb.y * Y);
+        a[1] = -0.5f * p.H * rb.w * (rb.z * Y + rb.y * X);
+        a[2] = -0.5f * rb.w * XX;
+        a[3] = -0.5f * rb.w * XY;
+        a[4] = -0.5f * rb.w * YY;
         a[5] = U;
         a[6] = a1.z; a[7] = a1.w;
-        a[8] = q.acc[i * 12 + 8];
+        a[8] = a8;
     } else {
 #pragma unroll
         for (int k = 0; k < 9; k++) a[k] = 0.f;
@@ -117,15 +130,12 @@ gauss_backward_kernel(GaussBwdParams q)
     float dmx = 0.f, dmy = 0.f, dmz = 0.f;
     float dscale[3] = {0.f, 0.f, 0.f}, drot[4] = {0.f, 0.f, 0.f, 0.f};
     if (rendered) {
-        const float mx = p.means3D[3 * i], my = p.means3D[3 * i + 1], mz = p.means3D[3 * i + 2];
         float cov3D[6];
-        float qr = 0.f, qx = 0.f, qy = 0.f, qz = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        const float qr = qv.x, qx = qv.y, qy = qv.z, qz = qv.w;
         if (p.cov3D_precomp) {
 #pragma unroll
             for (int k = 0; k < 6; k++) cov3D[k] = p.cov3D_precomp[6 * i + k];
         } else {
-            qr = p.rotations[4 * i]; qx = p.rotations[4 * i + 1]; qy = p.rotations[4 * i + 2]; qz = p.rotations[4 * i + 3];
-            s0 = p.scales[3 * i]; s1 = p.scales[3 * i + 1]; s2 = p.scales[3 * i + 2];
             compute_cov3d(s0, s1, s2, p.scale_modifier, qr, qx, qy, qz, cov3D);
         }
         // ---- computeCov2DCUDA (backward.cu:144-274) ----
@@ -261,7 +271,11 @@ int launch_gauss_backward(const FwdParams& p, const char* geom, const GeomLayout
     q.g = g;
     {
         StageTimer _t(ST_GAUSS_BWD, s);
-        gauss_backward_kernel<<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(q);
+        // tuning knob: 4 resident CTAs (64 registers, small spill) hide more memory latency than 3 (80 registers)
+        static const int minb = [] { const char* e = getenv("GSB_GAUSS_BWD_MINB"); return e ? atoi(e) : 4; }();
+        if (minb == 3) gauss_backward_kernel<3><<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(q);
+        else if (minb == 5) gauss_backward_kernel<5><<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(q);
+        else gauss_backward_kernel<4><<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(q);
         GSB_LAUNCH_CHECK();
     }
     return GSB_OK;
