@@ -138,5 +138,22 @@ CONFIGS = {
 }
 
 
+def raster_ordered(sc: Scene) -> Scene:
+    """Same map, Gaussians re-ordered tile by tile in raster order -- the memory order a real GSORB-SLAM map has:
+    `Render::InitGaussianPoint` / `AddGaussian` create Gaussians pixel by pixel (src/Render.cc:666-707, 617-655), so
+    neighbours in memory are neighbours on screen.  Exercises same-address contention of the binning atomics."""
+    cam = sc.cam
+    z = np.maximum(sc.means3D[:, 2], 1e-3)
+    u = sc.means3D[:, 0] / z * cam.fx + (cam.width - 1) / 2.0
+    v = sc.means3D[:, 1] / z * cam.fy + (cam.height - 1) / 2.0
+    key = (np.clip(v, -64, cam.height + 64).astype(np.int64) + 64) * (cam.width + 256) + np.clip(u, -64, cam.width + 64).astype(np.int64) + 64
+    order = np.argsort(key, kind="stable")
+    for name in ("means3D", "scales", "rotations", "opacities", "colors", "log_scales", "unnorm_quats", "logit_opacities"):
+        setattr(sc, name, np.ascontiguousarray(getattr(sc, name)[order]))
+    return sc
+
+
 def make_config(name: str, seed: int = 0) -> Scene:
+    if name.endswith("_raster"):
+        return raster_ordered(make_scene(seed=seed, **CONFIGS[name[:-len("_raster")]]))
     return make_scene(seed=seed, **CONFIGS[name])
