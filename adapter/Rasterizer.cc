@@ -220,6 +220,94 @@ torch::autograd::tensor_list _RasterizeGaussians::backward(torch::autograd::Auto
             opt(s[6], g_cov3D), torch::Tensor(), torch::Tensor()};
 }
 
+// ---- fused five-channel pass -------------------------------------------------------------------------
+torch::autograd::tensor_list rasterize_gaussians_fused(torch::Tensor means3D, torch::Tensor colors_precomp,
+                                                       torch::Tensor opacities, torch::Tensor scales, torch::Tensor rotations,
+                                                       GaussianRasterizationSettings raster_settings, bool z_attached)
+{
+    return _RasterizeGaussiansFused::apply(means3D, colors_precomp, opacities, scales, rotations, raster_settings, z_attached);
+}
+
+torch::autograd::tensor_list _RasterizeGaussiansFused::forward(torch::autograd::AutogradContext* ctx, torch::Tensor means3D,
+                                                               torch::Tensor colors_precomp, torch::Tensor opacities,
+                                                               torch::Tensor scales, torch::Tensor rotations,
+                                                               GaussianRasterizationSettings rs, bool z_attached)
+{
+    c10::cuda::CUDAGuard guard(means3D.device());
+    torch::Tensor none;
+    Marshalled m = marshal(rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, none, rs.viewmatrix,
+                           rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, none, 0, rs.camera_center,
+                           rs.prefiltered);
+    const int P = m.a.P, H = rs.image_height, W = rs.image_width;
+    auto fopts = means3D.options().dtype(torch::kFloat32);
+    auto bopts = torch::TensorOptions().dtype(torch::kByte).device(means3D.device());
+    torch::Tensor color = torch::zeros({3, H, W}, fopts), depth_sil = torch::zeros({2, H, W}, fopts);
+    torch::Tensor median = torch::zeros({1, H, W}, fopts), radii = torch::zeros({P}, means3D.options().dtype(torch::kInt32));
+    torch::Tensor geom, binning, img;
+    if (P != 0) {
+        // sync-free entry point over caller workspaces; the instance capacity is grown on overflow (one
+        // synchronisation to read the count, like the reference's cudaMemcpy at rasterizer_impl.cu:285)
+        static thread_local long long capacity_hint = 0;
+        long long cap = std::max<long long>(capacity_hint, 4ll * P + 4096);
+        geom = torch::empty({(long long)gsb_geometry_bytes(P)}, bopts);
+        img = torch::empty({(long long)gsb_image_bytes(W, H)}, bopts);
+        while (true) {
+            binning = torch::empty({(long long)gsb_binning_bytes(cap)}, bopts);
+            check(gsb_forward_fused_ws(&m.a, geom.data_ptr(), geom.numel(), binning.data_ptr(), binning.numel(), cap, img.data_ptr(),
+                                       img.numel(), color.data_ptr<float>(), depth_sil.data_ptr<float>(), median.data_ptr<float>(),
+                                       radii.data_ptr<int>(), stream()));
+            const long long R = gsb_num_rendered(geom.data_ptr(), stream());
+            if (R == GSB_ERR_OVERFLOW) { cap *= 2; continue; }
+            check(R);
+            capacity_hint = std::max(capacity_hint, R + R / 4);
+            break;
+        }
+    }
+    ctx->saved_data["scale_modifier"] = (double)rs.scale_modifier;
+    ctx->saved_data["tanfovx"] = (double)rs.tanfovx;
+    ctx->saved_data["tanfovy"] = (double)rs.tanfovy;
+    ctx->saved_data["z_attached"] = z_attached;
+    ctx->save_for_backward({rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.viewmatrix, rs.projmatrix,
+                            rs.camera_center, geom.defined() ? geom : torch::empty({0}, bopts),
+                            binning.defined() ? binning : torch::empty({0}, bopts), img.defined() ? img : torch::empty({0}, bopts)});
+    ctx->mark_non_differentiable({median, radii});
+    return {color, depth_sil, median, radii};
+}
+
+torch::autograd::tensor_list _RasterizeGaussiansFused::backward(torch::autograd::AutogradContext* ctx,
+                                                                torch::autograd::tensor_list grad_outputs)
+{
+    auto s = ctx->get_saved_variables();
+    const torch::Tensor &bg = s[0], &means3D = s[1], &radii = s[2], &colors = s[3], &scales = s[4], &rotations = s[5];
+    c10::cuda::CUDAGuard guard(means3D.device());
+    const int H = (int)grad_outputs[0].size(1), W = (int)grad_outputs[0].size(2);
+    torch::Tensor none;
+    Marshalled m = marshal(bg, means3D, colors, none, scales, rotations, (float)ctx->saved_data["scale_modifier"].toDouble(), none,
+                           s[6], s[7], (float)ctx->saved_data["tanfovx"].toDouble(), (float)ctx->saved_data["tanfovy"].toDouble(), H, W,
+                           none, 0, s[8], false);
+    const int P = m.a.P;
+    auto fopts = means3D.options().dtype(torch::kFloat32);
+    torch::Tensor g_means3D = torch::zeros({P, 3}, fopts), g_colors = torch::zeros({P, 3}, fopts);
+    torch::Tensor g_opacity = torch::zeros({P, 1}, fopts), g_scales = torch::zeros({P, 3}, fopts), g_rot = torch::zeros({P, 4}, fopts);
+    if (P != 0) {
+        auto dense = [&](const torch::Tensor& g, int ch) {   // an output the loss did not touch has an undefined gradient
+            return g.defined() ? g.to(torch::kFloat32).contiguous() : torch::zeros({ch, H, W}, fopts);
+        };
+        torch::Tensor dC = dense(grad_outputs[0], 3), dD = dense(grad_outputs[1], 2);
+        torch::Tensor side = torch::empty({P, 13}, fopts), g_z = torch::empty({P}, fopts);
+        gsb_grad_outputs g;
+        float* sp = side.data_ptr<float>();
+        g.dL_dmean2D = sp; g.dL_dconic = sp + 3ll * P; g.dL_dcov3D = sp + 7ll * P; g.dL_dsh = nullptr;
+        g.dL_dopacity = g_opacity.data_ptr<float>(); g.dL_dcolor = g_colors.data_ptr<float>();
+        g.dL_dmean3D = g_means3D.data_ptr<float>(); g.dL_dscale = g_scales.data_ptr<float>(); g.dL_drot = g_rot.data_ptr<float>();
+        check(gsb_backward_fused(&m.a, radii.data_ptr<int>(), s[9].data_ptr(), s[10].data_ptr(), s[11].data_ptr(), dC.data_ptr<float>(),
+                                 dD.data_ptr<float>(), &g, g_z.data_ptr<float>(), stream()));
+        if (ctx->saved_data["z_attached"].toBool()) g_means3D.select(1, 2).add_(g_z);
+    }
+    // gradients in the order of forward's arguments; settings / flag get none
+    return {g_means3D, g_colors, g_opacity, g_scales, g_rot, torch::Tensor(), torch::Tensor()};
+}
+
 torch::Tensor distCUDA2(const torch::Tensor& points, torch::Device device)
 {
     c10::cuda::CUDAGuard guard(device);

@@ -110,6 +110,10 @@ public:
         if (((scales.defined() || rotations.defined()) && cov3D_precomp.defined()) ||
             (!scales.defined() && !rotations.defined() && !cov3D_precomp.defined()))
             throw std::invalid_argument("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+        // absent optional inputs travel as 0-element tensors, as in the reference (Rasterizer.cuh:320-334): autograd's
+        // Function::apply needs every tensor argument to have a device
+        auto empty = [&](torch::Tensor& t) { if (!t.defined()) t = torch::empty({0}, means3D.options().requires_grad(false)); };
+        empty(shs); empty(colors_precomp); empty(scales); empty(rotations); empty(cov3D_precomp);
         auto result = rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
                                           device_num, raster_settings_);
         return {result[0], result[1], result[2]};
@@ -124,6 +128,26 @@ public:
 
 public:
     GaussianRasterizationSettings raster_settings_;
+};
+
+// ---- optional fast path (not in the reference): one five-channel pass instead of two ---------------
+// Render::RenderForFrame / RenderStartTraking rasterize the same geometry twice per iteration: colours
+// [r,g,b] and colours [z_cam, 1, 0] (src/Render.cc:445-448, :1068-1071).  rasterize_gaussians_fused
+// returns {color [3,H,W], depth_sil [2,H,W], median_depth [1,H,W], radii [P]} from ONE pass
+// (gsb_forward_fused_ws) with the gradients of both passes summed in ONE backward.  z_attached: the
+// z_cam colour is a function of means3D (mapping mode) -> its gradient is added to d(means3D).z;
+// false reproduces the detached colour of tracking mode (src/Render.cc:957).
+torch::autograd::tensor_list rasterize_gaussians_fused(torch::Tensor means3D, torch::Tensor colors_precomp,
+                                                       torch::Tensor opacities, torch::Tensor scales, torch::Tensor rotations,
+                                                       GaussianRasterizationSettings raster_settings, bool z_attached);
+
+class _RasterizeGaussiansFused : public torch::autograd::Function<_RasterizeGaussiansFused> {
+public:
+    static torch::autograd::tensor_list forward(torch::autograd::AutogradContext* ctx, torch::Tensor means3D,
+                                                torch::Tensor colors_precomp, torch::Tensor opacities, torch::Tensor scales,
+                                                torch::Tensor rotations, GaussianRasterizationSettings settings, bool z_attached);
+    static torch::autograd::tensor_list backward(torch::autograd::AutogradContext* ctx,
+                                                 torch::autograd::tensor_list grad_outputs);
 };
 
 // include/spatial.h: mean squared distance to the 3 nearest neighbours.

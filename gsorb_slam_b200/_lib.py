@@ -43,6 +43,8 @@ SIGNATURES = {
     "gsb_forward_ws": (_i, [C.POINTER(RasterArgs), _vp, _sz, _vp, _sz, _ll, _vp, _sz, _vp, _vp, _vp, _vp]),
     "gsb_num_rendered": (_ll, [_vp, _vp]),
     "gsb_backward": (_i, [C.POINTER(RasterArgs), _ll, _vp, _vp, _vp, _vp, _vp, C.POINTER(GradOutputs), _vp]),
+    "gsb_forward_fused_ws": (_i, [C.POINTER(RasterArgs), _vp, _sz, _vp, _sz, _ll, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "gsb_backward_fused": (_i, [C.POINTER(RasterArgs), _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(GradOutputs), _vp, _vp]),
     "gsb_visible_filter": (_i, [C.POINTER(RasterArgs), _vp, _vp]),
     "gsb_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
     "gsb_knn_workspace_bytes": (_sz, [_i]),

@@ -113,10 +113,10 @@ static int forward_stage1(const FwdParams& p, char* geom, const GeomLayout& GL, 
 
 static int forward_stage2(const FwdParams& p, char* geom, const GeomLayout& GL, char* binning, const BinningLayout& BL,
                           char* image, const ImageLayout& IL, long long grid_instances, float* out_color, float* out_depth,
-                          cudaStream_t s)
+                          float* out_depth_sil, cudaStream_t s)
 {
     if (int rc = launch_binning(p, geom, GL, binning, BL, image, IL, grid_instances, s)) return rc;
-    return launch_blend_forward(p, geom, GL, binning, BL, image, IL, out_color, out_depth, s);
+    return launch_blend_forward(p, geom, GL, binning, BL, image, IL, out_color, out_depth, out_depth_sil, s);
 }
 
 __global__ void unpack_geometry_kernel(int P, const SplatRec* __restrict__ rec, const int* __restrict__ radii,
@@ -223,13 +223,13 @@ int gsb_forward(const gsb_raster_args* args, gsb_alloc_fn geometry_alloc, void* 
     const BinningLayout BL = BinningLayout::make(R);
     char* binning = (char*)binning_alloc(binning_user, BL.total);
     if (!binning) return fail(GSB_ERR_WORKSPACE, "binning allocator returned NULL");
-    if (int rc = forward_stage2(p, geom, GL, binning, BL, image, IL, R, out_color, out_depth, s)) return rc;
+    if (int rc = forward_stage2(p, geom, GL, binning, BL, image, IL, R, out_color, out_depth, nullptr, s)) return rc;
     return (int)R;
 }
 
-int gsb_forward_ws(const gsb_raster_args* args, void* geometry, size_t geometry_bytes, void* binning, size_t binning_bytes,
-                   long long max_rendered, void* image, size_t image_bytes, float* out_color, float* out_depth, int* radii,
-                   gsb_stream_t stream)
+static int forward_ws_impl(const gsb_raster_args* args, void* geometry, size_t geometry_bytes, void* binning, size_t binning_bytes,
+                           long long max_rendered, void* image, size_t image_bytes, float* out_color, float* out_depth,
+                           float* out_depth_sil, int* radii, gsb_stream_t stream)
 {
     if (int rc = validate(args, true)) return rc;
     if (!out_color || !out_depth) return fail(GSB_ERR_INVALID_ARGUMENT, "out_color / out_depth are required");
@@ -243,7 +243,25 @@ int gsb_forward_ws(const gsb_raster_args* args, void* geometry, size_t geometry_
     if (!binning || binning_bytes < BL.total) return fail(GSB_ERR_WORKSPACE, "binning workspace too small (%zu < %zu)", binning_bytes, BL.total);
     cudaStream_t s = (cudaStream_t)stream;
     if (int rc = forward_stage1(p, (char*)geometry, GL, (char*)image, IL, radii, (uint32_t)max_rendered, s)) return rc;
-    return forward_stage2(p, (char*)geometry, GL, (char*)binning, BL, (char*)image, IL, max_rendered, out_color, out_depth, s);
+    return forward_stage2(p, (char*)geometry, GL, (char*)binning, BL, (char*)image, IL, max_rendered, out_color, out_depth,
+                          out_depth_sil, s);
+}
+
+int gsb_forward_ws(const gsb_raster_args* args, void* geometry, size_t geometry_bytes, void* binning, size_t binning_bytes,
+                   long long max_rendered, void* image, size_t image_bytes, float* out_color, float* out_depth, int* radii,
+                   gsb_stream_t stream)
+{
+    return forward_ws_impl(args, geometry, geometry_bytes, binning, binning_bytes, max_rendered, image, image_bytes, out_color,
+                           out_depth, nullptr, radii, stream);
+}
+
+int gsb_forward_fused_ws(const gsb_raster_args* args, void* geometry, size_t geometry_bytes, void* binning, size_t binning_bytes,
+                         long long max_rendered, void* image, size_t image_bytes, float* out_color, float* out_depth_sil,
+                         float* out_median_depth, int* radii, gsb_stream_t stream)
+{
+    if (!out_depth_sil) return fail(GSB_ERR_INVALID_ARGUMENT, "out_depth_sil is required");
+    return forward_ws_impl(args, geometry, geometry_bytes, binning, binning_bytes, max_rendered, image, image_bytes, out_color,
+                           out_median_depth, out_depth_sil, radii, stream);
 }
 
 long long gsb_num_rendered(const void* geometry, gsb_stream_t stream)
@@ -258,21 +276,36 @@ long long gsb_num_rendered(const void* geometry, gsb_stream_t stream)
     return (long long)h.num_rendered;
 }
 
-int gsb_backward(const gsb_raster_args* args, long long R, const int* radii, const void* geometry, const void* binning,
-                 const void* image, const float* dL_dpix, const gsb_grad_outputs* grads, gsb_stream_t stream)
+static int backward_impl(const gsb_raster_args* args, const int* radii, const void* geometry, const void* binning,
+                         const void* image, const float* dL_dpix, const float* dL_ddepth_sil, const gsb_grad_outputs* grads,
+                         float* dL_dzcolor, gsb_stream_t stream)
 {
     if (int rc = validate(args, true, false)) return rc;  // opacities are not an input of the backward (rasterizer.h:55-83)
     if (!geometry || !binning || !image) return fail(GSB_ERR_INVALID_ARGUMENT, "forward state blobs are required");
     if (!dL_dpix || !grads) return fail(GSB_ERR_INVALID_ARGUMENT, "dL_dpix / grads are required");
-    (void)R;  // tile ranges in the image blob already bound every list
     cudaStream_t s = (cudaStream_t)stream;
     const FwdParams p = make_params(args);
     const GeomLayout GL = GeomLayout::make(p.P);
     const ImageLayout IL = ImageLayout::make(p.W, p.H);
     char* geom = (char*)const_cast<void*>(geometry);  // the packed accumulators live in the blob
-    if (int rc = launch_blend_backward(p, geom, GL, (const char*)binning, (const char*)image, IL, dL_dpix, s))
+    if (int rc = launch_blend_backward(p, geom, GL, (const char*)binning, (const char*)image, IL, dL_dpix, dL_ddepth_sil, s))
         return rc;
-    return launch_gauss_backward(p, geom, GL, radii, *grads, s);
+    return launch_gauss_backward(p, geom, GL, radii, *grads, dL_dzcolor, s);
+}
+
+int gsb_backward(const gsb_raster_args* args, long long R, const int* radii, const void* geometry, const void* binning,
+                 const void* image, const float* dL_dpix, const gsb_grad_outputs* grads, gsb_stream_t stream)
+{
+    (void)R;  // tile ranges in the image blob already bound every list
+    return backward_impl(args, radii, geometry, binning, image, dL_dpix, nullptr, grads, nullptr, stream);
+}
+
+int gsb_backward_fused(const gsb_raster_args* args, const int* radii, const void* geometry, const void* binning,
+                       const void* image, const float* dL_dcolor, const float* dL_ddepth_sil, const gsb_grad_outputs* grads,
+                       float* dL_dzcolor, gsb_stream_t stream)
+{
+    if (!dL_ddepth_sil) return fail(GSB_ERR_INVALID_ARGUMENT, "dL_ddepth_sil is required");
+    return backward_impl(args, radii, geometry, binning, image, dL_dcolor, dL_ddepth_sil, grads, dL_dzcolor, stream);
 }
 
 int gsb_visible_filter(const gsb_raster_args* args, int* radii, gsb_stream_t stream)

@@ -33,13 +33,15 @@
 
 namespace gsb {
 
-template <int MINB, int NS, int HALVES>
+// CH = 5: backward of the fused RGB + depth / silhouette pass (see blend_fwd.cu): dL/dalpha sums over five channels,
+// and the gradient of the z_cam colour (sum of w * dL/dpix[3]) lands in accumulator slot 9.
+template <int MINB, int NS, int HALVES, int CH>
 __global__ void __launch_bounds__(256 / HALVES, MINB)
 blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__ binning,
                       const SplatRec* __restrict__ rec, int W, int H, const float* __restrict__ bg,
                       const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                       const uint32_t* __restrict__ tile_max_contrib, const float* __restrict__ dL_dpix,
-                      float* __restrict__ acc /* [P][12] */, const uint32_t* __restrict__ hits_tail,
+                      const float* __restrict__ dL_ddepth_sil, float* __restrict__ acc /* [P][12] */, const uint32_t* __restrict__ hits_tail,
                       const GeomHeader* __restrict__ hdr)
 {
     constexpr int BLEND_THREADS = 256 / HALVES, BLEND_BATCH = BLEND_THREADS, BLOCKS = HIT_BLOCKS / HALVES;
@@ -75,7 +77,15 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
         d1 = dL_dpix[HW + pix];
         d2 = dL_dpix[2 * HW + pix];
     }
-    const float bg_dot_dpixel = __ldg(bg) * d0 + __ldg(bg + 1) * d1 + __ldg(bg + 2) * d2;
+    float d3 = 0.f, d4 = 0.f;
+    if (CH == 5 && inside) {
+        d3 = dL_ddepth_sil[pix];
+        d4 = dL_ddepth_sil[HW + pix];
+    }
+    float bg_dot_dpixel = __ldg(bg) * d0 + __ldg(bg + 1) * d1 + __ldg(bg + 2) * d2;
+    if (CH == 5) bg_dot_dpixel += __ldg(bg) * d3 + __ldg(bg + 1) * d4;   // the depth pass blends over the same background tensor
+    float ar3 = 0.f, ar4 = 0.f, lc3 = 0.f, lc4 = 0.f;
+    const float d8k = (CH == 5 && (l8 & 4)) ? d3 : d2, d8s = (l8 & 4) ? d2 : d3;   // keep / send factors of sums 8 and 9
     const float dk = (l8 & 4) ? d1 : d0, ds = (l8 & 4) ? d0 : d1;   // stage-1 keep / send factors of the colour sums
     // accumulator slot of the sum lane l8 ends up with (GradAcc layout: {Su dx, Su dy, Su dx^2, Su dxdy, Su dy^2, Su, Sw dr, Sw dg, Sw db})
     const int acc_slot = l8 == 0 ? 0 : l8 == 1 ? 2 : l8 == 2 ? 3 : l8 == 3 ? 6 : l8 == 4 ? 1 : l8 == 5 ? 4 : l8 == 6 ? 5 : 7;
@@ -149,7 +159,14 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
                 const float a0 = fmaf(last_alpha, lc0, om * ar0);           // colour accumulated behind this splat
                 const float a1 = fmaf(last_alpha, lc1, om * ar1);
                 const float a2 = fmaf(last_alpha, lc2, om * ar2);
-                float dL_dalpha = Tn * fmaf(Cc.x - a0, d0, fmaf(Cc.y - a1, d1, (Cc.z - a2) * d2));
+                float chan = fmaf(Cc.x - a0, d0, fmaf(Cc.y - a1, d1, (Cc.z - a2) * d2));
+                float a3 = 0.f, a4 = 0.f;
+                if (CH == 5) {
+                    a3 = fmaf(last_alpha, lc3, om * ar3);
+                    a4 = fmaf(last_alpha, lc4, om * ar4);
+                    chan = fmaf(Cc.w - a3, d3, fmaf(1.0f - a4, d4, chan));
+                }
+                float dL_dalpha = Tn * chan;
                 dL_dalpha = fmaf(-T_final * inv, bg_dot_dpixel, dL_dalpha);
                 // raw moments of u = G * dL/dalpha; the conic / opacity / 0.5 W factors are per-Gaussian
                 // constants and are applied once, in gauss_bwd.cu
@@ -159,6 +176,10 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
                     T = Tn;
                     ar0 = a0; ar1 = a1; ar2 = a2;
                     lc0 = Cc.x; lc1 = Cc.y; lc2 = Cc.z;
+                    if (CH == 5) {
+                        ar3 = a3; ar4 = a4;
+                        lc3 = Cc.w; lc4 = 1.0f;
+                    }
                     last_alpha = alpha;
                 }
                 const uint32_t cb = __ballot_sync(0xffffffffu, contrib);
@@ -178,8 +199,9 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
                 float r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 4);
                 float r2 = k2 + __shfl_xor_sync(0xffffffffu, s2, 4);
                 float r3 = k3 + __shfl_xor_sync(0xffffffffu, s3, 4);
-                float v8 = wc * d2;
-                v8 += __shfl_xor_sync(0xffffffffu, v8, 4);
+                // sums 8 (S w d_b) and, with five channels, 9 (S w d_z): lanes 0-3 of the quarter end up with 8, lanes 4-7 with 9
+                float v8 = wc * d8k;
+                v8 += __shfl_xor_sync(0xffffffffu, CH == 5 ? wc * d8s : v8, 4);
                 {
                     const bool hi = l8 & 2;  // keep (r0, r1) on the low pair, (r2, r3) on the high pair
                     const float sa = hi ? r0 : r2, ka = hi ? r2 : r0;
@@ -200,6 +222,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
                     float* dst = acc + (size_t)s_ids[buf][e] * 12;
                     atomicAdd(dst + acc_slot, r0);
                     if (l8 == 0) atomicAdd(dst + 8, v8);
+                    if (CH == 5 && l8 == 4) atomicAdd(dst + 9, v8);
                 }
             }
         }
@@ -209,7 +232,8 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
 }
 
 int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, const char* binning,
-                          const char* image, const ImageLayout& IL, const float* dL_dpix, cudaStream_t s)
+                          const char* image, const ImageLayout& IL, const float* dL_dpix, const float* dL_ddepth_sil,
+                          cudaStream_t s)
 {
     if (p.W <= 0 || p.H <= 0 || p.P <= 0) return GSB_OK;
     GSB_CUDA_CHECK(cudaMemsetAsync(geom + GL.acc, 0, (size_t)p.P * sizeof(GradAcc), s));
@@ -220,21 +244,25 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
     static const int stages = [] { const char* e = getenv("GSB_BLEND_BWD_STAGES"); return e ? atoi(e) : 3; }();
     {
         StageTimer _t(ST_BLEND_BWD, s);
-#define GSB_BWD_LAUNCH(MB, NS, HV)                                                                                          \
+#define GSB_BWD_LAUNCH(MB, NS, HV) GSB_BWD_LAUNCH_CH(MB, NS, HV, 3)
+#define GSB_BWD_LAUNCH_CH(MB, NS, HV, CH)                                                                                          \
     do {                                                                                                                    \
         static const bool attr_set = [] {                                                                                   \
-            cudaFuncSetAttribute(blend_backward_kernel<MB, NS, HV>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   \
+            cudaFuncSetAttribute(blend_backward_kernel<MB, NS, HV, CH>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
             return true;                                                                                                    \
         }();                                                                                                                \
         (void)attr_set;                                                                                                     \
-        blend_backward_kernel<MB, NS, HV><<<dim3(IL.tiles_x, IL.tiles_y * HV), 256 / HV, 0, s>>>(                           \
+        blend_backward_kernel<MB, NS, HV, CH><<<dim3(IL.tiles_x, IL.tiles_y * HV), 256 / HV, 0, s>>>(                       \
             reinterpret_cast<const uint2*>(image + IL.ranges), binning, reinterpret_cast<const SplatRec*>(geom + GL.rec), p.W, \
             p.H, p.background, reinterpret_cast<const float*>(image + IL.final_T),                                          \
             reinterpret_cast<const uint32_t*>(image + IL.n_contrib), reinterpret_cast<const uint32_t*>(image + IL.tile_max_contrib), \
-            dL_dpix, reinterpret_cast<float*>(geom + GL.acc), reinterpret_cast<const uint32_t*>(image + IL.hits_tail),      \
+            dL_dpix, dL_ddepth_sil, reinterpret_cast<float*>(geom + GL.acc),                                               \
+            reinterpret_cast<const uint32_t*>(image + IL.hits_tail),                                                        \
             reinterpret_cast<const GeomHeader*>(geom + GL.header));                                                         \
     } while (0)
-        if (halves == 2) {
+        if (dL_ddepth_sil) {
+            GSB_BWD_LAUNCH_CH(4, 3, 1, 5);
+        } else if (halves == 2) {
             if (stages == 2) { if (minb == 8) GSB_BWD_LAUNCH(8, 2, 2); else if (minb == 10) GSB_BWD_LAUNCH(10, 2, 2); else GSB_BWD_LAUNCH(6, 2, 2); }
             else { if (minb == 8) GSB_BWD_LAUNCH(8, 3, 2); else if (minb == 10) GSB_BWD_LAUNCH(10, 3, 2); else GSB_BWD_LAUNCH(6, 3, 2); }
         } else {
@@ -242,6 +270,7 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
             else { if (minb == 3) GSB_BWD_LAUNCH(3, 3, 1); else GSB_BWD_LAUNCH(4, 3, 1); }
         }
 #undef GSB_BWD_LAUNCH
+#undef GSB_BWD_LAUNCH_CH
         GSB_LAUNCH_CHECK();
     }
     return GSB_OK;

@@ -23,11 +23,15 @@
 
 namespace gsb {
 
-template <int MINB, int NS, int HALVES>
+// CH = 3: the reference pass.  CH = 5: the RGB pass and the depth / silhouette pass of one mapping iteration
+// (src/Render.cc:445-448: colours [r, g, b] and [z_cam, 1, 0] over the SAME geometry) blended together; channel 3
+// accumulates depth * alpha * T, channel 4 alpha * T, with the operation order each has in its own reference pass.
+template <int MINB, int NS, int HALVES, int CH>
 __global__ void __launch_bounds__(256 / HALVES, MINB)
 blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                      const SplatRec* __restrict__ rec, int W, int H, const float* __restrict__ bg,
-                     float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ final_T,
+                     float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_depth_sil,
+                     float* __restrict__ final_T,
                      uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ tile_max_contrib,
                      uint32_t* __restrict__ hits_full, uint32_t* __restrict__ hits_tail,
                      GeomHeader* __restrict__ hdr, uint32_t layout_capacity)
@@ -57,7 +61,7 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     }
 
     bool done = !inside;
-    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, C3 = 0.f, C4 = 0.f, D = 0.f;
     uint32_t last = 0;
 
     const uint32_t* ids = point_list + range.x;
@@ -127,6 +131,10 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                     C0 = fmaf(__fmul_rn(Cc.x, alpha), T, C0);
                     C1 = fmaf(__fmul_rn(Cc.y, alpha), T, C1);
                     C2 = fmaf(__fmul_rn(Cc.z, alpha), T, C2);
+                    if (CH == 5) {
+                        C3 = fmaf(__fmul_rn(Cc.w, alpha), T, C3);   // colour z_cam = the splat's view-space depth
+                        C4 = fmaf(alpha, T, C4);                    // colour 1
+                    }
                     if (T > 0.5f) D = Cc.w;
                     T = test_T;
                     last = (uint32_t)(b * BLEND_BATCH + e + 1);
@@ -157,6 +165,10 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
         out_color[HW + pix] = fmaf(T, __ldg(bg + 1), C1);
         out_color[2 * HW + pix] = fmaf(T, __ldg(bg + 2), C2);
         out_depth[pix] = D;
+        if (CH == 5) {   // the depth pass shares the background tensor: its channels 0 / 1 get bg[0] / bg[1]
+            out_depth_sil[pix] = fmaf(T, __ldg(bg), C3);
+            out_depth_sil[HW + pix] = fmaf(T, __ldg(bg + 1), C4);
+        }
     }
     uint32_t m = last;
 #pragma unroll
@@ -172,7 +184,8 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
 }
 
 int launch_blend_forward(const FwdParams& p, char* geom, const GeomLayout& GL, char* binning, const BinningLayout& BL,
-                         char* image, const ImageLayout& IL, float* out_color, float* out_depth, cudaStream_t s)
+                         char* image, const ImageLayout& IL, float* out_color, float* out_depth, float* out_depth_sil,
+                         cudaStream_t s)
 {
     const uint32_t* point_list = reinterpret_cast<const uint32_t*>(binning + BL.point_list);
     if (p.W <= 0 || p.H <= 0) return GSB_OK;
@@ -183,21 +196,24 @@ int launch_blend_forward(const FwdParams& p, char* geom, const GeomLayout& GL, c
     static const int stages = [] { const char* e = getenv("GSB_BLEND_FWD_STAGES"); return e ? atoi(e) : 2; }();
     {
         StageTimer _t(ST_BLEND_FWD, s);
-#define GSB_FWD_LAUNCH(MB, NS, HV)                                                                                      \
+#define GSB_FWD_LAUNCH(MB, NS, HV) GSB_FWD_LAUNCH_CH(MB, NS, HV, 3)
+#define GSB_FWD_LAUNCH_CH(MB, NS, HV, CH)                                                                                      \
     do {                                                                                                                \
         static const bool attr_set = [] {  /* many resident CTAs x 12-37 KB: ask for the largest carve-out */          \
-            cudaFuncSetAttribute(blend_forward_kernel<MB, NS, HV>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
+            cudaFuncSetAttribute(blend_forward_kernel<MB, NS, HV, CH>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
             return true;                                                                                                \
         }();                                                                                                            \
         (void)attr_set;                                                                                                 \
-        blend_forward_kernel<MB, NS, HV><<<dim3(IL.tiles_x, IL.tiles_y * HV), 256 / HV, 0, s>>>(                        \
+        blend_forward_kernel<MB, NS, HV, CH><<<dim3(IL.tiles_x, IL.tiles_y * HV), 256 / HV, 0, s>>>(                    \
             reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec), \
-            p.W, p.H, p.background, out_color, out_depth, reinterpret_cast<float*>(image + IL.final_T),                 \
+            p.W, p.H, p.background, out_color, out_depth, out_depth_sil, reinterpret_cast<float*>(image + IL.final_T),  \
             reinterpret_cast<uint32_t*>(image + IL.n_contrib), reinterpret_cast<uint32_t*>(image + IL.tile_max_contrib), \
             reinterpret_cast<uint32_t*>(binning + BL.hits), reinterpret_cast<uint32_t*>(image + IL.hits_tail),          \
             reinterpret_cast<GeomHeader*>(geom + GL.header), (uint32_t)BL.capacity);                                    \
     } while (0)
-        if (halves == 2) {
+        if (out_depth_sil) {
+            GSB_FWD_LAUNCH_CH(6, 2, 1, 5);
+        } else if (halves == 2) {
             if (stages == 3) { if (minb == 12) GSB_FWD_LAUNCH(12, 3, 2); else GSB_FWD_LAUNCH(16, 3, 2); }
             else { if (minb == 12) GSB_FWD_LAUNCH(12, 2, 2); else GSB_FWD_LAUNCH(16, 2, 2); }
         } else {
@@ -205,6 +221,7 @@ int launch_blend_forward(const FwdParams& p, char* geom, const GeomLayout& GL, c
             else { if (minb == 8) GSB_FWD_LAUNCH(8, 2, 1); else GSB_FWD_LAUNCH(6, 2, 1); }
         }
 #undef GSB_FWD_LAUNCH
+#undef GSB_FWD_LAUNCH_CH
         GSB_LAUNCH_CHECK();
     }
     return GSB_OK;

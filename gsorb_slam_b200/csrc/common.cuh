@@ -41,7 +41,7 @@ static_assert(sizeof(SplatRec) == 48, "record must be 48 bytes");
 // Packed backward accumulators (one per Gaussian, 48 bytes, fp32 atomics / vector reds):
 //   a = { dL_dmean2D.x, dL_dmean2D.y, dL_dconic.x, dL_dconic.y }
 //   b = { dL_dconic.w, dL_dopacity, dL_dcolor.r, dL_dcolor.g }
-//   c = { dL_dcolor.b, -, -, - }
+//   c = { dL_dcolor.b, dL_dzcolor (fused 5-channel pass only), -, - }
 struct alignas(16) GradAcc {
     float4 a, b, c;
 };
@@ -353,11 +353,13 @@ int launch_sort_pairs(GeomHeader* hdr, uint64_t* const kbuf[2], uint32_t* const 
 int launch_binning(const FwdParams& p, char* geom, const GeomLayout& GL, char* binning, const BinningLayout& BL,
                    char* image, const ImageLayout& IL, long long grid_instances, cudaStream_t s);
 int launch_blend_forward(const FwdParams& p, char* geom, const GeomLayout& GL, char* binning, const BinningLayout& BL,
-                         char* image, const ImageLayout& IL, float* out_color, float* out_depth, cudaStream_t s);
+                         char* image, const ImageLayout& IL, float* out_color, float* out_depth, float* out_depth_sil,
+                         cudaStream_t s);
 int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, const char* binning,
-                          const char* image, const ImageLayout& IL, const float* dL_dpix, cudaStream_t s);
+                          const char* image, const ImageLayout& IL, const float* dL_dpix, const float* dL_ddepth_sil,
+                          cudaStream_t s);
 int launch_gauss_backward(const FwdParams& p, const char* geom, const GeomLayout& GL, const int* radii,
-                          const gsb_grad_outputs& g, cudaStream_t s);
+                          const gsb_grad_outputs& g, float* dL_dzcolor, cudaStream_t s);
 int launch_prologue(int P, const float* Tcw, const float* means_world, const float* logit, const float* quats,
                     const float* log_scales, float* means_cam, float* opac, float* rot, float* scales, cudaStream_t s);
 int launch_prologue_backward(int P, const float* Tcw, const float* means_world, const float* logit, const float* quats,

@@ -20,6 +20,7 @@ struct GaussBwdParams {
     const SplatRec* rec;       // conic + opacity for the moment -> gradient maps
     const uint8_t* clamped;    // SH clamp bits
     gsb_grad_outputs g;
+    float* dL_dzcolor;         // [P] or NULL: gradient of the depth pass' z_cam colour (fused 5-channel pass)
 };
 
 __device__ __forceinline__ void sh_backward(int deg, int M, const float* __restrict__ sh, float* __restrict__ dsh,
@@ -124,6 +125,7 @@ gauss_backward_kernel(GaussBwdParams q)
     if (g.dL_dmean2D) { g.dL_dmean2D[3 * i] = a[0]; g.dL_dmean2D[3 * i + 1] = a[1]; g.dL_dmean2D[3 * i + 2] = 0.f; }
     if (g.dL_dconic) { g.dL_dconic[4 * i] = a[2]; g.dL_dconic[4 * i + 1] = a[3]; g.dL_dconic[4 * i + 2] = 0.f; g.dL_dconic[4 * i + 3] = a[4]; }
     if (g.dL_dopacity) g.dL_dopacity[i] = a[5];
+    if (q.dL_dzcolor) q.dL_dzcolor[i] = rendered ? q.acc[i * 12 + 9] : 0.f;
     if (g.dL_dcolor) { g.dL_dcolor[3 * i] = a[6]; g.dL_dcolor[3 * i + 1] = a[7]; g.dL_dcolor[3 * i + 2] = a[8]; }
 
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -259,7 +261,7 @@ gauss_backward_kernel(GaussBwdParams q)
 }
 
 int launch_gauss_backward(const FwdParams& p, const char* geom, const GeomLayout& GL, const int* radii,
-                          const gsb_grad_outputs& g, cudaStream_t s)
+                          const gsb_grad_outputs& g, float* dL_dzcolor, cudaStream_t s)
 {
     if (p.P <= 0) return GSB_OK;
     GaussBwdParams q;
@@ -269,6 +271,7 @@ int launch_gauss_backward(const FwdParams& p, const char* geom, const GeomLayout
     q.rec = reinterpret_cast<const SplatRec*>(geom + GL.rec);
     q.clamped = reinterpret_cast<const uint8_t*>(geom + GL.clamped);
     q.g = g;
+    q.dL_dzcolor = dL_dzcolor;
     {
         StageTimer _t(ST_GAUSS_BWD, s);
         // tuning knob: 4 resident CTAs (64 registers, small spill) hide more memory latency than 3 (80 registers)

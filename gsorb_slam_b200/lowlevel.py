@@ -35,7 +35,7 @@ def _p(t):
 class Frame:
     def __init__(self, *, width, height, means3D, opacities, background, viewmatrix, projmatrix, tanfovx, tanfovy,
                  colors=None, shs=None, sh_degree=0, scales=None, rotations=None, cov3D=None, scale_modifier=1.0,
-                 campos=None, device="cuda:0", sync_free=False, max_rendered=None, run=True):
+                 campos=None, device="cuda:0", sync_free=False, max_rendered=None, run=True, fused=False):
         self.L = _lib.lib()
         self.device = torch.device(device)
         d = self.device
@@ -51,13 +51,15 @@ class Frame:
         self.view, self.proj = _dev(viewmatrix, d).reshape(16), _dev(projmatrix, d).reshape(16)
         self.campos = _dev(campos if campos is not None else np.zeros(3, np.float32), d)
         self.tanfovx, self.tanfovy, self.scale_modifier = float(tanfovx), float(tanfovy), float(scale_modifier)
-        self.sync_free = bool(sync_free)
+        self.fused = bool(fused)   # five-channel pass: RGB + [z_cam, 1] of the depth pass (gsb_forward_fused_ws)
+        self.sync_free = bool(sync_free) or self.fused
         self.max_rendered = int(max_rendered) if max_rendered is not None else 4 * self.P + 1024
         self.num_rendered = None
         self._args = self._make_args()
         self.color = torch.empty((3, self.H, self.W), dtype=torch.float32, device=d)
         self.depth = torch.empty((1, self.H, self.W), dtype=torch.float32, device=d)
         self.radii = torch.empty((self.P,), dtype=torch.int32, device=d)
+        self.depth_sil = torch.empty((2, self.H, self.W), dtype=torch.float32, device=d) if self.fused else None
         self.geom = self.binning = self.img = None
         self._grads = None
         if run:
@@ -86,7 +88,14 @@ class Frame:
     def forward(self):
         L = self.L
         with torch.cuda.device(self.device):
-            if self.sync_free:
+            if self.fused:
+                self._alloc_ws()
+                _lib.check(L.gsb_forward_fused_ws(C.byref(self._args), self.geom.data_ptr(), self.geom.numel(),
+                                                  self.binning.data_ptr(), self.binning.numel(), self.max_rendered,
+                                                  self.img.data_ptr(), self.img.numel(), self.color.data_ptr(),
+                                                  self.depth_sil.data_ptr(), self.depth.data_ptr(), _p(self.radii), self._stream()))
+                self.num_rendered = None
+            elif self.sync_free:
                 self._alloc_ws()
                 _lib.check(L.gsb_forward_ws(C.byref(self._args), self.geom.data_ptr(), self.geom.numel(),
                                             self.binning.data_ptr(), self.binning.numel(), self.max_rendered,
@@ -124,6 +133,20 @@ class Frame:
                  dL_drot=e(P, 4) if self.rotations is not None else None)
         go = GradOutputs(**{k: _p(v) for k, v in g.items()})
         self._grads = (g, go)
+        return g
+
+    def backward_fused(self, dL_dcolor, dL_ddepth_sil, reuse_outputs=False):
+        """Backward of the five-channel pass: the SUM of the RGB pass' and the depth pass' gradients, plus
+        ``dL_dzcolor`` [P], the gradient of the depth pass' z_cam colour."""
+        if self._grads is None or not reuse_outputs:
+            self.alloc_grads()
+        g, go = self._grads
+        dC, dD = _dev(dL_dcolor, self.device), _dev(dL_ddepth_sil, self.device)
+        g["dL_dzcolor"] = torch.empty(self.P, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.gsb_backward_fused(C.byref(self._args), _p(self.radii), self.geom.data_ptr(), self.binning.data_ptr(),
+                                                 self.img.data_ptr(), dC.data_ptr(), dD.data_ptr(), C.byref(go),
+                                                 g["dL_dzcolor"].data_ptr(), self._stream()))
         return g
 
     def backward(self, dL_dpix, reuse_outputs=False):

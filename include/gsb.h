@@ -154,6 +154,31 @@ int gsb_backward(const gsb_raster_args* args, long long R, const int* radii,
                  const float* dL_dpix, const gsb_grad_outputs* grads,
                  gsb_stream_t stream);
 
+/* ---- fused RGB + depth / silhouette pass (extension) ---------------------
+ * Every optimisation iteration of the reference rasterizes the SAME geometry twice: once with the
+ * Gaussians' colours and once with colours [z_cam, 1, 0] (depth and silhouette; src/Render.cc:445-448,
+ * :949-981), duplicating projection, binning, sort and every alpha evaluation.  These entry points
+ * blend five channels in one pass:
+ *   out_color        [3,H,W]  = the RGB pass' colour output;
+ *   out_depth_sil    [2,H,W]  = channels 0 / 1 of the depth pass (sum z alpha T + T bg[0], sum alpha T + T bg[1]),
+ *                               with z the view-space depth of the Gaussian (= z_cam in the reference's default
+ *                               mode: identity view matrix, pre-transformed means);
+ *   out_median_depth [1,H,W]  = the third output of either pass ("renderedSurdepth");
+ * bit-identical to the two separate passes.  The backward takes dL/d(out_color) and dL/d(out_depth_sil) and
+ * returns the SUM of the two passes' gradients (what autograd accumulates), plus dL_dzcolor [P] (may be NULL):
+ * the gradient of the z_cam colour, which the caller adds to dL/d(mean_cam).z when that colour is attached to
+ * the means (mapping mode; detached in tracking mode, src/Render.cc:957). */
+int gsb_forward_fused_ws(const gsb_raster_args* args,
+                         void* geometry, size_t geometry_bytes,
+                         void* binning, size_t binning_bytes, long long max_rendered,
+                         void* image, size_t image_bytes,
+                         float* out_color, float* out_depth_sil, float* out_median_depth, int* radii,
+                         gsb_stream_t stream);
+int gsb_backward_fused(const gsb_raster_args* args, const int* radii,
+                       const void* geometry, const void* binning, const void* image,
+                       const float* dL_dcolor, const float* dL_ddepth_sil,
+                       const gsb_grad_outputs* grads, float* dL_dzcolor, gsb_stream_t stream);
+
 /* ---- visibility helpers --------------------------------------------------------------*/
 /* Radii-only projection (Rasterizer::visible_filter): radii[P] fully written. */
 int gsb_visible_filter(const gsb_raster_args* args, int* radii, gsb_stream_t stream);

@@ -187,3 +187,118 @@ def test_full_size_digests_match_reference(P):
     np.testing.assert_array_equal(to_np(fr.color).view(np.uint32), c0.view(np.uint32))
     g2 = fr.backward(2.0 * sc.dL_dpix)
     assert rel_to_scale(to_np(g2["dL_dmean3D"]), 2.0 * to_np(g["dL_dmean3D"])) <= 1e-4
+
+
+@pytest.mark.parametrize("cfg", [dict(P=3000, intr=(160, 120, 130.0, 128.0), scale_mul=2.0, background=0.0),
+                                 dict(P=20000, intr=(100, 75, 90.0, 88.0), scale_mul=1.0, background=0.3),
+                                 dict(P=100_000, intr="tum", scale_mul=1.0, background=0.0)])
+def test_fused_five_channel_pass_equals_two_reference_passes(cfg):
+    """gsb_forward_fused_ws / gsb_backward_fused against what Render::RenderForFrame does today (src/Render.cc:445-448):
+    an RGB pass and a second pass over the same geometry with colours [z_cam, 1, 0].  Images bit-identical; the fused
+    gradients equal the sum of the two passes' gradients; dL_dzcolor equals the depth pass' colour gradient, channel 0."""
+    from gsorb_slam_b200.lowlevel import frame_from_scene
+    from gsorb_slam_b200.scene import make_scene
+    sc = make_scene(cfg["P"], cfg["intr"], seed=21, scale_mul=cfg["scale_mul"], background=cfg["background"])
+    H, W = sc.cam.height, sc.cam.width
+    rng = np.random.default_rng(5)
+    dC = sc.dL_dpix
+    dD = (rng.normal(0, 1, (2, H, W)) / (H * W)).astype(np.float32)
+    # the two reference-shaped passes through the plain entry points
+    rgb = frame_from_scene(sc)
+    g_rgb = {k: to_np(v) for k, v in rgb.backward(dC).items() if v is not None}
+    zcol = np.stack([sc.means3D[:, 2], np.ones(sc.P, np.float32), np.zeros(sc.P, np.float32)], 1).astype(np.float32)
+    dep = frame_from_scene(sc, colors=zcol)
+    dD3 = np.concatenate([dD, np.zeros((1, H, W), np.float32)], 0)
+    g_dep = {k: to_np(v) for k, v in dep.backward(dD3).items() if v is not None}
+    # the fused pass
+    fu = frame_from_scene(sc, fused=True)
+    g = {k: to_np(v) for k, v in fu.backward_fused(dC, dD).items() if v is not None}
+    np.testing.assert_array_equal(to_np(fu.color).view(np.uint32), to_np(rgb.color).view(np.uint32))
+    np.testing.assert_array_equal(to_np(fu.depth).view(np.uint32), to_np(rgb.depth).view(np.uint32))
+    np.testing.assert_array_equal(to_np(fu.depth_sil).view(np.uint32), to_np(dep.color)[:2].view(np.uint32))
+    np.testing.assert_array_equal(to_np(fu.radii), to_np(rgb.radii))
+    for k in ("dL_dmean3D", "dL_dscale", "dL_drot", "dL_dopacity", "dL_dmean2D", "dL_dconic", "dL_dcov3D"):
+        want = g_rgb[k] + g_dep[k]
+        assert rel_to_scale(g[k], want) <= 1e-5, k
+    assert rel_to_scale(g["dL_dcolor"], g_rgb["dL_dcolor"]) <= 1e-5
+    assert rel_to_scale(g["dL_dzcolor"], g_dep["dL_dcolor"][:, 0]) <= 1e-5
+
+
+def _adapter():
+    import importlib
+    import sys
+    import torch  # noqa: F401  (libtorch must be loaded first)
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "adapter"))
+    return importlib.import_module("gsb_adapter")
+
+
+def test_libtorch_adapter_drop_in_matches_python_operator():
+    """The C++ drop-in a GSORB-SLAM maintainer compiles (adapter/Rasterizer.{cuh,cc}: GaussianRasterizer::forward /
+    Visable / mark_visible, distCUDA2, autograd through _RasterizeGaussians) against the ctypes path on the same inputs."""
+    import torch
+    from gsorb_slam_b200.lowlevel import frame_from_scene
+    from gsorb_slam_b200.scene import make_scene
+    A = _adapter()
+    sc = make_scene(5000, (160, 120, 130.0, 128.0), seed=8, scale_mul=2.0)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    means = t(sc.means3D).requires_grad_(True)
+    opac, cols = t(sc.opacities)[:, None].requires_grad_(True), t(sc.colors).requires_grad_(True)
+    scales, rots = t(sc.scales).requires_grad_(True), t(sc.rotations).requires_grad_(True)
+    cam = sc.cam
+    common = (cam.height, cam.width, float(cam.tanfovx), float(cam.tanfovy), t(sc.background), 1.0,
+              t(cam.viewmatrix).reshape(4, 4), t(cam.projmatrix).reshape(4, 4))
+    color, radii, depth = A.forward(means, torch.zeros_like(means), opac, None, cols, scales, rots, None, *common, 0, t(cam.campos))
+    (color * t(sc.dL_dpix)).sum().backward()
+    fr = frame_from_scene(sc)
+    g = fr.backward(sc.dL_dpix)
+    np.testing.assert_array_equal(to_np(color).view(np.uint32), to_np(fr.color).view(np.uint32))
+    np.testing.assert_array_equal(to_np(depth).view(np.uint32), to_np(fr.depth).view(np.uint32))
+    np.testing.assert_array_equal(to_np(radii), to_np(fr.radii))
+    for got, k in ((means.grad, "dL_dmean3D"), (cols.grad, "dL_dcolor"), (opac.grad, "dL_dopacity"), (scales.grad, "dL_dscale"),
+                   (rots.grad, "dL_drot")):
+        assert rel_to_scale(to_np(got).reshape(to_np(g[k]).shape), to_np(g[k])) <= 1e-5, k
+    # Visable / mark_visible / distCUDA2
+    from oracle import gs_oracle
+    vis = A.visable(means.detach(), opac.detach(), scales.detach(), rots.detach(), *common, t(cam.campos))
+    np.testing.assert_array_equal(to_np(vis), to_np(fr.radii))
+    mv = A.mark_visible(means.detach(), common[6], common[7])
+    np.testing.assert_array_equal(to_np(mv).astype(bool), gs_oracle.mark_visible(sc.means3D, cam.viewmatrix, cam.projmatrix).astype(bool))
+    pts = t(sc.means3D[:2000])
+    np.testing.assert_array_equal(to_np(A.dist_cuda2(pts)).view(np.uint32), gs_oracle.knn_mean_dist2(sc.means3D[:2000]).view(np.uint32))
+    # error conventions of the reference surface (Rasterizer.cuh:310-316)
+    with pytest.raises((ValueError, RuntimeError)):
+        A.forward(means, torch.zeros_like(means), opac, None, None, scales, rots, None, *common, 0, t(cam.campos))
+
+
+def test_libtorch_adapter_fused_pass_sums_both_passes():
+    """rasterize_gaussians_fused (one five-channel pass, autograd) against two calls of GaussianRasterizer::forward with
+    colours [r,g,b] and [z,1,0], exactly what Render::RenderForFrame does today (src/Render.cc:445-448)."""
+    import torch
+    from gsorb_slam_b200.scene import make_scene
+    A = _adapter()
+    sc = make_scene(8000, (160, 120, 130.0, 128.0), seed=9, scale_mul=1.5)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    cam = sc.cam
+    H, W = cam.height, cam.width
+    common = (H, W, float(cam.tanfovx), float(cam.tanfovy), t(sc.background), 1.0, t(cam.viewmatrix).reshape(4, 4),
+              t(cam.projmatrix).reshape(4, 4))
+    rng = np.random.default_rng(3)
+    wC, wD = t(sc.dL_dpix), t((rng.normal(0, 1, (2, H, W)) / (H * W)).astype(np.float32))
+
+    def leaves():
+        return [t(a).requires_grad_(True) for a in (sc.means3D, sc.colors, sc.opacities[:, None], sc.scales, sc.rotations)]
+    m1, c1, o1, s1, r1 = leaves()
+    color, _, median = A.forward(m1, torch.zeros_like(m1), o1, None, c1, s1, r1, None, *common, 0, t(cam.campos))
+    zcol = torch.stack([m1[:, 2], torch.ones_like(m1[:, 2]), torch.zeros_like(m1[:, 2])], 1)   # attached to the means (mapping mode)
+    dcol, _, _ = A.forward(m1, torch.zeros_like(m1), o1, None, zcol, s1, r1, None, *common, 0, t(cam.campos))
+    ((color * wC).sum() + (dcol[:2] * wD).sum()).backward()
+    m2, c2, o2, s2, r2 = leaves()
+    fcolor, fds, fmed, fradii = A.forward_fused(m2, c2, o2, s2, r2, *common, t(cam.campos), True)
+    ((fcolor * wC).sum() + (fds * wD).sum()).backward()
+    np.testing.assert_array_equal(to_np(fcolor).view(np.uint32), to_np(color).view(np.uint32))
+    np.testing.assert_array_equal(to_np(fds).view(np.uint32), to_np(dcol[:2]).view(np.uint32))
+    np.testing.assert_array_equal(to_np(fmed).view(np.uint32), to_np(median).view(np.uint32))
+    for a, b, k in ((m2, m1, "means"), (c2, c1, "rgb"), (o2, o1, "opacity"), (s2, s1, "scales"), (r2, r1, "rotations")):
+        assert rel_to_scale(to_np(a.grad), to_np(b.grad)) <= 1e-5, k
