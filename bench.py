@@ -304,6 +304,45 @@ def run_ours(args):
                 "frame_alg_bytes": ab["frame"], "frame_frac_of_peak": ab["frame"] / (ms_per_step * 1e-3) / 1e9 / peak,
                 "stages": stages}
 
+    # ---- one optimisation iteration of Render::RenderForFrame (src/Render.cc:445-448): RGB pass + depth/silhouette pass ----
+    # two rasterizations over the same geometry (what the reference does) against the fused five-channel pass
+    iteration = None
+    if world == 1:
+        zcol = torch.stack([fr.means3D[:, 2], torch.ones_like(fr.means3D[:, 2]), torch.zeros_like(fr.means3D[:, 2])], 1).contiguous()
+        rgbcol = fr.colors
+        dD = torch.from_numpy((np.random.default_rng(7).normal(0, 1, (2, H, W)) / HW).astype(np.float32)).to(dev)
+        dD3 = torch.cat([dD, torch.zeros((1, H, W), device=dev)], 0).contiguous()
+        ds = torch.empty((2, H, W), dtype=torch.float32, device=dev)
+        zgrad = torch.empty(P, dtype=torch.float32, device=dev)
+
+        def fwd_bwd(colors, dpix):
+            fr._args.colors_precomp = colors.data_ptr()
+            _lib.check(L.gsb_forward_ws(C.byref(fr._args), fr.geom.data_ptr(), fr.geom.numel(), fr.binning.data_ptr(),
+                                        fr.binning.numel(), max_rendered, fr.img.data_ptr(), fr.img.numel(), fr.color.data_ptr(),
+                                        fr.depth.data_ptr(), fr.radii.data_ptr(), stream))
+            _lib.check(L.gsb_backward(C.byref(fr._args), -1, fr.radii.data_ptr(), fr.geom.data_ptr(), fr.binning.data_ptr(),
+                                      fr.img.data_ptr(), dpix.data_ptr(), C.byref(g), stream))
+
+        def two_pass():
+            fwd_bwd(zcol, dD3)
+            fwd_bwd(rgbcol, dL)
+
+        def fused():
+            fr._args.colors_precomp = rgbcol.data_ptr()
+            _lib.check(L.gsb_forward_fused_ws(C.byref(fr._args), fr.geom.data_ptr(), fr.geom.numel(), fr.binning.data_ptr(),
+                                              fr.binning.numel(), max_rendered, fr.img.data_ptr(), fr.img.numel(), fr.color.data_ptr(),
+                                              ds.data_ptr(), fr.depth.data_ptr(), fr.radii.data_ptr(), stream))
+            _lib.check(L.gsb_backward_fused(C.byref(fr._args), fr.radii.data_ptr(), fr.geom.data_ptr(), fr.binning.data_ptr(),
+                                            fr.img.data_ptr(), dL.data_ptr(), dD.data_ptr(), C.byref(g), zgrad.data_ptr(), stream))
+
+        it_steps = max(3, min(args.steps, 20))
+        ms_two = timed(two_pass, it_steps, 3) / it_steps
+        ms_fused = timed(fused, it_steps, 3) / it_steps
+        fr._args.colors_precomp = rgbcol.data_ptr()
+        iteration = {"what": "RGB pass + depth/silhouette pass of one mapping iteration, fwd+bwd, device-resident",
+                     "two_pass_ms": ms_two, "fused_five_channel_ms": ms_fused, "iterations_per_s_two_pass": 1000.0 / ms_two,
+                     "iterations_per_s_fused": 1000.0 / ms_fused, "steps": it_steps}
+
     # ---- cpu baseline (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -323,6 +362,8 @@ def run_ours(args):
                 "gpu_launches": launches_timed, "clocks": clk.summary(), "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if iteration is not None:
+            line["mapping_iteration"] = iteration
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

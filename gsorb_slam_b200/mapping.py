@@ -111,6 +111,40 @@ class MapOptimizer:
                                                g.ptr("quats"), g.ptr("scales"), self.dTcw.data_ptr(), s))
         return g
 
+    def render_fused(self, Tcw: torch.Tensor):
+        """Prologue + ONE five-channel rasterization: (color [3,H,W], depth_sil [2,H,W], median_depth [1,H,W], radii)
+        -- what Render::RenderForFrame gets from its depth pass and its RGB pass (src/Render.cc:445-448)."""
+        L, p, s = self.L, self.params, self._s()
+        self._Tcw = Tcw.to(self.dev, torch.float32).contiguous()
+        if not hasattr(self, "depth_sil"):
+            self.depth_sil = torch.empty((2, self.H, self.W), dtype=torch.float32, device=self.dev)
+            self.g_z = torch.empty(self.P, dtype=torch.float32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(L.gsb_prologue(self.P, self._Tcw.data_ptr(), p.ptr("means"), p.ptr("opacity"), p.ptr("quats"), p.ptr("scales"),
+                                      self.means_cam.data_ptr(), self.opac.data_ptr(), self.rot.data_ptr(), self.scales.data_ptr(), s))
+            _lib.check(L.gsb_forward_fused_ws(C.byref(self.args), self.geom.data_ptr(), self.geom.numel(), self.binning.data_ptr(),
+                                              self.binning.numel(), self.max_rendered, self.img.data_ptr(), self.img.numel(),
+                                              self.color.data_ptr(), self.depth_sil.data_ptr(), self.depth.data_ptr(),
+                                              self.radii.data_ptr(), s))
+        return self.color, self.depth_sil, self.depth, self.radii
+
+    def backward_fused(self, dL_dcolor: torch.Tensor, dL_ddepth_sil: torch.Tensor, z_attached: bool = True):
+        """Backward of ``render_fused`` into the packed gradient block.  ``z_attached``: the depth pass' z_cam colour is a
+        function of the means (mapping mode, src/Render.cc:973-976); False = tracking mode (detached, :957)."""
+        L, p, g, s = self.L, self.params, self.grads, self._s()
+        dC = dL_dcolor.to(self.dev, torch.float32).contiguous()
+        dD = dL_ddepth_sil.to(self.dev, torch.float32).contiguous()
+        with torch.cuda.device(self.dev):
+            _lib.check(L.gsb_backward_fused(C.byref(self.args), self.radii.data_ptr(), self.geom.data_ptr(), self.binning.data_ptr(),
+                                            self.img.data_ptr(), dC.data_ptr(), dD.data_ptr(), C.byref(self.gout), self.g_z.data_ptr(), s))
+            if z_attached:
+                self.g_means_cam[:, 2].add_(self.g_z)
+            _lib.check(L.gsb_prologue_backward(self.P, self._Tcw.data_ptr(), p.ptr("means"), p.ptr("opacity"), p.ptr("quats"),
+                                               p.ptr("scales"), self.g_means_cam.data_ptr(), self.g_opac.data_ptr(),
+                                               self.g_rot.data_ptr(), self.g_scales.data_ptr(), g.ptr("means"), g.ptr("opacity"),
+                                               g.ptr("quats"), g.ptr("scales"), self.dTcw.data_ptr(), s))
+        return g
+
     def adam(self):
         """torch::optim::Adam step on every group, reading the (all-reduced) gradient block in place."""
         self.t += 1
@@ -121,10 +155,7 @@ class MapOptimizer:
                                            self.exp_avg_sq.ptr(name), float(self.lr[name]), float(self.betas[0]), float(self.betas[1]),
                                            self.eps, self.t, s))
 
-    def step(self, Tcw: torch.Tensor, loss_grad: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], average: bool = False):
-        """One optimisation step on this rank's keyframe.  ``loss_grad(color, depth) -> dL/dcolor``."""
-        color, depth, _ = self.render(Tcw)
-        self.backward(loss_grad(color, depth))
+    def _exchange_and_adam(self, average: bool):
         if self.exchange is not None:
             self.exchange.allreduce(self.grads.flat, use_multicast=world()[1] >= 4)
             if average:
@@ -132,4 +163,19 @@ class MapOptimizer:
         else:
             allreduce_gradients(self.grads, average=average)
         self.adam()
+
+    def step_fused(self, Tcw: torch.Tensor, loss_grad: Callable, average: bool = False, z_attached: bool = True):
+        """One optimisation step with ONE rasterization.  ``loss_grad(color, depth_sil, median_depth) ->
+        (dL/dcolor [3,H,W], dL/ddepth_sil [2,H,W])``."""
+        color, depth_sil, median, _ = self.render_fused(Tcw)
+        dC, dD = loss_grad(color, depth_sil, median)
+        self.backward_fused(dC, dD, z_attached=z_attached)
+        self._exchange_and_adam(average)
+        return color, depth_sil
+
+    def step(self, Tcw: torch.Tensor, loss_grad: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], average: bool = False):
+        """One optimisation step on this rank's keyframe.  ``loss_grad(color, depth) -> dL/dcolor``."""
+        color, depth, _ = self.render(Tcw)
+        self.backward(loss_grad(color, depth))
+        self._exchange_and_adam(average)
         return color

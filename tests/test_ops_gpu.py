@@ -302,3 +302,55 @@ def test_libtorch_adapter_fused_pass_sums_both_passes():
     np.testing.assert_array_equal(to_np(fmed).view(np.uint32), to_np(median).view(np.uint32))
     for a, b, k in ((m2, m1, "means"), (c2, c1, "rgb"), (o2, o1, "opacity"), (s2, s1, "scales"), (r2, r1, "rotations")):
         assert rel_to_scale(to_np(a.grad), to_np(b.grad)) <= 1e-5, k
+
+
+def test_fused_mapping_step_matches_two_pass_torch_iteration():
+    """MapOptimizer.step_fused (prologue -> ONE five-channel rasterization -> summed backward -> pose gradient -> Adam) against
+    the reference-shaped iteration in torch: depth pass with colours [z_cam, 1, 0] attached to the means + RGB pass,
+    loss over colour, depth and silhouette, autograd, torch.optim.Adam (src/Render.cc:445-475)."""
+    import torch
+    import torch.nn.functional as F
+    from gsorb_slam_b200.mapping import DEFAULT_LR, MapOptimizer
+    from gsorb_slam_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+    from gsorb_slam_b200.scene import make_scene
+    sc = make_scene(2500, (128, 96, 110.0, 108.0), seed=23, scale_mul=2.0)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    H, W = sc.cam.height, sc.cam.width
+    ang = -0.1
+    Tcw = torch.eye(4, device=dev)
+    Tcw[:3, :3] = t(np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]], np.float32))
+    Tcw[:3, 3] = t(np.array([-0.03, 0.02, 0.05], np.float32))
+    world_means = (t(sc.means3D) - Tcw[:3, 3]) @ Tcw[:3, :3]
+    rng = np.random.default_rng(4)
+    wC = t(sc.dL_dpix) * 1e3
+    wD = t((rng.normal(0, 1, (2, H, W)) / (H * W)).astype(np.float32)) * 1e3
+    opt = MapOptimizer(world_means, sc.colors, sc.logit_opacities, sc.log_scales, sc.unnorm_quats, width=W, height=H,
+                       tanfovx=sc.cam.tanfovx, tanfovy=sc.cam.tanfovy, projmatrix=sc.cam.projmatrix, device=dev)
+    p = dict(means=world_means.clone().requires_grad_(True), rgb=t(sc.colors).requires_grad_(True),
+             opacity=t(sc.logit_opacities).reshape(-1, 1).requires_grad_(True), scales=t(sc.log_scales).requires_grad_(True),
+             quats=t(sc.unnorm_quats).requires_grad_(True))
+    Tcw_t = Tcw.clone().requires_grad_(True)
+    adam = torch.optim.Adam([{"params": [p[k]], "lr": DEFAULT_LR[k]} for k in p], eps=1e-15)
+    rs = GaussianRasterizationSettings(H, W, float(sc.cam.tanfovx), float(sc.cam.tanfovy), torch.zeros(3, device=dev), 1.0,
+                                       torch.eye(4, device=dev), t(sc.cam.projmatrix).reshape(4, 4), 0, torch.zeros(3, device=dev), False)
+    rast = GaussianRasterizer(rs)
+    for it in range(2):
+        N = p["means"].shape[0]
+        hom = torch.cat([p["means"], torch.ones(N, 1, device=dev)], 1).unsqueeze(-1)
+        mc = Tcw_t.repeat(N, 1, 1).bmm(hom)[:, :3, 0]
+        act = dict(opacities=torch.sigmoid(p["opacity"]), scales=torch.exp(p["scales"]), rotations=F.normalize(p["quats"]))
+        zcol = torch.stack([mc[:, 2], torch.ones_like(mc[:, 2]), torch.zeros_like(mc[:, 2])], 1)        # Render.cc:973-976
+        dimg, _, _ = rast.forward(mc, torch.zeros_like(mc), act["opacities"], colors_precomp=zcol, scales=act["scales"], rotations=act["rotations"])
+        color, _, _ = rast.forward(mc, torch.zeros_like(mc), act["opacities"], colors_precomp=p["rgb"], scales=act["scales"], rotations=act["rotations"])
+        adam.zero_grad()
+        Tcw_t.grad = None
+        ((color * wC).sum() + (dimg[:2] * wD).sum()).backward()
+        c2, ds2 = opt.step_fused(Tcw, lambda c, d, m: (wC, wD))
+        assert rel_to_scale(to_np(c2), to_np(color)) <= TOL_IMAGE and rel_to_scale(to_np(ds2), to_np(dimg[:2])) <= TOL_IMAGE
+        for k in p:
+            assert rel_to_scale(to_np(opt.grads[k]), to_np(p[k].grad)) <= TOL_GRAD, (it, k)
+        assert rel_to_scale(to_np(opt.dTcw), to_np(Tcw_t.grad[:3])) <= TOL_GRAD, "camera-pose gradient"
+        adam.step()
+        for k in p:
+            assert rel_to_scale(to_np(opt.params[k]), to_np(p[k])) <= 1e-5, (it, k)
