@@ -54,6 +54,7 @@ Marshalled marshal(const torch::Tensor& background, const torch::Tensor& means3D
     a.rotations = fptr(m.rotations); a.cov3D_precomp = fptr(m.cov3D); a.viewmatrix = fptr(m.view);
     a.projmatrix = fptr(m.proj); a.cam_pos = fptr(m.campos);
     a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy; a.prefiltered = prefiltered ? 1 : 0;
+    a.tile_row_begin = a.tile_row_end = 0;   // whole image (the tile-row shard is a multi-GPU extension)
     return m;
 }
 

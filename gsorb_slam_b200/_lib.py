@@ -22,7 +22,8 @@ class RasterArgs(C.Structure):
     _fields_ = [("P", _i), ("D", _i), ("M", _i), ("width", _i), ("height", _i), ("background", _vp),
                 ("means3D", _vp), ("shs", _vp), ("colors_precomp", _vp), ("opacities", _vp), ("scales", _vp),
                 ("scale_modifier", _f), ("rotations", _vp), ("cov3D_precomp", _vp), ("viewmatrix", _vp),
-                ("projmatrix", _vp), ("cam_pos", _vp), ("tan_fovx", _f), ("tan_fovy", _f), ("prefiltered", _i)]
+                ("projmatrix", _vp), ("cam_pos", _vp), ("tan_fovx", _f), ("tan_fovy", _f), ("prefiltered", _i),
+                ("tile_row_begin", _i), ("tile_row_end", _i)]
 
 
 class GradOutputs(C.Structure):

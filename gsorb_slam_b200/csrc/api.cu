@@ -63,6 +63,9 @@ static int validate(const gsb_raster_args* a, bool need_colors, bool need_opacit
     if (a->width <= 0 || a->height <= 0)
         return fail(GSB_ERR_INVALID_ARGUMENT, "image size must be positive (got %dx%d)", a->width, a->height);
     if (!(a->tan_fovx > 0.f) || !(a->tan_fovy > 0.f)) return fail(GSB_ERR_INVALID_ARGUMENT, "tan_fov must be positive");
+    if (a->tile_row_begin < 0 || a->tile_row_end < a->tile_row_begin || a->tile_row_end > (a->height + TILE_Y - 1) / TILE_Y)
+        return fail(GSB_ERR_INVALID_ARGUMENT, "tile row band [%d, %d) is outside the image's %d tile rows", a->tile_row_begin,
+                    a->tile_row_end, (a->height + TILE_Y - 1) / TILE_Y);
     if (!a->viewmatrix || !a->projmatrix) return fail(GSB_ERR_INVALID_ARGUMENT, "viewmatrix / projmatrix are required");
     if (a->P > 0) {
         if (!a->means3D) return fail(GSB_ERR_INVALID_ARGUMENT, "means3D must have dimensions (num_points, 3)");
@@ -93,6 +96,9 @@ static FwdParams make_params(const gsb_raster_args* a)
     p.P = a->P; p.D = a->D; p.M = a->shs ? a->M : 0; p.W = a->width; p.H = a->height;
     p.tiles_x = (a->width + TILE_X - 1) / TILE_X;
     p.tiles_y = (a->height + TILE_Y - 1) / TILE_Y;
+    const bool whole = a->tile_row_begin == 0 && a->tile_row_end == 0;
+    p.band_y0 = whole ? 0 : a->tile_row_begin;
+    p.band_y1 = whole ? p.tiles_y : a->tile_row_end;
     p.background = a->background; p.means3D = a->means3D; p.shs = a->shs; p.colors_precomp = a->colors_precomp;
     p.opacities = a->opacities; p.scales = a->scales; p.scale_modifier = a->scale_modifier; p.rotations = a->rotations;
     p.cov3D_precomp = a->cov3D_precomp; p.viewmatrix = a->viewmatrix; p.projmatrix = a->projmatrix; p.cam_pos = a->cam_pos;

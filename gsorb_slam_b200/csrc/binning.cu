@@ -97,7 +97,7 @@ tile_scan_kernel(const uint32_t* __restrict__ tile_count, uint2* __restrict__ ra
 __global__ void __launch_bounds__(DUP_THREADS)
 duplicate_kernel(int P, const SplatRec* __restrict__ rec, const int* __restrict__ radii, const uint4* __restrict__ ranks,
                  const uint2* __restrict__ ranges, uint32_t* __restrict__ cursor, const GeomHeader* __restrict__ hdr,
-                 uint64_t* __restrict__ pairs, int tiles_x, int tiles_y)
+                 uint64_t* __restrict__ pairs, int tiles_x, int tiles_y, int band_y0, int band_y1)
 {
     const int idx = blockIdx.x * DUP_THREADS + threadIdx.x;
     if (idx >= P) return;
@@ -112,6 +112,9 @@ duplicate_kernel(int P, const SplatRec* __restrict__ rec, const int* __restrict_
     const uint64_t record = ((uint64_t)__float_as_uint(depth) << 32) | (uint32_t)idx;
     uint32_t minx, miny, maxx, maxy;
     get_rect(a.x, a.y, radius, tiles_x, tiles_y, minx, miny, maxx, maxy);
+    miny = max(miny, (uint32_t)band_y0);   // the same band clamp as preprocess (tile-row shard)
+    maxy = min(maxy, (uint32_t)band_y1);
+    if (maxy <= miny) return;
     const uint32_t touched = (maxx - minx) * (maxy - miny);
     if (touched <= 4) {
         const uint32_t rk[4] = {rk4.x, rk4.y, rk4.z, rk4.w};
@@ -734,7 +737,7 @@ int launch_binning(const FwdParams& p, char* geom, const GeomLayout& GL, char* b
         duplicate_kernel<<<GL.num_blocks, DUP_THREADS, 0, s>>>(
             p.P, reinterpret_cast<const SplatRec*>(geom + GL.rec), reinterpret_cast<const int*>(geom + GL.radii),
             reinterpret_cast<const uint4*>(geom + GL.ranks), ranges, reinterpret_cast<uint32_t*>(image + IL.tile_cursor), hdr,
-            pairs, p.tiles_x, p.tiles_y);
+            pairs, p.tiles_x, p.tiles_y, p.band_y0, p.band_y1);
         GSB_LAUNCH_CHECK();
     }
     {

@@ -42,13 +42,13 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
                       const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                       const uint32_t* __restrict__ tile_max_contrib, const float* __restrict__ dL_dpix,
                       const float* __restrict__ dL_ddepth_sil, float* __restrict__ acc /* [P][12] */, const uint32_t* __restrict__ hits_tail,
-                      const GeomHeader* __restrict__ hdr)
+                      const GeomHeader* __restrict__ hdr, uint32_t band_y0)
 {
     constexpr int BLEND_THREADS = 256 / HALVES, BLEND_BATCH = BLEND_THREADS, BLOCKS = HIT_BLOCKS / HALVES;
     __shared__ StageBuf<NS, BLEND_BATCH> S;
     __shared__ uint32_t s_ids[NS][BLEND_BATCH];
     __shared__ uint32_t s_hits[NS][(BLEND_BATCH / 32) * BLOCKS];  // [window of the batch][4x2 block of this CTA]
-    const uint32_t tile_y = blockIdx.y / HALVES, half = blockIdx.y % HALVES;
+    const uint32_t tile_y = band_y0 + blockIdx.y / HALVES, half = blockIdx.y % HALVES;   // the grid covers the band's tile rows
     const uint32_t tile = tile_y * gridDim.x + blockIdx.x;
     const uint2 range = ranges[tile];
     const uint32_t len = range.y - range.x;
@@ -237,6 +237,7 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
 {
     if (p.W <= 0 || p.H <= 0 || p.P <= 0) return GSB_OK;
     GSB_CUDA_CHECK(cudaMemsetAsync(geom + GL.acc, 0, (size_t)p.P * sizeof(GradAcc), s));
+    if (p.band_y1 <= p.band_y0) return GSB_OK;   // empty tile-row band: all-zero accumulators
     // tuning knobs: CTA shape (whole tile / half tile), resident CTAs per SM the compiler must allow (the register
     // budget), depth of the staging ring
     static const int halves = [] { const char* e = getenv("GSB_BLEND_BWD_HALVES"); return e ? atoi(e) : 1; }();
@@ -252,13 +253,13 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
             return true;                                                                                                    \
         }();                                                                                                                \
         (void)attr_set;                                                                                                     \
-        blend_backward_kernel<MB, NS, HV, CH><<<dim3(IL.tiles_x, IL.tiles_y * HV), 256 / HV, 0, s>>>(                       \
+        blend_backward_kernel<MB, NS, HV, CH><<<dim3(IL.tiles_x, (p.band_y1 - p.band_y0) * HV), 256 / HV, 0, s>>>(                       \
             reinterpret_cast<const uint2*>(image + IL.ranges), binning, reinterpret_cast<const SplatRec*>(geom + GL.rec), p.W, \
             p.H, p.background, reinterpret_cast<const float*>(image + IL.final_T),                                          \
             reinterpret_cast<const uint32_t*>(image + IL.n_contrib), reinterpret_cast<const uint32_t*>(image + IL.tile_max_contrib), \
             dL_dpix, dL_ddepth_sil, reinterpret_cast<float*>(geom + GL.acc),                                               \
             reinterpret_cast<const uint32_t*>(image + IL.hits_tail),                                                        \
-            reinterpret_cast<const GeomHeader*>(geom + GL.header));                                                         \
+            reinterpret_cast<const GeomHeader*>(geom + GL.header), (uint32_t)p.band_y0);                                                       \
     } while (0)
         if (dL_ddepth_sil) {
             GSB_BWD_LAUNCH_CH(4, 3, 1, 5);

@@ -34,12 +34,12 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                      float* __restrict__ final_T,
                      uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ tile_max_contrib,
                      uint32_t* __restrict__ hits_full, uint32_t* __restrict__ hits_tail,
-                     GeomHeader* __restrict__ hdr, uint32_t layout_capacity)
+                     GeomHeader* __restrict__ hdr, uint32_t layout_capacity, uint32_t band_y0)
 {
     constexpr int BLEND_THREADS = 256 / HALVES, BLEND_BATCH = BLEND_THREADS;
     __shared__ StageBuf<NS, BLEND_BATCH> S;
     __shared__ uint32_t s_max[2];
-    const uint32_t tile_y = blockIdx.y / HALVES, half = blockIdx.y % HALVES;
+    const uint32_t tile_y = band_y0 + blockIdx.y / HALVES, half = blockIdx.y % HALVES;   // the grid covers the band's tile rows
     const uint32_t tile = tile_y * gridDim.x + blockIdx.x;
     const uint2 range = ranges[tile];
     const int n = (int)(range.y - range.x);
@@ -57,7 +57,7 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     const float ya0 = (float)by0, ya1 = (float)(by0 + 1), yb0 = (float)(by0 + 2), yb1 = (float)(by0 + 3);
     if (threadIdx.x == 0) {
         s_max[0] = s_max[1] = 0;
-        if (tile == 0 && half == 0) hdr->layout_capacity = layout_capacity;  // the backward pass locates the hit words with it
+        if (blockIdx.x == 0 && blockIdx.y == 0) hdr->layout_capacity = layout_capacity;  // the backward pass locates the hit words with it
     }
 
     bool done = !inside;
@@ -188,7 +188,7 @@ int launch_blend_forward(const FwdParams& p, char* geom, const GeomLayout& GL, c
                          cudaStream_t s)
 {
     const uint32_t* point_list = reinterpret_cast<const uint32_t*>(binning + BL.point_list);
-    if (p.W <= 0 || p.H <= 0) return GSB_OK;
+    if (p.W <= 0 || p.H <= 0 || p.band_y1 <= p.band_y0) return GSB_OK;
     // tuning knobs: CTA shape (whole tile / half tile), resident CTAs per SM the compiler must allow (the register
     // budget), depth of the staging ring
     static const int halves = [] { const char* e = getenv("GSB_BLEND_FWD_HALVES"); return e ? atoi(e) : 1; }();
@@ -204,12 +204,12 @@ int launch_blend_forward(const FwdParams& p, char* geom, const GeomLayout& GL, c
             return true;                                                                                                \
         }();                                                                                                            \
         (void)attr_set;                                                                                                 \
-        blend_forward_kernel<MB, NS, HV, CH><<<dim3(IL.tiles_x, IL.tiles_y * HV), 256 / HV, 0, s>>>(                    \
+        blend_forward_kernel<MB, NS, HV, CH><<<dim3(IL.tiles_x, (p.band_y1 - p.band_y0) * HV), 256 / HV, 0, s>>>(                    \
             reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec), \
             p.W, p.H, p.background, out_color, out_depth, out_depth_sil, reinterpret_cast<float*>(image + IL.final_T),  \
             reinterpret_cast<uint32_t*>(image + IL.n_contrib), reinterpret_cast<uint32_t*>(image + IL.tile_max_contrib), \
             reinterpret_cast<uint32_t*>(binning + BL.hits), reinterpret_cast<uint32_t*>(image + IL.hits_tail),          \
-            reinterpret_cast<GeomHeader*>(geom + GL.header), (uint32_t)BL.capacity);                                    \
+            reinterpret_cast<GeomHeader*>(geom + GL.header), (uint32_t)BL.capacity, (uint32_t)p.band_y0);                                    \
     } while (0)
         if (out_depth_sil) {
             GSB_FWD_LAUNCH_CH(6, 2, 1, 5);

@@ -324,6 +324,7 @@ struct StageTimer {
 // ---- launch entry points implemented in the other translation units ----------------------
 struct FwdParams {
     int P, D, M, W, H, tiles_x, tiles_y;
+    int band_y0, band_y1;   // tile rows [band_y0, band_y1) are binned and blended (tile-row shard); 0, tiles_y = all
     const float* background;
     const float* means3D;
     const float* shs;

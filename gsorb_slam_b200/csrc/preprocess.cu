@@ -154,13 +154,16 @@ preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ rad
         int radius = 0;
         if (o.visible) {
             radius = o.radius;
-            touched = (o.maxy - o.miny) * (o.maxx - o.minx);
+            // tile-row shard: only the rows of this rank's band are binned (radii stay those of the whole image)
+            const uint32_t by0 = max(o.miny, (uint32_t)p.band_y0), by1 = min(o.maxy, (uint32_t)p.band_y1);
+            const uint32_t rows = by1 > by0 ? by1 - by0 : 0u;
+            touched = rows * (o.maxx - o.minx);
             // First half of the binning: per-tile instance counts.  A Gaussian that joins at most four tile
             // lists (nearly all of them at SLAM splat sizes) keeps the slot each atomic returns, so `duplicate`
             // places its instances without a second round of atomics; larger ones are only counted here.
             if (touched <= 4) {
                 uint32_t rk[4] = {0u, 0u, 0u, 0u};
-                uint32_t tx = o.minx, ty = o.miny;
+                uint32_t tx = o.minx, ty = by0;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     if ((uint32_t)k < touched) {
@@ -170,7 +173,7 @@ preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ rad
                 }
                 ranks[idx] = make_uint4(rk[0], rk[1], rk[2], rk[3]);
             } else {
-                for (uint32_t ty = o.miny; ty < o.maxy; ty++)
+                for (uint32_t ty = by0; ty < by1; ty++)
                     for (uint32_t tx = o.minx; tx < o.maxx; tx++)
                         atomicAdd(&tile_count[(size_t)(ty * (uint32_t)p.tiles_x + tx) * TILE_CTR_STRIDE + 1], 1u);
             }

@@ -35,7 +35,7 @@ def _p(t):
 class Frame:
     def __init__(self, *, width, height, means3D, opacities, background, viewmatrix, projmatrix, tanfovx, tanfovy,
                  colors=None, shs=None, sh_degree=0, scales=None, rotations=None, cov3D=None, scale_modifier=1.0,
-                 campos=None, device="cuda:0", sync_free=False, max_rendered=None, run=True, fused=False):
+                 campos=None, device="cuda:0", sync_free=False, max_rendered=None, run=True, fused=False, tile_rows=None):
         self.L = _lib.lib()
         self.device = torch.device(device)
         d = self.device
@@ -51,15 +51,18 @@ class Frame:
         self.view, self.proj = _dev(viewmatrix, d).reshape(16), _dev(projmatrix, d).reshape(16)
         self.campos = _dev(campos if campos is not None else np.zeros(3, np.float32), d)
         self.tanfovx, self.tanfovy, self.scale_modifier = float(tanfovx), float(tanfovy), float(scale_modifier)
+        self.tile_rows = tile_rows  # (begin, end) tile rows rendered by this frame (tile-row shard); None = whole image
         self.fused = bool(fused)   # five-channel pass: RGB + [z_cam, 1] of the depth pass (gsb_forward_fused_ws)
         self.sync_free = bool(sync_free) or self.fused
         self.max_rendered = int(max_rendered) if max_rendered is not None else 4 * self.P + 1024
         self.num_rendered = None
         self._args = self._make_args()
-        self.color = torch.empty((3, self.H, self.W), dtype=torch.float32, device=d)
-        self.depth = torch.empty((1, self.H, self.W), dtype=torch.float32, device=d)
+        # a band render leaves the other rows untouched: zero-filled so that bands can be summed
+        mk = torch.zeros if tile_rows is not None else torch.empty
+        self.color = mk((3, self.H, self.W), dtype=torch.float32, device=d)
+        self.depth = mk((1, self.H, self.W), dtype=torch.float32, device=d)
         self.radii = torch.empty((self.P,), dtype=torch.int32, device=d)
-        self.depth_sil = torch.empty((2, self.H, self.W), dtype=torch.float32, device=d) if self.fused else None
+        self.depth_sil = mk((2, self.H, self.W), dtype=torch.float32, device=d) if self.fused else None
         self.geom = self.binning = self.img = None
         self._grads = None
         if run:
@@ -73,6 +76,8 @@ class Frame:
         a.rotations, a.cov3D_precomp = _p(self.rotations), _p(self.cov3D)
         a.viewmatrix, a.projmatrix, a.cam_pos = _p(self.view), _p(self.proj), _p(self.campos)
         a.tan_fovx, a.tan_fovy, a.prefiltered = self.tanfovx, self.tanfovy, 0
+        if self.tile_rows is not None:
+            a.tile_row_begin, a.tile_row_end = int(self.tile_rows[0]), int(self.tile_rows[1])
         return a
 
     def _stream(self):

@@ -47,7 +47,7 @@ extern "C" {
 #endif
 
 #define GSB_VERSION_MAJOR 0
-#define GSB_VERSION_MINOR 1
+#define GSB_VERSION_MINOR 2
 
 typedef enum gsb_status {
     GSB_OK = 0,
@@ -86,6 +86,11 @@ typedef struct gsb_raster_args {
     const float* cam_pos;        /* [3] (only read on the SH path) */
     float tan_fovx, tan_fovy;
     int prefiltered;             /* reference traps if a culled point was declared prefiltered; here: ignored */
+    /* Tile-row shard (multi-GPU; not in the reference): only the 16-pixel tile rows
+     * [tile_row_begin, tile_row_end) are binned, sorted and blended; pixels outside the band are NOT written,
+     * gradients hold this band's share (summing the bands' images and gradients gives the full frame).
+     * radii are unaffected.  0, 0 = the whole image. */
+    int tile_row_begin, tile_row_end;
 } gsb_raster_args;
 
 /* Gradient outputs of rasterizer.h:74-83.  Any pointer may be NULL to skip that output. */

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 def test_version_and_sizes():
     from gsorb_slam_b200 import _lib
     L = _lib.lib()
-    assert L.gsb_version() == (0 << 16) | 1
+    assert L.gsb_version() == (0 << 16) | 2
     g, i, b = C.c_size_t(), C.c_size_t(), C.c_size_t()
     assert L.gsb_workspace_query(1000, 640, 480, 5000, C.byref(g), C.byref(i), C.byref(b)) == 0
     assert g.value == L.gsb_geometry_bytes(1000) and g.value >= 1000 * 48

@@ -113,3 +113,36 @@ def test_depth_ties_and_large_splats_keep_reference_order(P, scale_mul):
     assert rel_to_scale(to_np(fr.color), orc.color) <= TOL_IMAGE
     for k in ("dL_dmean3D", "dL_dscale", "dL_drot", "dL_dopacity", "dL_dcolor"):
         assert rel_to_scale(to_np(g[k]), go[k].reshape(to_np(g[k]).shape)) <= TOL_GRAD, k
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("cuts", [(0, 3, 8), (0, 1, 2, 5, 8), (0, 8, 8)])
+def test_tile_row_bands_sum_to_the_full_frame(cuts, fused):
+    """Tile-row shard (BASELINE.json config #4): every band is rendered on its own (only its tile rows are binned,
+    sorted and blended), images are disjoint and gradients partial; their sums equal the whole-image render -- pixels bit for
+    bit, gradients up to fp32 summation order."""
+    from gsorb_slam_b200.lowlevel import frame_from_scene
+    from gsorb_slam_b200.scene import make_scene
+    sc = make_scene(6000, (160, 120, 130.0, 128.0), seed=17, scale_mul=3.0, background=0.0)   # 8 tile rows, splats span bands
+    H, W = sc.cam.height, sc.cam.width
+    dD = (np.random.default_rng(2).normal(0, 1, (2, H, W)) / (H * W)).astype(np.float32)
+    run = (lambda fr: fr.backward_fused(sc.dL_dpix, dD)) if fused else (lambda fr: fr.backward(sc.dL_dpix))
+    full = frame_from_scene(sc, fused=fused, max_rendered=1 << 17)
+    g_full = {k: to_np(v) for k, v in run(full).items() if v is not None}
+    color = np.zeros((3, H, W), np.float32)
+    depth = np.zeros((1, H, W), np.float32)
+    g_sum, rendered = None, 0
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        fr = frame_from_scene(sc, fused=fused, sync_free=True, tile_rows=(b, e), max_rendered=1 << 17)
+        if e > b:   # band rows only
+            assert to_np(fr.color)[:, :b * 16].sum() == 0 and to_np(fr.color)[:, min(e * 16, H):].sum() == 0
+        g = {k: to_np(v) for k, v in run(fr).items() if v is not None}
+        np.testing.assert_array_equal(to_np(fr.radii), to_np(full.radii))
+        color += to_np(fr.color); depth += to_np(fr.depth)
+        rendered += fr.rendered() if e > b else 0
+        g_sum = g if g_sum is None else {k: g_sum[k] + g[k] for k in g}
+    assert rendered == full.rendered()
+    np.testing.assert_array_equal(color.view(np.uint32), to_np(full.color).view(np.uint32))
+    np.testing.assert_array_equal(depth.view(np.uint32), to_np(full.depth).view(np.uint32))
+    for k in g_full:
+        assert rel_to_scale(g_sum[k], g_full[k]) <= 1e-5, k
