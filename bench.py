@@ -369,6 +369,112 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_tile_row(args):
+    """--shard tile_row (BASELINE.json config #4): ONE frame split over the ranks by bands of 16-pixel tile rows
+    (strong scaling).  Every rank projects all Gaussians, bins / sorts / blends only its band, the image bands are summed
+    across ranks (the loss needs the whole image), every rank back-propagates its band and the partial gradients are summed:
+    the whole [14,P] block (mapping) or, with --pose-only, just dL/dTcw (tracking iterations, 12 floats)."""
+    import torch
+    import torch.distributed as dist
+    from gsorb_slam_b200 import _lib
+    from gsorb_slam_b200.distributed import SymmetricExchange, tile_row_bands
+    from gsorb_slam_b200.lowlevel import frame_from_scene
+
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    sc = make_rank_scene(args.workload, 0)      # the same keyframe on every rank
+    P, W, H = sc.P, sc.cam.width, sc.cam.height
+    HW, tiles_x, tiles_y = W * H, (W + 15) // 16, (H + 15) // 16
+    max_rendered = 4 * P + 4096
+    full = frame_from_scene(sc, device=dev, sync_free=True, max_rendered=max_rendered)
+    rg = full.image_state()["ranges"].cpu().numpy().astype(np.int64)
+    per_row = (rg[:, 1] - rg[:, 0]).reshape(tiles_y, tiles_x).sum(1)
+    # a band costs its tile instances plus a fixed share of the per-Gaussian work: balance on instances
+    bands = tile_row_bands(tiles_y, world, weights=[float(x) + 1.0 for x in per_row])
+    b0, b1 = bands[rank]
+    R_full = full.rendered()
+    del full
+    xch = SymmetricExchange(4 * HW + 14 * P + 16, dev) if world > 1 else None
+    alloc = (lambda n: xch.alloc(n)) if xch is not None else (lambda n: torch.zeros(n, dtype=torch.float32, device=dev))
+    img_blk, block, dT = alloc(4 * HW), alloc(14 * P), alloc(16)
+    fr = frame_from_scene(sc, device=dev, sync_free=True, max_rendered=max_rendered, tile_rows=(b0, b1), run=False)
+    fr.color, fr.depth = img_blk[:3 * HW].view(3, H, W), img_blk[3 * HW:].view(1, H, W)
+    dL = torch.from_numpy(sc.dL_dpix).to(dev)
+    side = torch.empty(13 * P, dtype=torch.float32, device=dev)
+    g = _lib.GradOutputs()
+    bp, sp = block.data_ptr(), side.data_ptr()
+    g.dL_dmean3D, g.dL_dcolor, g.dL_dopacity, g.dL_dscale, g.dL_drot = bp, bp + 12 * P, bp + 24 * P, bp + 28 * P, bp + 40 * P
+    g.dL_dmean2D, g.dL_dconic, g.dL_dcov3D, g.dL_dsh = sp, sp + 12 * P, sp + 28 * P, None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    use_mc = bool(xch is not None and xch.multicast_ptr) and world >= 4
+
+    def step():
+        img_blk.zero_()
+        if b1 > b0:
+            fr.forward()
+        if xch is not None:
+            xch.allreduce(img_blk, use_multicast=use_mc)          # every rank now holds the whole image
+        if b1 > b0:
+            _lib.check(L.gsb_backward(C.byref(fr._args), -1, fr.radii.data_ptr(), fr.geom.data_ptr(), fr.binning.data_ptr(),
+                                      fr.img.data_ptr(), dL.data_ptr(), C.byref(g), stream))
+        else:
+            block.zero_()
+        if args.pose_only:   # tracking iteration: only dL/dTcw = sum_i g_i [p_i;1]^T leaves the rank (identity view: p = means3D)
+            _lib.check(L.gsb_pose_grad(P, fr.means3D.data_ptr(), g.dL_dmean3D, dT.data_ptr(), stream))
+            if xch is not None:
+                xch.allreduce(dT[:12], use_multicast=use_mc)
+        elif xch is not None:
+            xch.allreduce(block, use_multicast=use_mc)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    with ClockSampler(local) as clk:
+        ms = timed(step, args.steps, args.warmup) / args.steps
+    R_band = fr.rendered() if b1 > b0 else 0
+    counts = torch.tensor([R_band], dtype=torch.int64, device=dev)
+    if world > 1:
+        lst = [torch.zeros_like(counts) for _ in range(world)]
+        dist.all_gather(lst, counts)
+        counts = torch.cat(lst)
+    if rank == 0:
+        print(json.dumps({"metric": METRIC, "value": 1000.0 / ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic",
+                          "config": {"workload": f"{args.workload}: {P} Gaussians {W}x{H}, RGB pass fwd+bwd, seed 0, ONE frame over all ranks",
+                                     "parallelism": f"tile-row shard x{world}: bands {bands}; image bands summed, then "
+                                                    + ("dL/dTcw (12 floats) summed [pose-only / tracking]" if args.pose_only
+                                                       else "the [14,P] gradient block summed [mapping]") + " by the libgsb exchange kernel",
+                                     "num_rendered": R_full, "instances_per_band": [int(x) for x in counts.tolist()],
+                                     "l2": "flushed between steps (512 MiB memset, outside the event brackets)"},
+                          "clocks": clk.summary()}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def cpu_baseline(workload: str, budget_s: float = 20.0):
     """The oracle's per-pixel C++ loop on the host cores: whole frames of the same workload until ~budget_s."""
     from gsorb_slam_b200.scene import make_config
@@ -495,12 +601,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline_1m")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "p2p", "multimem"], help="N > 1: how the gradient block is all-reduced")
+    ap.add_argument("--shard", default="keyframe", choices=["keyframe", "tile_row"],
+                    help="N > 1: keyframe-batch shard (weak scaling, the default metric) or tile-row shard of ONE frame (strong scaling)")
+    ap.add_argument("--pose-only", action="store_true", help="--shard tile_row: exchange dL/dTcw only (tracking iteration)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="developer mode: value + per-stage times only (no e2e / cpu legs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args)
+    elif args.shard == "tile_row":
+        run_tile_row(args)
     else:
         run_ours(args)
 

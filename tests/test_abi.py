@@ -65,6 +65,22 @@ def test_validation_errors_match_reference_messages():
     assert rc == -3 and b"geometry workspace too small" in L.gsb_last_error()
     with pytest.raises(ValueError):
         _lib.check(-1)
+    # extensions: fused pass needs its extra output / gradient input, tile-row band must lie inside the image, exchange arguments
+    rc = L.gsb_forward_fused_ws(C.byref(a), dummy, 1 << 30, dummy, 1 << 30, 100, dummy, 1 << 30, dummy, None, dummy, None, None)
+    assert rc == -1 and b"out_depth_sil" in L.gsb_last_error()
+    g = _lib.GradOutputs()
+    rc = L.gsb_backward_fused(C.byref(a), None, dummy, dummy, dummy, dummy, None, C.byref(g), None, None)
+    assert rc == -1 and b"dL_ddepth_sil" in L.gsb_last_error()
+    a.tile_row_begin, a.tile_row_end = 2, 9   # 64 px = 4 tile rows
+    rc = L.gsb_forward_ws(C.byref(a), dummy, 1 << 30, dummy, 1 << 30, 100, dummy, 1 << 30, dummy, dummy, None, None)
+    assert rc == -1 and b"tile row band" in L.gsb_last_error()
+    a.tile_row_begin, a.tile_row_end = 0, 0
+    ptrs = (C.c_void_p * 2)(256, 512)
+    assert L.gsb_exchange_allreduce(None, ptrs, ptrs, 1002, 0, 2, None) == -1          # n % 4 != 0
+    assert L.gsb_exchange_allreduce(None, ptrs, ptrs, 1000, 2, 2, None) == -1          # rank out of range
+    assert L.gsb_exchange_allreduce(None, None, None, 1000, 0, 2, None) == -1          # missing mappings
+    assert L.gsb_exchange_allreduce(None, None, None, 1000, 0, 1, None) == 0           # world 1: no-op
+    assert L.gsb_exchange_sync_bytes(8) >= 2 * 148 * 8 * 4
 
 
 def test_operator_surface_mirrors_reference_names():
