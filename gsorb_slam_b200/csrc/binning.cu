@@ -272,10 +272,10 @@ __device__ __forceinline__ void tile_sort_regs(uint64_t* __restrict__ s /* smem,
 // per 2000-entry tile); those are put right afterwards by an odd-even transposition on the exact
 // 64-bit records, restricted to neighbours with equal quantised depth.  A comparator is then one
 // VIMNMX pair, a shuffle stage one SHFL + one VIMNMX per element.
-template <int E>
+template <int E, int THREADS>
 __device__ __forceinline__ void tile_sort_regs32(uint32_t* __restrict__ s, uint32_t (&a)[E])
 {
-    constexpr uint32_t N = E * TSORT_THREADS;
+    constexpr uint32_t N = E * THREADS;
     const uint32_t t = threadIdx.x, lane = t & 31;
 #pragma unroll
     for (uint32_t k = 2; k <= N; k <<= 1) {
@@ -306,7 +306,7 @@ __device__ __forceinline__ void tile_sort_regs32(uint32_t* __restrict__ s, uint3
             for (int r = 0; r < E; r++) s[t * E + r] = a[r];
             __syncthreads();
             const uint32_t half = k >> 1;
-            for (uint32_t p = t; p < N / 2; p += TSORT_THREADS) {
+            for (uint32_t p = t; p < N / 2; p += THREADS) {
                 const uint32_t blk = p / half, off = p % half;
                 const uint32_t i = blk * k + off, l = blk * k + (k - 1 - off);
                 const uint32_t x = s[i], y = s[l];
@@ -315,7 +315,7 @@ __device__ __forceinline__ void tile_sort_regs32(uint32_t* __restrict__ s, uint3
             }
             __syncthreads();
             for (; j >= 32u * E; j >>= 1) {
-                for (uint32_t p = t; p < N / 2; p += TSORT_THREADS) {
+                for (uint32_t p = t; p < N / 2; p += THREADS) {
                     const uint32_t i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), l = i | j;
                     const uint32_t x = s[i], y = s[l];
                     s[i] = min(x, y);
@@ -359,13 +359,13 @@ __device__ __forceinline__ void tile_sort_regs32(uint32_t* __restrict__ s, uint3
     __syncthreads();
 }
 
-template <int E>
+template <int E, int THREADS>
 __device__ __forceinline__ void tile_sort_class32(const uint2 r, const uint64_t* __restrict__ pairs,
                                                   uint32_t* __restrict__ point_list, uint32_t* __restrict__ s,
                                                   uint32_t* __restrict__ s_red)
 {
     constexpr int LOG_E = E == 1 ? 0 : E == 2 ? 1 : E == 4 ? 2 : E == 8 ? 3 : 4;
-    constexpr int IDX_BITS = 8 + LOG_E, DEPTH_BITS = 32 - IDX_BITS;
+    constexpr int IDX_BITS = (THREADS == 1024 ? 10 : 8) + LOG_E, DEPTH_BITS = 32 - IDX_BITS;
     constexpr uint32_t IDX_MASK = (1u << IDX_BITS) - 1u;
     const uint32_t n = r.y - r.x, t = threadIdx.x;
     const uint64_t* seg = pairs + r.x;
@@ -383,15 +383,16 @@ __device__ __forceinline__ void tile_sort_class32(const uint2 r, const uint64_t*
     }
     mn = __reduce_min_sync(0xffffffffu, mn);
     mx = __reduce_max_sync(0xffffffffu, mx);
+    __syncthreads();   // s_red may still be read by the previous tile's threads (persistent callers)
     if ((t & 31) == 0) {
         s_red[t >> 5] = mn;
-        s_red[8 + (t >> 5)] = mx;
+        s_red[32 + (t >> 5)] = mx;
     }
     __syncthreads();
 #pragma unroll
-    for (int w = 0; w < TSORT_THREADS / 32; w++) {
+    for (int w = 0; w < THREADS / 32; w++) {
         mn = min(mn, s_red[w]);
-        mx = max(mx, s_red[8 + w]);
+        mx = max(mx, s_red[32 + w]);
     }
     // largest quantised depth must stay below 2^DEPTH_BITS - 1 (the padding key is all ones)
     const int need = 32 - __clz(mx - mn + 1u);
@@ -402,7 +403,7 @@ __device__ __forceinline__ void tile_sort_class32(const uint2 r, const uint64_t*
         const uint32_t i = t * E + k;
         a[k] = i < n ? (((dep[k] - mn) >> shift) << IDX_BITS) | i : 0xffffffffu;
     }
-    tile_sort_regs32<E>(s, a);
+    tile_sort_regs32<E, THREADS>(s, a);
     // exact order between neighbours whose quantised depths collide: odd-even transposition on the
     // 64-bit records, until a whole round swaps nothing (runs are 2-3 entries long in practice)
     bool tie = false;
@@ -416,7 +417,7 @@ __device__ __forceinline__ void tile_sort_class32(const uint2 r, const uint64_t*
             bool swapped = false;
 #pragma unroll 1
             for (uint32_t phase = 0; phase < 2; phase++) {
-                for (uint32_t i = 2 * t + phase; i + 1 < n; i += 2 * TSORT_THREADS) {
+                for (uint32_t i = 2 * t + phase; i + 1 < n; i += 2 * THREADS) {
                     const uint32_t x = s[i], y = s[i + 1];
                     if ((x >> IDX_BITS) == (y >> IDX_BITS) && seg[x & IDX_MASK] > seg[y & IDX_MASK]) {
                         s[i] = y;
@@ -429,55 +430,44 @@ __device__ __forceinline__ void tile_sort_class32(const uint2 r, const uint64_t*
             if (!__syncthreads_or(swapped)) break;
         }
     }
-    for (uint32_t i = t; i < n; i += TSORT_THREADS) point_list[r.x + i] = (uint32_t)seg[s[i] & IDX_MASK];
+    for (uint32_t i = t; i < n; i += THREADS) point_list[r.x + i] = (uint32_t)seg[s[i] & IDX_MASK];
 }
 
 __global__ void __launch_bounds__(TSORT_THREADS)
 tile_sort_small_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list)
 {
     __shared__ __align__(16) uint32_t s[TSORT_SMALL];
-    __shared__ uint32_t s_red[16];
+    __shared__ uint32_t s_red[64];
     const uint2 r = ranges[blockIdx.x];
     const uint32_t n = r.y - r.x;
     if (n == 0 || n > (uint32_t)TSORT_SMALL) return;   // longer lists: the 128 KB / global classes
     const uint32_t npad = n <= 256 ? 256u : next_pow2(n);
     switch (npad) {
-        case 256: tile_sort_class32<1>(r, pairs, point_list, s, s_red); break;
-        case 512: tile_sort_class32<2>(r, pairs, point_list, s, s_red); break;
-        case 1024: tile_sort_class32<4>(r, pairs, point_list, s, s_red); break;
-        case 2048: tile_sort_class32<8>(r, pairs, point_list, s, s_red); break;
-        default: tile_sort_class32<16>(r, pairs, point_list, s, s_red); break;
+        case 256: tile_sort_class32<1, TSORT_THREADS>(r, pairs, point_list, s, s_red); break;
+        case 512: tile_sort_class32<2, TSORT_THREADS>(r, pairs, point_list, s, s_red); break;
+        case 1024: tile_sort_class32<4, TSORT_THREADS>(r, pairs, point_list, s, s_red); break;
+        case 2048: tile_sort_class32<8, TSORT_THREADS>(r, pairs, point_list, s, s_red); break;
+        default: tile_sort_class32<16, TSORT_THREADS>(r, pairs, point_list, s, s_red); break;
     }
 }
 
-template <int CAP, int THREADS, bool DYNAMIC>
-__global__ void __launch_bounds__(THREADS)
-tile_sort_smem_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list,
-                      int tiles, uint32_t lo_excl, uint32_t hi_incl, const GeomHeader* __restrict__ hdr)
+// Size class 4096 < n <= 16384: the same 32-bit keyed network with 1024 threads (8 or 16 keys per thread, 32 / 64 KB of
+// dynamic shared memory), one persistent CTA per SM looping over the tiles of the class.
+__global__ void __launch_bounds__(1024, 1)
+tile_sort_mid_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list,
+                     int tiles, const GeomHeader* __restrict__ hdr)
 {
-    if (hdr->max_tile_len <= lo_excl) return;   // no tile of this size class in the frame
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    __shared__ __align__(16) uint64_t stat_smem[DYNAMIC ? 1 : CAP];
-    uint64_t* s = DYNAMIC ? reinterpret_cast<uint64_t*>(dyn_smem) : stat_smem;
+    __shared__ uint32_t s_red[64];
+    if (hdr->max_tile_len <= (uint32_t)TSORT_SMALL) return;   // no tile of this size class in the frame
+    uint32_t* s = reinterpret_cast<uint32_t*>(dyn_smem);
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const uint2 r = ranges[tile];
         const uint32_t n = r.y - r.x;
-        if (n <= lo_excl || n > hi_incl) continue;   // another size class handles this tile
-        __syncthreads();                              // previous tile's readers are done with s[]
-        for (uint32_t i = threadIdx.x; i < n; i += THREADS) s[i] = pairs[r.x + i];
-        __syncthreads();
-        bitonic_network(n, next_pow2(n), THREADS, [&](uint32_t i, uint32_t l, bool sync) {
-            if (sync) {
-                __syncthreads();
-                return;
-            }
-            const uint64_t a = s[i], b = s[l];
-            if (a > b) {
-                s[i] = b;
-                s[l] = a;
-            }
-        });
-        for (uint32_t i = threadIdx.x; i < n; i += THREADS) point_list[r.x + i] = (uint32_t)s[i];
+        if (n <= (uint32_t)TSORT_SMALL || n > (uint32_t)TSORT_MID) continue;   // another size class handles this tile
+        __syncthreads();                                                      // previous tile's readers are done with s[]
+        if (n <= 8192u) tile_sort_class32<8, 1024>(r, pairs, point_list, s, s_red);
+        else tile_sort_class32<16, 1024>(r, pairs, point_list, s, s_red);
     }
 }
 
@@ -745,11 +735,9 @@ int launch_binning(const FwdParams& p, char* geom, const GeomLayout& GL, char* b
         tile_sort_small_kernel<<<tiles, TSORT_THREADS, 0, s>>>(ranges, pairs, point_list);
         GSB_LAUNCH_CHECK();
         if (grid_instances > TSORT_SMALL) {   // a longer tile list is only possible then
-            GSB_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_smem_kernel<TSORT_MID, 1024, true>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, TSORT_MID * 8));
+            GSB_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TSORT_MID * 4));
             const int g = tiles < NUM_SMS ? tiles : NUM_SMS;
-            tile_sort_smem_kernel<TSORT_MID, 1024, true><<<g, 1024, TSORT_MID * 8, s>>>(ranges, pairs, point_list, tiles,
-                                                                                       (uint32_t)TSORT_SMALL, (uint32_t)TSORT_MID, hdr);
+            tile_sort_mid_kernel<<<g, 1024, TSORT_MID * 4, s>>>(ranges, pairs, point_list, tiles, hdr);
             GSB_LAUNCH_CHECK();
         }
         if (grid_instances > TSORT_MID) {

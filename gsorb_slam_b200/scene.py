@@ -135,6 +135,10 @@ CONFIGS = {
     "headline_1m": dict(P=1_000_000, intr="tum"),
     "cfg3_2m": dict(P=2_000_000, intr="replica"),
     "cfg4_5m": dict(P=5_000_000, intr="scannet_hr"),
+    # stress variants of the headline map: 3x larger splats (long tile lists: the 128-KB sort class, saturated pixels)
+    # and a close-up where a third of the Gaussians are outside the frustum
+    "dense_1m": dict(P=1_000_000, intr="tum", scale_mul=3.0),
+    "culled_1m": dict(P=1_000_000, intr="tum", cull_frac=0.35),
 }
 
 
