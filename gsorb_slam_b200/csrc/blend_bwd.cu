@@ -35,7 +35,7 @@ namespace gsb {
 
 // CH = 5: backward of the fused RGB + depth / silhouette pass (see blend_fwd.cu): dL/dalpha sums over five channels,
 // and the gradient of the z_cam colour (sum of w * dL/dpix[3]) lands in accumulator slot 9.
-template <int MINB, int NS, int HALVES, int CH>
+template <int MINB, int NS, int HALVES, int CH, bool BULK>
 __global__ void __launch_bounds__(256 / HALVES, MINB)
 blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__ binning,
                       const SplatRec* __restrict__ rec, int W, int H, const float* __restrict__ bg,
@@ -45,7 +45,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
                       const GeomHeader* __restrict__ hdr, uint32_t band_y0)
 {
     constexpr int BLEND_THREADS = 256 / HALVES, BLEND_BATCH = BLEND_THREADS, BLOCKS = HIT_BLOCKS / HALVES;
-    __shared__ StageBuf<NS, BLEND_BATCH> S;
+    __shared__ StageRing<NS, BLEND_BATCH, BULK> S;
     __shared__ uint32_t s_ids[NS][BLEND_BATCH];
     __shared__ uint32_t s_hits[NS][(BLEND_BATCH / 32) * BLOCKS];  // [window of the batch][4x2 block of this CTA]
     const uint32_t tile_y = band_y0 + blockIdx.y / HALVES, half = blockIdx.y % HALVES;   // the grid covers the band's tile rows
@@ -105,13 +105,14 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
     };
     auto stage = [&](int k, int buf, uint32_t id) {
         s_ids[buf][threadIdx.x] = id;
-        stage_issue(S, buf, rec, id);
+        stage_issue(S, buf, rec, id, min(BLEND_BATCH, n - (batches - 1 - k) * BLEND_BATCH));
         // hit words of the batch: (BLEND_BATCH / 32) windows x BLOCKS blocks, one 4-byte copy per thread
         const uint32_t w = (uint32_t)(batches - 1 - k) * (BLEND_BATCH / 32) + threadIdx.x / BLOCKS;
         if (threadIdx.x < (BLEND_BATCH / 32) * BLOCKS && (int)(w * 32) < n)
             cp_async4(&s_hits[buf][threadIdx.x], hit_word(const_cast<uint32_t*>(hits_full), const_cast<uint32_t*>(hits_tail), tile,
                                                           range.x, len, w, half * BLOCKS + threadIdx.x % BLOCKS));
     };
+    S.init();
 #pragma unroll
     for (int i = 0; i < NS - 1; i++) {
         if (i < batches) stage(i, i, load_id(i));
@@ -121,7 +122,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
 
     int buf = 0;
     for (int k = 0; k < batches; k++) {
-        cp_async_wait<NS - 2>();
+        stage_wait(S, buf, k);
         __syncthreads();  // publishes batch k; everyone is finished with batch k-1, whose buffer is reused below
         {
             const int nbuf = buf == 0 ? NS - 1 : buf - 1;  // (k + NS - 1) % NS
@@ -142,9 +143,9 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
                 mask &= ~(1u << eb);
                 const int e = wi * 32 + eb;
                 const int pos = kb * BLEND_BATCH + e + 1;  // 1-based list position
-                const float4 A = S.a[buf][e];
-                const float4 B = S.b[buf][e];
-                const float4 Cc = S.c[buf][e];
+                const float4 A = S.A(buf, e);
+                const float4 B = S.B(buf, e);
+                const float4 Cc = S.C(buf, e);
                 const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
                 const float power = splat_power(dx, dy, B.x, B.y, B.z);
                 // Branch-free body: a lane that does not contribute carries u = wc = 0 through the sums and
@@ -245,15 +246,15 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
     static const int stages = [] { const char* e = getenv("GSB_BLEND_BWD_STAGES"); return e ? atoi(e) : 3; }();
     {
         StageTimer _t(ST_BLEND_BWD, s);
-#define GSB_BWD_LAUNCH(MB, NS, HV) GSB_BWD_LAUNCH_CH(MB, NS, HV, 3)
-#define GSB_BWD_LAUNCH_CH(MB, NS, HV, CH)                                                                                          \
+#define GSB_BWD_LAUNCH(MB, NS, HV) GSB_BWD_LAUNCH_CH(MB, NS, HV, 3, false)
+#define GSB_BWD_LAUNCH_CH(MB, NS, HV, CH, BK)                                                                                          \
     do {                                                                                                                    \
         static const bool attr_set = [] {                                                                                   \
-            cudaFuncSetAttribute(blend_backward_kernel<MB, NS, HV, CH>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
+            cudaFuncSetAttribute(blend_backward_kernel<MB, NS, HV, CH, BK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
             return true;                                                                                                    \
         }();                                                                                                                \
         (void)attr_set;                                                                                                     \
-        blend_backward_kernel<MB, NS, HV, CH><<<dim3(IL.tiles_x, (p.band_y1 - p.band_y0) * HV), 256 / HV, 0, s>>>(                       \
+        blend_backward_kernel<MB, NS, HV, CH, BK><<<dim3(IL.tiles_x, (p.band_y1 - p.band_y0) * HV), 256 / HV, 0, s>>>(                       \
             reinterpret_cast<const uint2*>(image + IL.ranges), binning, reinterpret_cast<const SplatRec*>(geom + GL.rec), p.W, \
             p.H, p.background, reinterpret_cast<const float*>(image + IL.final_T),                                          \
             reinterpret_cast<const uint32_t*>(image + IL.n_contrib), reinterpret_cast<const uint32_t*>(image + IL.tile_max_contrib), \
@@ -261,8 +262,11 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
             reinterpret_cast<const uint32_t*>(image + IL.hits_tail),                                                        \
             reinterpret_cast<const GeomHeader*>(geom + GL.header), (uint32_t)p.band_y0);                                                       \
     } while (0)
+        static const bool bulk = [] { const char* e = getenv("GSB_BLEND_STAGE"); return e ? e[0] == 'b' : GSB_DEFAULT_BULK; }();
         if (dL_ddepth_sil) {
-            GSB_BWD_LAUNCH_CH(4, 3, 1, 5);
+            if (bulk) GSB_BWD_LAUNCH_CH(4, 3, 1, 5, true); else GSB_BWD_LAUNCH_CH(4, 3, 1, 5, false);
+        } else if (bulk && halves == 1 && stages != 2 && minb != 3) {
+            GSB_BWD_LAUNCH_CH(4, 3, 1, 3, true);
         } else if (halves == 2) {
             if (stages == 2) { if (minb == 8) GSB_BWD_LAUNCH(8, 2, 2); else if (minb == 10) GSB_BWD_LAUNCH(10, 2, 2); else GSB_BWD_LAUNCH(6, 2, 2); }
             else { if (minb == 8) GSB_BWD_LAUNCH(8, 3, 2); else if (minb == 10) GSB_BWD_LAUNCH(10, 3, 2); else GSB_BWD_LAUNCH(6, 3, 2); }

@@ -26,7 +26,7 @@ namespace gsb {
 // CH = 3: the reference pass.  CH = 5: the RGB pass and the depth / silhouette pass of one mapping iteration
 // (src/Render.cc:445-448: colours [r, g, b] and [z_cam, 1, 0] over the SAME geometry) blended together; channel 3
 // accumulates depth * alpha * T, channel 4 alpha * T, with the operation order each has in its own reference pass.
-template <int MINB, int NS, int HALVES, int CH>
+template <int MINB, int NS, int HALVES, int CH, bool BULK>
 __global__ void __launch_bounds__(256 / HALVES, MINB)
 blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                      const SplatRec* __restrict__ rec, int W, int H, const float* __restrict__ bg,
@@ -37,7 +37,7 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                      GeomHeader* __restrict__ hdr, uint32_t layout_capacity, uint32_t band_y0)
 {
     constexpr int BLEND_THREADS = 256 / HALVES, BLEND_BATCH = BLEND_THREADS;
-    __shared__ StageBuf<NS, BLEND_BATCH> S;
+    __shared__ StageRing<NS, BLEND_BATCH, BULK> S;
     __shared__ uint32_t s_max[2];
     const uint32_t tile_y = band_y0 + blockIdx.y / HALVES, half = blockIdx.y % HALVES;   // the grid covers the band's tile rows
     const uint32_t tile = tile_y * gridDim.x + blockIdx.x;
@@ -69,10 +69,16 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
         const int e = b * BLEND_BATCH + (int)threadIdx.x;
         return e < n ? __ldg(ids + e) : 0xffffffffu;
     };
+    auto batch_count = [&](int b) { return min(BLEND_BATCH, n - b * BLEND_BATCH); };
+    S.init();
     // prologue: batches 0 .. NS-2 in flight, ids of batch NS-1 in a register
+    int issued = -1, waited = -1;   // highest batch issued / waited for (the bulk engine must drain before the CTA exits)
 #pragma unroll
     for (int i = 0; i < NS - 1; i++) {
-        if (i < batches) stage_issue(S, i, rec, load_id(i));
+        if (i < batches) {
+            stage_issue(S, i, rec, load_id(i), batch_count(i));
+            issued = i;
+        }
         cp_async_commit();
     }
     uint32_t id_next = NS - 1 < batches ? load_id(NS - 1) : 0xffffffffu;
@@ -80,12 +86,16 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     bool warp_done = done_bits == 0xffffffffu;
     int buf = 0;
     for (int b = 0; b < batches; b++) {
-        cp_async_wait<NS - 2>();  // this thread's copies of batch b have landed
+        stage_wait(S, buf, b);  // batch b has landed (LDGSTS: this thread's copies; bulk: the stage's mbarrier phase)
+        waited = b;
         // one barrier per batch: publishes batch b, and everyone is finished with batch b-1 (whose buffer is reused below)
         if (__syncthreads_count(warp_done) == BLEND_THREADS) break;  // every pixel of the tile is saturated
         {
             const int nbuf = buf == 0 ? NS - 1 : buf - 1;  // (b + NS - 1) % NS
-            if (b + NS - 1 < batches) stage_issue(S, nbuf, rec, id_next);
+            if (b + NS - 1 < batches) {
+                stage_issue(S, nbuf, rec, id_next, batch_count(b + NS - 1));
+                issued = b + NS - 1;
+            }
             cp_async_commit();
             if (b + NS < batches) id_next = load_id(b + NS);
         }
@@ -96,7 +106,7 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                 const int j = c0 + (int)lane;
                 bool hxa = false, hxb = false, hya = false, hyb = false;
                 if (j < cnt) {
-                    const float4 A = S.a[buf][j];
+                    const float4 A = S.A(buf, j);
                     const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&A.z));
                     const float lox = A.x - e.x, hix = A.x + e.x, loy = A.y - e.y, hiy = A.y + e.y;
                     hxa = !(hix < xa0 || lox > xa1);
@@ -115,8 +125,8 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                     const int e = c0 + (act ? __ffs(mask) - 1 : 0);
                     const uint32_t bit = mask & (0u - mask);
                     mask ^= bit;
-                    const float4 A = S.a[buf][e];
-                    const float4 B = S.b[buf][e];
+                    const float4 A = S.A(buf, e);
+                    const float4 B = S.B(buf, e);
                     const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
                     const float power = splat_power(dx, dy, B.x, B.y, B.z);
                     if (!act || done || power > 0.0f || power < A.w) continue;
@@ -127,7 +137,7 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                         done = true;
                         continue;
                     }
-                    const float4 Cc = S.c[buf][e];
+                    const float4 Cc = S.C(buf, e);
                     C0 = fmaf(__fmul_rn(Cc.x, alpha), T, C0);
                     C1 = fmaf(__fmul_rn(Cc.y, alpha), T, C1);
                     C2 = fmaf(__fmul_rn(Cc.z, alpha), T, C2);
@@ -157,6 +167,8 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
         buf = buf == NS - 1 ? 0 : buf + 1;
     }
     cp_async_wait<0>();
+    if (BULK)   // copies still in flight target this CTA's shared memory: wait for them before it is released
+        for (int k = waited + 1; k <= issued; k++) stage_wait(S, k % NS, k);
     if (inside) {
         const size_t HW = (size_t)W * H, pix = (size_t)py * W + px;
         final_T[pix] = T;
@@ -196,23 +208,26 @@ int launch_blend_forward(const FwdParams& p, char* geom, const GeomLayout& GL, c
     static const int stages = [] { const char* e = getenv("GSB_BLEND_FWD_STAGES"); return e ? atoi(e) : 2; }();
     {
         StageTimer _t(ST_BLEND_FWD, s);
-#define GSB_FWD_LAUNCH(MB, NS, HV) GSB_FWD_LAUNCH_CH(MB, NS, HV, 3)
-#define GSB_FWD_LAUNCH_CH(MB, NS, HV, CH)                                                                                      \
+#define GSB_FWD_LAUNCH(MB, NS, HV) GSB_FWD_LAUNCH_CH(MB, NS, HV, 3, false)
+#define GSB_FWD_LAUNCH_CH(MB, NS, HV, CH, BK)                                                                                      \
     do {                                                                                                                \
         static const bool attr_set = [] {  /* many resident CTAs x 12-37 KB: ask for the largest carve-out */          \
-            cudaFuncSetAttribute(blend_forward_kernel<MB, NS, HV, CH>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
+            cudaFuncSetAttribute(blend_forward_kernel<MB, NS, HV, CH, BK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
             return true;                                                                                                \
         }();                                                                                                            \
         (void)attr_set;                                                                                                 \
-        blend_forward_kernel<MB, NS, HV, CH><<<dim3(IL.tiles_x, (p.band_y1 - p.band_y0) * HV), 256 / HV, 0, s>>>(                    \
+        blend_forward_kernel<MB, NS, HV, CH, BK><<<dim3(IL.tiles_x, (p.band_y1 - p.band_y0) * HV), 256 / HV, 0, s>>>(                    \
             reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec), \
             p.W, p.H, p.background, out_color, out_depth, out_depth_sil, reinterpret_cast<float*>(image + IL.final_T),  \
             reinterpret_cast<uint32_t*>(image + IL.n_contrib), reinterpret_cast<uint32_t*>(image + IL.tile_max_contrib), \
             reinterpret_cast<uint32_t*>(binning + BL.hits), reinterpret_cast<uint32_t*>(image + IL.hits_tail),          \
             reinterpret_cast<GeomHeader*>(geom + GL.header), (uint32_t)BL.capacity, (uint32_t)p.band_y0);                                    \
     } while (0)
+        static const bool bulk = [] { const char* e = getenv("GSB_BLEND_STAGE"); return e ? e[0] == 'b' : GSB_DEFAULT_BULK; }();
         if (out_depth_sil) {
-            GSB_FWD_LAUNCH_CH(6, 2, 1, 5);
+            if (bulk) GSB_FWD_LAUNCH_CH(6, 2, 1, 5, true); else GSB_FWD_LAUNCH_CH(6, 2, 1, 5, false);
+        } else if (bulk && halves == 1 && stages != 3 && minb != 8) {
+            GSB_FWD_LAUNCH_CH(6, 2, 1, 3, true);
         } else if (halves == 2) {
             if (stages == 3) { if (minb == 12) GSB_FWD_LAUNCH(12, 3, 2); else GSB_FWD_LAUNCH(16, 3, 2); }
             else { if (minb == 12) GSB_FWD_LAUNCH(12, 2, 2); else GSB_FWD_LAUNCH(16, 2, 2); }
