@@ -354,7 +354,20 @@ def run_ours(args):
         ms_two = timed(two_pass, it_steps, 3) / it_steps
         ms_fused = timed(fused, it_steps, 3) / it_steps
         fr._args.colors_precomp = rgbcol.data_ptr()
+        # the COMPLETE iteration through the fused host-side step: prologue + five-channel pass + fused L1/SSIM/depth loss and
+        # its gradient + summed backward + prologue backward (pose gradient) + Adam on the packed [14,P] block
+        from gsorb_slam_b200.mapping import MapOptimizer
+        mo = MapOptimizer(sc.means3D, sc.colors, sc.logit_opacities, sc.log_scales, sc.unnorm_quats, width=W, height=H,
+                          tanfovx=sc.cam.tanfovx, tanfovy=sc.cam.tanfovy, projmatrix=sc.cam.projmatrix, device=dev,
+                          max_rendered=max_rendered)
+        Tcw_id = torch.eye(4, device=dev)
+        gt_c = fr.color.clone().clamp(0, 1)
+        gt_d = torch.rand(H, W, device=dev) * 5 + 0.5
+        ms_full = timed(lambda: mo.step_slam(Tcw_id, gt_c, gt_d), it_steps, 3) / it_steps
+        del mo
         iteration = {"what": "RGB pass + depth/silhouette pass of one mapping iteration, fwd+bwd, device-resident",
+                     "complete_iteration_ms": ms_full,
+                     "complete_iteration": "MapOptimizer.step_slam: prologue + fused pass + fused L1/SSIM/depth loss + backward + pose gradient + Adam, no torch op",
                      "two_pass_ms": ms_two, "fused_five_channel_ms": ms_fused, "iterations_per_s_two_pass": 1000.0 / ms_two,
                      "iterations_per_s_fused": 1000.0 / ms_fused, "steps": it_steps}
 

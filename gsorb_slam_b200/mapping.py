@@ -173,6 +173,32 @@ class MapOptimizer:
         self._exchange_and_adam(average)
         return color, depth_sil
 
+    def step_slam(self, Tcw: torch.Tensor, gt_color: torch.Tensor, gt_depth: torch.Tensor, lambda_: float = 0.8,
+                  w_image: float = 1.0, w_depth: float = 0.7, w_surdepth: float = 0.35, average: bool = False):
+        """One complete mapping iteration of Render::RenderForFrame (src/Render.cc:420-476) without a single torch op on the
+        hot path: prologue -> ONE five-channel rasterization -> fused L1 + SSIM + depth loss and its gradient
+        (gsb_mapping_loss) -> summed backward -> prologue backward -> exchange -> Adam.  Weights default to
+        Examples/RGB-D/replica.yaml:89-94.  Returns the 8 loss terms (device tensor: l1, ssim, depth_l1, surdepth_l1, total,
+        n_valid, n_valid_sur, 0); the scale regularisers (Render.cc:462-467) are the caller's."""
+        L, s = self.L, self._s()
+        color, depth_sil, median, _ = self.render_fused(Tcw)
+        if not hasattr(self, "_loss_scratch"):
+            nb = int(L.gsb_loss_scratch_bytes(self.W, self.H))
+            self._loss_scratch = torch.empty(nb, dtype=torch.uint8, device=self.dev)
+            self._gC = torch.empty((3, self.H, self.W), dtype=torch.float32, device=self.dev)
+            self._gD = torch.empty((2, self.H, self.W), dtype=torch.float32, device=self.dev)
+            self.loss_terms = torch.empty(8, dtype=torch.float32, device=self.dev)
+        gtc = gt_color.to(self.dev, torch.float32).contiguous()
+        gtd = gt_depth.to(self.dev, torch.float32).contiguous()
+        with torch.cuda.device(self.dev):
+            _lib.check(L.gsb_mapping_loss(self.W, self.H, color.data_ptr(), depth_sil.data_ptr(), median.data_ptr(), gtc.data_ptr(),
+                                          gtd.data_ptr(), float(lambda_), float(w_image), float(w_depth), float(w_surdepth),
+                                          self._gC.data_ptr(), self._gD.data_ptr(), self.loss_terms.data_ptr(),
+                                          self._loss_scratch.data_ptr(), self._loss_scratch.numel(), s))
+        self.backward_fused(self._gC, self._gD, z_attached=True)
+        self._exchange_and_adam(average)
+        return self.loss_terms
+
     def step(self, Tcw: torch.Tensor, loss_grad: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], average: bool = False):
         """One optimisation step on this rank's keyframe.  ``loss_grad(color, depth) -> dL/dcolor``."""
         color, depth, _ = self.render(Tcw)

@@ -232,6 +232,23 @@ int gsb_adam_step(long long n, float* param, const float* grad, float* exp_avg, 
                   float lr, float beta1, float beta2, float eps, long long step,
                   gsb_stream_t stream);
 
+/* ---- fused loss of one mapping iteration (extension) ------------------------
+ * The producer of dL/dpixel in Render::RenderForFrame (src/Render.cc:454-469) and its autograd, in two kernels:
+ *   loss = w_image * (lambda * mean|I - G| + (1 - lambda) * (1 - SSIM(I, G)))
+ *        + w_depth * mean_{G_d > 0} |D - G_d|  +  w_surdepth * mean_{G_d > 0, S > 0.99} |M - G_d|
+ * with I = color [3,H,W], (D, S) = depth_sil [2,H,W], M = median_depth [1,H,W] (no gradient: Rasterizer.cuh:210),
+ * G / G_d the ground-truth image / depth; SSIM exactly as src/Utils.cc:68-100 builds it (11x11 window from the
+ * reference's off-centre 1-D weights, zero padding, C1 = 0.01^2, C2 = 0.03^2, global mean).  depth_sil, median_depth,
+ * gt_depth, dL_ddepth_sil may be NULL (image term only).  Outputs: dL_dcolor [3,H,W], dL_ddepth_sil [2,H,W] and
+ * loss_terms[8] on the DEVICE = {l1, ssim, depth_l1, surdepth_l1, total, n_valid, n_valid_sur, 0}.  The scale
+ * regularisers of Render.cc:462-467 act on the parameters, not on pixels, and stay with the caller. */
+size_t gsb_loss_scratch_bytes(int width, int height);
+int gsb_mapping_loss(int width, int height, const float* color, const float* depth_sil, const float* median_depth,
+                     const float* gt_color, const float* gt_depth,
+                     float lambda_, float w_image, float w_depth, float w_surdepth,
+                     float* dL_dcolor, float* dL_ddepth_sil, float* loss_terms,
+                     void* scratch, size_t scratch_bytes, gsb_stream_t stream);
+
 /* ---- multi-GPU exchange step (the reference is single-GPU) ----------------------
  * In-place SUM all-reduce of n fp32 values (n % 4 == 0) that live at the same offset of a
  * symmetric, peer-mapped allocation on every rank of one NVLink / NVSwitch box -- the packed

@@ -426,3 +426,76 @@ def test_forward_backward_are_cuda_graph_capturable():
     torch.cuda.synchronize()
     assert rel_to_scale(to_np(fr.color), want[0]) <= 1e-5
     assert rel_to_scale(to_np(g["dL_dmean3D"]), want[1]) <= 1e-4 and rel_to_scale(to_np(g["dL_dopacity"]), want[2]) <= 1e-4
+
+
+def _reference_window(device):
+    """src/Utils.cc:68-80 (GaussianGenerator / CreateWindow) in torch float32."""
+    import math
+    import torch
+    g = torch.tensor([math.exp(-(math.floor((x - 11) / 2.0) ** 2) / (2.0 * 1.5 * 1.5)) for x in range(11)], dtype=torch.float32)
+    g = (g / g.sum()).unsqueeze(1)
+    return g.mm(g.t()).unsqueeze(0).unsqueeze(0).expand(3, 1, 11, 11).contiguous().to(device)
+
+
+@pytest.mark.parametrize("W,H", [(160, 120), (100, 75), (640, 480)])
+def test_fused_mapping_loss_matches_torch_autograd(W, H):
+    """gsb_mapping_loss against the libtorch expression of Render::RenderForFrame (src/Render.cc:454-469; SSIM of
+    src/Utils.cc:81-100 with its off-centre window) differentiated by autograd."""
+    import torch
+    import torch.nn.functional as F
+    from gsorb_slam_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(W)
+    gt = torch.rand(3, H, W, device=dev, generator=gen)
+    img = (gt + 0.1 * torch.randn(3, H, W, device=dev, generator=gen)).clamp(0, 1).requires_grad_(True)
+    gtd = torch.rand(H, W, device=dev, generator=gen) * 5 + 0.3
+    gtd[torch.rand(H, W, device=dev, generator=gen) < 0.2] = 0.0                        # invalid depth pixels
+    ds = torch.stack([gtd + 0.05 * torch.randn(H, W, device=dev, generator=gen), torch.rand(H, W, device=dev, generator=gen) * 0.05 + 0.96]).requires_grad_(True)
+    med = gtd + 0.1 * torch.randn(H, W, device=dev, generator=gen)
+    lam, w_im, w_d, w_s = 0.8, 1.0, 0.7, 0.35                                             # replica.yaml:90-94
+    win = _reference_window(dev)
+    conv = lambda t: F.conv2d(t.unsqueeze(0), win, padding=5, groups=3)
+    mu1, mu2 = conv(img), conv(gt)
+    s11, s22, s12 = conv(img * img) - mu1 * mu1, conv(gt * gt) - mu2 * mu2, conv(img * gt) - mu1 * mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    ssim = (((2 * mu1 * mu2 + C1) * (2 * s12 + C2)) / ((mu1 * mu1 + mu2 * mu2 + C1) * (s11 + s22 + C2))).mean()
+    l1 = (img - gt).abs().mean()
+    valid = gtd > 0
+    dl = (ds[0] - gtd).abs()[valid].mean()
+    sl = (med - gtd).abs()[valid & (ds[1] > 0.99)].mean()
+    total = w_im * (lam * l1 + (1 - lam) * (1 - ssim)) + w_d * dl + w_s * sl
+    total.backward()
+    gC, gD, terms = torch.empty(3, H, W, device=dev), torch.empty(2, H, W, device=dev), torch.empty(8, device=dev)
+    nb = int(L.gsb_loss_scratch_bytes(W, H))
+    scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
+    _lib.check(L.gsb_mapping_loss(W, H, img.data_ptr(), ds.data_ptr(), med.data_ptr(), gt.data_ptr(), gtd.data_ptr(), lam, w_im, w_d, w_s,
+                                  gC.data_ptr(), gD.data_ptr(), terms.data_ptr(), scratch.data_ptr(), nb, torch.cuda.current_stream().cuda_stream))
+    tt = to_np(terms)
+    for got, want, name in ((tt[0], l1, "l1"), (tt[1], ssim, "ssim"), (tt[2], dl, "depth"), (tt[3], sl, "surdepth"), (tt[4], total, "total")):
+        assert abs(float(got) - float(want.detach())) <= 1e-5 * max(1.0, abs(float(want.detach()))), name
+    assert int(tt[5]) == int(valid.sum()) and int(tt[6]) == int((valid & (ds[1] > 0.99)).sum())
+    assert rel_to_scale(to_np(gC), to_np(img.grad)) <= 1e-4
+    assert rel_to_scale(to_np(gD), to_np(ds.grad)) <= 1e-5
+
+
+def test_complete_slam_iteration_decreases_its_loss():
+    """MapOptimizer.step_slam end to end: a perturbed map optimised against images rendered from the unperturbed one must
+    reduce the fused loss monotonically enough (first vs. last of 25 iterations) and keep every parameter finite."""
+    import torch
+    from gsorb_slam_b200.lowlevel import frame_from_scene
+    from gsorb_slam_b200.mapping import MapOptimizer
+    from gsorb_slam_b200.scene import make_scene
+    sc = make_scene(20_000, (160, 120, 130.0, 128.0), seed=51, scale_mul=1.5)
+    dev = torch.device("cuda:0")
+    tgt = frame_from_scene(sc, fused=True, max_rendered=1 << 19)
+    gt_c, gt_d = tgt.color.clone(), tgt.depth_sil[0].clone()
+    rng = np.random.default_rng(0)
+    opt = MapOptimizer(sc.means3D, np.clip(sc.colors + rng.normal(0, 0.15, sc.colors.shape), 0, 1).astype(np.float32),
+                       sc.logit_opacities, sc.log_scales + rng.normal(0, 0.1, sc.log_scales.shape).astype(np.float32),
+                       sc.unnorm_quats, width=160, height=120, tanfovx=sc.cam.tanfovx, tanfovy=sc.cam.tanfovy,
+                       projmatrix=sc.cam.projmatrix, device=dev, max_rendered=1 << 19)
+    Tcw = torch.eye(4, device=dev)
+    losses = [float(opt.step_slam(Tcw, gt_c, gt_d)[4]) for _ in range(25)]
+    assert np.isfinite(losses).all() and losses[-1] < 0.8 * losses[0], losses
+    assert bool(torch.isfinite(opt.params.flat).all())
