@@ -13,15 +13,18 @@
 //   1. preprocess counts instances per tile (atomics on T counters),
 //   2. one CTA scans the T counts -> every tile's [start, end) segment = the tile ranges
 //      (identifyTileRanges disappears) and num_rendered,
-//   3. duplicate claims slots in the segments with per-tile cursors and writes
-//      (depth bits << 32 | id) records -- bucketed by tile, arbitrary order inside a tile,
-//   4. one CTA per tile sorts its segment in SHARED memory (a tile's list fits: up to 4096
-//      entries in 32 KB, up to 16384 in 128 KB of the 227 KB an sm_100 CTA can own) with a
-//      bitonic network on the full 64-bit record and writes the ids out.
-// Ordering by (depth bits, id) is exactly the order the reference's stable radix sort
-// produces (instances are emitted in ascending id, so ties keep id order), hence the sorted
-// list is bit-identical -- while every instance is written twice and read twice instead of
-// seven times.  Tiles longer than 16384 entries fall back to a global-memory network.
+//   3. duplicate writes (depth bits << 32 | id) records into the segments -- bucketed by tile, arbitrary order inside
+//      a tile; Gaussians touching <= 4 tiles use the slots their counting atomics returned (no second atomic round),
+//      larger ones claim slots in the tail of each segment,
+//   4. one CTA per tile sorts its segment on ONE 32-bit key per record -- the depth rebased to the tile's minimum and
+//      quantised to the bits left above the record's index in the segment -- with a register / shuffle / shared-memory
+//      bitonic network (VIMNMX comparators), then repairs the few neighbours whose quantised depths collide by an
+//      odd-even transposition on the exact 64-bit records, and writes the ids out.  Size classes: n <= 4096 (256
+//      threads, 16 KB), n <= 16384 (1024 threads, 64 KB, one persistent CTA per SM), longer: a 64-bit network in
+//      global memory (pathological inputs only).
+// Ordering by (depth bits, id) is exactly the order the reference's stable radix sort produces (instances are emitted
+// in ascending id, so ties keep id order), hence the sorted list is bit-identical -- while every instance is written
+// twice and read twice instead of seven times.
 #include "common.cuh"
 
 namespace gsb {
@@ -167,101 +170,9 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t n)
     return n <= 1 ? 1u : 1u << (32 - __clz(n - 1));
 }
 
-constexpr int TSORT_SMALL = 4096;    // entries, 32 KB
-constexpr int TSORT_MID = 16384;     // entries, 128 KB
+constexpr int TSORT_SMALL = 4096;    // entries, 16 KB of 32-bit keys
+constexpr int TSORT_MID = 16384;     // entries, 64 KB
 constexpr int TSORT_THREADS = 256;
-
-// Register-resident bitonic sort of E * 256 records by one 256-thread CTA (blocked layout:
-// thread t owns elements t*E .. t*E+E-1).  Of the log2(n)(log2(n)+1)/2 comparator stages only
-// those that cross warps (stride >= 32 E) go through shared memory; strides inside a warp are
-// 64-bit shuffles and strides inside a thread are register compare-exchanges.
-__device__ __forceinline__ void cx(uint64_t& lo, uint64_t& hi)
-{
-    const uint64_t a = lo, b = hi;
-    const bool sw = a > b;
-    lo = sw ? b : a;
-    hi = sw ? a : b;
-}
-
-template <int E>
-__device__ __forceinline__ void tile_sort_regs(uint64_t* __restrict__ s /* smem, E*256 records, padded with ~0 */)
-{
-    constexpr uint32_t N = E * TSORT_THREADS;
-    const uint32_t t = threadIdx.x, lane = t & 31;
-    uint64_t a[E];
-#pragma unroll
-    for (int r = 0; r < E; r++) a[r] = s[t * E + r];
-#pragma unroll
-    for (uint32_t k = 2; k <= N; k <<= 1) {
-        // ---- flip step of the merge of size k ----
-        if (k <= (uint32_t)E) {
-#pragma unroll
-            for (int b0 = 0; b0 < E; b0 += (int)k)
-#pragma unroll
-                for (int o = 0; o < (int)k / 2; o++) cx(a[b0 + o], a[b0 + (int)k - 1 - o]);
-        } else if (k <= 32u * E) {
-            const uint32_t m = k / E;  // 2..32 threads per k-block
-            uint64_t other[E];
-#pragma unroll
-            for (int r = 0; r < E; r++) other[r] = __shfl_xor_sync(0xffffffffu, a[E - 1 - r], m - 1);
-            const bool lower = (lane & (m >> 1)) == 0;
-#pragma unroll
-            for (int r = 0; r < E; r++) a[r] = lower ? (a[r] < other[r] ? a[r] : other[r]) : (a[r] > other[r] ? a[r] : other[r]);
-        }
-        uint32_t j = k >> 2;  // first stride of the half-cleaners
-        if (k > 32u * E) {
-            // cross-warp part of this merge in shared memory: flip, then strides >= 32 E
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < E; r++) s[t * E + r] = a[r];
-            __syncthreads();
-            const uint32_t half = k >> 1;
-            for (uint32_t p = t; p < N / 2; p += TSORT_THREADS) {
-                const uint32_t blk = p / half, off = p % half;
-                const uint32_t i = blk * k + off, l = blk * k + (k - 1 - off);
-                const uint64_t x = s[i], y = s[l];
-                if (x > y) { s[i] = y; s[l] = x; }
-            }
-            __syncthreads();
-            for (; j >= 32u * E; j >>= 1) {
-                for (uint32_t p = t; p < N / 2; p += TSORT_THREADS) {
-                    const uint32_t i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), l = i | j;
-                    const uint64_t x = s[i], y = s[l];
-                    if (x > y) { s[i] = y; s[l] = x; }
-                }
-                __syncthreads();
-            }
-#pragma unroll
-            for (int r = 0; r < E; r++) a[r] = s[t * E + r];
-        }
-        // ---- half-cleaners inside a warp (shuffles) ----
-#pragma unroll
-        for (uint32_t jj = 16u * E; jj >= (uint32_t)E; jj >>= 1) {
-            if (jj <= j && jj >= 1) {
-                const uint32_t m = jj / E;
-                const bool lower = (lane & m) == 0;
-#pragma unroll
-                for (int r = 0; r < E; r++) {
-                    const uint64_t o = __shfl_xor_sync(0xffffffffu, a[r], m);
-                    a[r] = lower ? (a[r] < o ? a[r] : o) : (a[r] > o ? a[r] : o);
-                }
-            }
-        }
-        // ---- half-cleaners inside a thread (registers) ----
-#pragma unroll
-        for (int jj = E / 2; jj >= 1; jj >>= 1) {
-            if ((uint32_t)jj <= j) {
-#pragma unroll
-                for (int r = 0; r < E; r++)
-                    if ((r & jj) == 0) cx(a[r], a[r | jj]);
-            }
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < E; r++) s[t * E + r] = a[r];
-    __syncthreads();
-}
 
 // ---- 32-bit keyed variant (the common size classes, n <= 4096) ----------------------------------
 // A tile's records are (depth bits << 32 | id).  Sorting 64-bit records costs a two-instruction

@@ -346,7 +346,6 @@ int launch_tile_scan(char* geom, const GeomLayout& GL, char* image, const ImageL
                      cudaStream_t s);
 int launch_visible_filter(const FwdParams& p, int* radii, cudaStream_t s);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s);
-int sort_passes_for(int tiles);
 int launch_sort_pairs(GeomHeader* hdr, uint64_t* const kbuf[2], uint32_t* const vbuf[2], int start, int passes,
                       uint32_t* hist, uint32_t* lookback, int sort_tiles, cudaStream_t s);
 // grid_instances: host-side upper bound on the instance count used to size the sort grid
@@ -371,7 +370,5 @@ int launch_adam(long long n, float* param, const float* grad, float* m, float* v
                 float eps, long long step, cudaStream_t s);
 size_t knn_workspace_bytes(int P);
 int launch_knn(int P, const float* points, float* mean_dist2, char* ws, cudaStream_t s);
-int launch_unpack_geometry(int P, const SplatRec* rec, const uint32_t* tiles_touched, float* depths, float* means2D,
-                           float* conic_opacity, uint32_t* tt_out, cudaStream_t s);
 
 }  // namespace gsb
