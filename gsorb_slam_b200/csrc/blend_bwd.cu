@@ -131,13 +131,19 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
             id_next = load_id(k + NS);
         }
         const int kb = batches - 1 - k;
-#pragma unroll 1
-        for (int wi = BLEND_BATCH / 32 - 1; wi >= 0; wi--) {
-            const int w = kb * (BLEND_BATCH / 32) + wi;
-            if (w * 32 >= n) continue;
-            uint32_t mask = w <= wq_last ? s_hits[buf][wi * BLOCKS + lwarp * 4 + q] : 0u;
-            // ---- gradient pass: every quarter-warp walks the entries that hit ITS block, back to front ----
-            while (__any_sync(0xffffffffu, mask != 0)) {
+        // Every quarter-warp walks the hit words of ITS 4x2 block through the whole batch at its own pace (window after
+        // window, back to front): the warp iterates max-over-quarters of the BATCH's visit counts instead of the sum over
+        // windows of per-window maxima -- about 11 % fewer iterations at the headline workload.
+        const int wi_lo = 0;
+        int wi = min(BLEND_BATCH / 32 - 1, (n - 1 - kb * BLEND_BATCH) >> 5);   // last window of the batch that holds entries < n
+        auto fetch = [&](int wv) -> uint32_t {
+            return (kb * (BLEND_BATCH / 32) + wv) <= wq_last ? s_hits[buf][wv * BLOCKS + lwarp * 4 + q] : 0u;
+        };
+        uint32_t mask = fetch(wi);
+        {
+            while (true) {
+                if (mask == 0u && wi > wi_lo) mask = fetch(--wi);   // this quarter moves on to its next window (one per iteration)
+                if (!__any_sync(0xffffffffu, mask != 0u)) break;
                 const bool act = mask != 0;
                 const int eb = act ? 31 - __clz(mask) : 0;
                 mask &= ~(1u << eb);
