@@ -143,7 +143,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
         {
             while (true) {
                 if (mask == 0u && wi > wi_lo) mask = fetch(--wi);   // this quarter moves on to its next window (one per iteration)
-                if (!__any_sync(0xffffffffu, mask != 0u)) break;
+                if (!__any_sync(0xffffffffu, mask != 0u || wi > wi_lo)) break;   // nothing queued and no window left, in any quarter
                 const bool act = mask != 0;
                 const int eb = act ? 31 - __clz(mask) : 0;
                 mask &= ~(1u << eb);
