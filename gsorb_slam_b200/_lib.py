@@ -56,6 +56,8 @@ SIGNATURES = {
     "gsb_adam_step": (_i, [_ll, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _ll, _vp]),
     "gsb_loss_scratch_bytes": (_sz, [_i, _i]),
     "gsb_mapping_loss": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gsb_backproject_scratch_bytes": (_sz, [_i, _i]),
+    "gsb_backproject": (_i, [_i, _i, _vp, _vp, _vp, _f, _f, _f, _f, C.POINTER(_f), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gsb_exchange_sync_bytes": (_sz, [_i]),
     "gsb_exchange_allreduce": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), _ll, _i, _i, _vp]),
     "gsb_host_scratch_bytes": (_sz, [_i, _i, _i, _i, _ll]),

@@ -249,6 +249,22 @@ int gsb_mapping_loss(int width, int height, const float* color, const float* dep
                      float* dL_dcolor, float* dL_ddepth_sil, float* loss_terms,
                      void* scratch, size_t scratch_bytes, gsb_stream_t stream);
 
+/* ---- densification: back-projection of selected pixels (extension) ------
+ * GPU twin of the host loops Render::ProjectPixel / Render::InitGaussianPoint (src/Render.cc:617-655, :666-707) and of the
+ * parameter initialisation of Gaussian::AddGaussianPoints (src/Gaussian.cc:50-74, SinglePixel scales).  For every pixel
+ * with mask >= 250 (mask NULL: every pixel) and depth > 0, in row-major pixel order (= the ids the reference assigns):
+ *   mean = Twc [((j-cx) z/fx, (i-cy) z/fy, z); 1], rgb = image[:, i, j], log_scale = log(|mean.z| / ((fx+fy)/2)) x 3,
+ *   unnorm_quat = (1,0,0,0), logit_opacity = 1.
+ * mask [H,W] u8, depth [H,W], image [3,H,W] are DEVICE pointers; Twc_host is 16 floats, row-major, on the HOST.  Rows
+ * beyond `capacity` are dropped; *count (DEVICE int) receives the number of selected pixels either way.  max_z
+ * (DEVICE float, may be NULL) is raised to the largest selected depth (Render::mMaxZ; initialise it to the running
+ * value).  Any of rgb / log_scales / unnorm_quats / logit_opacities may be NULL. */
+size_t gsb_backproject_scratch_bytes(int width, int height);
+int gsb_backproject(int width, int height, const uint8_t* mask, const float* depth, const float* image,
+                    float fx, float fy, float cx, float cy, const float* Twc_host, int capacity,
+                    float* means, float* rgb, float* log_scales, float* unnorm_quats, float* logit_opacities,
+                    int* count, float* max_z, void* scratch, size_t scratch_bytes, gsb_stream_t stream);
+
 /* ---- multi-GPU exchange step (the reference is single-GPU) ----------------------
  * In-place SUM all-reduce of n fp32 values (n % 4 == 0) that live at the same offset of a
  * symmetric, peer-mapped allocation on every rank of one NVLink / NVSwitch box -- the packed

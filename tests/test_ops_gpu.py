@@ -499,3 +499,58 @@ def test_complete_slam_iteration_decreases_its_loss():
     losses = [float(opt.step_slam(Tcw, gt_c, gt_d)[4]) for _ in range(25)]
     assert np.isfinite(losses).all() and losses[-1] < 0.8 * losses[0], losses
     assert bool(torch.isfinite(opt.params.flat).all())
+
+
+@pytest.mark.parametrize("W,H,use_mask", [(160, 120, True), (101, 77, False), (640, 480, True)])
+def test_backproject_matches_the_reference_host_loop(W, H, use_mask):
+    """gsb_backproject against a numpy restatement of Render::ProjectPixel + Gaussian::AddGaussianPoints (SinglePixel):
+    same rows in the same (row-major pixel) order, same count and max depth."""
+    import ctypes as C
+    import torch
+    from gsorb_slam_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(W + H)
+    depth = rng.uniform(0.3, 6.0, (H, W)).astype(np.float32)
+    depth[rng.random((H, W)) < 0.15] = 0.0
+    mask = np.where(rng.random((H, W)) < 0.4, 255, rng.integers(0, 250, (H, W))).astype(np.uint8)
+    image = rng.random((3, H, W)).astype(np.float32)
+    fx, fy, cx, cy = np.float32(517.3), np.float32(516.5), np.float32(W / 2 - 0.7), np.float32(H / 2 + 0.3)
+    ang = 0.3
+    Twc = np.eye(4, dtype=np.float32)
+    Twc[:3, :3] = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]], np.float32)
+    Twc[:3, 3] = [0.2, -0.1, 0.4]
+    sel = (depth > 0) & ((mask >= 250) if use_mask else True)
+    ii, jj = np.nonzero(sel)                                   # row-major order, as the CPU double loop
+    z = depth[ii, jj]
+    x = ((jj.astype(np.float32) - cx) * z) / fx
+    y = ((ii.astype(np.float32) - cy) * z) / fy
+    pc = np.stack([x, y, z, np.ones_like(z)], 1).astype(np.float32)
+    pw = (pc.astype(np.float64) @ Twc.astype(np.float64).T)[:, :3]
+    want_ls = np.log(np.sqrt((pw[:, 2] / ((float(fx) + float(fy)) * 0.5)) ** 2))
+    K = len(z)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_depth, d_mask, d_img = t(depth), t(mask), t(image)
+    cap = K + 10
+    means, rgb, ls = torch.zeros(cap, 3, device=dev), torch.zeros(cap, 3, device=dev), torch.zeros(cap, 3, device=dev)
+    quat, op = torch.zeros(cap, 4, device=dev), torch.zeros(cap, device=dev)
+    count, maxz = torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(1, device=dev)
+    nb = int(L.gsb_backproject_scratch_bytes(W, H))
+    scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
+    Th = (C.c_float * 16)(*Twc.reshape(-1).tolist())
+    _lib.check(L.gsb_backproject(W, H, d_mask.data_ptr() if use_mask else None, d_depth.data_ptr(), d_img.data_ptr(), float(fx), float(fy),
+                                 float(cx), float(cy), Th, cap, means.data_ptr(), rgb.data_ptr(), ls.data_ptr(), quat.data_ptr(),
+                                 op.data_ptr(), count.data_ptr(), maxz.data_ptr(), scratch.data_ptr(), nb, torch.cuda.current_stream().cuda_stream))
+    assert int(count.item()) == K
+    assert float(maxz.item()) == float(z.max())
+    assert np.abs(to_np(means)[:K] - pw).max() <= 2e-6 * np.abs(pw).max()
+    np.testing.assert_array_equal(to_np(rgb)[:K], image[:, ii, jj].T)
+    assert np.abs(to_np(ls)[:K] - want_ls[:, None]).max() <= 1e-5
+    np.testing.assert_array_equal(to_np(quat)[:K], np.tile(np.array([1, 0, 0, 0], np.float32), (K, 1)))
+    np.testing.assert_array_equal(to_np(op)[:K], np.ones(K, np.float32))
+    assert float(to_np(means)[K:].sum()) == 0.0                 # nothing written past the count
+    # capacity smaller than the count: rows are dropped, the count is still reported
+    _lib.check(L.gsb_backproject(W, H, d_mask.data_ptr() if use_mask else None, d_depth.data_ptr(), d_img.data_ptr(), float(fx), float(fy),
+                                 float(cx), float(cy), Th, K // 2, means.data_ptr(), None, None, None, None, count.data_ptr(), None,
+                                 scratch.data_ptr(), nb, torch.cuda.current_stream().cuda_stream))
+    assert int(count.item()) == K
