@@ -302,8 +302,7 @@ torch::autograd::tensor_list _RasterizeGaussiansFused::backward(torch::autograd:
         g.dL_dopacity = g_opacity.data_ptr<float>(); g.dL_dcolor = g_colors.data_ptr<float>();
         g.dL_dmean3D = g_means3D.data_ptr<float>(); g.dL_dscale = g_scales.data_ptr<float>(); g.dL_drot = g_rot.data_ptr<float>();
         check(gsb_backward_fused(&m.a, radii.data_ptr<int>(), s[9].data_ptr(), s[10].data_ptr(), s[11].data_ptr(), dC.data_ptr<float>(),
-                                 dD.data_ptr<float>(), &g, g_z.data_ptr<float>(), stream()));
-        if (ctx->saved_data["z_attached"].toBool()) g_means3D.select(1, 2).add_(g_z);
+                                 dD.data_ptr<float>(), &g, g_z.data_ptr<float>(), ctx->saved_data["z_attached"].toBool() ? 1 : 0, stream()));
     }
     // gradients in the order of forward's arguments; settings / flag get none
     return {g_means3D, g_colors, g_opacity, g_scales, g_rot, torch::Tensor(), torch::Tensor()};

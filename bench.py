@@ -357,7 +357,7 @@ def run_ours(args):
                                               fr.binning.numel(), max_rendered, fr.img.data_ptr(), fr.img.numel(), fr.color.data_ptr(),
                                               ds.data_ptr(), fr.depth.data_ptr(), fr.radii.data_ptr(), stream))
             _lib.check(L.gsb_backward_fused(C.byref(fr._args), fr.radii.data_ptr(), fr.geom.data_ptr(), fr.binning.data_ptr(),
-                                            fr.img.data_ptr(), dL.data_ptr(), dD.data_ptr(), C.byref(g), zgrad.data_ptr(), stream))
+                                            fr.img.data_ptr(), dL.data_ptr(), dD.data_ptr(), C.byref(g), zgrad.data_ptr(), 1, stream))
 
         it_steps = max(3, min(args.steps, 20))
         ms_two = timed(two_pass, it_steps, 3) / it_steps

@@ -45,7 +45,7 @@ SIGNATURES = {
     "gsb_num_rendered": (_ll, [_vp, _vp]),
     "gsb_backward": (_i, [C.POINTER(RasterArgs), _ll, _vp, _vp, _vp, _vp, _vp, C.POINTER(GradOutputs), _vp]),
     "gsb_forward_fused_ws": (_i, [C.POINTER(RasterArgs), _vp, _sz, _vp, _sz, _ll, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
-    "gsb_backward_fused": (_i, [C.POINTER(RasterArgs), _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(GradOutputs), _vp, _vp]),
+    "gsb_backward_fused": (_i, [C.POINTER(RasterArgs), _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(GradOutputs), _vp, _i, _vp]),
     "gsb_visible_filter": (_i, [C.POINTER(RasterArgs), _vp, _vp]),
     "gsb_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
     "gsb_knn_workspace_bytes": (_sz, [_i]),
@@ -60,6 +60,7 @@ SIGNATURES = {
     "gsb_backproject": (_i, [_i, _i, _vp, _vp, _vp, _f, _f, _f, _f, C.POINTER(_f), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gsb_exchange_sync_bytes": (_sz, [_i]),
     "gsb_exchange_allreduce": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), _ll, _i, _i, _vp]),
+    "gsb_adam_step_groups": (_i, [_i, C.POINTER(_ll), C.POINTER(_f), _vp, _vp, _vp, _vp, _f, _f, _f, _ll, _vp]),
     "gsb_host_scratch_bytes": (_sz, [_i, _i, _i, _i, _ll]),
     "gsb_forward_backward_host": (_ll, [C.POINTER(RasterArgs), _ll, _vp, _vp, _vp, _vp, C.POINTER(GradOutputs), _vp, _sz, _vp]),
     "gsb_debug_image_state": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),

@@ -284,7 +284,7 @@ long long gsb_num_rendered(const void* geometry, gsb_stream_t stream)
 
 static int backward_impl(const gsb_raster_args* args, const int* radii, const void* geometry, const void* binning,
                          const void* image, const float* dL_dpix, const float* dL_ddepth_sil, const gsb_grad_outputs* grads,
-                         float* dL_dzcolor, gsb_stream_t stream)
+                         float* dL_dzcolor, int z_attached, gsb_stream_t stream)
 {
     if (int rc = validate(args, true, false)) return rc;  // opacities are not an input of the backward (rasterizer.h:55-83)
     if (!geometry || !binning || !image) return fail(GSB_ERR_INVALID_ARGUMENT, "forward state blobs are required");
@@ -296,22 +296,22 @@ static int backward_impl(const gsb_raster_args* args, const int* radii, const vo
     char* geom = (char*)const_cast<void*>(geometry);  // the packed accumulators live in the blob
     if (int rc = launch_blend_backward(p, geom, GL, (const char*)binning, (const char*)image, IL, dL_dpix, dL_ddepth_sil, s))
         return rc;
-    return launch_gauss_backward(p, geom, GL, radii, *grads, dL_dzcolor, s);
+    return launch_gauss_backward(p, geom, GL, radii, *grads, dL_dzcolor, z_attached, s);
 }
 
 int gsb_backward(const gsb_raster_args* args, long long R, const int* radii, const void* geometry, const void* binning,
                  const void* image, const float* dL_dpix, const gsb_grad_outputs* grads, gsb_stream_t stream)
 {
     (void)R;  // tile ranges in the image blob already bound every list
-    return backward_impl(args, radii, geometry, binning, image, dL_dpix, nullptr, grads, nullptr, stream);
+    return backward_impl(args, radii, geometry, binning, image, dL_dpix, nullptr, grads, nullptr, 0, stream);
 }
 
 int gsb_backward_fused(const gsb_raster_args* args, const int* radii, const void* geometry, const void* binning,
                        const void* image, const float* dL_dcolor, const float* dL_ddepth_sil, const gsb_grad_outputs* grads,
-                       float* dL_dzcolor, gsb_stream_t stream)
+                       float* dL_dzcolor, int z_attached, gsb_stream_t stream)
 {
     if (!dL_ddepth_sil) return fail(GSB_ERR_INVALID_ARGUMENT, "dL_ddepth_sil is required");
-    return backward_impl(args, radii, geometry, binning, image, dL_dcolor, dL_ddepth_sil, grads, dL_dzcolor, stream);
+    return backward_impl(args, radii, geometry, binning, image, dL_dcolor, dL_ddepth_sil, grads, dL_dzcolor, z_attached, stream);
 }
 
 int gsb_visible_filter(const gsb_raster_args* args, int* radii, gsb_stream_t stream)
@@ -380,6 +380,17 @@ int gsb_adam_step(long long n, float* param, const float* grad, float* exp_avg, 
     if (n < 0 || step < 1 || (n > 0 && (!param || !grad || !exp_avg || !exp_avg_sq)))
         return fail(GSB_ERR_INVALID_ARGUMENT, "adam_step: bad arguments");
     return launch_adam(n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, (cudaStream_t)stream);
+}
+
+int gsb_adam_step_groups(int ngroups, const long long* group_sizes_host, const float* lrs_host, float* param, const float* grad,
+                         float* exp_avg, float* exp_avg_sq, float beta1, float beta2, float eps, long long step, gsb_stream_t stream)
+{
+    if (ngroups < 0 || ngroups > 8 || step < 1 || (ngroups > 0 && (!group_sizes_host || !lrs_host || !param || !grad || !exp_avg || !exp_avg_sq)))
+        return fail(GSB_ERR_INVALID_ARGUMENT, "adam_step_groups: need 0 <= ngroups <= 8, step >= 1 and all arrays");
+    for (int g = 0; g < ngroups; g++)
+        if (group_sizes_host[g] < 0) return fail(GSB_ERR_INVALID_ARGUMENT, "adam_step_groups: negative group size");
+    return launch_adam_groups(ngroups, group_sizes_host, lrs_host, param, grad, exp_avg, exp_avg_sq, beta1, beta2, eps, step,
+                              (cudaStream_t)stream);
 }
 
 // ---- host-buffer convenience ----------------------------------------------------------------

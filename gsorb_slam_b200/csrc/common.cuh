@@ -359,7 +359,7 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
                           const char* image, const ImageLayout& IL, const float* dL_dpix, const float* dL_ddepth_sil,
                           cudaStream_t s);
 int launch_gauss_backward(const FwdParams& p, const char* geom, const GeomLayout& GL, const int* radii,
-                          const gsb_grad_outputs& g, float* dL_dzcolor, cudaStream_t s);
+                          const gsb_grad_outputs& g, float* dL_dzcolor, int z_attached, cudaStream_t s);
 int launch_prologue(int P, const float* Tcw, const float* means_world, const float* logit, const float* quats,
                     const float* log_scales, float* means_cam, float* opac, float* rot, float* scales, cudaStream_t s);
 int launch_prologue_backward(int P, const float* Tcw, const float* means_world, const float* logit, const float* quats,
@@ -368,6 +368,8 @@ int launch_prologue_backward(int P, const float* Tcw, const float* means_world, 
                              float* dTcw, cudaStream_t s);
 int launch_adam(long long n, float* param, const float* grad, float* m, float* v, float lr, float beta1, float beta2,
                 float eps, long long step, cudaStream_t s);
+int launch_adam_groups(int ngroups, const long long* sizes, const float* lrs, float* param, const float* grad, float* m, float* v,
+                       float beta1, float beta2, float eps, long long step, cudaStream_t s);
 size_t knn_workspace_bytes(int P);
 int launch_knn(int P, const float* points, float* mean_dist2, char* ws, cudaStream_t s);
 

@@ -123,6 +123,32 @@ adam_kernel(long long n, float* __restrict__ param, const float* __restrict__ gr
     }
 }
 
+// The whole packed block in ONE launch: group g covers [bound[g-1], bound[g]) and has its own learning rate
+// (torch::optim::Adam with one param group per tensor, src/Gaussian.cc:158-175).
+struct AdamGroups {
+    long long bound[8];   // exclusive end of each group
+    float step_size[8];   // lr_g / bias_correction1
+    int n;
+};
+__global__ void __launch_bounds__(EX_THREADS)
+adam_groups_kernel(long long total, float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
+                   float* __restrict__ v, float beta1, float beta2, float eps, float inv_sqrt_bc2, AdamGroups G)
+{
+    for (long long i = (long long)blockIdx.x * EX_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * EX_THREADS) {
+        float step_size = G.step_size[0];
+#pragma unroll
+        for (int g = 1; g < 8; g++)
+            if (g < G.n && i >= G.bound[g - 1]) step_size = G.step_size[g];
+        const float gr = grad[i];
+        const float mi = m[i] + (gr - m[i]) * (1.0f - beta1);
+        const float vi = v[i] * beta2 + (1.0f - beta2) * gr * gr;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+        param[i] = param[i] - step_size * (mi / denom);
+    }
+}
+
 static int grid_for(long long n)
 {
     long long g = (n + EX_THREADS - 1) / EX_THREADS;
@@ -162,6 +188,25 @@ int launch_adam(long long n, float* param, const float* grad, float* m, float* v
     const float step_size = (float)((double)lr / bc1);
     const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
     adam_kernel<<<grid_for(n), EX_THREADS, 0, s>>>(n, param, grad, m, v, beta1, beta2, eps, step_size, inv_sqrt_bc2);
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+
+int launch_adam_groups(int ngroups, const long long* sizes, const float* lrs, float* param, const float* grad, float* m, float* v,
+                       float beta1, float beta2, float eps, long long step, cudaStream_t s)
+{
+    AdamGroups G;
+    G.n = ngroups;
+    long long total = 0;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    for (int g = 0; g < 8; g++) {
+        if (g < ngroups) total += sizes[g];
+        G.bound[g] = total;
+        G.step_size[g] = g < ngroups ? (float)((double)lrs[g] / bc1) : 0.f;
+    }
+    if (total == 0) return GSB_OK;
+    StageTimer _t(ST_OTHER, s);
+    adam_groups_kernel<<<grid_for(total), EX_THREADS, 0, s>>>(total, param, grad, m, v, beta1, beta2, eps, (float)(1.0 / sqrt(bc2)), G);
     GSB_LAUNCH_CHECK();
     return GSB_OK;
 }

@@ -21,6 +21,7 @@ struct GaussBwdParams {
     const uint8_t* clamped;    // SH clamp bits
     gsb_grad_outputs g;
     float* dL_dzcolor;         // [P] or NULL: gradient of the depth pass' z_cam colour (fused 5-channel pass)
+    int z_attached;            // add that gradient to dL_dmean3D.z (the colour is a function of the mean: mapping mode)
 };
 
 __device__ __forceinline__ void sh_backward(int deg, int M, const float* __restrict__ sh, float* __restrict__ dsh,
@@ -251,6 +252,7 @@ gauss_backward_kernel(GaussBwdParams q)
     } else if (p.shs && g.dL_dsh) {
         for (int k = 0; k < p.M * 3; k++) g.dL_dsh[i * p.M * 3 + k] = 0.f;
     }
+    if (q.z_attached && rendered) dmz += q.acc[i * 12 + 9];
     if (g.dL_dmean3D) { g.dL_dmean3D[3 * i] = dmx; g.dL_dmean3D[3 * i + 1] = dmy; g.dL_dmean3D[3 * i + 2] = dmz; }
     if (g.dL_dcov3D) {
 #pragma unroll
@@ -261,7 +263,7 @@ gauss_backward_kernel(GaussBwdParams q)
 }
 
 int launch_gauss_backward(const FwdParams& p, const char* geom, const GeomLayout& GL, const int* radii,
-                          const gsb_grad_outputs& g, float* dL_dzcolor, cudaStream_t s)
+                          const gsb_grad_outputs& g, float* dL_dzcolor, int z_attached, cudaStream_t s)
 {
     if (p.P <= 0) return GSB_OK;
     GaussBwdParams q;
@@ -272,6 +274,7 @@ int launch_gauss_backward(const FwdParams& p, const char* geom, const GeomLayout
     q.clamped = reinterpret_cast<const uint8_t*>(geom + GL.clamped);
     q.g = g;
     q.dL_dzcolor = dL_dzcolor;
+    q.z_attached = z_attached;
     {
         StageTimer _t(ST_GAUSS_BWD, s);
         // tuning knob: 4 resident CTAs (64 registers, small spill) hide more memory latency than 3 (80 registers)

@@ -140,7 +140,7 @@ class Frame:
         self._grads = (g, go)
         return g
 
-    def backward_fused(self, dL_dcolor, dL_ddepth_sil, reuse_outputs=False):
+    def backward_fused(self, dL_dcolor, dL_ddepth_sil, reuse_outputs=False, z_attached=False):
         """Backward of the five-channel pass: the SUM of the RGB pass' and the depth pass' gradients, plus
         ``dL_dzcolor`` [P], the gradient of the depth pass' z_cam colour."""
         if self._grads is None or not reuse_outputs:
@@ -151,7 +151,7 @@ class Frame:
         with torch.cuda.device(self.device):
             _lib.check(self.L.gsb_backward_fused(C.byref(self._args), _p(self.radii), self.geom.data_ptr(), self.binning.data_ptr(),
                                                  self.img.data_ptr(), dC.data_ptr(), dD.data_ptr(), C.byref(go),
-                                                 g["dL_dzcolor"].data_ptr(), self._stream()))
+                                                 g["dL_dzcolor"].data_ptr(), 1 if z_attached else 0, self._stream()))
         return g
 
     def backward(self, dL_dpix, reuse_outputs=False):

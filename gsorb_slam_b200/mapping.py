@@ -136,9 +136,8 @@ class MapOptimizer:
         dD = dL_ddepth_sil.to(self.dev, torch.float32).contiguous()
         with torch.cuda.device(self.dev):
             _lib.check(L.gsb_backward_fused(C.byref(self.args), self.radii.data_ptr(), self.geom.data_ptr(), self.binning.data_ptr(),
-                                            self.img.data_ptr(), dC.data_ptr(), dD.data_ptr(), C.byref(self.gout), self.g_z.data_ptr(), s))
-            if z_attached:
-                self.g_means_cam[:, 2].add_(self.g_z)
+                                            self.img.data_ptr(), dC.data_ptr(), dD.data_ptr(), C.byref(self.gout), self.g_z.data_ptr(),
+                                            1 if z_attached else 0, s))
             _lib.check(L.gsb_prologue_backward(self.P, self._Tcw.data_ptr(), p.ptr("means"), p.ptr("opacity"), p.ptr("quats"),
                                                p.ptr("scales"), self.g_means_cam.data_ptr(), self.g_opac.data_ptr(),
                                                self.g_rot.data_ptr(), self.g_scales.data_ptr(), g.ptr("means"), g.ptr("opacity"),
@@ -146,14 +145,17 @@ class MapOptimizer:
         return g
 
     def adam(self):
-        """torch::optim::Adam step on every group, reading the (all-reduced) gradient block in place."""
+        """torch::optim::Adam step on every group, reading the (all-reduced) gradient block in place: ONE launch over the
+        packed [14, P] block with a learning rate per group (gsb_adam_step_groups)."""
         self.t += 1
         L, s = self.L, self._s()
+        if not hasattr(self, "_adam_sizes"):
+            self._adam_sizes = (C.c_longlong * len(GROUPS))(*[w * self.P for _, w in GROUPS])
+        lrs = (C.c_float * len(GROUPS))(*[float(self.lr[name]) for name, _ in GROUPS])
         with torch.cuda.device(self.dev):
-            for name, w in GROUPS:
-                _lib.check(L.gsb_adam_step(w * self.P, self.params.ptr(name), self.grads.ptr(name), self.exp_avg.ptr(name),
-                                           self.exp_avg_sq.ptr(name), float(self.lr[name]), float(self.betas[0]), float(self.betas[1]),
-                                           self.eps, self.t, s))
+            _lib.check(L.gsb_adam_step_groups(len(GROUPS), self._adam_sizes, lrs, self.params.flat.data_ptr(), self.grads.flat.data_ptr(),
+                                              self.exp_avg.flat.data_ptr(), self.exp_avg_sq.flat.data_ptr(), float(self.betas[0]),
+                                              float(self.betas[1]), self.eps, self.t, s))
 
     def _exchange_and_adam(self, average: bool):
         if self.exchange is not None:

@@ -171,8 +171,9 @@ int gsb_backward(const gsb_raster_args* args, long long R, const int* radii,
  *   out_median_depth [1,H,W]  = the third output of either pass ("renderedSurdepth");
  * bit-identical to the two separate passes.  The backward takes dL/d(out_color) and dL/d(out_depth_sil) and
  * returns the SUM of the two passes' gradients (what autograd accumulates), plus dL_dzcolor [P] (may be NULL):
- * the gradient of the z_cam colour, which the caller adds to dL/d(mean_cam).z when that colour is attached to
- * the means (mapping mode; detached in tracking mode, src/Render.cc:957). */
+ * the gradient of the z_cam colour.  With z_attached != 0 that gradient is also added to dL_dmean3D[:, 2] -- the
+ * colour is a function of the means in mapping mode (identity view matrix: z_cam = mean.z); 0 reproduces the
+ * detached colour of tracking mode (src/Render.cc:957). */
 int gsb_forward_fused_ws(const gsb_raster_args* args,
                          void* geometry, size_t geometry_bytes,
                          void* binning, size_t binning_bytes, long long max_rendered,
@@ -182,7 +183,7 @@ int gsb_forward_fused_ws(const gsb_raster_args* args,
 int gsb_backward_fused(const gsb_raster_args* args, const int* radii,
                        const void* geometry, const void* binning, const void* image,
                        const float* dL_dcolor, const float* dL_ddepth_sil,
-                       const gsb_grad_outputs* grads, float* dL_dzcolor, gsb_stream_t stream);
+                       const gsb_grad_outputs* grads, float* dL_dzcolor, int z_attached, gsb_stream_t stream);
 
 /* ---- visibility helpers --------------------------------------------------------------*/
 /* Radii-only projection (Rasterizer::visible_filter): radii[P] fully written. */
@@ -282,6 +283,13 @@ int gsb_backproject(int width, int height, const uint8_t* mask, const float* dep
 size_t gsb_exchange_sync_bytes(int world);
 int gsb_exchange_allreduce(void* multicast_ptr, void* const* peer_ptrs, void* const* sync_ptrs,
                            long long n, int rank, int world, gsb_stream_t stream);
+
+/* The same update over a packed block of `ngroups` (<= 8) contiguous parameter groups with one learning rate each
+ * (one torch param group per tensor, src/Gaussian.cc:158-175) in ONE launch.  group_sizes_host / lrs_host are HOST arrays;
+ * param / grad / exp_avg / exp_avg_sq hold sum(group_sizes) values. */
+int gsb_adam_step_groups(int ngroups, const long long* group_sizes_host, const float* lrs_host,
+                         float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                         float beta1, float beta2, float eps, long long step, gsb_stream_t stream);
 
 /* ---- host-buffer convenience (bench "e2e" leg and quick integration tests) -------------
  * One forward + backward with every array in HOST memory (pinned recommended): copies the

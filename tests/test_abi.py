@@ -69,7 +69,7 @@ def test_validation_errors_match_reference_messages():
     rc = L.gsb_forward_fused_ws(C.byref(a), dummy, 1 << 30, dummy, 1 << 30, 100, dummy, 1 << 30, dummy, None, dummy, None, None)
     assert rc == -1 and b"out_depth_sil" in L.gsb_last_error()
     g = _lib.GradOutputs()
-    rc = L.gsb_backward_fused(C.byref(a), None, dummy, dummy, dummy, dummy, None, C.byref(g), None, None)
+    rc = L.gsb_backward_fused(C.byref(a), None, dummy, dummy, dummy, dummy, None, C.byref(g), None, 0, None)
     assert rc == -1 and b"dL_ddepth_sil" in L.gsb_last_error()
     a.tile_row_begin, a.tile_row_end = 2, 9   # 64 px = 4 tile rows
     rc = L.gsb_forward_ws(C.byref(a), dummy, 1 << 30, dummy, 1 << 30, 100, dummy, 1 << 30, dummy, dummy, None, None)
