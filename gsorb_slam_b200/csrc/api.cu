@@ -111,7 +111,7 @@ static FwdParams make_params(const gsb_raster_args* a)
 static int forward_stage1(const FwdParams& p, char* geom, const GeomLayout& GL, char* image, const ImageLayout& IL, int* radii,
                           uint32_t capacity, cudaStream_t s)
 {
-    GSB_CUDA_CHECK(cudaMemsetAsync(geom + GL.header, 0, sizeof(GeomHeader), s));
+    // the header needs no clearing: the scan kernel writes every field the rasterizer reads
     GSB_CUDA_CHECK(cudaMemsetAsync(image + IL.tile_count, 0, (size_t)IL.tiles_x * IL.tiles_y * 4 * TILE_CTR_STRIDE, s));
     if (int rc = launch_preprocess(p, geom, GL, image, IL, radii, s)) return rc;
     return launch_tile_scan(geom, GL, image, IL, capacity, p.P, s);

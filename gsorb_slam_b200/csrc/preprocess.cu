@@ -12,6 +12,7 @@
 // Layout: the reference scatters the projected state over seven SoA arrays (79 B/Gaussian);
 // here one 48-byte SplatRec per Gaussian carries everything the blend kernels gather, and
 // the AoS float3 inputs are staged through shared memory with 128-bit coalesced loads.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace gsb {
@@ -122,7 +123,8 @@ __device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh,
 
 // One thread per Gaussian, 256 per CTA.  Emits the packed record, radii, tiles_touched and
 // the CTA's tile-count sum (first level of the two-level scan).
-__global__ void __launch_bounds__(PRE_THREADS)
+template <int MINB>
+__global__ void __launch_bounds__(PRE_THREADS, MINB)
 preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ radii_blob, int* __restrict__ radii_out,
                   uint32_t* __restrict__ tiles_touched, uint4* __restrict__ ranks, uint32_t* __restrict__ tile_count,
                   uint8_t* __restrict__ clamped_out, int aligned_means, int aligned_scales, int aligned_colors)
@@ -229,11 +231,16 @@ int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, char
     auto al = [](const void* q) { return q && (reinterpret_cast<uintptr_t>(q) & 15) == 0 ? 1 : 0; };
     {
         StageTimer _t(ST_PREPROCESS, s);
-        preprocess_kernel<<<GL.num_blocks, PRE_THREADS, 0, s>>>(
-            p, reinterpret_cast<SplatRec*>(geom + GL.rec), reinterpret_cast<int*>(geom + GL.radii), radii_out,
-            reinterpret_cast<uint32_t*>(geom + GL.tiles_touched), reinterpret_cast<uint4*>(geom + GL.ranks),
-            reinterpret_cast<uint32_t*>(image + IL.tile_count),
-            reinterpret_cast<uint8_t*>(geom + GL.clamped), al(p.means3D), al(p.scales), al(p.colors_precomp));
+        // tuning knob: resident CTAs per SM the compiler must allow (the kernel is latency bound: occupancy against registers)
+        static const int minb = [] { const char* e = getenv("GSB_PREPROCESS_MINB"); return e ? atoi(e) : 8; }();
+#define GSB_PRE_LAUNCH(MB)                                                                                                \
+    preprocess_kernel<MB><<<GL.num_blocks, PRE_THREADS, 0, s>>>(                                                          \
+        p, reinterpret_cast<SplatRec*>(geom + GL.rec), reinterpret_cast<int*>(geom + GL.radii), radii_out,                \
+        reinterpret_cast<uint32_t*>(geom + GL.tiles_touched), reinterpret_cast<uint4*>(geom + GL.ranks),                  \
+        reinterpret_cast<uint32_t*>(image + IL.tile_count), reinterpret_cast<uint8_t*>(geom + GL.clamped),                \
+        al(p.means3D), al(p.scales), al(p.colors_precomp))
+        if (minb == 6) GSB_PRE_LAUNCH(6); else if (minb == 5) GSB_PRE_LAUNCH(5); else GSB_PRE_LAUNCH(8);
+#undef GSB_PRE_LAUNCH
         GSB_LAUNCH_CHECK();
     }
     return GSB_OK;
