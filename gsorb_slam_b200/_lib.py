@@ -58,6 +58,9 @@ SIGNATURES = {
     "gsb_mapping_loss": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gsb_backproject_scratch_bytes": (_sz, [_i, _i]),
     "gsb_backproject": (_i, [_i, _i, _vp, _vp, _vp, _f, _f, _f, _f, C.POINTER(_f), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gsb_prune_scratch_bytes": (_sz, [_i]),
+    "gsb_low_opacity_keep": (_i, [_i, _vp, _f, _vp, _vp]),
+    "gsb_prune_rows": (_i, [_i, _vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i), _vp, _vp, _sz, _vp]),
     "gsb_exchange_sync_bytes": (_sz, [_i]),
     "gsb_exchange_allreduce": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), _ll, _i, _i, _vp]),
     "gsb_adam_step_groups": (_i, [_i, C.POINTER(_ll), C.POINTER(_f), _vp, _vp, _vp, _vp, _f, _f, _f, _ll, _vp]),

@@ -123,6 +123,54 @@ densify_scatter_kernel(DensifyParams q, const uint32_t* __restrict__ block_offse
     }
 }
 
+// ---- prune: order-preserving compaction of per-Gaussian rows --------------------------------------------
+// Gaussian::RemovePoints / PruneOptimizer (src/Gaussian.cc:209-239) index_select every parameter tensor and both Adam
+// moments by the surviving rows, one tensor at a time; here one scan of the keep flags and ONE scatter kernel move up to
+// 16 row-major tensors (parameters, exp_avg, exp_avg_sq of every group).
+constexpr int PRUNE_MAX_TENSORS = 16;
+struct PruneTensors {
+    const float* src[PRUNE_MAX_TENSORS];
+    float* dst[PRUNE_MAX_TENSORS];
+    int width[PRUNE_MAX_TENSORS];
+    int n;
+};
+
+__global__ void __launch_bounds__(DN_THREADS)
+prune_count_kernel(int P, const uint8_t* __restrict__ keep, uint32_t* __restrict__ block_count)
+{
+    const int i = blockIdx.x * DN_THREADS + threadIdx.x;
+    const int c = __syncthreads_count(i < P && keep[i] != 0);
+    if (threadIdx.x == 0) block_count[blockIdx.x] = (uint32_t)c;
+}
+
+__global__ void __launch_bounds__(DN_THREADS)
+prune_scatter_kernel(int P, const uint8_t* __restrict__ keep, const uint32_t* __restrict__ block_offset, PruneTensors T)
+{
+    __shared__ uint32_t s_warp[DN_THREADS / 32];
+    const int i = blockIdx.x * DN_THREADS + threadIdx.x;
+    const bool sel = i < P && keep[i] != 0;
+    const uint32_t b = __ballot_sync(0xffffffffu, sel);
+    if (lane_id() == 0) s_warp[threadIdx.x >> 5] = __popc(b);
+    __syncthreads();
+    uint32_t row = block_offset[blockIdx.x];
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) row += s_warp[w];
+    if (!sel) return;
+    row += __popc(b & ((1u << lane_id()) - 1u));
+    for (int t = 0; t < T.n; t++) {
+        const int w = T.width[t];
+        const float* s = T.src[t] + (size_t)i * w;
+        float* d = T.dst[t] + (size_t)row * w;
+        for (int k = 0; k < w; k++) d[k] = s[k];
+    }
+}
+
+__global__ void __launch_bounds__(DN_THREADS)
+low_opacity_keep_kernel(int P, const float* __restrict__ logit, float threshold, uint8_t* __restrict__ keep)
+{
+    const int i = blockIdx.x * DN_THREADS + threadIdx.x;
+    if (i < P) keep[i] = (1.0f / (1.0f + expf(-logit[i])) < threshold) ? 0 : 1;   // Gaussian::RemoveLowOpcitiesGaussian
+}
+
 }  // namespace gsb
 
 using namespace gsb;
@@ -163,6 +211,63 @@ int gsb_backproject(int width, int height, const uint8_t* mask, const float* dep
     densify_scan_kernel<<<1, 1024, 0, s>>>(blocks, bc, count);
     GSB_LAUNCH_CHECK();
     densify_scatter_kernel<<<blocks, DN_THREADS, 0, s>>>(q, bc);
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+
+size_t gsb_prune_scratch_bytes(int P)
+{
+    return align_up(((size_t)(P > 0 ? P : 0) + DN_THREADS - 1) / DN_THREADS * sizeof(uint32_t) + sizeof(uint32_t), 256);
+}
+
+int gsb_low_opacity_keep(int P, const float* logit_opacities, float threshold, uint8_t* keep, gsb_stream_t stream)
+{
+    if (P < 0 || (P > 0 && (!logit_opacities || !keep))) {
+        set_error("low_opacity_keep: bad arguments");
+        return GSB_ERR_INVALID_ARGUMENT;
+    }
+    if (P == 0) return GSB_OK;
+    low_opacity_keep_kernel<<<(P + DN_THREADS - 1) / DN_THREADS, DN_THREADS, 0, (cudaStream_t)stream>>>(P, logit_opacities, threshold, keep);
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+
+int gsb_prune_rows(int P, const uint8_t* keep, int ntensors, const float* const* src_host, float* const* dst_host,
+                   const int* widths_host, int* count, void* scratch, size_t scratch_bytes, gsb_stream_t stream)
+{
+    if (P < 0 || ntensors < 0 || ntensors > PRUNE_MAX_TENSORS || !count || (P > 0 && !keep) ||
+        (ntensors > 0 && (!src_host || !dst_host || !widths_host))) {
+        set_error("prune_rows: need P >= 0, 0 <= ntensors <= %d, keep, count and the tensor tables", PRUNE_MAX_TENSORS);
+        return GSB_ERR_INVALID_ARGUMENT;
+    }
+    if (!scratch || scratch_bytes < gsb_prune_scratch_bytes(P)) {
+        set_error("prune_rows: scratch too small");
+        return GSB_ERR_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    PruneTensors T;
+    T.n = ntensors;
+    for (int t = 0; t < PRUNE_MAX_TENSORS; t++) {
+        T.src[t] = t < ntensors ? src_host[t] : nullptr;
+        T.dst[t] = t < ntensors ? dst_host[t] : nullptr;
+        T.width[t] = t < ntensors ? widths_host[t] : 0;
+        if (t < ntensors && (P > 0) && (!T.src[t] || !T.dst[t] || T.width[t] <= 0)) {
+            set_error("prune_rows: tensor %d has a NULL pointer or a non-positive width", t);
+            return GSB_ERR_INVALID_ARGUMENT;
+        }
+    }
+    const int blocks = (P + DN_THREADS - 1) / DN_THREADS;
+    uint32_t* bc = static_cast<uint32_t*>(scratch);
+    if (blocks == 0) {
+        GSB_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int), s));
+        return GSB_OK;
+    }
+    StageTimer _t(ST_OTHER, s);
+    prune_count_kernel<<<blocks, DN_THREADS, 0, s>>>(P, keep, bc);
+    GSB_LAUNCH_CHECK();
+    densify_scan_kernel<<<1, 1024, 0, s>>>(blocks, bc, count);
+    GSB_LAUNCH_CHECK();
+    prune_scatter_kernel<<<blocks, DN_THREADS, 0, s>>>(P, keep, bc, T);
     GSB_LAUNCH_CHECK();
     return GSB_OK;
 }

@@ -266,6 +266,17 @@ int gsb_backproject(int width, int height, const uint8_t* mask, const float* dep
                     float* means, float* rgb, float* log_scales, float* unnorm_quats, float* logit_opacities,
                     int* count, float* max_z, void* scratch, size_t scratch_bytes, gsb_stream_t stream);
 
+/* ---- prune (extension) ---------------------------------------------------
+ * gsb_low_opacity_keep: keep[i] = !(sigmoid(logit_opacity[i]) < threshold)  (Gaussian::RemoveLowOpcitiesGaussian, pruneOpcities 0.005).
+ * gsb_prune_rows: order-preserving compaction of up to 16 row-major per-Gaussian tensors [P, width_k] -> [K, width_k] by the
+ * keep flags in ONE pass -- what Gaussian::RemovePoints / PruneOptimizer (src/Gaussian.cc:209-239) do with one index_select per
+ * parameter tensor and per Adam moment.  src_host / dst_host / widths_host are HOST tables of DEVICE pointers / widths (dst != src);
+ * *count (DEVICE int) receives K. */
+size_t gsb_prune_scratch_bytes(int P);
+int gsb_low_opacity_keep(int P, const float* logit_opacities, float threshold, uint8_t* keep, gsb_stream_t stream);
+int gsb_prune_rows(int P, const uint8_t* keep, int ntensors, const float* const* src_host, float* const* dst_host,
+                   const int* widths_host, int* count, void* scratch, size_t scratch_bytes, gsb_stream_t stream);
+
 /* ---- multi-GPU exchange step (the reference is single-GPU) ----------------------
  * In-place SUM all-reduce of n fp32 values (n % 4 == 0) that live at the same offset of a
  * symmetric, peer-mapped allocation on every rank of one NVLink / NVSwitch box -- the packed

@@ -554,3 +554,36 @@ def test_backproject_matches_the_reference_host_loop(W, H, use_mask):
                                  float(cx), float(cy), Th, K // 2, means.data_ptr(), None, None, None, None, count.data_ptr(), None,
                                  scratch.data_ptr(), nb, torch.cuda.current_stream().cuda_stream))
     assert int(count.item()) == K
+
+
+def test_prune_rows_matches_index_select():
+    """gsb_low_opacity_keep + gsb_prune_rows against torch: sigmoid(logit) < 0.005 mask and index_select of parameters and
+    Adam moments (Gaussian::RemoveLowOpcitiesGaussian / RemovePoints / PruneOptimizer, src/Gaussian.cc:209-239)."""
+    import ctypes as C
+    import torch
+    from gsorb_slam_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(3)
+    for P in (0, 1, 1000, 123_457):
+        logit = torch.randn(P, device=dev, generator=gen) * 4 - 3
+        keep = torch.empty(P, dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(L.gsb_low_opacity_keep(P, logit.data_ptr(), 0.005, keep.data_ptr(), stream))
+        want_keep = ~(torch.sigmoid(logit) < 0.005)
+        assert int((keep.bool() != want_keep).sum()) <= max(1, P // 100000)      # expf vs torch sigmoid at the threshold
+        widths = [3, 3, 1, 3, 4, 3, 4]
+        src = [torch.randn(P, w, device=dev, generator=gen) for w in widths]
+        K = int(keep.sum())
+        dst = [torch.full((max(K, 1), w), -7.0, device=dev) for w in widths]
+        n = len(widths)
+        sp = (C.c_void_p * n)(*[t.data_ptr() for t in src]); dp = (C.c_void_p * n)(*[t.data_ptr() for t in dst])
+        wd = (C.c_int * n)(*widths)
+        count = torch.zeros(1, dtype=torch.int32, device=dev)
+        nb = int(L.gsb_prune_scratch_bytes(P))
+        scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
+        _lib.check(L.gsb_prune_rows(P, keep.data_ptr(), n, sp, dp, wd, count.data_ptr(), scratch.data_ptr(), nb, stream))
+        assert int(count.item()) == K
+        idx = torch.nonzero(keep.bool()).squeeze(-1)
+        for s_t, d_t in zip(src, dst):
+            assert torch.equal(d_t[:K], s_t.index_select(0, idx))
