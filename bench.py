@@ -323,7 +323,14 @@ def run_ours(args):
             traffic = json.load(open(tp)).get(dom)
         except Exception:
             traffic = None
+    # secondary figure: (pixel, splat) pairs the reference's loop would walk = every pixel's list position at
+    # which it stopped, summed; the blend kernels are pair / instruction bound, not byte bound
+    pairs = int(fr.image_state()["n_contrib"].to(torch.int64).sum().item())
+    fwd_ms = stages.get("blend_forward", {}).get("ms_per_step")
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "frac_of_nominal_8TBs": achieved / 8000.0, "frame_frac_of_nominal_8TBs": ab["frame"] / (ms_per_step * 1e-3) / 1e9 / 8000.0,
+                "pairs_per_pass": pairs, "pairs_per_s_blend_forward": (pairs / (fwd_ms * 1e-3)) if fwd_ms else None,
+                "diagnosis": "blend kernels are instruction-issue bound (ncu: ~74 % issue-active, DRAM 3-5 %); see DESIGN.md section 3",
                 "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": ab[dom], "kernel_ms": dom_ms,
                 "frame_alg_bytes": ab["frame"], "frame_frac_of_peak": ab["frame"] / (ms_per_step * 1e-3) / 1e9 / peak,
                 "stages": stages}
@@ -528,7 +535,11 @@ def cpu_baseline(workload: str, budget_s: float = 20.0):
         el = time.time() - t0
         if el > budget_s or n >= 8:
             break
-    return {"value": n / el, "unit": UNIT, "cores": gs_oracle.num_threads(), "kind": "port",
+    try:
+        model = next(l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name"))
+    except Exception:
+        model = "unknown"
+    return {"value": n / el, "unit": UNIT, "cores": gs_oracle.num_threads(), "kind": "port", "cpu_model": model,
             "sample": f"{n} full frame(s) fwd+bwd of {workload} through oracle/gs_oracle.cpp (OpenMP, pre-binned tile lists) in {el:.1f} s"}
 
 
