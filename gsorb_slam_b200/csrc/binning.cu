@@ -32,58 +32,82 @@ namespace gsb {
 constexpr int DUP_THREADS = 256;
 
 // ---- K2: one CTA scans the per-tile counts into segments ---------------------------------------
-__global__ void __launch_bounds__(1024)
+// Thread t owns the consecutive tiles [t * per, (t + 1) * per): one pass of loads, a block-wide exclusive scan of the
+// per-thread sums, one pass of stores (a single round of memory latency instead of one per 1024 tiles).
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_MAX_PER = 16;   // up to 16384 tiles in registers (a 2048 x 2048 image); larger images take the slow loop
+__global__ void __launch_bounds__(SCAN_THREADS)
 tile_scan_kernel(const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges, uint32_t* __restrict__ cursor,
                  int tiles, GeomHeader* __restrict__ hdr, uint32_t capacity, int P)
 {
     __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry, s_maxlen;
-    if (threadIdx.x == 0) {
-        s_carry = 0;
-        s_maxlen = 0;
+    __shared__ uint32_t s_maxlen;
+    if (threadIdx.x == 0) s_maxlen = 0;
+    const int per = (tiles + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int t0 = threadIdx.x * per;
+    uint2 cnt[SCAN_MAX_PER];
+    uint32_t sum = 0, maxlen = 0;
+    if (per <= SCAN_MAX_PER) {
+#pragma unroll
+        for (int k = 0; k < SCAN_MAX_PER; k++) {
+            const int i = t0 + k;
+            cnt[k] = (k < per && i < tiles) ? *reinterpret_cast<const uint2*>(tile_count + (size_t)i * TILE_CTR_STRIDE) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < SCAN_MAX_PER; k++) {
+            const uint32_t x = cnt[k].x + cnt[k].y;   // instances of small (slot known) + large (slot claimed later) Gaussians
+            sum += x;
+            maxlen = max(maxlen, x);
+        }
+    } else {
+        for (int k = 0; k < per; k++) {
+            const int i = t0 + k;
+            if (i < tiles) {
+                const uint2 c = *reinterpret_cast<const uint2*>(tile_count + (size_t)i * TILE_CTR_STRIDE);
+                sum += c.x + c.y;
+                maxlen = max(maxlen, c.x + c.y);
+            }
+        }
     }
+    // block-wide exclusive scan of `sum`
+    uint32_t v = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane_id() >= (uint32_t)o) v += u;
+    }
+    if (lane_id() == 31) s_warp[threadIdx.x >> 5] = v;
+    maxlen = __reduce_max_sync(0xffffffffu, maxlen);
     __syncthreads();
-    uint32_t maxlen = 0;
-    for (int base = 0; base < tiles; base += 1024) {
-        const int i = base + threadIdx.x;
-        const uint2 cnt = i < tiles ? *reinterpret_cast<const uint2*>(tile_count + (size_t)i * TILE_CTR_STRIDE) : make_uint2(0u, 0u);
-        const uint32_t x = cnt.x + cnt.y;   // instances of small (slot known) + large (slot claimed later) Gaussians
-        maxlen = max(maxlen, x);
-        uint32_t v = x;
+    if (lane_id() == 0) atomicMax(&s_maxlen, maxlen);
+    if (threadIdx.x < 32) {
+        uint32_t w = s_warp[threadIdx.x];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-            if (lane_id() >= (uint32_t)o) v += t;
+            const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane_id() >= (uint32_t)o) w += u;
         }
-        if (lane_id() == 31) s_warp[threadIdx.x >> 5] = v;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            uint32_t w = s_warp[threadIdx.x];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane_id() >= (uint32_t)o) w += t;
-            }
-            s_warp[threadIdx.x] = w;
-        }
-        __syncthreads();
-        const uint32_t warp_excl = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0u;
-        const uint32_t carry = s_carry;
-        if (i < tiles) {
-            const uint32_t start = carry + warp_excl + v - x;
-            // a too-small binning capacity truncates the tail of the tile-major list (overflow is latched below)
-            ranges[i] = make_uint2(min(start, capacity), min(start + x, capacity));
-            cursor[(size_t)i * TILE_CTR_STRIDE] = start + cnt.x;   // large Gaussians fill the tail of the segment
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = carry + warp_excl + v;
-        __syncthreads();
+        s_warp[threadIdx.x] = w;
     }
-    maxlen = __reduce_max_sync(0xffffffffu, maxlen);
-    if (lane_id() == 0) atomicMax(&s_maxlen, maxlen);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t total = s_carry;
+    uint32_t start = ((threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0u) + v - sum;
+    auto emit = [&](int i, uint2 c) {
+        const uint32_t x = c.x + c.y;
+        // a too-small binning capacity truncates the tail of the tile-major list (overflow is latched below)
+        ranges[i] = make_uint2(min(start, capacity), min(start + x, capacity));
+        cursor[(size_t)i * TILE_CTR_STRIDE] = start + c.x;   // large Gaussians fill the tail of the segment
+        start += x;
+    };
+    if (per <= SCAN_MAX_PER) {
+#pragma unroll
+        for (int k = 0; k < SCAN_MAX_PER; k++)
+            if (k < per && t0 + k < tiles) emit(t0 + k, cnt[k]);
+    } else {
+        for (int k = 0; k < per && t0 + k < tiles; k++)
+            emit(t0 + k, *reinterpret_cast<const uint2*>(tile_count + (size_t)(t0 + k) * TILE_CTR_STRIDE));
+    }
+    if (threadIdx.x == SCAN_THREADS - 1) {
+        const uint32_t total = s_warp[31];
         hdr->max_tile_len = s_maxlen;
         hdr->magic = GEOM_MAGIC;
         hdr->P = P;
@@ -362,10 +386,11 @@ tile_sort_small_kernel(const uint2* __restrict__ ranges, const uint64_t* __restr
     }
 }
 
-// Size class 4096 < n <= 16384: the same 32-bit keyed network with 1024 threads (8 or 16 keys per thread, 32 / 64 KB of
-// dynamic shared memory), one persistent CTA per SM looping over the tiles of the class.
+// Size class n > 4096: up to 16384 entries the same 32-bit keyed network with 1024 threads (8 or 16 keys per thread, 32 / 64 KB
+// of dynamic shared memory), beyond that a 64-bit network in global memory; one persistent CTA per SM looping over the tiles of
+// the class (the launch exits at once when the frame's longest list fits the 256-thread kernel).
 __global__ void __launch_bounds__(1024, 1)
-tile_sort_mid_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list,
+tile_sort_mid_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list,
                      int tiles, const GeomHeader* __restrict__ hdr)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -375,38 +400,27 @@ tile_sort_mid_kernel(const uint2* __restrict__ ranges, const uint64_t* __restric
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const uint2 r = ranges[tile];
         const uint32_t n = r.y - r.x;
-        if (n <= (uint32_t)TSORT_SMALL || n > (uint32_t)TSORT_MID) continue;   // another size class handles this tile
+        if (n <= (uint32_t)TSORT_SMALL) continue;                             // the 256-thread kernel handles this tile
         __syncthreads();                                                      // previous tile's readers are done with s[]
         if (n <= 8192u) tile_sort_class32<8, 1024>(r, pairs, point_list, s, s_red);
-        else tile_sort_class32<16, 1024>(r, pairs, point_list, s, s_red);
-    }
-}
-
-// Fallback for tiles with more than TSORT_MID entries: the same network on global memory, one
-// 1024-thread CTA per such tile (correct for any length; pathological inputs only).
-__global__ void __launch_bounds__(1024)
-tile_sort_global_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list,
-                        int tiles, uint32_t lo_excl, const GeomHeader* __restrict__ hdr)
-{
-    if (hdr->max_tile_len <= lo_excl) return;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const uint2 r = ranges[tile];
-        const uint32_t n = r.y - r.x;
-        if (n <= lo_excl) continue;
-        uint64_t* s = pairs + r.x;
-        bitonic_network(n, next_pow2(n), 1024, [&](uint32_t i, uint32_t l, bool sync) {
-            if (sync) {
-                __threadfence_block();
-                __syncthreads();
-                return;
-            }
-            const uint64_t a = s[i], b = s[l];
-            if (a > b) {
-                s[i] = b;
-                s[l] = a;
-            }
-        });
-        for (uint32_t i = threadIdx.x; i < n; i += 1024) point_list[r.x + i] = (uint32_t)s[i];
+        else if (n <= (uint32_t)TSORT_MID) tile_sort_class32<16, 1024>(r, pairs, point_list, s, s_red);
+        else {
+            // more than 16384 entries in one tile (pathological inputs): the 64-bit network in place, in global memory
+            uint64_t* g = pairs + r.x;
+            bitonic_network(n, next_pow2(n), 1024, [&](uint32_t i, uint32_t l, bool sync) {
+                if (sync) {
+                    __threadfence_block();
+                    __syncthreads();
+                    return;
+                }
+                const uint64_t a = g[i], b = g[l];
+                if (a > b) {
+                    g[i] = b;
+                    g[l] = a;
+                }
+            });
+            for (uint32_t i = threadIdx.x; i < n; i += 1024) point_list[r.x + i] = (uint32_t)g[i];
+        }
     }
 }
 
@@ -649,11 +663,6 @@ int launch_binning(const FwdParams& p, char* geom, const GeomLayout& GL, char* b
             GSB_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TSORT_MID * 4));
             const int g = tiles < NUM_SMS ? tiles : NUM_SMS;
             tile_sort_mid_kernel<<<g, 1024, TSORT_MID * 4, s>>>(ranges, pairs, point_list, tiles, hdr);
-            GSB_LAUNCH_CHECK();
-        }
-        if (grid_instances > TSORT_MID) {
-            const int g = tiles < NUM_SMS ? tiles : NUM_SMS;
-            tile_sort_global_kernel<<<g, 1024, 0, s>>>(ranges, pairs, point_list, tiles, (uint32_t)TSORT_MID, hdr);
             GSB_LAUNCH_CHECK();
         }
     }
