@@ -112,9 +112,9 @@ static int forward_stage1(const FwdParams& p, char* geom, const GeomLayout& GL, 
                           uint32_t capacity, cudaStream_t s)
 {
     // the header needs no clearing: the scan kernel writes every field the rasterizer reads
-    GSB_CUDA_CHECK(cudaMemsetAsync(image + IL.tile_count, 0, (size_t)IL.tiles_x * IL.tiles_y * 4 * TILE_CTR_STRIDE, s));
-    if (int rc = launch_preprocess(p, geom, GL, image, IL, radii, s)) return rc;
-    return launch_tile_scan(geom, GL, image, IL, capacity, p.P, s);
+    GSB_CUDA_CHECK(cudaMemsetAsync(image + IL.tile_count, 0, ((size_t)IL.tiles_x * IL.tiles_y + 1) * 4 * TILE_CTR_STRIDE, s));
+    if (p.P > 0) return launch_preprocess(p, geom, GL, image, IL, radii, capacity, s);   // its last CTA also scans the tile counts
+    return launch_tile_scan(geom, GL, image, IL, capacity, p.P, s);                       // empty map: all-empty segments
 }
 
 static int forward_stage2(const FwdParams& p, char* geom, const GeomLayout& GL, char* binning, const BinningLayout& BL,

@@ -26,96 +26,19 @@
 // in ascending id, so ties keep id order), hence the sorted list is bit-identical -- while every instance is written
 // twice and read twice instead of seven times.
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace gsb {
 
 constexpr int DUP_THREADS = 256;
 
-// ---- K2: one CTA scans the per-tile counts into segments ---------------------------------------
-// Thread t owns the consecutive tiles [t * per, (t + 1) * per): one pass of loads, a block-wide exclusive scan of the
-// per-thread sums, one pass of stores (a single round of memory latency instead of one per 1024 tiles).
+// ---- K2: the stand-alone scan launch (only an EMPTY map takes it: otherwise the last preprocess CTA scans, scan.cuh) ----
 constexpr int SCAN_THREADS = 1024;
-constexpr int SCAN_MAX_PER = 16;   // up to 16384 tiles in registers (a 2048 x 2048 image); larger images take the slow loop
 __global__ void __launch_bounds__(SCAN_THREADS)
 tile_scan_kernel(const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges, uint32_t* __restrict__ cursor,
                  int tiles, GeomHeader* __restrict__ hdr, uint32_t capacity, int P)
 {
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_maxlen;
-    if (threadIdx.x == 0) s_maxlen = 0;
-    const int per = (tiles + SCAN_THREADS - 1) / SCAN_THREADS;
-    const int t0 = threadIdx.x * per;
-    uint2 cnt[SCAN_MAX_PER];
-    uint32_t sum = 0, maxlen = 0;
-    if (per <= SCAN_MAX_PER) {
-#pragma unroll
-        for (int k = 0; k < SCAN_MAX_PER; k++) {
-            const int i = t0 + k;
-            cnt[k] = (k < per && i < tiles) ? *reinterpret_cast<const uint2*>(tile_count + (size_t)i * TILE_CTR_STRIDE) : make_uint2(0u, 0u);
-        }
-#pragma unroll
-        for (int k = 0; k < SCAN_MAX_PER; k++) {
-            const uint32_t x = cnt[k].x + cnt[k].y;   // instances of small (slot known) + large (slot claimed later) Gaussians
-            sum += x;
-            maxlen = max(maxlen, x);
-        }
-    } else {
-        for (int k = 0; k < per; k++) {
-            const int i = t0 + k;
-            if (i < tiles) {
-                const uint2 c = *reinterpret_cast<const uint2*>(tile_count + (size_t)i * TILE_CTR_STRIDE);
-                sum += c.x + c.y;
-                maxlen = max(maxlen, c.x + c.y);
-            }
-        }
-    }
-    // block-wide exclusive scan of `sum`
-    uint32_t v = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane_id() >= (uint32_t)o) v += u;
-    }
-    if (lane_id() == 31) s_warp[threadIdx.x >> 5] = v;
-    maxlen = __reduce_max_sync(0xffffffffu, maxlen);
-    __syncthreads();
-    if (lane_id() == 0) atomicMax(&s_maxlen, maxlen);
-    if (threadIdx.x < 32) {
-        uint32_t w = s_warp[threadIdx.x];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane_id() >= (uint32_t)o) w += u;
-        }
-        s_warp[threadIdx.x] = w;
-    }
-    __syncthreads();
-    uint32_t start = ((threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0u) + v - sum;
-    auto emit = [&](int i, uint2 c) {
-        const uint32_t x = c.x + c.y;
-        // a too-small binning capacity truncates the tail of the tile-major list (overflow is latched below)
-        ranges[i] = make_uint2(min(start, capacity), min(start + x, capacity));
-        cursor[(size_t)i * TILE_CTR_STRIDE] = start + c.x;   // large Gaussians fill the tail of the segment
-        start += x;
-    };
-    if (per <= SCAN_MAX_PER) {
-#pragma unroll
-        for (int k = 0; k < SCAN_MAX_PER; k++)
-            if (k < per && t0 + k < tiles) emit(t0 + k, cnt[k]);
-    } else {
-        for (int k = 0; k < per && t0 + k < tiles; k++)
-            emit(t0 + k, *reinterpret_cast<const uint2*>(tile_count + (size_t)(t0 + k) * TILE_CTR_STRIDE));
-    }
-    if (threadIdx.x == SCAN_THREADS - 1) {
-        const uint32_t total = s_warp[31];
-        hdr->max_tile_len = s_maxlen;
-        hdr->magic = GEOM_MAGIC;
-        hdr->P = P;
-        hdr->num_rendered = total;
-        hdr->num_rendered_clamped = min(total, capacity);
-        hdr->overflow = total > capacity ? 1u : 0u;
-        hdr->capacity = capacity;
-    }
+    tile_scan_body<SCAN_THREADS, 16>(tile_count, ranges, cursor, tiles, hdr, capacity, P);
 }
 
 // ---- K3: one thread per Gaussian writes its instances into the tile segments ---------------------

@@ -108,7 +108,7 @@ struct ImageLayout {
         // ~2 M atomics of a frame are not funnelled through the few slices a dense array maps to
         // word 0: instances of Gaussians touching <= 4 tiles (their atomics return the slot, kept in GeomLayout::ranks);
         // word 1: instances of larger Gaussians (slots claimed by `duplicate` through tile_cursor)
-        L.tile_count = take(T * 4 * TILE_CTR_STRIDE);
+        L.tile_count = take((T + 1) * 4 * TILE_CTR_STRIDE);   // + one slot: completion counter of the preprocess CTAs
         L.tile_cursor = take(T * 4 * TILE_CTR_STRIDE);   // next free slot for the larger Gaussians of each tile
         L.hits_tail = take(T * HIT_BLOCKS * 4);          // hit words of each tile's last, partial window (blend kernels)
         L.total = off;
@@ -341,7 +341,7 @@ struct FwdParams {
 };
 
 int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, char* image, const ImageLayout& IL,
-                      int* radii_out, cudaStream_t s);
+                      int* radii_out, uint32_t capacity, cudaStream_t s);
 int launch_tile_scan(char* geom, const GeomLayout& GL, char* image, const ImageLayout& IL, uint32_t capacity, int P,
                      cudaStream_t s);
 int launch_visible_filter(const FwdParams& p, int* radii, cudaStream_t s);

@@ -14,6 +14,7 @@
 // the AoS float3 inputs are staged through shared memory with 128-bit coalesced loads.
 #include <cstdlib>
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace gsb {
 
@@ -127,7 +128,8 @@ template <int MINB>
 __global__ void __launch_bounds__(PRE_THREADS, MINB)
 preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ radii_blob, int* __restrict__ radii_out,
                   uint32_t* __restrict__ tiles_touched, uint4* __restrict__ ranks, uint32_t* __restrict__ tile_count,
-                  uint8_t* __restrict__ clamped_out, int aligned_means, int aligned_scales, int aligned_colors)
+                  uint8_t* __restrict__ clamped_out, int aligned_means, int aligned_scales, int aligned_colors,
+                  uint2* __restrict__ ranges, uint32_t* __restrict__ cursor, GeomHeader* __restrict__ hdr, uint32_t capacity)
 {
     __shared__ __align__(16) float s_mean[PRE_THREADS * 3];
     __shared__ __align__(16) float s_scale[PRE_THREADS * 3];
@@ -222,10 +224,24 @@ preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ rad
         if (radii_out) radii_out[idx] = radius;
         tiles_touched[idx] = touched;
     }
+    // K2 without a launch: the last CTA to get here turns the tile counts into segments (scan.cuh).  The completion counter
+    // lives one slot past the tile counters and is zeroed with them.
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();   // this CTA's counting atomics are performed before it reports
+        const int tiles = p.tiles_x * p.tiles_y;
+        s_last = atomicAdd(&tile_count[(size_t)tiles * TILE_CTR_STRIDE], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        tile_scan_body<PRE_THREADS, 6>(tile_count, ranges, cursor, p.tiles_x * p.tiles_y, hdr, capacity, p.P);
+    }
 }
 
 int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, char* image, const ImageLayout& IL,
-                      int* radii_out, cudaStream_t s)
+                      int* radii_out, uint32_t capacity, cudaStream_t s)
 {
     if (p.P <= 0) return GSB_OK;
     auto al = [](const void* q) { return q && (reinterpret_cast<uintptr_t>(q) & 15) == 0 ? 1 : 0; };
@@ -238,7 +254,8 @@ int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, char
         p, reinterpret_cast<SplatRec*>(geom + GL.rec), reinterpret_cast<int*>(geom + GL.radii), radii_out,                \
         reinterpret_cast<uint32_t*>(geom + GL.tiles_touched), reinterpret_cast<uint4*>(geom + GL.ranks),                  \
         reinterpret_cast<uint32_t*>(image + IL.tile_count), reinterpret_cast<uint8_t*>(geom + GL.clamped),                \
-        al(p.means3D), al(p.scales), al(p.colors_precomp))
+        al(p.means3D), al(p.scales), al(p.colors_precomp), reinterpret_cast<uint2*>(image + IL.ranges),                 \
+        reinterpret_cast<uint32_t*>(image + IL.tile_cursor), reinterpret_cast<GeomHeader*>(geom + GL.header), capacity)
         if (minb == 6) GSB_PRE_LAUNCH(6); else if (minb == 5) GSB_PRE_LAUNCH(5); else GSB_PRE_LAUNCH(8);
 #undef GSB_PRE_LAUNCH
         GSB_LAUNCH_CHECK();
