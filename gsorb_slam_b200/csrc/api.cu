@@ -446,14 +446,20 @@ long long gsb_forward_backward_host(const gsb_raster_args* host_args, long long 
     // A second, per-thread cached stream carries the transfers that can overlap kernels: the upload of dL/dpixel
     // (needed only by the backward) runs under the forward pass, the download of image / depth / radii under the
     // backward pass.  PCIe is full duplex and the two directions use different copy engines.
-    static thread_local cudaStream_t s2 = nullptr;
-    static thread_local cudaEvent_t ev_dl = nullptr, ev_fwd = nullptr, ev_img = nullptr;
-    if (!s2) {
-        GSB_CUDA_CHECK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
-        GSB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_dl, cudaEventDisableTiming));
-        GSB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fwd, cudaEventDisableTiming));
-        GSB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_img, cudaEventDisableTiming));
+    struct SideStream { cudaStream_t s2 = nullptr; cudaEvent_t ev_dl = nullptr, ev_fwd = nullptr, ev_img = nullptr; };
+    static thread_local SideStream side[64];   // one per device this thread has used (streams and events are per device)
+    int device = 0;
+    GSB_CUDA_CHECK(cudaGetDevice(&device));
+    if (device < 0 || device >= 64) return fail(GSB_ERR_UNSUPPORTED, "device ordinal %d out of range", device);
+    SideStream& ss = side[device];
+    if (!ss.s2) {
+        GSB_CUDA_CHECK(cudaStreamCreateWithFlags(&ss.s2, cudaStreamNonBlocking));
+        GSB_CUDA_CHECK(cudaEventCreateWithFlags(&ss.ev_dl, cudaEventDisableTiming));
+        GSB_CUDA_CHECK(cudaEventCreateWithFlags(&ss.ev_fwd, cudaEventDisableTiming));
+        GSB_CUDA_CHECK(cudaEventCreateWithFlags(&ss.ev_img, cudaEventDisableTiming));
     }
+    cudaStream_t s2 = ss.s2;
+    cudaEvent_t ev_dl = ss.ev_dl, ev_fwd = ss.ev_fwd, ev_img = ss.ev_img;
     char* d = (char*)device_scratch;
     const size_t Pz = (size_t)P, HW = (size_t)W * H;
     auto up_on = [&](cudaStream_t st, size_t off, const void* src, size_t bytes) -> const float* {

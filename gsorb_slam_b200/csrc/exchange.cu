@@ -36,6 +36,13 @@ struct XchPtrs {
     uint32_t* sync[XCH_MAX_WORLD];   // ... and of every rank's handshake scratch
 };
 
+constexpr unsigned long long XCH_TIMEOUT_NS = 60ull * 1000 * 1000 * 1000;   // 60 s of rank skew, then a device-side trap
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ uint32_t cas_release_sys(uint32_t* p, uint32_t cmp, uint32_t val)
 {
     uint32_t old;
@@ -57,8 +64,12 @@ __device__ __forceinline__ void pairwise_barrier(const XchPtrs& X, int rank, int
         const int peer = threadIdx.x;
         uint32_t* theirs = X.sync[peer] + (size_t)blockIdx.x * XCH_MAX_WORLD + rank;   // my flag in the peer's scratch
         uint32_t* mine = X.sync[rank] + (size_t)blockIdx.x * XCH_MAX_WORLD + peer;     // the peer's flag in my scratch
-        while (cas_release_sys(theirs, 0u, 1u) != 0u) {}   // put (waits until the previous signal was consumed)
-        while (cas_acquire_sys(mine, 1u, 0u) != 1u) {}     // wait and consume
+        // bounded spins: a rank that never launches (it failed earlier) must surface as a CUDA error here, not hang the box
+        const unsigned long long t0 = globaltimer_ns();
+        while (cas_release_sys(theirs, 0u, 1u) != 0u)      // put (waits until the previous signal was consumed)
+            if (globaltimer_ns() - t0 > XCH_TIMEOUT_NS) __trap();
+        while (cas_acquire_sys(mine, 1u, 0u) != 1u)        // wait and consume
+            if (globaltimer_ns() - t0 > XCH_TIMEOUT_NS) __trap();
     }
     __syncthreads();
 }
