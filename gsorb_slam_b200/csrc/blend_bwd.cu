@@ -135,11 +135,12 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
         // window, back to front): the warp iterates max-over-quarters of the BATCH's visit counts instead of the sum over
         // windows of per-window maxima -- about 11 % fewer iterations at the headline workload.
         const int wi_lo = 0;
-        int wi = min(BLEND_BATCH / 32 - 1, (n - 1 - kb * BLEND_BATCH) >> 5);   // last window of the batch that holds entries < n
-        auto fetch = [&](int wv) -> uint32_t {
-            return (kb * (BLEND_BATCH / 32) + wv) <= wq_last ? s_hits[buf][wv * BLOCKS + lwarp * 4 + q] : 0u;
-        };
-        uint32_t mask = fetch(wi);
+        // first window of the batch this quarter has to visit: the last one holding entries < n, and not past the quarter's
+        // own last hit window (wq_last); negative = nothing for this quarter in the batch
+        const int wtop = min(min(BLEND_BATCH / 32 - 1, (n - 1 - kb * BLEND_BATCH) >> 5), wq_last - kb * (BLEND_BATCH / 32));
+        auto fetch = [&](int wv) -> uint32_t { return s_hits[buf][wv * BLOCKS + lwarp * 4 + q]; };
+        int wi = max(wtop, 0);
+        uint32_t mask = wtop >= 0 ? fetch(wi) : 0u;
         {
             while (true) {
                 if (mask == 0u && wi > wi_lo) mask = fetch(--wi);   // this quarter moves on to its next window (one per iteration)
