@@ -388,6 +388,26 @@ def run_ours(args):
                      "iterations_per_s_fused": 1000.0 / ms_fused, "steps": it_steps}
 
     clk.__exit__(None, None, None)
+    # ---- parity of the benchmarked frame against the reference kernels (BASELINE.json metric: "PSNR vs ref") ----
+    parity = None
+    if rank == 0 and world == 1:
+        try:
+            from oracle import gs_ref
+            if gs_ref.available():
+                fr._args.colors_precomp = fr.colors.data_ptr()
+                step()
+                torch.cuda.synchronize()
+                ref = gs_ref.frame_from_scene(sc)
+                diff = (fr.color - ref.color).abs()
+                mse = float((diff.double() ** 2).mean())
+                parity = {"against": "reference CUDA kernels (oracle/_ref) on the same frame", "image_max_abs_diff": float(diff.max()),
+                          "image_bit_identical": bool(torch.equal(fr.color, ref.color)),
+                          "depth_bit_identical": bool(torch.equal(fr.depth, ref.depth)),
+                          "psnr_db": None if mse == 0.0 else 10.0 * float(np.log10(1.0 / mse)),
+                          "psnr_note": "null = infinite (zero mean squared error)"}
+                del ref
+        except Exception as e:   # the checker is optional on the bench box
+            parity = {"against": "unavailable", "error": type(e).__name__}
     # ---- cpu baseline (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -409,6 +429,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if iteration is not None:
             line["mapping_iteration"] = iteration
+        if parity is not None:
+            line["parity"] = parity
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
