@@ -25,8 +25,13 @@
 // Ordering by (depth bits, id) is exactly the order the reference's stable radix sort produces (instances are emitted
 // in ascending id, so ties keep id order), hence the sorted list is bit-identical -- while every instance is written
 // twice and read twice instead of seven times.
+#include <cstdlib>
 #include "common.cuh"
 #include "scan.cuh"
+
+#ifndef GSB_DEFAULT_TILE_RADIX
+#define GSB_DEFAULT_TILE_RADIX false
+#endif
 
 namespace gsb {
 
@@ -217,13 +222,87 @@ __device__ __forceinline__ void tile_sort_regs32(uint32_t* __restrict__ s, uint3
     __syncthreads();
 }
 
+// Alternative to the comparator network for the same 32-bit keys: a stable LSD radix sort in shared memory over the
+// quantised-depth field only (three 7-bit digits; the index bits below it never need sorting: neighbours with equal
+// quantised depth are put in exact order by the fix-up pass anyway).  Warp-striped ranking with match.any, as in the
+// onesweep pass further down, minus the global look-back.  O(n) per pass instead of O(n log^2 n) compare-exchanges.
+constexpr int TR_BITS = 7, TR_RADIX = 1 << TR_BITS, TR_PASSES = 3, TR_QBITS = TR_BITS * TR_PASSES;   // 21 depth bits
 template <int E, int THREADS>
+__device__ __forceinline__ void tile_radix_sort32(uint32_t* __restrict__ s, uint32_t (&a)[E], uint32_t* __restrict__ cnt /*[THREADS/32][128]*/,
+                                                  uint32_t* __restrict__ dstart /*[128 + 32]*/, int idx_bits)
+{
+    constexpr int WARPS = THREADS / 32;
+    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31, lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < E; k++) s[t * E + k] = a[k];   // any initial order: the segment is unordered
+    uint32_t* s_w = dstart + TR_RADIX;                 // per-warp totals of the digit scan
+#pragma unroll 1
+    for (int pass = 0; pass < TR_PASSES; pass++) {
+        const int shift = idx_bits + TR_BITS * pass;
+        __syncthreads();   // s[] complete; the previous pass' readers of cnt / dstart are done
+        for (uint32_t i = t; i < (uint32_t)(WARPS * TR_RADIX); i += THREADS) cnt[i] = 0;
+        uint32_t key[E], loc[E];
+#pragma unroll
+        for (int it = 0; it < E; it++) key[it] = s[warp * (32 * E) + it * 32 + lane];   // warp-striped: position order = (warp, it, lane)
+        __syncthreads();   // counters zeroed, every key is in a register (s[] may be overwritten below)
+#pragma unroll
+        for (int it = 0; it < E; it++) {
+            const uint32_t d = (key[it] >> shift) & (TR_RADIX - 1);
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) {
+                base = cnt[warp * TR_RADIX + d];
+                cnt[warp * TR_RADIX + d] = base + __popc(peers);
+            }
+            base = __shfl_sync(0xffffffffu, base, leader);
+            loc[it] = base + __popc(peers & lt_mask);
+            __syncwarp();
+        }
+        __syncthreads();
+        // digit t: exclusive prefix over the warps, total count; then an exclusive scan of the totals over the 128 digits
+        uint32_t count = 0;
+        if (t < (uint32_t)TR_RADIX) {
+#pragma unroll 4
+            for (int w = 0; w < WARPS; w++) {
+                const uint32_t c = cnt[w * TR_RADIX + t];
+                cnt[w * TR_RADIX + t] = count;
+                count += c;
+            }
+        }
+        uint32_t v = count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= (uint32_t)o) v += u;
+        }
+        if (lane == 31 && warp < TR_RADIX / 32) s_w[warp] = v;
+        __syncthreads();
+        if (t < (uint32_t)TR_RADIX) {
+            uint32_t before = 0;
+#pragma unroll
+            for (int w = 0; w < TR_RADIX / 32; w++)
+                if (w < (int)warp) before += s_w[w];
+            dstart[t] = before + v - count;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < E; it++) {
+            const uint32_t d = (key[it] >> shift) & (TR_RADIX - 1);
+            s[dstart[d] + cnt[warp * TR_RADIX + d] + loc[it]] = key[it];
+        }
+    }
+    __syncthreads();
+}
+
+template <int E, int THREADS, bool RADIX>
 __device__ __forceinline__ void tile_sort_class32(const uint2 r, const uint64_t* __restrict__ pairs,
                                                   uint32_t* __restrict__ point_list, uint32_t* __restrict__ s,
-                                                  uint32_t* __restrict__ s_red)
+                                                  uint32_t* __restrict__ s_red, uint32_t* __restrict__ s_cnt)
 {
     constexpr int LOG_E = E == 1 ? 0 : E == 2 ? 1 : E == 4 ? 2 : E == 8 ? 3 : 4;
-    constexpr int IDX_BITS = (THREADS == 1024 ? 10 : 8) + LOG_E, DEPTH_BITS = 32 - IDX_BITS;
+    constexpr int IDX_BITS = (THREADS == 1024 ? 10 : 8) + LOG_E;
+    constexpr int DEPTH_BITS = RADIX ? (32 - IDX_BITS < TR_QBITS ? 32 - IDX_BITS : TR_QBITS) : 32 - IDX_BITS;
     constexpr uint32_t IDX_MASK = (1u << IDX_BITS) - 1u;
     const uint32_t n = r.y - r.x, t = threadIdx.x;
     const uint64_t* seg = pairs + r.x;
@@ -261,7 +340,8 @@ __device__ __forceinline__ void tile_sort_class32(const uint2 r, const uint64_t*
         const uint32_t i = t * E + k;
         a[k] = i < n ? (((dep[k] - mn) >> shift) << IDX_BITS) | i : 0xffffffffu;
     }
-    tile_sort_regs32<E, THREADS>(s, a);
+    if (RADIX) tile_radix_sort32<E, THREADS>(s, a, s_cnt, s_cnt + (THREADS / 32) * TR_RADIX, IDX_BITS);
+    else tile_sort_regs32<E, THREADS>(s, a);
     // exact order between neighbours whose quantised depths collide: odd-even transposition on the
     // 64-bit records, until a whole round swaps nothing (runs are 2-3 entries long in practice)
     bool tie = false;
@@ -291,33 +371,37 @@ __device__ __forceinline__ void tile_sort_class32(const uint2 r, const uint64_t*
     for (uint32_t i = t; i < n; i += THREADS) point_list[r.x + i] = (uint32_t)seg[s[i] & IDX_MASK];
 }
 
+template <bool RADIX>
 __global__ void __launch_bounds__(TSORT_THREADS)
 tile_sort_small_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list)
 {
     __shared__ __align__(16) uint32_t s[TSORT_SMALL];
     __shared__ uint32_t s_red[64];
+    __shared__ uint32_t s_cnt[RADIX ? (TSORT_THREADS / 32) * TR_RADIX + TR_RADIX + 32 : 1];
     const uint2 r = ranges[blockIdx.x];
     const uint32_t n = r.y - r.x;
     if (n == 0 || n > (uint32_t)TSORT_SMALL) return;   // longer lists: the 128 KB / global classes
     const uint32_t npad = n <= 256 ? 256u : next_pow2(n);
     switch (npad) {
-        case 256: tile_sort_class32<1, TSORT_THREADS>(r, pairs, point_list, s, s_red); break;
-        case 512: tile_sort_class32<2, TSORT_THREADS>(r, pairs, point_list, s, s_red); break;
-        case 1024: tile_sort_class32<4, TSORT_THREADS>(r, pairs, point_list, s, s_red); break;
-        case 2048: tile_sort_class32<8, TSORT_THREADS>(r, pairs, point_list, s, s_red); break;
-        default: tile_sort_class32<16, TSORT_THREADS>(r, pairs, point_list, s, s_red); break;
+        case 256: tile_sort_class32<1, TSORT_THREADS, false>(r, pairs, point_list, s, s_red, s_cnt); break;
+        case 512: tile_sort_class32<2, TSORT_THREADS, false>(r, pairs, point_list, s, s_red, s_cnt); break;
+        case 1024: tile_sort_class32<4, TSORT_THREADS, RADIX>(r, pairs, point_list, s, s_red, s_cnt); break;
+        case 2048: tile_sort_class32<8, TSORT_THREADS, RADIX>(r, pairs, point_list, s, s_red, s_cnt); break;
+        default: tile_sort_class32<16, TSORT_THREADS, RADIX>(r, pairs, point_list, s, s_red, s_cnt); break;
     }
 }
 
 // Size class n > 4096: up to 16384 entries the same 32-bit keyed network with 1024 threads (8 or 16 keys per thread, 32 / 64 KB
 // of dynamic shared memory), beyond that a 64-bit network in global memory; one persistent CTA per SM looping over the tiles of
 // the class (the launch exits at once when the frame's longest list fits the 256-thread kernel).
+template <bool RADIX>
 __global__ void __launch_bounds__(1024, 1)
 tile_sort_mid_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list,
                      int tiles, const GeomHeader* __restrict__ hdr)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ uint32_t s_red[64];
+    __shared__ uint32_t s_cnt[RADIX ? 32 * TR_RADIX + TR_RADIX + 32 : 1];
     if (hdr->max_tile_len <= (uint32_t)TSORT_SMALL) return;   // no tile of this size class in the frame
     uint32_t* s = reinterpret_cast<uint32_t*>(dyn_smem);
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -325,8 +409,8 @@ tile_sort_mid_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ pa
         const uint32_t n = r.y - r.x;
         if (n <= (uint32_t)TSORT_SMALL) continue;                             // the 256-thread kernel handles this tile
         __syncthreads();                                                      // previous tile's readers are done with s[]
-        if (n <= 8192u) tile_sort_class32<8, 1024>(r, pairs, point_list, s, s_red);
-        else if (n <= (uint32_t)TSORT_MID) tile_sort_class32<16, 1024>(r, pairs, point_list, s, s_red);
+        if (n <= 8192u) tile_sort_class32<8, 1024, RADIX>(r, pairs, point_list, s, s_red, s_cnt);
+        else if (n <= (uint32_t)TSORT_MID) tile_sort_class32<16, 1024, RADIX>(r, pairs, point_list, s, s_red, s_cnt);
         else {
             // more than 16384 entries in one tile (pathological inputs): the 64-bit network in place, in global memory
             uint64_t* g = pairs + r.x;
@@ -580,12 +664,20 @@ int launch_binning(const FwdParams& p, char* geom, const GeomLayout& GL, char* b
     }
     {
         StageTimer _t(ST_TILE_SORT, s);
-        tile_sort_small_kernel<<<tiles, TSORT_THREADS, 0, s>>>(ranges, pairs, point_list);
+        // tuning knob: per-tile sort engine (comparator network / shared-memory radix sort) on the same 32-bit keys
+        static const bool radix = [] { const char* e = getenv("GSB_TILE_SORT"); return e ? e[0] == 'r' : GSB_DEFAULT_TILE_RADIX; }();
+        if (radix) tile_sort_small_kernel<true><<<tiles, TSORT_THREADS, 0, s>>>(ranges, pairs, point_list);
+        else tile_sort_small_kernel<false><<<tiles, TSORT_THREADS, 0, s>>>(ranges, pairs, point_list);
         GSB_LAUNCH_CHECK();
         if (grid_instances > TSORT_SMALL) {   // a longer tile list is only possible then
-            GSB_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TSORT_MID * 4));
             const int g = tiles < NUM_SMS ? tiles : NUM_SMS;
-            tile_sort_mid_kernel<<<g, 1024, TSORT_MID * 4, s>>>(ranges, pairs, point_list, tiles, hdr);
+            if (radix) {
+                GSB_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_mid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSORT_MID * 4));
+                tile_sort_mid_kernel<true><<<g, 1024, TSORT_MID * 4, s>>>(ranges, pairs, point_list, tiles, hdr);
+            } else {
+                GSB_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_mid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSORT_MID * 4));
+                tile_sort_mid_kernel<false><<<g, 1024, TSORT_MID * 4, s>>>(ranges, pairs, point_list, tiles, hdr);
+            }
             GSB_LAUNCH_CHECK();
         }
     }
