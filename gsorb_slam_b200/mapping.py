@@ -83,6 +83,19 @@ class MapOptimizer:
                                 dL_dcolor=self.grads.ptr("rgb"), dL_dmean3D=self.g_means_cam.data_ptr(), dL_dsh=None,
                                 dL_dscale=self.g_scales.data_ptr(), dL_drot=self.g_rot.data_ptr())
 
+    def save_ply(self, path: str) -> None:
+        """Write the map as the reference's GaussianModel.ply (src/Utils.cc:182-280; read by scripts/replay.py)."""
+        from .ply import save_gaussian_model
+        c = lambda name: self.params[name].detach().cpu().numpy()
+        save_gaussian_model(path, c("means"), c("rgb"), c("opacity"), c("scales"), c("quats"))
+
+    @classmethod
+    def from_ply(cls, path: str, **kwargs) -> "MapOptimizer":
+        """Resume from a GaussianModel.ply written by the reference or by ``save_ply``."""
+        from .ply import load_gaussian_model
+        m = load_gaussian_model(path)
+        return cls(m["means"], m["rgb"], m["logit_opacities"], m["log_scales"], m["unnorm_quats"], **kwargs)
+
     def _s(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
 
