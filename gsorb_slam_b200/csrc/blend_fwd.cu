@@ -13,10 +13,14 @@
 //     quarter-warp walks only ITS survivors, so a pixel evaluates the few splats that can
 //     reach its block instead of every splat binned to the tile;
 //   * a quarter / warp retires as soon as its pixels are saturated;
-//   * splat records are one 48-byte gather (3 x 16-byte cp.async straight into shared
-//     memory, double buffered, ids prefetched two batches ahead) instead of four separate
-//     arrays plus a per-pair colour read from global memory;
-//   * the tile's highest n_contrib is recorded for the backward pass.
+//   * splat records are one 48-byte gather straight into a ring of shared-memory buffers
+//     (stage.cuh: 3 x 16-byte cp.async per record, or one 48-byte bulk copy; one CTA barrier per
+//     batch, ids prefetched one batch ahead of the copies) instead of four separate arrays plus a
+//     per-pair colour read from global memory;
+//   * per window of 32 list entries and per 4x2 block the kernel records WHICH entries were
+//     blended into at least one pixel of the block (the "hit words"): the backward pass walks
+//     exactly those, and starts at the highest n_contrib of each half tile, also recorded here;
+//   * CH = 5 blends the depth / silhouette pass of the same iteration in the same walk.
 #include <cstdlib>
 #include "common.cuh"
 #include "stage.cuh"

@@ -1,5 +1,5 @@
-// preprocess.cu -- per-Gaussian projection (K1), tile-count scan (K2), radii-only filter (K10)
-// and frustum mask (K11) for sm_100a.
+// preprocess.cu -- per-Gaussian projection + per-tile instance counting (K1), with the tile-count scan
+// (K2, scan.cuh) run by the last CTA to finish; radii-only filter (K10) and frustum mask (K11); sm_100a.
 //
 // Replaces (reference file:line, behaviour only -- nothing is copied):
 //   FORWARD::preprocess / preprocessCUDA      forward.cu:155-256
@@ -12,6 +12,9 @@
 // Layout: the reference scatters the projected state over seven SoA arrays (79 B/Gaussian);
 // here one 48-byte SplatRec per Gaussian carries everything the blend kernels gather, and
 // the AoS float3 inputs are staged through shared memory with 128-bit coalesced loads.
+// Binning starts here: every (Gaussian, tile) instance is counted with an atomic whose return
+// value is the instance's slot inside the tile's segment (kept for `duplicate`, binning.cu), and
+// the tile-row band of a sharded frame (gsb_raster_args::tile_row_begin / _end) is applied.
 #include <cstdlib>
 #include "common.cuh"
 #include "scan.cuh"
