@@ -161,3 +161,71 @@ def make_config(name: str, seed: int = 0) -> Scene:
     if name.endswith("_raster"):
         return raster_ordered(make_scene(seed=seed, **CONFIGS[name[:-len("_raster")]]))
     return make_scene(seed=seed, **CONFIGS[name])
+
+
+# ---- BASELINE.json config #2 ("camera-pose backward enabled"): a camera that is NOT at the origin ----------------------
+def cfg2_pose() -> np.ndarray:
+    ay, ax = 0.07, -0.03
+    Ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
+    Rx = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
+    T = np.eye(4)
+    T[:3, :3] = Ry @ Rx
+    T[:3, 3] = [0.12, -0.04, 0.25]
+    return T.astype(np.float32)
+
+
+def pose_transform_f32(Tcw: np.ndarray, means_world: np.ndarray) -> np.ndarray:
+    """src/Render.cc:750-752 (``Tcw.repeat(N,1,1).bmm([mean;1])``) restated with a FIXED fp32 operation order (products
+    rounded, summed left to right) so that the golden generator and the tests hand bit-identical camera-frame means to the
+    reference kernels and to libgsb."""
+    T = Tcw.astype(np.float32)
+    m = means_world.astype(np.float32)
+    out = np.empty_like(m)
+    for r in range(3):
+        out[:, r] = ((T[r, 0] * m[:, 0] + T[r, 1] * m[:, 1]) + T[r, 2] * m[:, 2]) + T[r, 3]
+    return out
+
+
+def quantised_raster_scene(P: int, intr: str = "tum", seed: int = 0, depth_factor: float = 5000.0, planes: int = 24) -> Scene:
+    """What ``Render::InitWorld`` / ``InitGaussianPoint`` (src/Render.cc:496-553, 666-707) really produce: one Gaussian per
+    valid depth pixel, back-projected at an identity pose from a depth image whose values are QUANTISED (TUM
+    ``DepthMapFactor`` 5000, Replica 16-bit PNG), created in raster order.  Piecewise-planar depth (``planes`` fronto-
+    parallel patches) so that a tile holds hundreds of EXACTLY equal view-space depths -- the worst case of the tile
+    sort's tie handling, which continuous synthetic depths never exercise."""
+    sc = make_scene(P, intr, seed=seed)
+    cam = sc.cam
+    rng = np.random.default_rng(seed + 1000)
+    f32 = np.float32
+    z = sc.means3D[:, 2].copy()
+    vis = z > 0.2
+    u = sc.means3D[:, 0] / np.where(vis, z, 1) * f32(cam.fx) + f32((cam.width - 1) / 2.0)
+    v = sc.means3D[:, 1] / np.where(vis, z, 1) * f32(cam.fy) + f32((cam.height - 1) / 2.0)
+    # depth = one of `planes` levels chosen by the screen cell (6 x 4 patches), then quantised to 1/depth_factor metres
+    cell = (np.clip(u / cam.width * 6, 0, 5.999).astype(np.int64) + 6 * np.clip(v / cam.height * 4, 0, 3.999).astype(np.int64)) % planes
+    levels = rng.uniform(0.8, 5.0, planes)
+    zq = (np.round(levels[cell] * depth_factor) / depth_factor).astype(f32)
+    znew = np.where(vis, zq, z).astype(f32)
+    sc.means3D[:, 0] = np.where(vis, (u - f32((cam.width - 1) / 2.0)) / f32(cam.fx) * znew, sc.means3D[:, 0])
+    sc.means3D[:, 1] = np.where(vis, (v - f32((cam.height - 1) / 2.0)) / f32(cam.fy) * znew, sc.means3D[:, 1])
+    sc.means3D[:, 2] = znew
+    fm = f32((cam.fx + cam.fy) / 2.0)
+    sc.log_scales = np.repeat(np.log(np.maximum(np.abs(znew), f32(0.05)) / fm)[:, None], 3, 1).astype(f32)   # isotropic, Gaussian.cc:60-66
+    sc.scales = np.exp(sc.log_scales).astype(f32)
+    return raster_ordered(sc)
+
+
+def make_large_case(name: str):
+    """name -> (scene whose ``means3D`` are the camera-frame means handed to the rasterizer, extras).  The cases behind
+    tests/golden/large_digests.json; ``tum_<P>`` are the round-1 names of cfg1_100k / headline_1m."""
+    if name.startswith("tum_"):
+        return make_scene(int(name[4:]), "tum", seed=0), {}
+    if name == "cfg2_500k_pose":
+        sc = make_config("cfg2_500k")
+        Tcw = cfg2_pose()
+        Twc = np.linalg.inv(Tcw.astype(np.float64))
+        means_world = (sc.means3D.astype(np.float64) @ Twc[:3, :3].T + Twc[:3, 3]).astype(np.float32)
+        sc.means3D = pose_transform_f32(Tcw, means_world)
+        return sc, dict(Tcw=Tcw, means_world=means_world)
+    if name == "quantised_1m":
+        return quantised_raster_scene(1_000_000), {}
+    return make_config(name), {}

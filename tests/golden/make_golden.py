@@ -104,6 +104,15 @@ def run_oracle(kw, dL):
     return out
 
 
+GOLDEN_DIR = os.path.dirname(os.path.abspath(__file__))
+
+def large_case(name):
+    """name -> (scene whose means3D are the camera-frame means handed to the rasterizer, extras for the golden file).
+    tum_<P> are the round-1 names of cfg1_100k / headline_1m (kept so their fixtures stay valid)."""
+    from gsorb_slam_b200.scene import make_large_case
+    return make_large_case(name)
+
+
 INT_KEYS = ["radii", "n_contrib", "ranges", "point_list", "tiles_touched", "num_rendered"]
 FLOAT_KEYS = ["color", "depth", "final_T", "depths", "means2D", "conic_opacity", "dL_dmean2D", "dL_dconic",
               "dL_dopacity", "dL_dcolor", "dL_dmean3D", "dL_dcov3D", "dL_dscale", "dL_drot", "dL_dsh"]
@@ -166,12 +175,15 @@ def time_ref(kw, dL, iters=20, warm=5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "golden"))
-    ap.add_argument("--large", default="100000,1000000")
+    ap.add_argument("--large", default="tum_100000,tum_1000000,cfg2_500k_pose,cfg3_2m,cfg4_5m,quantised_1m,dense_1m,culled_1m")
+    ap.add_argument("--skip-small", action="store_true", help="only the large digests (small fixtures stay as committed)")
     ap.add_argument("--time", action="store_true", help="also time the reference kernels (fwd, bwd)")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     report = {}
-    for name, (sc, extra) in small_cases().items():
+    if os.path.exists(os.path.join(GOLDEN_DIR, "oracle_vs_reference.json")):
+        report = json.load(open(os.path.join(GOLDEN_DIR, "oracle_vs_reference.json")))
+    for name, (sc, extra) in ({} if args.skip_small else small_cases()).items():
         kw = frame_kwargs(sc, extra)
         ref = run_ref(kw, sc.dL_dpix)
         orc = run_oracle(kw, sc.dL_dpix)
@@ -180,34 +192,37 @@ def main():
         inputs["in_dL_dpix"] = sc.dL_dpix
         np.savez_compressed(os.path.join(args.out, f"{name}.npz"), **inputs, **{("ref_" + k): v for k, v in ref.items()})
         print(name, "R", int(ref["num_rendered"]), json.dumps({k: v for k, v in report[name].items() if k in ("radii", "point_list", "color", "dL_dmean3D")}), flush=True)
-    # simple_knn fixture
-    from oracle import gs_ref, gs_oracle
-    pts = make_scene(5000, "tum", seed=7).means3D
-    knn_ref = gs_ref.knn_mean_dist2(pts).cpu().numpy()
-    knn_orc = gs_oracle.knn_mean_dist2(pts)
-    report["knn_5000"] = dict(max_abs=float(np.abs(knn_ref - knn_orc).max()), bit_equal=bool(np.array_equal(knn_ref, knn_orc)))
-    np.savez_compressed(os.path.join(args.out, "knn_5000.npz"), in_points=pts, ref_mean_dist2=knn_ref)
-    print("knn", report["knn_5000"], flush=True)
-    # visible_filter / mark_visible fixture (1.2x image, unchanged tanfov: src/Render.cc:784-831)
-    sc = make_scene(4000, "tum", seed=8)
-    vf = dict(width=int(sc.cam.width * 1.2), height=int(sc.cam.height * 1.2), means3D=sc.means3D, scales=sc.scales,
-              rotations=sc.rotations, viewmatrix=sc.cam.viewmatrix, projmatrix=sc.cam.projmatrix,
-              tanfovx=sc.cam.tanfovx, tanfovy=sc.cam.tanfovy)
-    r_ref = gs_ref.visible_filter(**vf).cpu().numpy()
-    r_orc = gs_oracle.visible_filter(**vf)
-    m_ref = gs_ref.mark_visible(sc.means3D, sc.cam.viewmatrix, sc.cam.projmatrix).cpu().numpy()
-    m_orc = gs_oracle.mark_visible(sc.means3D, sc.cam.viewmatrix, sc.cam.projmatrix)
-    report["visible_filter_4000"] = dict(radii_equal=bool(np.array_equal(r_ref, r_orc)), mark_equal=bool(np.array_equal(m_ref, m_orc)))
-    np.savez_compressed(os.path.join(args.out, "visible_4000.npz"), **{("in_" + k): np.asarray(v) for k, v in vf.items()},
-                        ref_radii=r_ref, ref_present=m_ref)
-    print("visible", report["visible_filter_4000"], flush=True)
+    if not args.skip_small:
+        # simple_knn fixture
+        from oracle import gs_ref, gs_oracle
+        pts = make_scene(5000, "tum", seed=7).means3D
+        knn_ref = gs_ref.knn_mean_dist2(pts).cpu().numpy()
+        knn_orc = gs_oracle.knn_mean_dist2(pts)
+        report["knn_5000"] = dict(max_abs=float(np.abs(knn_ref - knn_orc).max()), bit_equal=bool(np.array_equal(knn_ref, knn_orc)))
+        np.savez_compressed(os.path.join(args.out, "knn_5000.npz"), in_points=pts, ref_mean_dist2=knn_ref)
+        print("knn", report["knn_5000"], flush=True)
+        # visible_filter / mark_visible fixture (1.2x image, unchanged tanfov: src/Render.cc:784-831)
+        sc = make_scene(4000, "tum", seed=8)
+        vf = dict(width=int(sc.cam.width * 1.2), height=int(sc.cam.height * 1.2), means3D=sc.means3D, scales=sc.scales,
+                  rotations=sc.rotations, viewmatrix=sc.cam.viewmatrix, projmatrix=sc.cam.projmatrix,
+                  tanfovx=sc.cam.tanfovx, tanfovy=sc.cam.tanfovy)
+        r_ref = gs_ref.visible_filter(**vf).cpu().numpy()
+        r_orc = gs_oracle.visible_filter(**vf)
+        m_ref = gs_ref.mark_visible(sc.means3D, sc.cam.viewmatrix, sc.cam.projmatrix).cpu().numpy()
+        m_orc = gs_oracle.mark_visible(sc.means3D, sc.cam.viewmatrix, sc.cam.projmatrix)
+        report["visible_filter_4000"] = dict(radii_equal=bool(np.array_equal(r_ref, r_orc)), mark_equal=bool(np.array_equal(m_ref, m_orc)))
+        np.savez_compressed(os.path.join(args.out, "visible_4000.npz"), **{("in_" + k): np.asarray(v) for k, v in vf.items()},
+                            ref_radii=r_ref, ref_present=m_ref)
+        print("visible", report["visible_filter_4000"], flush=True)
 
     digests, timing = {}, {}
-    for P in [int(x) for x in args.large.split(",") if x]:
-        sc = make_scene(P, "tum", seed=0)
+    if os.path.exists(os.path.join(GOLDEN_DIR, "large_digests.json")):
+        digests = json.load(open(os.path.join(GOLDEN_DIR, "large_digests.json")))
+    for name in [x for x in args.large.split(",") if x]:
+        sc, extra_out = large_case(name)
+        P = sc.P
         kw = frame_kwargs(sc, {})
         ref = run_ref(kw, sc.dL_dpix)
-        name = f"tum_{P}"
         digests[name] = digest_large(ref, sc.cam.width, sc.cam.height)
         sub = {k: ref[k][..., ::10, ::10].copy() for k in ("color", "depth")}
         sub["final_T"] = ref["final_T"][::10, ::10].copy()
@@ -215,6 +230,16 @@ def main():
         idx = np.arange(0, P, max(1, P // 4096))
         for k in ("dL_dmean3D", "dL_dscale", "dL_drot", "dL_dopacity", "dL_dcolor", "dL_dmean2D", "dL_dconic", "radii"):
             sub[k] = ref[k][idx].copy()
+        # per-tensor scale of the FULL reference gradient (the denominators of the 1e-3 contract)
+        for k in ("dL_dmean3D", "dL_dscale", "dL_drot", "dL_dopacity", "dL_dcolor", "dL_dmean2D", "dL_dconic"):
+            digests[name][k + "_absmax"] = float(np.abs(ref[k]).max())
+        if "Tcw" in extra_out:
+            # camera-pose backward: dL/dTcw[0:3,:] = sum_i g_i [p_i;1]^T over the reference's dL_dmean3D
+            # (camera frame) and the world-frame means, accumulated in float64
+            g = ref["dL_dmean3D"].astype(np.float64)
+            pw = np.concatenate([extra_out["means_world"].astype(np.float64), np.ones((P, 1))], 1)
+            sub["dL_dTcw"] = (g.T @ pw)
+            sub["Tcw"] = extra_out["Tcw"]
         np.savez_compressed(os.path.join(args.out, f"{name}_sample.npz"), sample_idx=idx, **sub)
         if P <= 200000:
             t0 = time.time()
@@ -225,6 +250,7 @@ def main():
         if args.time:
             timing[name] = time_ref(kw, sc.dL_dpix)
             print("timing", name, json.dumps(timing[name]), flush=True)
+        del ref
     json.dump(digests, open(os.path.join(args.out, "large_digests.json"), "w"), indent=1)
     json.dump(report, open(os.path.join(args.out, "oracle_vs_reference.json"), "w"), indent=1)
     if timing:

@@ -144,16 +144,29 @@ def test_host_buffer_entry_point_equals_device_path():
         assert rel_to_scale(g[k], to_np(gd[k]).reshape(g[k].shape)) <= 1e-5, k   # atomics order only
 
 
-@pytest.mark.parametrize("P", [100_000, 1_000_000])
-def test_full_size_digests_match_reference(P):
-    """BASELINE.json sizes (100 k and the 1 M headline at 640x480): SHA-256 digests of every integer output and strided
-    samples of the images / gradients against what the reference kernels produced on the same seeded scene."""
+# Every BASELINE.json config at full size (plus the stress variants of the headline map); digests and samples were
+# produced by the UNMODIFIED reference kernels on a B200 (tests/golden/make_golden.py, log in make_golden_r02.log).
+#   tum_100000 = config #1 (100 k @640x480), tum_1000000 = the headline, cfg2_500k_pose = config #2 (500 k, camera NOT at
+#   the origin, dL/dTcw checked), cfg3_2m = config #3 (2 M @1200x680: 3 225 tiles, ragged last tile row, 44-bit reference sort
+#   keys), cfg4_5m = config #4 (5 M @1296x968: 4 941 tiles, 45-bit keys), quantised_1m = InitWorld-like map with hundreds of
+#   EXACTLY equal depths per tile, dense_1m = 3x larger splats (128-KB sort class), culled_1m = a third outside the frustum.
+LARGE_CASES = ["tum_100000", "tum_1000000", "cfg2_500k_pose", "cfg3_2m", "cfg4_5m", "quantised_1m", "dense_1m", "culled_1m"]
+GRAD_NAMES = ("dL_dmean3D", "dL_dscale", "dL_drot", "dL_dopacity", "dL_dcolor", "dL_dmean2D", "dL_dconic")
+
+
+@pytest.mark.parametrize("name", LARGE_CASES)
+def test_full_size_digests_match_reference(name):
+    """SHA-256 digests of every integer output (radii, sorted instance list, tile ranges, n_contrib), bit-exact strided samples
+    of colour / depth / final transmittance and 1e-3 samples of every gradient against what the reference kernels produced on
+    the same seeded scene; config #2 also checks the camera-pose gradient dL/dTcw."""
+    import torch
+    from gsorb_slam_b200 import _lib
     from gsorb_slam_b200.lowlevel import frame_from_scene
-    from gsorb_slam_b200.scene import make_scene
-    dig = json.load(open(os.path.join(GOLDEN, "large_digests.json")))[f"tum_{P}"]
-    smp = np.load(os.path.join(GOLDEN, f"tum_{P}_sample.npz"))
-    sc = make_scene(P, "tum", seed=0)
-    fr = frame_from_scene(sc)
+    from gsorb_slam_b200.scene import make_large_case
+    dig = json.load(open(os.path.join(GOLDEN, "large_digests.json")))[name]
+    smp = np.load(os.path.join(GOLDEN, f"{name}_sample.npz"))
+    sc, extra = make_large_case(name)
+    fr = frame_from_scene(sc, max_rendered=dig["num_rendered"] + 4096, sync_free=True)
     g = fr.backward(sc.dL_dpix)
     assert fr.rendered() == dig["num_rendered"]
     radii = to_np(fr.radii)
@@ -169,10 +182,27 @@ def test_full_size_digests_match_reference(P):
     np.testing.assert_array_equal(depth[..., ::10, ::10].view(np.uint32), smp["depth"].view(np.uint32))
     np.testing.assert_array_equal(to_np(ims["final_T"])[::10, ::10].view(np.uint32), smp["final_T"].view(np.uint32))
     idx = smp["sample_idx"]
-    for k in ("dL_dmean3D", "dL_dscale", "dL_drot", "dL_dopacity", "dL_dcolor", "dL_dmean2D", "dL_dconic"):
+    for k in GRAD_NAMES:
         ours = to_np(g[k])[idx].reshape(smp[k].shape)
-        scale = max(np.abs(to_np(g[k])).max(), 1e-30)
-        assert np.abs(ours - smp[k]).max() / scale <= TOL_GRAD, k
+        # the denominator is the max of the FULL reference tensor, recorded by the generator
+        assert np.abs(ours - smp[k]).max() / max(dig[k + "_absmax"], 1e-30) <= TOL_GRAD, k
+    if "Tcw" in extra:
+        # camera-pose backward: dL/dTcw[0:3,:] = sum_i g_i [p_i;1]^T, reduced on the device by gsb_pose_grad
+        dev = fr.device
+        mw = torch.from_numpy(extra["means_world"]).to(dev)
+        dT = torch.empty((3, 4), dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().gsb_pose_grad(sc.P, mw.data_ptr(), g["dL_dmean3D"].data_ptr(), dT.data_ptr(),
+                                            torch.cuda.current_stream(dev).cuda_stream))
+        ref = smp["dL_dTcw"]
+        assert np.abs(to_np(dT).astype(np.float64) - ref).max() / np.abs(ref).max() <= TOL_GRAD
+        # ... and the library's own prologue reproduces the camera-frame means the golden run was fed, to fp32 rounding
+        from gsorb_slam_b200.scene import pose_transform_f32
+        mc = torch.empty_like(mw)
+        Tc = torch.from_numpy(extra["Tcw"]).to(dev).contiguous()
+        _lib.check(_lib.lib().gsb_prologue(sc.P, Tc.data_ptr(), mw.data_ptr(), None, None, None, mc.data_ptr(), None, None, None,
+                                           torch.cuda.current_stream(dev).cuda_stream))
+        want = pose_transform_f32(extra["Tcw"], extra["means_world"])
+        assert np.abs(to_np(mc) - want).max() <= 2e-6 * np.abs(want).max()
     # properties that do not need the reference: sortedness of every tile list, idempotence, linearity of the backward
     rg = to_np(ims["ranges"]).astype(np.int64)
     depths = to_np(fr.geometry_state()["depths"])
@@ -185,8 +215,58 @@ def test_full_size_digests_match_reference(P):
     c0 = color.copy()
     fr.forward()
     np.testing.assert_array_equal(to_np(fr.color).view(np.uint32), c0.view(np.uint32))
+    g1 = to_np(g["dL_dmean3D"]).copy()
     g2 = fr.backward(2.0 * sc.dL_dpix)
-    assert rel_to_scale(to_np(g2["dL_dmean3D"]), 2.0 * to_np(g["dL_dmean3D"])) <= 1e-4
+    assert rel_to_scale(to_np(g2["dL_dmean3D"]), 2.0 * g1) <= 1e-4
+
+
+@pytest.mark.parametrize("name", LARGE_CASES)
+def test_elementwise_gradient_error_against_live_reference(name):
+    """north_star: "gradients within 1e-3".  The digest test bounds max|ours - ref| / max|ref| per tensor; this one looks at
+    EVERY element: relative error |ours - ref| / |ref| over the elements with |ref| > 1e-4 max|ref| (smaller ones are
+    cancellation residue of ~50 fp32 atomics in either implementation), against the reference run live on this GPU, next to
+    the reference's own run-to-run spread (its atomics are unordered).  The distribution is written to
+    gpurun_out/grad_error_<name>.json."""
+    from oracle import gs_ref
+    if not gs_ref.available():
+        pytest.skip("oracle/_ref/libgsref.so not on this box")
+    import torch
+    from gsorb_slam_b200.lowlevel import frame_from_scene
+    from gsorb_slam_b200.scene import make_large_case
+    dig = json.load(open(os.path.join(GOLDEN, "large_digests.json")))[name]
+    sc, _ = make_large_case(name)
+    fr = frame_from_scene(sc, max_rendered=dig["num_rendered"] + 4096, sync_free=True)
+    g = fr.backward(sc.dL_dpix)
+    rf = gs_ref.frame_from_scene(sc)
+    gr = rf.backward(sc.dL_dpix)
+    gr2 = rf.backward(sc.dL_dpix)
+    torch.cuda.synchronize()
+    report = {}
+    for k in GRAD_NAMES:
+        ref = gr[k].double().reshape(sc.P, -1)
+        ours = g[k].double().reshape(sc.P, -1)
+        ref2 = gr2[k].double().reshape(sc.P, -1)
+        if k == "dL_dconic":   # slot 2 of the [P,2,2] tensor is never written by the reference (backward.cu:549-551)
+            ref, ours, ref2 = ref[:, [0, 1, 3]], ours[:, [0, 1, 3]], ref2[:, [0, 1, 3]]
+        scale = ref.abs().max().clamp_min(1e-30)
+        big = ref.abs() > 1e-4 * scale
+        rel = ((ours - ref).abs() / ref.abs().clamp_min(1e-30))[big]
+        rel_self = ((ref2 - ref).abs() / ref.abs().clamp_min(1e-30))[big]
+        q = torch.tensor([0.5, 0.99, 0.999, 0.9999], dtype=torch.float64, device=rel.device)
+        sub = rel[:: max(1, rel.numel() // 4_000_000)]   # torch.quantile caps its input size
+        sub_self = rel_self[:: max(1, rel_self.numel() // 4_000_000)]
+        report[k] = dict(elements=int(big.sum()), of=int(big.numel()),
+                         frac_rel_gt_1e3=float((rel > 1e-3).double().mean()),
+                         quantiles_50_99_999_9999=[float(x) for x in torch.quantile(sub, q)],
+                         max_rel=float(rel.max()), max_abs_over_scale=float(((ours - ref).abs().max() / scale)),
+                         reference_vs_itself_frac_rel_gt_1e3=float((rel_self > 1e-3).double().mean()),
+                         reference_vs_itself_quantiles=[float(x) for x in torch.quantile(sub_self, q)])
+    os.makedirs(os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out"), exist_ok=True)
+    json.dump(report, open(os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out", f"grad_error_{name}.json"), "w"), indent=1)
+    for k, r in report.items():
+        assert r["max_abs_over_scale"] <= TOL_GRAD, (k, r)
+        # elementwise: all but a vanishing fraction of the significant elements are within 1e-3 of the reference
+        assert r["frac_rel_gt_1e3"] <= max(1e-3, 3 * r["reference_vs_itself_frac_rel_gt_1e3"]), (k, r)
 
 
 @pytest.mark.parametrize("cfg", [dict(P=3000, intr=(160, 120, 130.0, 128.0), scale_mul=2.0, background=0.0),
