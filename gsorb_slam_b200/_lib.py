@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgsb.so")
+# GSB_LIB: developer override (e.g. the tuning build libgsb_tune.so of `make -C gsorb_slam_b200/csrc tune`)
+LIB_PATH = os.environ.get("GSB_LIB") or os.path.join(_HERE, "libgsb.so")
 
 GSB_OK = 0
 ERRORS = {-1: "GSB_ERR_INVALID_ARGUMENT", -2: "GSB_ERR_CUDA", -3: "GSB_ERR_WORKSPACE", -4: "GSB_ERR_OVERFLOW",

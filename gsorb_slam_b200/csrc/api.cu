@@ -74,6 +74,12 @@ static int validate(const gsb_raster_args* a, bool need_colors, bool need_opacit
             return fail(GSB_ERR_INVALID_ARGUMENT, "scales and rotations must be given together");
         if (has_sr == (a->cov3D_precomp != nullptr))
             return fail(GSB_ERR_INVALID_ARGUMENT, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+        // the kernels read rotations with 128-bit and cov3D_precomp with 64-bit loads (preprocess.cu, gauss_bwd.cu): a
+        // misaligned pointer would be a sticky CUDA fault for the whole context, so it is refused here (include/gsb.h)
+        if (a->rotations && (reinterpret_cast<uintptr_t>(a->rotations) & 15))
+            return fail(GSB_ERR_INVALID_ARGUMENT, "rotations must be 16-byte aligned");
+        if (a->cov3D_precomp && (reinterpret_cast<uintptr_t>(a->cov3D_precomp) & 7))
+            return fail(GSB_ERR_INVALID_ARGUMENT, "cov3D_precomp must be 8-byte aligned");
         if (need_colors) {
             if (need_opacity && !a->opacities) return fail(GSB_ERR_INVALID_ARGUMENT, "opacities are required");
             if ((a->shs != nullptr) == (a->colors_precomp != nullptr))

@@ -44,7 +44,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
                       const float* __restrict__ dL_ddepth_sil, float* __restrict__ acc /* [P][12] */, const uint32_t* __restrict__ hits_tail,
                       const GeomHeader* __restrict__ hdr, uint32_t band_y0)
 {
-    constexpr int BLEND_THREADS = 256 / HALVES, BLEND_BATCH = BLEND_THREADS, BLOCKS = HIT_BLOCKS / HALVES;
+    constexpr int HIT_BLOCKS = 32; constexpr int BLEND_THREADS = 256 / HALVES, BLEND_BATCH = BLEND_THREADS, BLOCKS = HIT_BLOCKS / HALVES;
     __shared__ StageRing<NS, BLEND_BATCH, BULK> S;
     __shared__ uint32_t s_ids[NS][BLEND_BATCH];
     __shared__ uint32_t s_hits[NS][(BLEND_BATCH / 32) * BLOCKS];  // [window of the batch][4x2 block of this CTA]
@@ -108,9 +108,13 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
         stage_issue(S, buf, rec, id, min(BLEND_BATCH, n - (batches - 1 - k) * BLEND_BATCH));
         // hit words of the batch: (BLEND_BATCH / 32) windows x BLOCKS blocks, one 4-byte copy per thread
         const uint32_t w = (uint32_t)(batches - 1 - k) * (BLEND_BATCH / 32) + threadIdx.x / BLOCKS;
-        if (threadIdx.x < (BLEND_BATCH / 32) * BLOCKS && (int)(w * 32) < n)
-            cp_async4(&s_hits[buf][threadIdx.x], hit_word(const_cast<uint32_t*>(hits_full), const_cast<uint32_t*>(hits_tail), tile,
-                                                          range.x, len, w, half * BLOCKS + threadIdx.x % BLOCKS));
+        if (threadIdx.x < (BLEND_BATCH / 32) * BLOCKS && (int)(w * 32) < n) {
+            const uint32_t blk = half * BLOCKS + threadIdx.x % BLOCKS, wp = blk >> 2, qq = blk & 3;
+            const uint4* row = reinterpret_cast<const uint4*>(hit_words(const_cast<uint32_t*>(hits_full), const_cast<uint32_t*>(hits_tail), tile, range.x, len, w));
+            const uint32_t i4 = (wp * 32 + (qq >> 1) * 16 + (qq & 1) * 4) >> 2;
+            const uint4 u = row[i4], v = row[i4 + 2];
+            s_hits[buf][threadIdx.x] = u.x | u.y | u.z | u.w | v.x | v.y | v.z | v.w;
+        }
     };
     S.init();
 #pragma unroll

@@ -6,20 +6,23 @@
 // depth = depth of the last splat blended while T > 0.5, n_contrib = list position of the
 // last blended splat, colour = C + T * bg, planar CHW output.
 //
-// What is different from the reference kernel (design, not results):
-//   * one CTA per 16x16 tile as before, but each QUARTER-WARP owns a 4x2 pixel block: per 32
-//     staged splats a warp runs one cull pass (lane j tests splat j's conservative footprint
-//     box, computed in preprocess, against the warp's four blocks -> four ballots), then every
-//     quarter-warp walks only ITS survivors, so a pixel evaluates the few splats that can
-//     reach its block instead of every splat binned to the tile;
-//   * a quarter / warp retires as soon as its pixels are saturated;
-//   * splat records are one 48-byte gather straight into a ring of shared-memory buffers
-//     (stage.cuh: 3 x 16-byte cp.async per record, or one 48-byte bulk copy; one CTA barrier per
-//     batch, ids prefetched one batch ahead of the copies) instead of four separate arrays plus a
-//     per-pair colour read from global memory;
-//   * per window of 32 list entries and per 4x2 block the kernel records WHICH entries were
-//     blended into at least one pixel of the block (the "hit words"): the backward pass walks
-//     exactly those, and starts at the highest n_contrib of each half tile, also recorded here;
+// Work decomposition (round 2; the round-1 kernel walked the tile list per 4x2 pixel block, four blocks in lock step
+// per warp, and issued 9.6 warp-instructions per blended pair -- 27 % of its lane slots did useful work):
+//   * one CTA per 16x16 tile, a warp owns an 8x4 pixel region, a LANE owns ONE pixel and pops ITS OWN candidates;
+//   * per window of 32 staged splats a warp builds the 32 x 32 bit matrix "splat j's conservative alpha >= 1/255
+//     footprint box covers pixel p" with lane = splat (two float->int conversions per axis, the 8-column and 4-row
+//     coverage bits multiplied out into a 32-pixel word) and TRANSPOSES it across the warp with a five-stage shuffle
+//     butterfly (two byte permutes, three rotate + bit-select stages), so that lane = pixel holds the bit mask of its
+//     own candidates in a register;
+//   * every lane then pops its candidates of the window in list order; the warp iterates max-over-lanes of the
+//     per-PIXEL candidate counts (157 iterations per warp at the headline workload instead of 191 with per-block
+//     lists; tests/decomposition_model.py).  The exact tests of forward.cu:346-362 are applied to every candidate, so
+//     results are unchanged;
+//   * the bits a lane actually blended are its hit word of the window: one word per (window, pixel), written
+//     coalesced (BinningLayout::hits / ImageLayout::hits_tail); the backward pass replays exactly those pairs and needs
+//     no alpha test;
+//   * splat records are one 48-byte gather straight into a ring of shared-memory buffers (stage.cuh: 3 x 16-byte
+//     cp.async per record; one CTA barrier per batch, ids prefetched one batch ahead of the copies);
 //   * CH = 5 blends the depth / silhouette pass of the same iteration in the same walk.
 #include <cstdlib>
 #include "common.cuh"
@@ -27,11 +30,60 @@
 
 namespace gsb {
 
+// 32 x 32 bit-matrix transpose across a warp: in: lane j holds row j (bit p = column p); out: lane p holds column p.
+// Five butterfly stages; stage s exchanges the off-diagonal s x s blocks of every 2s x 2s block.  The two byte-granular
+// stages are ONE byte permute each (selector chosen per lane), the three bit-granular ones a rotate of the partner's
+// word (left by s for the lane without bit s, right by s for the other: the bits that wrap land under the mask) and
+// one bit-select: 13 instructions instead of the 35 of the select-by-lane formulation.
+struct TransposeConsts {
+    uint32_t sel16, sel8;      // PRMT selectors
+    uint32_t m4, m2, m1;       // bits this lane KEEPS of its own word
+    uint32_t r4, r2, r1;       // left-rotation of the partner's word
+    __device__ __forceinline__ TransposeConsts(uint32_t lane)
+    {
+        sel16 = (lane & 16) ? 0x3276u : 0x5410u;   // hi: (x & 0xffff0000) | (y >> 16);  lo: (x & 0xffff) | (y << 16)
+        sel8 = (lane & 8) ? 0x3715u : 0x6240u;     // hi: (x & 0xff00ff00) | ((y >> 8) & 0x00ff00ff);  lo: (x & 0x00ff00ff) | ((y << 8) & 0xff00ff00)
+        m4 = (lane & 4) ? 0xf0f0f0f0u : 0x0f0f0f0fu; r4 = (lane & 4) ? 28u : 4u;
+        m2 = (lane & 2) ? 0xccccccccu : 0x33333333u; r2 = (lane & 2) ? 30u : 2u;
+        m1 = (lane & 1) ? 0xaaaaaaaau : 0x55555555u; r1 = (lane & 1) ? 31u : 1u;
+        // opaque to the optimiser: the eight words stay in registers instead of being re-derived from the lane id in every window
+        asm volatile("" : "+r"(sel16), "+r"(sel8), "+r"(m4), "+r"(m2), "+r"(m1), "+r"(r4), "+r"(r2), "+r"(r1));
+    }
+    __device__ __forceinline__ uint32_t operator()(uint32_t x) const
+    {
+        x = __byte_perm(x, __shfl_xor_sync(0xffffffffu, x, 16), sel16);
+        x = __byte_perm(x, __shfl_xor_sync(0xffffffffu, x, 8), sel8);
+        uint32_t y;
+        y = __shfl_xor_sync(0xffffffffu, x, 4); x = (x & m4) | (__funnelshift_l(y, y, r4) & ~m4);
+        y = __shfl_xor_sync(0xffffffffu, x, 2); x = (x & m2) | (__funnelshift_l(y, y, r2) & ~m2);
+        y = __shfl_xor_sync(0xffffffffu, x, 1); x = (x & m1) | (__funnelshift_l(y, y, r1) & ~m1);
+        return x;
+    }
+};
+
+// ((1 << width) - 1) << pos with pos and width clamped to [0, 32]
+__device__ __forceinline__ uint32_t bit_mask(int pos, int width)
+{
+    uint32_t d;
+    asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(d) : "r"(pos), "r"(width));
+    return d;
+}
+
+// The CTA's shared memory, in ONE struct so that the order is fixed: the walk forms record addresses from
+// "entry = 32 window + ffs(mask) - 1", which is -1 for a lane that has nothing to pop -- a[0][-1] must be mapped memory
+// (the value is never used).
+template <int NS>
+struct FwdSmem {
+    uint32_t guard[4];   // a[0][-1]
+    StageRing<NS, BLEND_THREADS, false> ring;
+    uint32_t max_contrib;
+};
+
 // CH = 3: the reference pass.  CH = 5: the RGB pass and the depth / silhouette pass of one mapping iteration
 // (src/Render.cc:445-448: colours [r, g, b] and [z_cam, 1, 0] over the SAME geometry) blended together; channel 3
 // accumulates depth * alpha * T, channel 4 alpha * T, with the operation order each has in its own reference pass.
-template <int MINB, int NS, int HALVES, int CH, bool BULK>
-__global__ void __launch_bounds__(256 / HALVES, MINB)
+template <int MINB, int NS, int CH>
+__global__ void __launch_bounds__(BLEND_THREADS, MINB)
 blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                      const SplatRec* __restrict__ rec, int W, int H, const float* __restrict__ bg,
                      float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_depth_sil,
@@ -40,139 +92,132 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                      uint32_t* __restrict__ hits_full, uint32_t* __restrict__ hits_tail,
                      GeomHeader* __restrict__ hdr, uint32_t layout_capacity, uint32_t band_y0)
 {
-    constexpr int BLEND_THREADS = 256 / HALVES, BLEND_BATCH = BLEND_THREADS;
-    __shared__ StageRing<NS, BLEND_BATCH, BULK> S;
-    __shared__ uint32_t s_max[2];
-    const uint32_t tile_y = band_y0 + blockIdx.y / HALVES, half = blockIdx.y % HALVES;   // the grid covers the band's tile rows
+    constexpr int BATCH = BLEND_THREADS, WINS = BATCH / 32;
+    __shared__ FwdSmem<NS> SM;
+    StageRing<NS, BATCH, false>& S = SM.ring;
+    const uint32_t tile_y = band_y0 + blockIdx.y;   // the grid covers the band's tile rows
     const uint32_t tile = tile_y * gridDim.x + blockIdx.x;
     const uint2 range = ranges[tile];
     const int n = (int)(range.y - range.x);
-    const int batches = (n + BLEND_BATCH - 1) / BLEND_BATCH;
-    // warp (numbered 0..7 over the whole tile) -> 8x4 pixel block of the tile; quarter-warp q -> 4x2 sub-block; lane -> pixel
-    const uint32_t warp = half * (8 / HALVES) + (threadIdx.x >> 5), lane = lane_id();
-    const uint32_t q = lane >> 3, l8 = lane & 7, qshift = q * 8;
+    const int batches = (n + BATCH - 1) / BATCH;
+    // warp -> 8x4 pixel region of the tile; lane -> pixel (column lane & 7, row lane >> 3) = bit index of the coverage words
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bx0 = blockIdx.x * TILE_X + (warp & 1) * 8, by0 = tile_y * TILE_Y + (warp >> 1) * 4;
-    const int px = bx0 + (q & 1) * 4 + (l8 & 3), py = by0 + (q >> 1) * 2 + (l8 >> 2);
+    const int px = bx0 + (int)(lane & 7), py = by0 + (int)(lane >> 3);
     const bool inside = px < W && py < H;
-    const float pxf = (float)px, pyf = (float)py;
-    // sub-block extents used by the cull pass (pixel centres): x halves [bx0, bx0+3], [bx0+4, bx0+7];
-    // y halves [by0, by0+1], [by0+2, by0+3]
-    const float xa0 = (float)bx0, xa1 = (float)(bx0 + 3), xb0 = (float)(bx0 + 4), xb1 = (float)(bx0 + 7);
-    const float ya0 = (float)by0, ya1 = (float)(by0 + 1), yb0 = (float)(by0 + 2), yb1 = (float)(by0 + 3);
-    if (threadIdx.x == 0) {
-        s_max[0] = s_max[1] = 0;
+    float pxf = (float)px, pyf = (float)py;
+    int rx0 = bx0, ry0 = by0;
+    asm volatile("" : "+f"(pxf), "+f"(pyf), "+r"(rx0), "+r"(ry0));   // stay in registers (not re-derived from the thread id per window)
+    if (tid == 0) {
+        SM.max_contrib = 0;
         if (blockIdx.x == 0 && blockIdx.y == 0) hdr->layout_capacity = layout_capacity;  // the backward pass locates the hit words with it
     }
 
-    bool done = !inside;
+    uint32_t done = inside ? 0u : 1u;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, C3 = 0.f, C4 = 0.f, D = 0.f;
     uint32_t last = 0;
 
     const uint32_t* ids = point_list + range.x;
     auto load_id = [&](int b) -> uint32_t {
-        const int e = b * BLEND_BATCH + (int)threadIdx.x;
+        const int e = b * BATCH + (int)tid;
         return e < n ? __ldg(ids + e) : 0xffffffffu;
     };
-    auto batch_count = [&](int b) { return min(BLEND_BATCH, n - b * BLEND_BATCH); };
-    S.init();
     // prologue: batches 0 .. NS-2 in flight, ids of batch NS-1 in a register
-    int issued = -1, waited = -1;   // highest batch issued / waited for (the bulk engine must drain before the CTA exits)
 #pragma unroll
     for (int i = 0; i < NS - 1; i++) {
-        if (i < batches) {
-            stage_issue(S, i, rec, load_id(i), batch_count(i));
-            issued = i;
-        }
+        if (i < batches) stage_issue(S, i, rec, load_id(i), 0);
         cp_async_commit();
     }
     uint32_t id_next = NS - 1 < batches ? load_id(NS - 1) : 0xffffffffu;
-    uint32_t done_bits = __ballot_sync(0xffffffffu, done);
-    bool warp_done = done_bits == 0xffffffffu;
+    bool warp_done = __all_sync(0xffffffffu, done != 0);
+    const TransposeConsts transpose(lane);
     int buf = 0;
     for (int b = 0; b < batches; b++) {
-        stage_wait(S, buf, b);  // batch b has landed (LDGSTS: this thread's copies; bulk: the stage's mbarrier phase)
-        waited = b;
+        stage_wait(S, buf, b);  // this thread's copies of batch b have landed
         // one barrier per batch: publishes batch b, and everyone is finished with batch b-1 (whose buffer is reused below)
-        if (__syncthreads_count(warp_done) == BLEND_THREADS) break;  // every pixel of the tile is saturated
+        if (__syncthreads_count(warp_done) == BATCH) break;  // every pixel of the tile is saturated
         {
             const int nbuf = buf == 0 ? NS - 1 : buf - 1;  // (b + NS - 1) % NS
-            if (b + NS - 1 < batches) {
-                stage_issue(S, nbuf, rec, id_next, batch_count(b + NS - 1));
-                issued = b + NS - 1;
-            }
+            if (b + NS - 1 < batches) stage_issue(S, nbuf, rec, id_next, 0);
             cp_async_commit();
             if (b + NS < batches) id_next = load_id(b + NS);
         }
         if (!warp_done) {
-            const int cnt = min(BLEND_BATCH, n - b * BLEND_BATCH);
-            for (int c0 = 0; c0 < cnt; c0 += 32) {
-                // ---- cull pass: lane j tests staged splat c0+j against the four 4x2 sub-blocks ----
-                const int j = c0 + (int)lane;
-                bool hxa = false, hxb = false, hya = false, hyb = false;
-                if (j < cnt) {
-                    const float4 A = S.A(buf, j);
+            const int cnt = min(BATCH, n - b * BATCH);
+            const int nwin = (cnt + 31) >> 5;
+            // hit words of the batch: rows of 256 words, window after window; the list's last, partial window has its own row
+            uint32_t* hp = hits_full + ((size_t)(range.x >> 5) + (size_t)(b * WINS)) * HIT_PIXELS + tid;
+            const int wtail = (n >> 5) - b * WINS;   // first window of this batch that is not a full one
+            for (int w = 0; w < nwin; w++, hp += HIT_PIXELS) {
+                const float4* const ra = &S.a[buf][w * 32];   // the window's records: a at ra[], b at ra[NS * BATCH], c at ra[2 * NS * BATCH]
+                // ---- cull: lane = splat builds the coverage word of its splat over the warp's 32 pixels; transpose ----
+                uint32_t mask;
+                {
+                    const float4 A = ra[lane];
                     const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&A.z));
-                    const float lox = A.x - e.x, hix = A.x + e.x, loy = A.y - e.y, hiy = A.y + e.y;
-                    hxa = !(hix < xa0 || lox > xa1);
-                    hxb = !(hix < xb0 || lox > xb1);
-                    hya = !(hiy < ya0 || loy > ya1);
-                    hyb = !(hiy < yb0 || loy > yb1);
+                    // pixel column bx0 + c is a candidate iff A.x - e.x <= bx0 + c <= A.x + e.x (rows alike): the footprint box of
+                    // preprocess.cu against pixel centres, as the round-1 block test, but per pixel.  Columns [clo, chi] of the
+                    // region's 8, rows [rlo, rhi] of its 4; an empty range gives width 0.
+                    const int clo = max(__float2int_ru(A.x - e.x) - rx0, 0), chi = min(__float2int_rd(A.x + e.x) - rx0, 7);
+                    const int rlo = max(__float2int_ru(A.y - e.y) - ry0, 0), rhi = min(__float2int_rd(A.y + e.y) - ry0, 3);
+                    const uint32_t colm = bit_mask(clo, max(chi - clo + 1, 0));
+                    const uint32_t rowm = bit_mask(rlo, max(rhi - rlo + 1, 0));
+                    uint32_t pm = ((rowm * 0x00204081u) & 0x01010101u) * colm;   // row bits spread to bytes, each byte = the column bits
+                    if (w * 32 + (int)lane >= cnt) pm = 0;   // the slot holds a stale record of an earlier batch
+                    mask = transpose(pm);
+                    if (done) mask = 0;
                 }
-                const uint32_t m0 = __ballot_sync(0xffffffffu, hxa && hya), m1 = __ballot_sync(0xffffffffu, hxb && hya);
-                const uint32_t m2 = __ballot_sync(0xffffffffu, hxa && hyb), m3 = __ballot_sync(0xffffffffu, hxb && hyb);
-                uint32_t mask = q == 0 ? m0 : q == 1 ? m1 : q == 2 ? m2 : m3;
-                if (((done_bits >> qshift) & 0xffu) == 0xffu) mask = 0;  // this quarter is saturated
-                uint32_t lane_hits = 0;  // entries of this window blended into THIS pixel
-                // ---- blend pass: every quarter-warp walks ITS survivors, in list order ----
+                // ---- walk: every lane pops ITS candidates of the window, in list order ----
+                uint32_t hits = 0;
+                const uint32_t pos0 = (uint32_t)(b * BATCH + w * 32) + 1u;
                 while (__any_sync(0xffffffffu, mask != 0)) {
+                    const int f = __ffs(mask) - 1;                 // -1 for a lane with nothing to pop: reads a mapped, unused record
+                    uint32_t bit;                                  // 1 << f, 0 when f = -1 (PTX shl clamps the amount; C++ << would be undefined)
+                    asm("shl.b32 %0, 1, %1;" : "=r"(bit) : "r"(f));
                     const bool act = mask != 0;
-                    const int e = c0 + (act ? __ffs(mask) - 1 : 0);
-                    const uint32_t bit = mask & (0u - mask);
                     mask ^= bit;
-                    const float4 A = S.A(buf, e);
-                    const float4 B = S.B(buf, e);
+                    const float4 A = ra[f];
+                    const float4 B = ra[f + NS * BATCH];           // S.b[buf][w * 32 + f]
                     const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
                     const float power = splat_power(dx, dy, B.x, B.y, B.z);
-                    if (!act || done || power > 0.0f || power < A.w) continue;
-                    const float alpha = fminf(0.99f, __fmul_rn(B.w, expf(power)));
-                    if (alpha < 1.0f / 255.0f) continue;
-                    const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-                    if (test_T < 0.0001f) {
-                        done = true;
-                        continue;
+                    if (act && !(power > 0.0f) && !(power < A.w)) {
+                        const float alpha = fminf(0.99f, __fmul_rn(B.w, expf(power)));
+                        if (!(alpha < 1.0f / 255.0f)) {
+                            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                            if (test_T < 0.0001f) {
+                                asm volatile("" ::: "memory");   // keeps this rare block a branch target (no speculative select chains in the hot path)
+                                mask = 0;
+                                done = 1u;
+                            } else {
+                                const float4 Cc = ra[f + 2 * NS * BATCH];   // S.c[buf][w * 32 + f]
+                                C0 = fmaf(__fmul_rn(Cc.x, alpha), T, C0);
+                                C1 = fmaf(__fmul_rn(Cc.y, alpha), T, C1);
+                                C2 = fmaf(__fmul_rn(Cc.z, alpha), T, C2);
+                                if (CH == 5) {
+                                    C3 = fmaf(__fmul_rn(Cc.w, alpha), T, C3);   // colour z_cam = the splat's view-space depth
+                                    C4 = fmaf(alpha, T, C4);                    // colour 1
+                                }
+                                if (T > 0.5f) D = Cc.w;
+                                T = test_T;
+                                last = pos0 + (uint32_t)f;
+                                hits |= bit;
+                            }
+                        }
                     }
-                    const float4 Cc = S.C(buf, e);
-                    C0 = fmaf(__fmul_rn(Cc.x, alpha), T, C0);
-                    C1 = fmaf(__fmul_rn(Cc.y, alpha), T, C1);
-                    C2 = fmaf(__fmul_rn(Cc.z, alpha), T, C2);
-                    if (CH == 5) {
-                        C3 = fmaf(__fmul_rn(Cc.w, alpha), T, C3);   // colour z_cam = the splat's view-space depth
-                        C4 = fmaf(alpha, T, C4);                    // colour 1
-                    }
-                    if (T > 0.5f) D = Cc.w;
-                    T = test_T;
-                    last = (uint32_t)(b * BLEND_BATCH + e + 1);
-                    lane_hits |= bit;
                 }
-                // hit word of (window, 4x2 block): OR over the quarter's 8 lanes
-                lane_hits |= __shfl_xor_sync(0xffffffffu, lane_hits, 4);
-                lane_hits |= __shfl_xor_sync(0xffffffffu, lane_hits, 2);
-                lane_hits |= __shfl_xor_sync(0xffffffffu, lane_hits, 1);
-                if (l8 == 0)
-                    *hit_word(hits_full, hits_tail, tile, range.x, (uint32_t)n, (uint32_t)(b * (BLEND_BATCH / 32) + (c0 >> 5)),
-                              warp * 4 + q) = lane_hits;
-                done_bits = __ballot_sync(0xffffffffu, done);
-                if (done_bits == 0xffffffffu) {
-                    warp_done = true;
-                    break;
+                // hit word of (window, pixel): [window][pixel of the tile], coalesced
+                if (w == wtail) {   // once per tile
+                    asm volatile("" ::: "memory");
+                    hp = hits_tail + (size_t)tile * HIT_PIXELS + tid;
                 }
+                *hp = hits;
+                warp_done = __all_sync(0xffffffffu, done != 0);
+                if (warp_done) break;
             }
         }
         buf = buf == NS - 1 ? 0 : buf + 1;
     }
     cp_async_wait<0>();
-    if (BULK)   // copies still in flight target this CTA's shared memory: wait for them before it is released
-        for (int k = waited + 1; k <= issued; k++) stage_wait(S, k % NS, k);
     if (inside) {
         const size_t HW = (size_t)W * H, pix = (size_t)py * W + px;
         final_T[pix] = T;
@@ -186,63 +231,49 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
             out_depth_sil[HW + pix] = fmaf(T, __ldg(bg + 1), C4);
         }
     }
-    uint32_t m = last;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0 && m) atomicMax(&s_max[warp >> 2], m);
+    // highest n_contrib of the tile: the backward pass starts there
+    const uint32_t m = __reduce_max_sync(0xffffffffu, last);
+    __syncthreads();   // max_contrib was zeroed by thread 0 before this barrier
+    if (lane == 0 && m) atomicMax(&SM.max_contrib, m);
     __syncthreads();
-    // highest n_contrib of the upper and of the lower half of the tile (the backward pass starts there)
-    if (HALVES == 2) {
-        if (threadIdx.x == 0) tile_max_contrib[2 * tile + half] = s_max[half];
-    } else {
-        if (threadIdx.x < 2) tile_max_contrib[2 * tile + threadIdx.x] = s_max[threadIdx.x];
-    }
+    if (tid == 0) tile_max_contrib[2 * tile] = tile_max_contrib[2 * tile + 1] = SM.max_contrib;
+}
+
+template <int MINB, int CH>
+static void launch_fwd(const FwdParams& p, char* geom, const GeomLayout& GL, char* binning, const BinningLayout& BL, char* image,
+                       const ImageLayout& IL, float* out_color, float* out_depth, float* out_depth_sil, cudaStream_t s)
+{
+    constexpr int NS = 2;
+    // many resident CTAs x 24 KB: ask for the largest shared-memory carve-out (once per process and kernel)
+    static const cudaError_t attr = cudaFuncSetAttribute(blend_forward_kernel<MINB, NS, CH>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    (void)attr;
+    blend_forward_kernel<MINB, NS, CH><<<dim3(IL.tiles_x, p.band_y1 - p.band_y0), BLEND_THREADS, 0, s>>>(
+        reinterpret_cast<const uint2*>(image + IL.ranges), reinterpret_cast<const uint32_t*>(binning + BL.point_list),
+        reinterpret_cast<const SplatRec*>(geom + GL.rec), p.W, p.H, p.background, out_color, out_depth, out_depth_sil,
+        reinterpret_cast<float*>(image + IL.final_T), reinterpret_cast<uint32_t*>(image + IL.n_contrib),
+        reinterpret_cast<uint32_t*>(image + IL.tile_max_contrib), reinterpret_cast<uint32_t*>(binning + BL.hits),
+        reinterpret_cast<uint32_t*>(image + IL.hits_tail), reinterpret_cast<GeomHeader*>(geom + GL.header), (uint32_t)BL.capacity,
+        (uint32_t)p.band_y0);
 }
 
 int launch_blend_forward(const FwdParams& p, char* geom, const GeomLayout& GL, char* binning, const BinningLayout& BL,
                          char* image, const ImageLayout& IL, float* out_color, float* out_depth, float* out_depth_sil,
                          cudaStream_t s)
 {
-    const uint32_t* point_list = reinterpret_cast<const uint32_t*>(binning + BL.point_list);
     if (p.W <= 0 || p.H <= 0 || p.band_y1 <= p.band_y0) return GSB_OK;
-    // tuning knobs: CTA shape (whole tile / half tile), resident CTAs per SM the compiler must allow (the register
-    // budget), depth of the staging ring
-    static const int halves = [] { const char* e = getenv("GSB_BLEND_FWD_HALVES"); return e ? atoi(e) : 1; }();
-    static const int minb = [] { const char* e = getenv("GSB_BLEND_FWD_MINB"); return e ? atoi(e) : 0; }();
-    static const int stages = [] { const char* e = getenv("GSB_BLEND_FWD_STAGES"); return e ? atoi(e) : 2; }();
-    {
-        StageTimer _t(ST_BLEND_FWD, s);
-#define GSB_FWD_LAUNCH(MB, NS, HV) GSB_FWD_LAUNCH_CH(MB, NS, HV, 3, false)
-#define GSB_FWD_LAUNCH_CH(MB, NS, HV, CH, BK)                                                                                      \
-    do {                                                                                                                \
-        static const bool attr_set = [] {  /* many resident CTAs x 12-37 KB: ask for the largest carve-out */          \
-            cudaFuncSetAttribute(blend_forward_kernel<MB, NS, HV, CH, BK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
-            return true;                                                                                                \
-        }();                                                                                                            \
-        (void)attr_set;                                                                                                 \
-        blend_forward_kernel<MB, NS, HV, CH, BK><<<dim3(IL.tiles_x, (p.band_y1 - p.band_y0) * HV), 256 / HV, 0, s>>>(                    \
-            reinterpret_cast<const uint2*>(image + IL.ranges), point_list, reinterpret_cast<const SplatRec*>(geom + GL.rec), \
-            p.W, p.H, p.background, out_color, out_depth, out_depth_sil, reinterpret_cast<float*>(image + IL.final_T),  \
-            reinterpret_cast<uint32_t*>(image + IL.n_contrib), reinterpret_cast<uint32_t*>(image + IL.tile_max_contrib), \
-            reinterpret_cast<uint32_t*>(binning + BL.hits), reinterpret_cast<uint32_t*>(image + IL.hits_tail),          \
-            reinterpret_cast<GeomHeader*>(geom + GL.header), (uint32_t)BL.capacity, (uint32_t)p.band_y0);                                    \
+    StageTimer _t(ST_BLEND_FWD, s);
+#define GSB_FWD(MB)                                                                                                   \
+    do {                                                                                                              \
+        if (out_depth_sil) launch_fwd<MB, 5>(p, geom, GL, binning, BL, image, IL, out_color, out_depth, out_depth_sil, s); \
+        else launch_fwd<MB, 3>(p, geom, GL, binning, BL, image, IL, out_color, out_depth, out_depth_sil, s);          \
     } while (0)
-        static const bool bulk = [] { const char* e = getenv("GSB_BLEND_STAGE"); return e ? e[0] == 'b' : GSB_DEFAULT_BULK; }();
-        if (out_depth_sil) {
-            if (bulk) GSB_FWD_LAUNCH_CH(6, 2, 1, 5, true); else GSB_FWD_LAUNCH_CH(6, 2, 1, 5, false);
-        } else if (bulk && halves == 1 && stages != 3 && minb != 8) {
-            GSB_FWD_LAUNCH_CH(6, 2, 1, 3, true);
-        } else if (halves == 2) {
-            if (stages == 3) { if (minb == 12) GSB_FWD_LAUNCH(12, 3, 2); else GSB_FWD_LAUNCH(16, 3, 2); }
-            else { if (minb == 12) GSB_FWD_LAUNCH(12, 2, 2); else GSB_FWD_LAUNCH(16, 2, 2); }
-        } else {
-            if (stages == 3) GSB_FWD_LAUNCH(6, 3, 1);
-            else { if (minb == 8) GSB_FWD_LAUNCH(8, 2, 1); else GSB_FWD_LAUNCH(6, 2, 1); }
-        }
-#undef GSB_FWD_LAUNCH
-#undef GSB_FWD_LAUNCH_CH
-        GSB_LAUNCH_CHECK();
-    }
+#ifdef GSB_TUNING   // developer builds only (make tune): resident CTAs per SM the compiler must allow = the register budget
+    static const int minb = [] { const char* e = getenv("GSB_BLEND_FWD_MINB"); return e ? atoi(e) : 0; }();
+    if (minb == 5) GSB_FWD(5); else if (minb == 7) GSB_FWD(7); else if (minb == 8) GSB_FWD(8); else
+#endif
+    GSB_FWD(6);
+#undef GSB_FWD
+    GSB_LAUNCH_CHECK();
     return GSB_OK;
 }
 

@@ -20,8 +20,9 @@ constexpr int TILE_X = 16;   // config.h:16 (tile-rect membership is part of the
 constexpr int TILE_Y = 16;   // config.h:17
 constexpr int NUM_SMS = 148; // B200
 constexpr int TILE_CTR_STRIDE = 64;  // words between per-tile atomic counters (256 B)
-constexpr int HIT_BLOCKS = 32;       // 4x2-pixel blocks per 16x16 tile (one quarter-warp each)
-constexpr int HIT_WINDOW = 32;       // list entries covered by one hit word
+constexpr int BLEND_THREADS = TILE_X * TILE_Y;   // one blend CTA per tile, one thread per pixel
+constexpr int HIT_PIXELS = TILE_X * TILE_Y;      // hit words per window of a tile's list: one per pixel
+constexpr int HIT_WINDOW = 32;                   // list entries covered by one hit word
 
 // ---------------------------------------------------------------------------------------
 // Packed per-Gaussian splat record: 48 bytes, 16-byte aligned, gathered by the blend
@@ -103,14 +104,14 @@ struct ImageLayout {
         L.final_T = take(HW * 4);
         L.n_contrib = take(HW * 4);
         L.ranges = take(T * 8);
-        L.tile_max_contrib = take(T * 8);   // highest n_contrib of the upper / lower half of each tile
+        L.tile_max_contrib = take(T * 8);   // highest n_contrib of each tile (both words)
         // one counter per TILE_CTR_STRIDE words: adjacent tiles land in different L2 slices, so the
         // ~2 M atomics of a frame are not funnelled through the few slices a dense array maps to
         // word 0: instances of Gaussians touching <= 4 tiles (their atomics return the slot, kept in GeomLayout::ranks);
         // word 1: instances of larger Gaussians (slots claimed by `duplicate` through tile_cursor)
         L.tile_count = take((T + 1) * 4 * TILE_CTR_STRIDE);   // + one slot: completion counter of the preprocess CTAs
         L.tile_cursor = take(T * 4 * TILE_CTR_STRIDE);   // next free slot for the larger Gaussians of each tile
-        L.hits_tail = take(T * HIT_BLOCKS * 4);          // hit words of each tile's last, partial window (blend kernels)
+        L.hits_tail = take(T * HIT_PIXELS * 4);          // hit words of each tile's last, partial window (blend kernels)
         L.total = off;
         return L;
     }
@@ -127,11 +128,12 @@ struct BinningLayout {
     // point_list sits at offset 0 whatever the capacity (gsb_backward relies on it): the
     // depth-sorted Gaussian ids, tile after tile.  `pairs` holds the unsorted
     // (depth bits << 32 | id) records bucketed by tile.  `hits` holds, per full 32-entry window
-    // of a tile's list and per 4x2-pixel block, the bit mask of the entries that were blended
-    // into at least one pixel of the block (written by the forward blend, consumed by the
-    // backward blend).  Window w of a tile whose list starts at s lives at index (s >> 5) + w,
+    // of a tile's list and per PIXEL of the tile (thread order of the blend kernels: warp = 8x4
+    // region, lane = row-major pixel of the region), the bit mask of the entries that were blended
+    // into that pixel (written by the forward blend; the backward blend replays exactly those
+    // pairs).  Window w of a tile whose list starts at s lives at row (s >> 5) + w (256 words),
     // which never collides with the next tile's windows; each tile's last, partial window is
-    // kept in the image blob (ImageLayout::hits_tail).
+    // kept in the image blob (ImageLayout::hits_tail).  32 B per instance.
     size_t point_list, hits, pairs, total;
     long long capacity;
     __host__ __device__ static BinningLayout make(long long cap)
@@ -142,7 +144,7 @@ struct BinningLayout {
         if (cap < 1) cap = 1;
         L.capacity = cap;
         L.point_list = take((size_t)cap * 4 + 64);
-        L.hits = take(((size_t)cap / HIT_WINDOW + 1) * HIT_BLOCKS * 4);
+        L.hits = take(((size_t)cap / HIT_WINDOW + 1) * HIT_PIXELS * 4);
         L.pairs = take((size_t)cap * 8);
         L.total = off;
         return L;

@@ -137,13 +137,12 @@ __device__ __forceinline__ float rcp_approx(float x)
     return r;
 }
 
-// Address of the hit word of (window w, block) of a tile whose list is [start, start + len)
+// Row of HIT_PIXELS hit words of window w of a tile whose list is [start, start + len)
 // (see BinningLayout::hits / ImageLayout::hits_tail).
-__device__ __forceinline__ uint32_t* hit_word(uint32_t* hits_full, uint32_t* hits_tail, uint32_t tile, uint32_t start,
-                                              uint32_t len, uint32_t w, uint32_t block)
+__device__ __forceinline__ uint32_t* hit_words(uint32_t* hits_full, uint32_t* hits_tail, uint32_t tile, uint32_t start,
+                                               uint32_t len, uint32_t w)
 {
-    return w < (len >> 5) ? hits_full + ((size_t)(start >> 5) + w) * HIT_BLOCKS + block
-                          : hits_tail + (size_t)tile * HIT_BLOCKS + block;
+    return w < (len >> 5) ? hits_full + ((size_t)(start >> 5) + w) * HIT_PIXELS : hits_tail + (size_t)tile * HIT_PIXELS;
 }
 
 }  // namespace gsb

@@ -104,15 +104,18 @@ class SymmetricExchange:
         return t
 
     def allreduce(self, t: torch.Tensor, use_multicast: bool = True):
-        """In-place sum over the ranks of a tensor obtained from ``alloc`` (numel % 4 == 0)."""
+        """In-place sum over the ranks of a tensor obtained from ``alloc``.  The kernel moves 16-byte words: a length that
+        is not a multiple of 4 floats (the ``[14, P]`` block of an odd P) is rounded up into the padding ``alloc`` reserved
+        behind the tensor, which is zero on every rank and stays zero."""
         C = self._C
         off = t.data_ptr() - self.buf.data_ptr()
-        if off < 0 or off + t.numel() * 4 > self.capacity * 4 or t.numel() % 4:
-            raise ValueError("tensor is not a 16-byte-granular slice of the symmetric allocation")
+        n4 = (t.numel() + 3) // 4 * 4
+        if off < 0 or off % 16 or off + n4 * 4 > self.capacity * 4:
+            raise ValueError("tensor is not a 16-byte-aligned slice of the symmetric allocation")
         peer = (C.c_void_p * self.world)(*[int(p) + off for p in self.hdl.buffer_ptrs])
         mc = self.multicast_ptr + off if (self.multicast_ptr and use_multicast) else None
         stream = torch.cuda.current_stream(self.dev).cuda_stream
-        self._lib.check(self.L.gsb_exchange_allreduce(mc, peer, self._sync, t.numel(), self.rank, self.world, stream))
+        self._lib.check(self.L.gsb_exchange_allreduce(mc, peer, self._sync, n4, self.rank, self.world, stream))
 
 
 def allreduce_gradients(block: GradBlock, average: bool = False, group=None, async_op: bool = False):
@@ -138,7 +141,9 @@ def shard_keyframes(keyframes: List, rank: Optional[int] = None, world_size: Opt
 def tile_row_bands(tiles_y: int, world_size: int, weights: Optional[List[float]] = None) -> List[Tuple[int, int]]:
     """Contiguous bands ``[begin, end)`` of tile rows, one per rank, covering ``[0, tiles_y)``.
     ``weights`` (per tile row, e.g. instance counts of the previous frame) balances the bands by
-    load instead of by height; bands may be empty when there are more ranks than rows."""
+    load instead of by height; bands may be empty when there are more ranks than rows (or one row carries most of the load).
+    An empty band is returned as ``(k, k)``; hand it to the rasterizer through ``band_for_rasterizer`` -- in
+    ``gsb_raster_args`` the pair ``(0, 0)`` means "the whole image"."""
     if world_size <= 0:
         raise ValueError("world_size must be positive")
     if weights is None:
@@ -159,6 +164,16 @@ def tile_row_bands(tiles_y: int, world_size: int, weights: Optional[List[float]]
         bands.append((begin, end))
         begin = end
     return bands
+
+
+def band_for_rasterizer(band: Tuple[int, int], tiles_y: int) -> Tuple[int, int]:
+    """``gsb_raster_args::tile_row_begin / tile_row_end`` for a band of ``tile_row_bands``.  ``(0, 0)`` is the C ABI's
+    "no shard" value (a zero-initialised args struct renders the whole image), so an EMPTY band -- which ``tile_row_bands``
+    legitimately returns as ``(0, 0)`` when the first rows are heavy -- is moved to the equivalent ``(tiles_y, tiles_y)``."""
+    b0, b1 = int(band[0]), int(band[1])
+    if b1 <= b0:
+        return (int(tiles_y), int(tiles_y))
+    return (b0, b1)
 
 
 def broadcast_densification(new_rows: Optional[torch.Tensor], src: int = 0, group=None) -> torch.Tensor:

@@ -77,7 +77,9 @@ class Frame:
         a.viewmatrix, a.projmatrix, a.cam_pos = _p(self.view), _p(self.proj), _p(self.campos)
         a.tan_fovx, a.tan_fovy, a.prefiltered = self.tanfovx, self.tanfovy, 0
         if self.tile_rows is not None:
-            a.tile_row_begin, a.tile_row_end = int(self.tile_rows[0]), int(self.tile_rows[1])
+            # an empty band must not be (0, 0): that pair is the C ABI's "whole image" (include/gsb.h, gsb_raster_args)
+            from .distributed import band_for_rasterizer
+            a.tile_row_begin, a.tile_row_end = band_for_rasterizer(self.tile_rows, (self.H + 15) // 16)
         return a
 
     def _stream(self):

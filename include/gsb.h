@@ -79,8 +79,8 @@ typedef struct gsb_raster_args {
     const float* opacities;      /* [P] */
     const float* scales;         /* [P,3] or NULL */
     float scale_modifier;
-    const float* rotations;      /* [P,4] (w,x,y,z), used as given, NOT normalised (forward.cu:127) */
-    const float* cov3D_precomp;  /* [P,6] or NULL (exactly one of scales+rotations / cov3D_precomp) */
+    const float* rotations;      /* [P,4] (w,x,y,z), used as given, NOT normalised (forward.cu:127); 16-byte aligned */
+    const float* cov3D_precomp;  /* [P,6] or NULL (exactly one of scales+rotations / cov3D_precomp); 8-byte aligned */
     const float* viewmatrix;     /* [16] */
     const float* projmatrix;     /* [16] */
     const float* cam_pos;        /* [3] (only read on the SH path) */
@@ -89,7 +89,8 @@ typedef struct gsb_raster_args {
     /* Tile-row shard (multi-GPU; not in the reference): only the 16-pixel tile rows
      * [tile_row_begin, tile_row_end) are binned, sorted and blended; pixels outside the band are NOT written,
      * gradients hold this band's share (summing the bands' images and gradients gives the full frame).
-     * radii are unaffected.  0, 0 = the whole image. */
+     * radii are unaffected.  0, 0 = the whole image (what a zero-initialised struct asks for); an EMPTY band is therefore
+     * passed as (k, k) with k > 0, e.g. (tile rows of the image, same): nothing is binned or blended, all gradients are 0. */
     int tile_row_begin, tile_row_end;
 } gsb_raster_args;
 

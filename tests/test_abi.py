@@ -75,6 +75,16 @@ def test_validation_errors_match_reference_messages():
     rc = L.gsb_forward_ws(C.byref(a), dummy, 1 << 30, dummy, 1 << 30, 100, dummy, 1 << 30, dummy, dummy, None, None)
     assert rc == -1 and b"tile row band" in L.gsb_last_error()
     a.tile_row_begin, a.tile_row_end = 0, 0
+    # pointer alignment the kernels rely on (128-bit loads of rotations, 64-bit loads of cov3D_precomp)
+    a.rotations = C.c_void_p(256 + 4)
+    rc = L.gsb_forward_ws(C.byref(a), dummy, 1 << 30, dummy, 1 << 30, 100, dummy, 1 << 30, dummy, dummy, None, None)
+    assert rc == -1 and b"rotations must be 16-byte aligned" in L.gsb_last_error()
+    a.rotations = a.scales = None
+    a.cov3D_precomp = C.c_void_p(256 + 4)
+    rc = L.gsb_forward_ws(C.byref(a), dummy, 1 << 30, dummy, 1 << 30, 100, dummy, 1 << 30, dummy, dummy, None, None)
+    assert rc == -1 and b"cov3D_precomp must be 8-byte aligned" in L.gsb_last_error()
+    a.cov3D_precomp = None
+    a.rotations = a.scales = dummy
     ptrs = (C.c_void_p * 2)(256, 512)
     assert L.gsb_exchange_allreduce(None, ptrs, ptrs, 1002, 0, 2, None) == -1          # n % 4 != 0
     assert L.gsb_exchange_allreduce(None, ptrs, ptrs, 1000, 2, 2, None) == -1          # rank out of range

@@ -1,10 +1,12 @@
-# usage: gpu_sweep.sh "ENV1=v ENV2=v" "ENV1=v" ...   (one bench --quick run per argument; "" = defaults)
-mkdir -p gpurun_out; : > gpurun_out/sweep.json
-for spec in "$@"; do env $spec python bench.py --quick --steps 30 >> gpurun_out/sweep.json 2>&1; done
-python - <<'PY'
-import json
-for l in open('gpurun_out/sweep.json'):
-    try: d=json.loads(l)
-    except Exception: print(l.strip()[:200]); continue
-    print(round(d['value']), d['env'], {k:v for k,v in d['stages_us'].items()})
-PY
+# knob sweep on the tuning build: bash tools/gpu_sweep.sh TAG VAR=a,b,c [VAR2=...]   (each value: one quick bench line)
+TAG=${1:-sweep}; shift
+mkdir -p gpurun_out
+export GSB_LIB=$PWD/gsorb_slam_b200/libgsb_tune.so
+for spec in "$@"; do
+  var=${spec%%=*}; vals=${spec#*=}
+  for v in ${vals//,/ }; do
+    echo "== $var=$v" >> gpurun_out/${TAG}_sweep.txt
+    env $var=$v timeout 300 python bench.py --quick --steps 30 2>/dev/null | cut -c1-400 >> gpurun_out/${TAG}_sweep.txt
+  done
+done
+cat gpurun_out/${TAG}_sweep.txt
