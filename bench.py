@@ -39,6 +39,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+E2E_DEPTH = int(os.environ.get("GSB_BENCH_E2E_DEPTH", "3"))   # host-fed frames in flight in the e2e leg
 METRIC = "fwd+bwd frames/sec @1M Gaussians 640x480"
 UNIT = "frames/s"
 
@@ -163,7 +164,7 @@ def run_ours(args):
     if world > 1 and args.exchange != "nccl":
         try:
             from gsorb_slam_b200.distributed import SymmetricExchange
-            xch = SymmetricExchange(14 * P, dev)
+            xch = SymmetricExchange((14 * P + 64) * (1 + E2E_DEPTH), dev)   # the timed block + one per e2e slot
             use_mc = bool(xch.multicast_ptr) and (args.exchange == "multimem" or (args.exchange == "auto" and world >= 4))
             xch_kind = "libgsb multimem (NVSwitch in-switch reduce)" if use_mc else "libgsb P2P (peer loads/stores over NVLink)"
         except Exception as e:   # no symmetric memory on this box
@@ -191,6 +192,30 @@ def run_ours(args):
                 xch.allreduce(block, use_multicast=use_mc)
             else:
                 dist.all_reduce(block)
+
+    # N > 1: the exchange kernel is CHECKED here, on this box, against NCCL's all-reduce of the same per-rank blocks
+    exchange_checked = None
+    if world > 1:
+        fr.forward()
+        _lib.check(L.gsb_backward(C.byref(fr._args), -1, fr.radii.data_ptr(), fr.geom.data_ptr(), fr.binning.data_ptr(),
+                                  fr.img.data_ptr(), dL.data_ptr(), C.byref(g), stream))
+        want = block.clone()
+        dist.all_reduce(want)
+        if xch is not None:
+            xch.allreduce(block, use_multicast=use_mc)
+        else:
+            dist.all_reduce(block)
+        torch.cuda.synchronize()
+        err = float((block - want).abs().max().item())
+        scale = float(want.abs().max().item())
+        same_everywhere = block.clone()
+        dist.broadcast(same_everywhere, src=0)
+        exchange_checked = {"against": "torch.distributed all_reduce (NCCL) of the same blocks", "max_abs_err": err,
+                            "max_abs_err_over_scale": err / max(scale, 1e-30), "bit_equal_to_nccl": bool(torch.equal(block, want)),
+                            "replicas_bit_identical": bool(torch.equal(block, same_everywhere)), "finite": bool(torch.isfinite(block).all().item())}
+        flag = torch.tensor([0 if (err <= 1e-5 * scale and exchange_checked["replicas_bit_identical"]) else 1], device=dev)
+        dist.all_reduce(flag)
+        exchange_checked["ok_on_all_ranks"] = int(flag.item()) == 0
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -271,27 +296,132 @@ def run_ours(args):
     ha.scales, ha.scale_modifier, ha.rotations = h["scales"].data_ptr(), 1.0, h["rots"].data_ptr()
     ha.viewmatrix, ha.projmatrix, ha.cam_pos = h["view"].data_ptr(), h["proj"].data_ptr(), h["campos"].data_ptr()
     ha.tan_fovx, ha.tan_fovy = float(sc.cam.tanfovx), float(sc.cam.tanfovy)
-    ho = dict(color=torch.empty((3, H, W)).pin_memory(), depth=torch.empty((1, H, W)).pin_memory(),
-              radii=torch.empty(P, dtype=torch.int32).pin_memory(), block=torch.empty(14 * P).pin_memory())
-    hg = _lib.GradOutputs()
-    hb = ho["block"].data_ptr()
-    hg.dL_dmean3D, hg.dL_dcolor, hg.dL_dopacity, hg.dL_dscale, hg.dL_drot = hb, hb + 12 * P, hb + 24 * P, hb + 28 * P, hb + 40 * P
-    nscratch = int(L.gsb_host_scratch_bytes(P, 0, W, H, max_rendered))
-    scratch = torch.empty(nscratch, dtype=torch.uint8, device=dev)
     h2d = sum(h[k].numel() * 4 for k in h)
     d2h = (3 * HW + HW + P + 14 * P) * 4
+    # Three frames in flight, each on its own stream with its own device state and pinned output set: every step uploads ITS
+    # inputs and downloads ITS image, depth, radii and gradient block; frame i's download runs under frame i+1's upload and
+    # frame i+2's kernels (PCIe is full duplex, the copy engines are separate from the SMs).
+    #   N = 1: gsb_forward_backward_host_async through gsorb_slam_b200/host.py (HostPipeline).
+    #   N > 1: the same pipeline spelled out over the device entry points, because the exchange step sits between the backward
+    #          and the gradient download: upload -> gsb_forward_ws + gsb_backward into the slot's block of the symmetric
+    #          allocation -> gsb_exchange_allreduce on ONE exchange stream (all ranks issue the slots in the same order; the
+    #          handshake scratch is shared) -> download of the REDUCED block.
+    if world == 1:
+        from gsorb_slam_b200.host import HostPipeline
+        pipe = HostPipeline(P, W, H, max_rendered=max_rendered, depth=E2E_DEPTH, device=dev)
+        slot_streams = [sl.stream for sl in pipe.slots]
 
-    def step_e2e():
-        rc = L.gsb_forward_backward_host(C.byref(ha), max_rendered, h["dL"].data_ptr(), ho["color"].data_ptr(), ho["depth"].data_ptr(),
-                                         ho["radii"].data_ptr(), C.byref(hg), scratch.data_ptr(), nscratch, stream)
-        _lib.check(rc)
-        if world > 1:   # the exchange step of the sharded loop, on the device copy of the block is not available here:
-            pass        # e2e at N > 1 = N independent host-fed replicas (documented in DESIGN.md)
+        def e2e_submit(i):
+            pipe.submit(ha, h["dL"].data_ptr())
 
-    e2e_steps = max(3, min(args.steps, 20))
-    ms_e2e = timed(step_e2e, e2e_steps, 3) / e2e_steps
+        def e2e_drain():
+            pipe.drain()
+        e2e_api = f"gsb_forward_backward_host_async, {E2E_DEPTH} frames in flight (HostPipeline, pinned host buffers)"
+        e2e_probe = lambda: (pipe.slots[0].color, pipe.slots[0].block)
+    else:
+        class _Slot:
+            pass
+        xs = torch.cuda.Stream(device=dev)   # exchange stream
+        slots = []
+        for k in range(E2E_DEPTH):
+            sl = _Slot()
+            sl.stream = torch.cuda.Stream(device=dev)
+            sl.fr = frame_from_scene(sc, device=dev, sync_free=True, max_rendered=max_rendered, run=False)
+            sl.fr._alloc_ws()
+            sl.dL = torch.empty_like(dL)
+            sl.block = xch.alloc(14 * P) if xch is not None else torch.empty(14 * P, dtype=torch.float32, device=dev)
+            sl.g = _lib.GradOutputs()
+            bp2 = sl.block.data_ptr()
+            sl.g.dL_dmean3D, sl.g.dL_dcolor, sl.g.dL_dopacity, sl.g.dL_dscale, sl.g.dL_drot = bp2, bp2 + 12 * P, bp2 + 24 * P, bp2 + 28 * P, bp2 + 40 * P
+            sl.g.dL_dmean2D, sl.g.dL_dconic, sl.g.dL_dcov3D, sl.g.dL_dsh = sp, sp + 12 * P, sp + 28 * P, None
+            sl.out = dict(color=torch.empty((3, H, W)).pin_memory(), depth=torch.empty((1, H, W)).pin_memory(),
+                          radii=torch.empty(P, dtype=torch.int32).pin_memory(), block=torch.empty(14 * P).pin_memory())
+            sl.e1, sl.e2 = torch.cuda.Event(), torch.cuda.Event()
+            slots.append(sl)
+        slot_streams = [sl.stream for sl in slots] + [xs]
+        up_pairs = lambda f: ((f.means3D, h["means"]), (f.colors, h["colors"]), (f.opacities, h["opac"]), (f.scales, h["scales"]),
+                              (f.rotations, h["rots"]), (f.bg, h["bg"]), (f.view, h["view"]), (f.proj, h["proj"]), (f.campos, h["campos"]))
+
+        def e2e_submit(i):
+            sl = slots[i % E2E_DEPTH]
+            f = sl.fr
+            sl.stream.synchronize()   # the slot's previous frame has landed in its host buffers
+            with torch.cuda.stream(sl.stream):
+                for dst, src in up_pairs(f):
+                    dst.copy_(src.view(dst.shape), non_blocking=True)
+                sl.dL.copy_(h["dL"], non_blocking=True)
+                st = sl.stream.cuda_stream
+                _lib.check(L.gsb_forward_ws(C.byref(f._args), f.geom.data_ptr(), f.geom.numel(), f.binning.data_ptr(), f.binning.numel(),
+                                            max_rendered, f.img.data_ptr(), f.img.numel(), f.color.data_ptr(), f.depth.data_ptr(),
+                                            f.radii.data_ptr(), st))
+                _lib.check(L.gsb_backward(C.byref(f._args), -1, f.radii.data_ptr(), f.geom.data_ptr(), f.binning.data_ptr(),
+                                          f.img.data_ptr(), sl.dL.data_ptr(), C.byref(sl.g), st))
+                sl.e1.record(sl.stream)
+                sl.out["color"].copy_(f.color, non_blocking=True)
+                sl.out["depth"].copy_(f.depth, non_blocking=True)
+                sl.out["radii"].copy_(f.radii, non_blocking=True)
+            xs.wait_event(sl.e1)
+            with torch.cuda.stream(xs):
+                if xch is not None:
+                    xch.allreduce(sl.block, use_multicast=use_mc)
+                else:
+                    dist.all_reduce(sl.block)
+                sl.e2.record(xs)
+            sl.stream.wait_event(sl.e2)
+            with torch.cuda.stream(sl.stream):
+                sl.out["block"].copy_(sl.block, non_blocking=True)
+
+        def e2e_drain():
+            for sl in slots:
+                sl.stream.synchronize()
+        e2e_api = (f"pinned host buffers -> gsb_forward_ws + gsb_backward -> exchange ({xch_kind}) -> download of the reduced block; "
+                   f"{E2E_DEPTH} frames in flight per rank")
+        e2e_probe = lambda: (slots[0].out["color"], slots[0].out["block"])
+
+    def e2e_run(steps):
+        """K pipelined steps bracketed by two events on the current stream (every slot stream starts after the first and is
+        joined before the second): device time of the whole region; max over ranks below."""
+        cur = torch.cuda.current_stream(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(cur)
+        for st in slot_streams:
+            st.wait_event(a)
+        for i in range(steps):
+            e2e_submit(i)
+        e2e_drain()
+        for st in slot_streams:
+            e = torch.cuda.Event()
+            e.record(st)
+            cur.wait_event(e)
+        b.record(cur)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b)
+
+    e2e_steps = max(6, min(args.steps, 30))
+    e2e_run(4)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e2e_run(e2e_steps)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_e2e = ms / e2e_steps
     e2e_value = world * 1000.0 / ms_e2e
-    e2e_ok = bool(np.isfinite(ho["color"].numpy()).all())
+    pc, pb = e2e_probe()
+    e2e_ok = bool(np.isfinite(pc.numpy()).all()) and bool(np.isfinite(pb.numpy()).all())
+    # serial latency of ONE host-fed frame (upload -> kernels -> download, nothing else in flight), for reference
+    ms_e2e_single = None
+    if world == 1:
+        nscratch = pipe.nscratch
+        hg1 = pipe.slots[0].grads
+
+        def step_single():
+            _lib.check(L.gsb_forward_backward_host(C.byref(ha), max_rendered, h["dL"].data_ptr(), pipe.slots[0].color.data_ptr(),
+                                                   pipe.slots[0].depth.data_ptr(), pipe.slots[0].radii.data_ptr(), C.byref(hg1),
+                                                   pipe.slots[0].scratch.data_ptr(), nscratch, stream))
+        ms_e2e_single = timed(step_single, 8, 2) / 8
 
     # ---- roofline: per-stage device time over the same number of steps ----
     for _ in range(2):
@@ -421,9 +551,12 @@ def run_ours(args):
                            "l2": "flushed between steps (512 MiB memset, outside the event brackets)",
                            "parallelism": "single GPU" if world == 1 else f"keyframe-batch shard x{world} + one sum all-reduce of the [14,P] gradient block: {xch_kind}"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
-                        "steps": e2e_steps, "finite": e2e_ok,
-                        "api": "gsb_forward_backward_host (pinned host buffers)"},
+                        "steps": e2e_steps, "finite": e2e_ok, "api": e2e_api, "frames_in_flight": E2E_DEPTH,
+                        "single_frame_latency_ms": ms_e2e_single,
+                        "l2": "every step's inputs arrive from host memory (no flush needed)"},
                 "gpu_launches": launches_timed, "clocks": clk.summary(), "roofline": roofline}
+        if exchange_checked is not None:
+            line["exchange_checked"] = exchange_checked
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if iteration is not None:

@@ -67,6 +67,7 @@ SIGNATURES = {
     "gsb_adam_step_groups": (_i, [_i, C.POINTER(_ll), C.POINTER(_f), _vp, _vp, _vp, _vp, _f, _f, _f, _ll, _vp]),
     "gsb_host_scratch_bytes": (_sz, [_i, _i, _i, _i, _ll]),
     "gsb_forward_backward_host": (_ll, [C.POINTER(RasterArgs), _ll, _vp, _vp, _vp, _vp, C.POINTER(GradOutputs), _vp, _sz, _vp]),
+    "gsb_forward_backward_host_async": (_i, [C.POINTER(RasterArgs), _ll, _vp, _vp, _vp, _vp, C.POINTER(GradOutputs), _vp, _sz, _vp, _vp]),
     "gsb_debug_image_state": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "gsb_debug_binning_state": (_i, [_vp, _vp, _ll, _vp, _vp]),
     "gsb_debug_geometry_state": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),

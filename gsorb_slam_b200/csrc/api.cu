@@ -96,6 +96,16 @@ static int validate(const gsb_raster_args* a, bool need_colors, bool need_opacit
     return GSB_OK;
 }
 
+// host-buffer entry points: the arrays are copied into 256-byte aligned device scratch, so host alignment is irrelevant
+static int validate_host(const gsb_raster_args* a)
+{
+    if (!a) return fail(GSB_ERR_INVALID_ARGUMENT, "args is NULL");
+    gsb_raster_args t = *a;
+    if (t.rotations) t.rotations = reinterpret_cast<const float*>(uintptr_t(256));
+    if (t.cov3D_precomp) t.cov3D_precomp = reinterpret_cast<const float*>(uintptr_t(256));
+    return validate(&t, true);
+}
+
 static FwdParams make_params(const gsb_raster_args* a)
 {
     FwdParams p;
@@ -436,12 +446,18 @@ size_t gsb_host_scratch_bytes(int P, int M, int width, int height, long long max
     return HostLayout::make(P, M, width, height, max_rendered).total;
 }
 
-long long gsb_forward_backward_host(const gsb_raster_args* host_args, long long max_rendered, const float* dL_dpix_host,
-                                    float* out_color_host, float* out_depth_host, int* radii_host,
-                                    const gsb_grad_outputs* host_grads, void* device_scratch, size_t device_scratch_bytes,
-                                    gsb_stream_t stream)
+// Shared body of the two host-buffer entry points.  Three streams per frame: ALL uploads go through one per-thread upload
+// stream, ALL downloads through one per-thread download stream (a stream that alternates directions gets little of the
+// link's duplex bandwidth: tools/pcie_pipe_probe.py measured 2.0 ms per 60 + 65 MB step that way against 1.36 ms with one
+// stream per direction), the kernels run on the caller's `stream`, events chain the three.  Inside one frame the upload of
+// dL/dpixel runs under the forward pass and the download of image / depth / radii under the backward pass; across frames in
+// flight (gsb_forward_backward_host_async with K scratch sets and K streams) frame i's gradient download runs under
+// frame i+1's kernels and frame i+2's upload.  `stream` completes only after the frame's last download.
+static int host_frame(const gsb_raster_args* host_args, long long max_rendered, const float* dL_dpix_host, float* out_color_host,
+                      float* out_depth_host, int* radii_host, const gsb_grad_outputs* host_grads, void* device_scratch,
+                      size_t device_scratch_bytes, unsigned int* status_host, gsb_stream_t stream)
 {
-    if (int rc = validate(host_args, true)) return rc;
+    if (int rc = validate_host(host_args)) return rc;
     if (max_rendered < 0 || max_rendered >= (1ll << 30)) return fail(GSB_ERR_INVALID_ARGUMENT, "max_rendered out of range");
     const gsb_raster_args& h = *host_args;
     const int P = h.P, M = h.shs ? h.M : 0, W = h.width, H = h.height;
@@ -449,31 +465,29 @@ long long gsb_forward_backward_host(const gsb_raster_args* host_args, long long 
     if (!device_scratch || device_scratch_bytes < L.total)
         return fail(GSB_ERR_WORKSPACE, "device scratch too small (%zu < %zu)", device_scratch_bytes, L.total);
     cudaStream_t s = (cudaStream_t)stream;
-    // A second, per-thread cached stream carries the transfers that can overlap kernels: the upload of dL/dpixel
-    // (needed only by the backward) runs under the forward pass, the download of image / depth / radii under the
-    // backward pass.  PCIe is full duplex and the two directions use different copy engines.
-    struct SideStream { cudaStream_t s2 = nullptr; cudaEvent_t ev_dl = nullptr, ev_fwd = nullptr, ev_img = nullptr; };
-    static thread_local SideStream side[64];   // one per device this thread has used (streams and events are per device)
+    struct HostStreams { cudaStream_t up = nullptr, dn = nullptr; cudaEvent_t ev_prev, ev_params, ev_dl, ev_fwd, ev_bwd, ev_dn; };
+    static thread_local HostStreams streams[64];   // one set per device this thread has used (streams and events are per device)
     int device = 0;
     GSB_CUDA_CHECK(cudaGetDevice(&device));
     if (device < 0 || device >= 64) return fail(GSB_ERR_UNSUPPORTED, "device ordinal %d out of range", device);
-    SideStream& ss = side[device];
-    if (!ss.s2) {
-        GSB_CUDA_CHECK(cudaStreamCreateWithFlags(&ss.s2, cudaStreamNonBlocking));
-        GSB_CUDA_CHECK(cudaEventCreateWithFlags(&ss.ev_dl, cudaEventDisableTiming));
-        GSB_CUDA_CHECK(cudaEventCreateWithFlags(&ss.ev_fwd, cudaEventDisableTiming));
-        GSB_CUDA_CHECK(cudaEventCreateWithFlags(&ss.ev_img, cudaEventDisableTiming));
+    HostStreams& hs = streams[device];
+    if (!hs.up) {
+        GSB_CUDA_CHECK(cudaStreamCreateWithFlags(&hs.up, cudaStreamNonBlocking));
+        GSB_CUDA_CHECK(cudaStreamCreateWithFlags(&hs.dn, cudaStreamNonBlocking));
+        for (cudaEvent_t* e : {&hs.ev_prev, &hs.ev_params, &hs.ev_dl, &hs.ev_fwd, &hs.ev_bwd, &hs.ev_dn})
+            GSB_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
-    cudaStream_t s2 = ss.s2;
-    cudaEvent_t ev_dl = ss.ev_dl, ev_fwd = ss.ev_fwd, ev_img = ss.ev_img;
     char* d = (char*)device_scratch;
     const size_t Pz = (size_t)P, HW = (size_t)W * H;
-    auto up_on = [&](cudaStream_t st, size_t off, const void* src, size_t bytes) -> const float* {
+    auto up = [&](size_t off, const void* src, size_t bytes) -> const float* {
         if (!src || !bytes) return nullptr;
-        cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, hs.up);
         return reinterpret_cast<const float*>(d + off);
     };
-    auto up = [&](size_t off, const void* src, size_t bytes) { return up_on(s, off, src, bytes); };
+    // an event is consumed by the cudaStreamWaitEvent issued right after its record (the wait snapshots the record), so the
+    // per-thread events can be re-recorded by the next frame while this one is still in flight
+    GSB_CUDA_CHECK(cudaEventRecord(hs.ev_prev, s));            // the scratch may still be in use by earlier work on `stream`
+    GSB_CUDA_CHECK(cudaStreamWaitEvent(hs.up, hs.ev_prev, 0));
     gsb_raster_args a = h;
     a.means3D = up(L.means, h.means3D, Pz * 12);
     a.colors_precomp = up(L.colors, h.colors_precomp, Pz * 12);
@@ -486,23 +500,22 @@ long long gsb_forward_backward_host(const gsb_raster_args* host_args, long long 
     a.viewmatrix = up(L.view, h.viewmatrix, 64);
     a.projmatrix = up(L.proj, h.projmatrix, 64);
     a.cam_pos = up(L.campos, h.cam_pos, 12);
-    GSB_CUDA_CHECK(cudaEventRecord(ev_fwd, s));       // s2 must not start before earlier work on `stream` (scratch reuse)
-    GSB_CUDA_CHECK(cudaStreamWaitEvent(s2, ev_fwd, 0));
-    const float* dpix = dL_dpix_host ? up_on(s2, L.dpix, dL_dpix_host, HW * 12) : nullptr;
-    GSB_CUDA_CHECK(cudaEventRecord(ev_dl, s2));
+    GSB_CUDA_CHECK(cudaEventRecord(hs.ev_params, hs.up));
+    const float* dpix = dL_dpix_host ? up(L.dpix, dL_dpix_host, HW * 12) : nullptr;
+    GSB_CUDA_CHECK(cudaEventRecord(hs.ev_dl, hs.up));
     GSB_CUDA_CHECK(cudaGetLastError());
     float* oc = reinterpret_cast<float*>(d + L.out_color);
     float* od = reinterpret_cast<float*>(d + L.out_depth);
     int* rd = reinterpret_cast<int*>(d + L.radii);
+    GSB_CUDA_CHECK(cudaStreamWaitEvent(s, hs.ev_params, 0));
     if (int rc = gsb_forward_ws(&a, d + L.geom, L.GL.total, d + L.binning, L.BL.total, max_rendered, d + L.image, L.IL.total, oc,
                                 od, rd, stream))
         return rc;
-    GSB_CUDA_CHECK(cudaEventRecord(ev_fwd, s));
-    GSB_CUDA_CHECK(cudaStreamWaitEvent(s2, ev_fwd, 0));
-    if (out_color_host) GSB_CUDA_CHECK(cudaMemcpyAsync(out_color_host, oc, HW * 12, cudaMemcpyDeviceToHost, s2));
-    if (out_depth_host) GSB_CUDA_CHECK(cudaMemcpyAsync(out_depth_host, od, HW * 4, cudaMemcpyDeviceToHost, s2));
-    if (radii_host && P) GSB_CUDA_CHECK(cudaMemcpyAsync(radii_host, rd, Pz * 4, cudaMemcpyDeviceToHost, s2));
-    GSB_CUDA_CHECK(cudaEventRecord(ev_img, s2));
+    GSB_CUDA_CHECK(cudaEventRecord(hs.ev_fwd, s));
+    GSB_CUDA_CHECK(cudaStreamWaitEvent(hs.dn, hs.ev_fwd, 0));
+    if (out_color_host) cudaMemcpyAsync(out_color_host, oc, HW * 12, cudaMemcpyDeviceToHost, hs.dn);
+    if (out_depth_host) cudaMemcpyAsync(out_depth_host, od, HW * 4, cudaMemcpyDeviceToHost, hs.dn);
+    if (radii_host && P) cudaMemcpyAsync(radii_host, rd, Pz * 4, cudaMemcpyDeviceToHost, hs.dn);
     if (dpix && host_grads) {
         gsb_grad_outputs g;
         auto dev = [&](size_t off, const float* host) { return host ? reinterpret_cast<float*>(d + off) : nullptr; };
@@ -511,20 +524,47 @@ long long gsb_forward_backward_host(const gsb_raster_args* host_args, long long 
         g.dL_dmean3D = dev(L.g_mean3D, host_grads->dL_dmean3D); g.dL_dcov3D = dev(L.g_cov3D, host_grads->dL_dcov3D);
         g.dL_dsh = M ? dev(L.g_sh, host_grads->dL_dsh) : nullptr; g.dL_dscale = a.scales ? dev(L.g_scale, host_grads->dL_dscale) : nullptr;
         g.dL_drot = a.rotations ? dev(L.g_rot, host_grads->dL_drot) : nullptr;
-        GSB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_dl, 0));
+        GSB_CUDA_CHECK(cudaStreamWaitEvent(s, hs.ev_dl, 0));
         if (int rc = gsb_backward(&a, -1, rd, d + L.geom, d + L.binning, d + L.image, dpix, &g, stream)) return rc;
+        GSB_CUDA_CHECK(cudaEventRecord(hs.ev_bwd, s));
+        GSB_CUDA_CHECK(cudaStreamWaitEvent(hs.dn, hs.ev_bwd, 0));
         auto down = [&](float* host, const float* devp, size_t bytes) {
-            if (host && devp && bytes) cudaMemcpyAsync(host, devp, bytes, cudaMemcpyDeviceToHost, s);
+            if (host && devp && bytes) cudaMemcpyAsync(host, devp, bytes, cudaMemcpyDeviceToHost, hs.dn);
         };
         down(host_grads->dL_dmean2D, g.dL_dmean2D, Pz * 12); down(host_grads->dL_dconic, g.dL_dconic, Pz * 16);
         down(host_grads->dL_dopacity, g.dL_dopacity, Pz * 4); down(host_grads->dL_dcolor, g.dL_dcolor, Pz * 12);
         down(host_grads->dL_dmean3D, g.dL_dmean3D, Pz * 12); down(host_grads->dL_dcov3D, g.dL_dcov3D, Pz * 24);
         down(host_grads->dL_dsh, g.dL_dsh, Pz * M * 12); down(host_grads->dL_dscale, g.dL_dscale, Pz * 12);
         down(host_grads->dL_drot, g.dL_drot, Pz * 16);
-        GSB_CUDA_CHECK(cudaGetLastError());
     }
-    GSB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_img, 0));   // `stream` completes only after the side stream's downloads
-    return gsb_num_rendered(d + L.geom, stream);
+    if (status_host)   // GeomHeader words {num_rendered, num_rendered_clamped, overflow}
+        cudaMemcpyAsync(status_host, d + L.geom + offsetof(GeomHeader, num_rendered), 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, hs.dn);
+    GSB_CUDA_CHECK(cudaEventRecord(hs.ev_dn, hs.dn));
+    GSB_CUDA_CHECK(cudaStreamWaitEvent(s, hs.ev_dn, 0));   // `stream` completes only after the frame's downloads
+    GSB_CUDA_CHECK(cudaGetLastError());
+    return GSB_OK;
+}
+
+long long gsb_forward_backward_host(const gsb_raster_args* host_args, long long max_rendered, const float* dL_dpix_host,
+                                    float* out_color_host, float* out_depth_host, int* radii_host,
+                                    const gsb_grad_outputs* host_grads, void* device_scratch, size_t device_scratch_bytes,
+                                    gsb_stream_t stream)
+{
+    if (int rc = host_frame(host_args, max_rendered, dL_dpix_host, out_color_host, out_depth_host, radii_host, host_grads,
+                            device_scratch, device_scratch_bytes, nullptr, stream))
+        return rc;
+    const HostLayout L = HostLayout::make(host_args->P, host_args->shs ? host_args->M : 0, host_args->width, host_args->height, max_rendered);
+    return gsb_num_rendered((char*)device_scratch + L.geom, stream);
+}
+
+int gsb_forward_backward_host_async(const gsb_raster_args* host_args, long long max_rendered, const float* dL_dpix_host,
+                                    float* out_color_host, float* out_depth_host, int* radii_host,
+                                    const gsb_grad_outputs* host_grads, void* device_scratch, size_t device_scratch_bytes,
+                                    unsigned int* status_host, gsb_stream_t stream)
+{
+    if (!status_host) return fail(GSB_ERR_INVALID_ARGUMENT, "status_host (3 x uint32 of pinned host memory) is required");
+    return host_frame(host_args, max_rendered, dL_dpix_host, out_color_host, out_depth_host, radii_host, host_grads, device_scratch,
+                      device_scratch_bytes, status_host, stream);
 }
 
 // ---- introspection ----------------------------------------------------------------------------

@@ -315,6 +315,19 @@ long long gsb_forward_backward_host(const gsb_raster_args* host_args, long long 
                                     const gsb_grad_outputs* host_grads,
                                     void* device_scratch, size_t device_scratch_bytes,
                                     gsb_stream_t stream);
+/* The same frame, fully ASYNCHRONOUS: kernels on `stream`, uploads / downloads on the library's per-thread upload / download
+ * streams (chained to `stream` by events; `stream` completes only after the frame's last download); returns at once.
+ * `status_host` (3 x uint32 of PINNED host memory) receives {num_rendered, instances actually binned, overflow latch} when
+ * `stream` gets there (overflow != 0: the frame was truncated to max_rendered instances -- grow the scratch and resubmit).
+ * Meant for K frames in flight -- K device scratch sets, K streams, K sets of host output buffers: PCIe is full duplex and
+ * the copy engines are separate from the SMs, so frame i's gradient download runs under frame i+1's upload and frame i+2's
+ * kernels (gsorb_slam_b200/host.py: HostPipeline).  The host arrays must stay valid until `stream` has drained. */
+int gsb_forward_backward_host_async(const gsb_raster_args* host_args, long long max_rendered,
+                                    const float* dL_dpix_host,
+                                    float* out_color_host, float* out_depth_host, int* radii_host,
+                                    const gsb_grad_outputs* host_grads,
+                                    void* device_scratch, size_t device_scratch_bytes,
+                                    unsigned int* status_host, gsb_stream_t stream);
 
 /* ---- introspection for parity tests ----------------------------------------------------
  * Copies of internal state into caller DEVICE buffers (any pointer may be NULL):

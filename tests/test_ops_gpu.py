@@ -144,6 +144,58 @@ def test_host_buffer_entry_point_equals_device_path():
         assert rel_to_scale(g[k], to_np(gd[k]).reshape(g[k].shape)) <= 1e-5, k   # atomics order only
 
 
+def test_host_pipeline_keeps_frames_in_flight_and_matches_the_device_path():
+    """gsb_forward_backward_host_async through HostPipeline: seven frames of two different scenes over three slots; every
+    frame's image is bit-identical to the device-resident path and its gradients equal up to the order of the atomics."""
+    import torch
+    from gsorb_slam_b200 import _lib
+    from gsorb_slam_b200.host import HostPipeline
+    from gsorb_slam_b200.lowlevel import frame_from_scene
+    from gsorb_slam_b200.scene import make_scene
+    scenes = [make_scene(20000, (160, 120, 130.0, 128.0), seed=s, scale_mul=2.0) for s in (11, 12)]
+    P, W, H = scenes[0].P, scenes[0].cam.width, scenes[0].cam.height
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.float32)).pin_memory()
+    hosts, args, refs = [], [], []
+    for sc in scenes:
+        h = dict(means=pin(sc.means3D), colors=pin(sc.colors), opac=pin(sc.opacities), scales=pin(sc.scales), rots=pin(sc.rotations),
+                 bg=pin(sc.background), view=pin(sc.cam.viewmatrix), proj=pin(sc.cam.projmatrix), campos=pin(sc.cam.campos), dL=pin(sc.dL_dpix))
+        a = _lib.RasterArgs()
+        a.P, a.D, a.M, a.width, a.height = P, 0, 0, W, H
+        a.background, a.means3D, a.colors_precomp, a.opacities = h["bg"].data_ptr(), h["means"].data_ptr(), h["colors"].data_ptr(), h["opac"].data_ptr()
+        a.scales, a.scale_modifier, a.rotations = h["scales"].data_ptr(), 1.0, h["rots"].data_ptr()
+        a.viewmatrix, a.projmatrix, a.cam_pos = h["view"].data_ptr(), h["proj"].data_ptr(), h["campos"].data_ptr()
+        a.tan_fovx, a.tan_fovy = float(sc.cam.tanfovx), float(sc.cam.tanfovy)
+        hosts.append(h); args.append(a)
+        fr = frame_from_scene(sc)
+        g = fr.backward(sc.dL_dpix)
+        refs.append(dict(color=to_np(fr.color).copy(), radii=to_np(fr.radii).copy(), R=fr.rendered(),
+                         block=np.concatenate([to_np(g[k]).reshape(-1) for k in ("dL_dmean3D", "dL_dcolor", "dL_dopacity", "dL_dscale", "dL_drot")])))
+    pipe = HostPipeline(P, W, H, max_rendered=1 << 18, depth=3)
+    order = [0, 1, 1, 0, 1, 0, 0]
+    done = []
+
+    def check(slot, which):
+        r = refs[which]
+        assert int(slot.status[0]) == r["R"]
+        np.testing.assert_array_equal(slot.color.numpy().view(np.uint32), r["color"].view(np.uint32))
+        np.testing.assert_array_equal(slot.radii.numpy(), r["radii"])
+        assert rel_to_scale(slot.block.numpy(), r["block"]) <= 1e-5
+
+    inflight = []
+    for which in order:
+        if len(inflight) == 3:
+            check(pipe.wait(), inflight.pop(0))
+        pipe.submit(args[which], hosts[which]["dL"].data_ptr())
+        inflight.append(which)
+    while inflight:
+        check(pipe.wait(), inflight.pop(0))
+    # capacity overflow is reported per frame, not silently truncated
+    small = HostPipeline(P, W, H, max_rendered=1000, depth=2)
+    small.submit(args[0], hosts[0]["dL"].data_ptr())
+    with pytest.raises(ValueError, match="OVERFLOW"):
+        small.wait()
+
+
 # Every BASELINE.json config at full size (plus the stress variants of the headline map); digests and samples were
 # produced by the UNMODIFIED reference kernels on a B200 (tests/golden/make_golden.py, log in make_golden_r02.log).
 #   tum_100000 = config #1 (100 k @640x480), tum_1000000 = the headline, cfg2_500k_pose = config #2 (500 k, camera NOT at
