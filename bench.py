@@ -106,8 +106,8 @@ class ClockSampler:
 
 def make_rank_scene(workload: str, rank: int):
     """Replicated Gaussians (seed 0); every rank looks at them from its own keyframe pose."""
-    from gsorb_slam_b200.scene import make_config
-    sc = make_config(workload, seed=0)
+    from gsorb_slam_b200.scene import CONFIGS, make_config, make_large_case
+    sc = make_config(workload, seed=0) if (workload in CONFIGS or workload.endswith("_raster")) else make_large_case(workload)[0]
     if rank > 0:
         ang = 0.01 * rank
         Tcw = np.eye(4, dtype=np.float32)
@@ -151,7 +151,9 @@ def run_ours(args):
     sc = make_rank_scene(args.workload, rank)
     P, W, H = sc.P, sc.cam.width, sc.cam.height
     HW = W * H
-    max_rendered = args.max_rendered or 4 * P + 4096
+    # binning capacity: 4 P + 4096 instances unless this frame needs more (a first, exactly sized forward tells)
+    R0 = frame_from_scene(sc, device=dev).rendered()
+    max_rendered = args.max_rendered or max(4 * P + 4096, R0 + 4096)
     fr = frame_from_scene(sc, device=dev, sync_free=True, max_rendered=max_rendered)
     R = fr.rendered()
     V = int((fr.radii > 0).sum().item())

@@ -295,8 +295,104 @@ __device__ __forceinline__ void tile_radix_sort32(uint32_t* __restrict__ s, uint
     __syncthreads();
 }
 
+// 64-bit network on the tile's own (depth bits << 32 | id) records, in place in global memory (L2): the exact, bounded last
+// resort of the 32-bit keyed sort below, and the size class of lists longer than 16384 entries.
+template <int THREADS>
+__device__ __forceinline__ void tile_sort_exact64(uint64_t* __restrict__ g, uint32_t n, uint32_t* __restrict__ out)
+{
+    bitonic_network(n, next_pow2(n), THREADS, [&](uint32_t i, uint32_t l, bool sync) {
+        if (sync) {
+            __threadfence_block();
+            __syncthreads();
+            return;
+        }
+        const uint64_t a = g[i], b = g[l];
+        if (a > b) {
+            g[i] = b;
+            g[l] = a;
+        }
+    });
+    for (uint32_t i = threadIdx.x; i < n; i += THREADS) out[i] = (uint32_t)g[i];
+}
+
+// Rare path of the 32-bit keyed sort, out of line so that its registers do not weigh on the common path: s[0..n) holds the
+// tile's keys (quantised depth << IDX_BITS | slot) sorted, but there are long runs of equal quantised depth.  If every run is
+// a run of EXACTLY equal depths (quantised sensor depths: two surfaces in one tile, ids too spread for the exact key) the
+// order inside a run is the id order, and a second pass of the same network on (position of the run's first entry,
+// id - min id) finishes the job; anything else goes to the exact 64-bit network.
+template <int E, int THREADS, int IDX_BITS, bool RADIX>
+__device__ __noinline__ void tile_sort_long_runs(uint64_t* __restrict__ seg, uint32_t n, uint32_t* __restrict__ s,
+                                                 uint32_t* __restrict__ s_red, uint32_t* __restrict__ out)
+{
+    constexpr uint32_t IDX_MASK = (1u << IDX_BITS) - 1u;
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    // (a) last run start at or before each of this thread's E positions (0 = none inside the thread)
+    uint32_t start[E];
+    uint32_t run = 0;
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+        const uint32_t i = t * E + k;
+        if (i < n && i > 0 && (s[i - 1] >> IDX_BITS) != (s[i] >> IDX_BITS)) run = i;
+        start[k] = run;
+    }
+    uint32_t incl = run;   // inclusive max-scan over the warp's threads
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl = max(incl, up);
+    }
+    uint32_t prev = __shfl_up_sync(0xffffffffu, incl, 1);   // ... exclusive
+    if (lane == 0) prev = 0;
+    __syncthreads();
+    if (lane == 31) s_red[warp] = incl;
+    // (b) are all runs pure, and do (run start, id) fit one word?
+    uint32_t imn = 0xffffffffu, imx = 0u;
+    for (uint32_t i = t; i < n; i += THREADS) {
+        const uint32_t id = (uint32_t)seg[i];
+        imn = min(imn, id);
+        imx = max(imx, id);
+    }
+    bool impure = false;
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+        const uint32_t i = t * E + k;
+        if (i < n && i > 0 && (s[i - 1] >> IDX_BITS) == (s[i] >> IDX_BITS))
+            impure |= (uint32_t)(seg[s[i - 1] & IDX_MASK] >> 32) != (uint32_t)(seg[s[i] & IDX_MASK] >> 32);
+    }
+    imn = __reduce_min_sync(0xffffffffu, imn);
+    imx = __reduce_max_sync(0xffffffffu, imx);
+    if (lane == 0) {
+        s_red[32 + warp] = imn;
+        s_red[64 + warp] = imx;
+    }
+    impure = __syncthreads_or(impure);
+    for (uint32_t w = 0; w < warp; w++) prev = max(prev, s_red[w]);   // last run start in the warps before this one
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; w++) {
+        imn = min(imn, s_red[32 + w]);
+        imx = max(imx, s_red[64 + w]);
+    }
+    const int idneed = 32 - __clz(imx - imn);
+    if (RADIX || impure || IDX_BITS + idneed > 32) {
+        tile_sort_exact64<THREADS>(seg, n, out);
+        return;
+    }
+    // (c) second pass
+    uint32_t a[E];
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+        const uint32_t i = t * E + k;
+        a[k] = i < n ? (max(start[k], prev) << idneed) | ((uint32_t)seg[s[i] & IDX_MASK] - imn) : 0xffffffffu;
+    }
+    tile_sort_regs32<E, THREADS>(s, a);   // (its first shared-memory write is behind a CTA barrier: every s[] read above is done)
+    const uint32_t idmask = idneed >= 32 ? 0xffffffffu : (1u << idneed) - 1u;
+    for (uint32_t i = t; i < n; i += THREADS) out[i] = (s[i] & idmask) + imn;
+}
+
+constexpr int TIE_ROUNDS = 8;   // odd-even rounds spent on neighbours whose quantised depths collide before the exact sort takes over
+
 template <int E, int THREADS, bool RADIX>
-__device__ __forceinline__ void tile_sort_class32(const uint2 r, const uint64_t* __restrict__ pairs,
+__device__ __forceinline__ void tile_sort_class32(const uint2 r, uint64_t* __restrict__ pairs,
                                                   uint32_t* __restrict__ point_list, uint32_t* __restrict__ s,
                                                   uint32_t* __restrict__ s_red, uint32_t* __restrict__ s_cnt)
 {
@@ -305,7 +401,7 @@ __device__ __forceinline__ void tile_sort_class32(const uint2 r, const uint64_t*
     constexpr int DEPTH_BITS = RADIX ? (32 - IDX_BITS < TR_QBITS ? 32 - IDX_BITS : TR_QBITS) : 32 - IDX_BITS;
     constexpr uint32_t IDX_MASK = (1u << IDX_BITS) - 1u;
     const uint32_t n = r.y - r.x, t = threadIdx.x;
-    const uint64_t* seg = pairs + r.x;
+    uint64_t* seg = pairs + r.x;
     // depth bits of this thread's E consecutive records, tile-wide minimum and maximum
     uint32_t dep[E];
     uint32_t mn = 0xffffffffu, mx = 0u;
@@ -331,27 +427,69 @@ __device__ __forceinline__ void tile_sort_class32(const uint2 r, const uint64_t*
         mn = min(mn, s_red[w]);
         mx = max(mx, s_red[32 + w]);
     }
-    // largest quantised depth must stay below 2^DEPTH_BITS - 1 (the padding key is all ones)
+    // largest depth field must stay below all ones (the padding key is all ones)
     const int need = 32 - __clz(mx - mn + 1u);
+    // Exact keys when (depth - min) above (id - min id) fits one word: no quantisation, no ties, no fix-up.  This is what a
+    // map straight out of Render::InitWorld gives (raster-ordered ids, a few distinct QUANTISED depths per tile).  The id range
+    // is only looked at when the tile's depth range is narrow enough for that to be possible (never on continuous depths).
+    bool exact = false;
+    uint32_t imn = 0u;
+    int idneed = 32;
+    if (!RADIX && need <= 20) {   // CTA-uniform
+        uint32_t imx = 0u;
+        imn = 0xffffffffu;
+        for (uint32_t i = t; i < n; i += THREADS) {
+            const uint32_t id = (uint32_t)seg[i];
+            imn = min(imn, id);
+            imx = max(imx, id);
+        }
+        imn = __reduce_min_sync(0xffffffffu, imn);
+        imx = __reduce_max_sync(0xffffffffu, imx);
+        if ((t & 31) == 0) {
+            s_red[64 + (t >> 5)] = imn;
+            s_red[96 + (t >> 5)] = imx;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; w++) {
+            imn = min(imn, s_red[64 + w]);
+            imx = max(imx, s_red[96 + w]);
+        }
+        idneed = 32 - __clz(imx - imn);   // bits of the id range; 0 when the tile holds one Gaussian
+        exact = need + idneed <= 32;
+    }
     const int shift = need > DEPTH_BITS ? need - DEPTH_BITS : 0;
     uint32_t a[E];
 #pragma unroll
     for (int k = 0; k < E; k++) {
         const uint32_t i = t * E + k;
-        a[k] = i < n ? (((dep[k] - mn) >> shift) << IDX_BITS) | i : 0xffffffffu;
+        uint32_t key = 0xffffffffu;
+        if (i < n) {
+            if (exact) key = ((dep[k] - mn) << idneed) | ((uint32_t)seg[i] - imn);   // idneed <= 31 here (need >= 1)
+            else key = (((dep[k] - mn) >> shift) << IDX_BITS) | i;
+        }
+        a[k] = key;
     }
     if (RADIX) tile_radix_sort32<E, THREADS>(s, a, s_cnt, s_cnt + (THREADS / 32) * TR_RADIX, IDX_BITS);
     else tile_sort_regs32<E, THREADS>(s, a);
-    // exact order between neighbours whose quantised depths collide: odd-even transposition on the
-    // 64-bit records, until a whole round swaps nothing (runs are 2-3 entries long in practice)
+    if (exact) {
+        const uint32_t idmask = (1u << idneed) - 1u;
+        for (uint32_t i = t; i < n; i += THREADS) point_list[r.x + i] = (s[i] & idmask) + imn;
+        return;
+    }
+    // exact order between neighbours whose quantised depths collide: odd-even transposition on the 64-bit records (runs are
+    // 2-3 entries long on continuous depths) -- for at most TIE_ROUNDS rounds; a list with longer runs of equal quantised depth
+    // (quantised sensor depths straddling a discontinuity, adversarial inputs) is sorted exactly by the 64-bit network instead
     bool tie = false;
 #pragma unroll
     for (int k = 0; k < E; k++) {
         const uint32_t i = t * E + k;
         if (i + 1 < n) tie |= (s[i] >> IDX_BITS) == (s[i + 1] >> IDX_BITS);
     }
-    if (__syncthreads_or(tie)) {
-        while (true) {
+    if (const int tied_threads = __syncthreads_count(tie)) {
+        bool unsorted = true;
+        // ties all over the list (a tile of quantised sensor depths): the bounded repair cannot succeed, skip it
+        for (int round = 0; round < TIE_ROUNDS && unsorted && tied_threads <= THREADS / 8; round++) {
             bool swapped = false;
 #pragma unroll 1
             for (uint32_t phase = 0; phase < 2; phase++) {
@@ -365,18 +503,22 @@ __device__ __forceinline__ void tile_sort_class32(const uint2 r, const uint64_t*
                 }
                 __syncthreads();
             }
-            if (!__syncthreads_or(swapped)) break;
+            unsorted = __syncthreads_or(swapped);
+        }
+        if (unsorted) {
+            tile_sort_long_runs<E, THREADS, IDX_BITS, RADIX>(seg, n, s, s_red, point_list + r.x);
+            return;
         }
     }
     for (uint32_t i = t; i < n; i += THREADS) point_list[r.x + i] = (uint32_t)seg[s[i] & IDX_MASK];
 }
 
 template <bool RADIX>
-__global__ void __launch_bounds__(TSORT_THREADS)
-tile_sort_small_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list)
+__global__ void __launch_bounds__(TSORT_THREADS, 5)
+tile_sort_small_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list)
 {
     __shared__ __align__(16) uint32_t s[TSORT_SMALL];
-    __shared__ uint32_t s_red[64];
+    __shared__ uint32_t s_red[128];
     __shared__ uint32_t s_cnt[RADIX ? (TSORT_THREADS / 32) * TR_RADIX + TR_RADIX + 32 : 1];
     const uint2 r = ranges[blockIdx.x];
     const uint32_t n = r.y - r.x;
@@ -400,7 +542,7 @@ tile_sort_mid_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ pa
                      int tiles, const GeomHeader* __restrict__ hdr)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    __shared__ uint32_t s_red[64];
+    __shared__ uint32_t s_red[128];
     __shared__ uint32_t s_cnt[RADIX ? 32 * TR_RADIX + TR_RADIX + 32 : 1];
     if (hdr->max_tile_len <= (uint32_t)TSORT_SMALL) return;   // no tile of this size class in the frame
     uint32_t* s = reinterpret_cast<uint32_t*>(dyn_smem);
@@ -413,20 +555,7 @@ tile_sort_mid_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ pa
         else if (n <= (uint32_t)TSORT_MID) tile_sort_class32<16, 1024, RADIX>(r, pairs, point_list, s, s_red, s_cnt);
         else {
             // more than 16384 entries in one tile (pathological inputs): the 64-bit network in place, in global memory
-            uint64_t* g = pairs + r.x;
-            bitonic_network(n, next_pow2(n), 1024, [&](uint32_t i, uint32_t l, bool sync) {
-                if (sync) {
-                    __threadfence_block();
-                    __syncthreads();
-                    return;
-                }
-                const uint64_t a = g[i], b = g[l];
-                if (a > b) {
-                    g[i] = b;
-                    g[l] = a;
-                }
-            });
-            for (uint32_t i = threadIdx.x; i < n; i += 1024) point_list[r.x + i] = (uint32_t)g[i];
+            tile_sort_exact64<1024>(pairs + r.x, n, point_list + r.x);
         }
     }
 }

@@ -115,6 +115,61 @@ def test_depth_ties_and_large_splats_keep_reference_order(P, scale_mul):
         assert rel_to_scale(to_np(g[k]), go[k].reshape(to_np(g[k]).shape)) <= TOL_GRAD, k
 
 
+@pytest.mark.parametrize("case", ["one_plane", "two_planes_wide_ids", "many_planes_colliding", "long_list"])
+def test_tile_sort_is_exact_and_bounded_on_equal_depths(case):
+    """The adversarial inputs of the per-tile sort (VERDICT r01 "depth-tie cliff"): thousands of EXACTLY equal view-space
+    depths inside one tile -- what Render::InitWorld produces from a quantised depth image (src/Render.cc:496-553).
+      one_plane              every splat of a tile at the same depth: the exact (depth, id) key fits one word
+      two_planes_wide_ids    two far-apart depths per tile and ids spread over 4 M: the exact key does NOT fit, runs of
+                             ~2000 equal quantised depths -> bounded tie repair gives up, the 64-bit network sorts the tile
+      many_planes_colliding  depths a few ulps apart (distinct, but equal after quantisation) mixed with exact ties
+      long_list              > 4096 entries in one tile, all at the same depth (the 1024-thread size class)
+    Order must equal the CPU oracle's stable (tile, depth, id) order and the frame must finish in bounded time (the round-1
+    odd-even repair needed one round of three CTA barriers per entry of the longest run)."""
+    import time
+    import torch
+    from gsorb_slam_b200.lowlevel import frame_from_scene
+    from gsorb_slam_b200.scene import make_scene
+    from oracle import gs_oracle
+    rng = np.random.default_rng(5)
+    P = {"one_plane": 16_000, "two_planes_wide_ids": 16_000, "many_planes_colliding": 16_000, "long_list": 60_000}[case]
+    sc = make_scene(P, (64, 64, 64.0, 64.0), seed=9, cull_frac=0.0)     # 16 tiles, ~1000 (3750) centres per tile
+    z = sc.means3D[:, 2].copy()
+    if case in ("one_plane", "long_list"):
+        znew = np.full(P, 2.5, np.float32)
+    elif case == "two_planes_wide_ids":
+        znew = np.where(rng.random(P) < 0.5, 1.0, 4.0).astype(np.float32)
+    else:
+        base = np.float32(2.0)
+        ulps = rng.integers(0, 6, P).astype(np.uint32)                  # 6 distinct depths within 5 ulps of each other
+        znew = (np.full(P, base, np.float32).view(np.uint32) + ulps).view(np.float32)
+        znew[::7] = np.float32(7.0)                                     # a far plane widens the tile's depth range: quantisation on
+    sc.means3D[:, 0] *= znew / z
+    sc.means3D[:, 1] *= znew / z
+    sc.means3D[:, 2] = znew
+    if case == "two_planes_wide_ids":
+        # spread the ids: pad the map with culled Gaussians so that the tile's id range needs 22 bits
+        big = 4_000_000
+        order = np.sort(rng.choice(big, P, replace=False))
+        pad = lambda a, fill: (lambda out: (out.__setitem__(order, a), out)[1])(np.full((big,) + a.shape[1:], fill, a.dtype))
+        sc.means3D = pad(sc.means3D, 0.0); sc.means3D[:, 2][np.setdiff1d(np.arange(big), order, assume_unique=True)] = -1.0
+        sc.scales, sc.rotations, sc.opacities, sc.colors = pad(sc.scales, 1e-3), pad(sc.rotations, 0.5), pad(sc.opacities, 0.5), pad(sc.colors, 0.5)
+    fr = frame_from_scene(sc, sync_free=True, max_rendered=8 * P + 4096)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for _ in range(3):
+        fr.forward()
+    torch.cuda.synchronize()
+    per_frame = (time.time() - t0) / 3
+    orc = gs_oracle.frame_from_scene(sc)
+    ob = orc.binning()
+    assert fr.rendered() == orc.num_rendered
+    np.testing.assert_array_equal(to_np(fr.binning_state()["point_list"]).astype(np.uint32), ob["point_list"])
+    np.testing.assert_array_equal(to_np(fr.image_state()["ranges"]).astype(np.uint32), ob["ranges"])
+    assert rel_to_scale(to_np(fr.color), orc.color) <= TOL_IMAGE
+    assert per_frame < 0.05, f"{case}: {per_frame * 1e3:.1f} ms per forward"
+
+
 @pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("cuts", [(0, 3, 8), (0, 1, 2, 5, 8), (0, 8, 8)])
 def test_tile_row_bands_sum_to_the_full_frame(cuts, fused):
