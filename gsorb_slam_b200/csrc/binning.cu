@@ -747,8 +747,7 @@ int launch_sort_pairs(GeomHeader* hdr, uint64_t* const kbuf[2], uint32_t* const 
         sort_histogram_kernel<<<hist_grid, SORT_THREADS, 0, s>>>(kbuf[cur], hdr, hist, passes);
         GSB_LAUNCH_CHECK();
     }
-    GSB_CUDA_CHECK(cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)sizeof(SortSmem)));
+    GSB_SET_ATTR_ONCE(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
     for (int pass = 0; pass < passes; pass++) {
         {
             StageTimer _t(ST_SORT_PASS, s);
@@ -793,18 +792,22 @@ int launch_binning(const FwdParams& p, char* geom, const GeomLayout& GL, char* b
     }
     {
         StageTimer _t(ST_TILE_SORT, s);
-        // tuning knob: per-tile sort engine (comparator network / shared-memory radix sort) on the same 32-bit keys
-        static const bool radix = [] { const char* e = getenv("GSB_TILE_SORT"); return e ? e[0] == 'r' : GSB_DEFAULT_TILE_RADIX; }();
+        // per-tile sort engine: comparator network; the shared-memory radix sort on the same 32-bit keys is a developer option
+        bool radix = GSB_DEFAULT_TILE_RADIX;
+#ifdef GSB_TUNING
+        static const bool radix_env = [] { const char* e = getenv("GSB_TILE_SORT"); return e ? e[0] == 'r' : GSB_DEFAULT_TILE_RADIX; }();
+        radix = radix_env;
+#endif
         if (radix) tile_sort_small_kernel<true><<<tiles, TSORT_THREADS, 0, s>>>(ranges, pairs, point_list);
         else tile_sort_small_kernel<false><<<tiles, TSORT_THREADS, 0, s>>>(ranges, pairs, point_list);
         GSB_LAUNCH_CHECK();
         if (grid_instances > TSORT_SMALL) {   // a longer tile list is only possible then
             const int g = tiles < NUM_SMS ? tiles : NUM_SMS;
             if (radix) {
-                GSB_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_mid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSORT_MID * 4));
+                GSB_SET_ATTR_ONCE(tile_sort_mid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSORT_MID * 4);
                 tile_sort_mid_kernel<true><<<g, 1024, TSORT_MID * 4, s>>>(ranges, pairs, point_list, tiles, hdr);
             } else {
-                GSB_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_mid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSORT_MID * 4));
+                GSB_SET_ATTR_ONCE(tile_sort_mid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSORT_MID * 4);
                 tile_sort_mid_kernel<false><<<g, 1024, TSORT_MID * 4, s>>>(ranges, pairs, point_list, tiles, hdr);
             }
             GSB_LAUNCH_CHECK();

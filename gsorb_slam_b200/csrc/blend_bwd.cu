@@ -252,9 +252,13 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
     if (p.band_y1 <= p.band_y0) return GSB_OK;   // empty tile-row band: all-zero accumulators
     // tuning knobs: CTA shape (whole tile / half tile), resident CTAs per SM the compiler must allow (the register
     // budget), depth of the staging ring
+#ifdef GSB_TUNING   // developer builds only (make tune)
     static const int halves = [] { const char* e = getenv("GSB_BLEND_BWD_HALVES"); return e ? atoi(e) : 1; }();
     static const int minb = [] { const char* e = getenv("GSB_BLEND_BWD_MINB"); return e ? atoi(e) : 0; }();
     static const int stages = [] { const char* e = getenv("GSB_BLEND_BWD_STAGES"); return e ? atoi(e) : 3; }();
+#else
+    constexpr int halves = 1, minb = 0, stages = 3;
+#endif
     {
         StageTimer _t(ST_BLEND_BWD, s);
 #define GSB_BWD_LAUNCH(MB, NS, HV) GSB_BWD_LAUNCH_CH(MB, NS, HV, 3, false)
@@ -273,7 +277,11 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
             reinterpret_cast<const uint32_t*>(image + IL.hits_tail),                                                        \
             reinterpret_cast<const GeomHeader*>(geom + GL.header), (uint32_t)p.band_y0);                                                       \
     } while (0)
+#ifdef GSB_TUNING
         static const bool bulk = [] { const char* e = getenv("GSB_BLEND_STAGE"); return e ? e[0] == 'b' : GSB_DEFAULT_BULK; }();
+#else
+        constexpr bool bulk = GSB_DEFAULT_BULK;
+#endif
         if (dL_ddepth_sil) {
             if (bulk) GSB_BWD_LAUNCH_CH(4, 3, 1, 5, true); else GSB_BWD_LAUNCH_CH(4, 3, 1, 5, false);
         } else if (bulk && halves == 1 && stages != 2 && minb != 3) {

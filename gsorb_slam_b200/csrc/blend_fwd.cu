@@ -245,8 +245,7 @@ static void launch_fwd(const FwdParams& p, char* geom, const GeomLayout& GL, cha
 {
     constexpr int NS = 2;
     // many resident CTAs x 24 KB: ask for the largest shared-memory carve-out (once per process and kernel)
-    static const cudaError_t attr = cudaFuncSetAttribute(blend_forward_kernel<MINB, NS, CH>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    (void)attr;
+    GSB_SET_ATTR_ONCE((blend_forward_kernel<MINB, NS, CH>), cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     blend_forward_kernel<MINB, NS, CH><<<dim3(IL.tiles_x, p.band_y1 - p.band_y0), BLEND_THREADS, 0, s>>>(
         reinterpret_cast<const uint2*>(image + IL.ranges), reinterpret_cast<const uint32_t*>(binning + BL.point_list),
         reinterpret_cast<const SplatRec*>(geom + GL.rec), p.W, p.H, p.background, out_color, out_depth, out_depth_sil,

@@ -313,6 +313,18 @@ struct StageTimer {
         }                                                                                 \
     } while (0)
 
+// cudaFuncSetAttribute once per kernel and device (not on every launch); a benign race at worst sets it twice
+#define GSB_SET_ATTR_ONCE(kernel, attr, value)                                            \
+    do {                                                                                  \
+        static bool _done[64] = {};                                                       \
+        int _d = 0;                                                                       \
+        cudaGetDevice(&_d);                                                               \
+        if (_d >= 0 && _d < 64 && !_done[_d]) {                                           \
+            cudaFuncSetAttribute(kernel, attr, value);                                    \
+            _done[_d] = true;                                                             \
+        }                                                                                 \
+    } while (0)
+
 #define GSB_LAUNCH_CHECK()                                                                \
     do {                                                                                  \
         gsb::count_launch();                                                              \

@@ -250,8 +250,12 @@ int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, char
     auto al = [](const void* q) { return q && (reinterpret_cast<uintptr_t>(q) & 15) == 0 ? 1 : 0; };
     {
         StageTimer _t(ST_PREPROCESS, s);
-        // tuning knob: resident CTAs per SM the compiler must allow (the kernel is latency bound: occupancy against registers)
-        static const int minb = [] { const char* e = getenv("GSB_PREPROCESS_MINB"); return e ? atoi(e) : 8; }();
+        // resident CTAs per SM the compiler must allow (the kernel is latency bound: occupancy against registers): 8, measured
+        int minb = 8;
+#ifdef GSB_TUNING
+        static const int minb_env = [] { const char* e = getenv("GSB_PREPROCESS_MINB"); return e ? atoi(e) : 8; }();
+        minb = minb_env;
+#endif
 #define GSB_PRE_LAUNCH(MB)                                                                                                \
     preprocess_kernel<MB><<<GL.num_blocks, PRE_THREADS, 0, s>>>(                                                          \
         p, reinterpret_cast<SplatRec*>(geom + GL.rec), reinterpret_cast<int*>(geom + GL.radii), radii_out,                \

@@ -67,13 +67,16 @@ def _dev(a, dtype=torch.float32):
 
 
 class _Scratch:
-    """resizeFunctional of src/Rasterizer.cu:127-134: a byte tensor that is zero-filled on growth."""
+    """resizeFunctional of src/Rasterizer.cu:127-134: a byte tensor that is zero-filled on growth.  ``keep``: the tensor
+    survives the call and is handed back as is when it is large enough (the "kernels only" timing variant of SURVEY.md 8d:
+    no allocation and no fill inside the timed region)."""
 
-    def __init__(self):
+    def __init__(self, keep: bool = False):
         self.t = torch.empty(0, dtype=torch.uint8, device="cuda")
 
         def cb(_user, nbytes):
-            self.t = torch.zeros(int(nbytes), dtype=torch.uint8, device="cuda")
+            if not (keep and self.t.numel() >= int(nbytes)):
+                self.t = torch.zeros(int(nbytes), dtype=torch.uint8, device="cuda")
             return self.t.data_ptr()
         self.cb = _ALLOC(cb)
 
@@ -83,7 +86,9 @@ class RefFrame:
 
     def __init__(self, *, width, height, means3D, opacities, background, viewmatrix, projmatrix, tanfovx,
                  tanfovy, colors=None, shs=None, sh_degree=0, scales=None, rotations=None, cov3D=None,
-                 scale_modifier=1.0, campos=None, run=True):
+                 scale_modifier=1.0, campos=None, run=True, reuse=False):
+        self.reuse = bool(reuse)   # keep outputs / scratch / gradient tensors across calls ("kernels only" timing)
+        self._grads = None
         self.W, self.H = int(width), int(height)
         self.means3D = _dev(means3D)
         self.P = int(self.means3D.shape[0])
@@ -102,10 +107,11 @@ class RefFrame:
 
     def forward(self):
         """RasterizeGaussiansCUDA (src/Rasterizer.cu:136-217): fresh zeroed outputs + scratch per call."""
-        self.color = torch.zeros((3, self.H, self.W), dtype=torch.float32, device="cuda")
-        self.depth = torch.zeros((1, self.H, self.W), dtype=torch.float32, device="cuda")
-        self.radii = torch.zeros(self.P, dtype=torch.int32, device="cuda")
-        self.geom, self.binning, self.img = _Scratch(), _Scratch(), _Scratch()
+        if not (self.reuse and hasattr(self, "color")):
+            self.color = torch.zeros((3, self.H, self.W), dtype=torch.float32, device="cuda")
+            self.depth = torch.zeros((1, self.H, self.W), dtype=torch.float32, device="cuda")
+            self.radii = torch.zeros(self.P, dtype=torch.int32, device="cuda")
+            self.geom, self.binning, self.img = _Scratch(self.reuse), _Scratch(self.reuse), _Scratch(self.reuse)
         self.num_rendered = lib().ref_forward(
             self.geom.cb, None, self.binning.cb, None, self.img.cb, None, self.P, self.D, self.M, _p(self.bg),
             self.W, self.H, _p(self.means3D), _p(self.shs), _p(self.colors), _p(self.opacities), _p(self.scales),
@@ -118,8 +124,14 @@ class RefFrame:
         P, M = self.P, self.M
         dL = _dev(dL_dpix)
         z = lambda *s: torch.zeros(s, dtype=torch.float32, device="cuda")
-        g = dict(dL_dmean2D=z(P, 3), dL_dconic=z(P, 4), dL_dopacity=z(P), dL_dcolor=z(P, 3), dL_dmean3D=z(P, 3),
-                 dL_dcov3D=z(P, 6), dL_dsh=z(P, max(M, 1), 3), dL_dscale=z(P, 3), dL_drot=z(P, 4))
+        if self.reuse and self._grads is not None:
+            g = self._grads
+            for v in g.values():   # the kernels accumulate with atomics: the zero state is part of their contract
+                v.zero_()
+        else:
+            g = dict(dL_dmean2D=z(P, 3), dL_dconic=z(P, 4), dL_dopacity=z(P), dL_dcolor=z(P, 3), dL_dmean3D=z(P, 3),
+                     dL_dcov3D=z(P, 6), dL_dsh=z(P, max(M, 1), 3), dL_dscale=z(P, 3), dL_drot=z(P, 4))
+            self._grads = g if self.reuse else None
         lib().ref_backward(P, self.D, self.M, self.num_rendered, _p(self.bg), self.W, self.H, _p(self.means3D),
                            _p(self.shs), _p(self.colors), _p(self.scales), self.scale_modifier, _p(self.rotations),
                            _p(self.cov3D), _p(self.view), _p(self.proj), _p(self.campos), self.tanfovx, self.tanfovy,
