@@ -54,7 +54,8 @@ SIGNATURES = {
     "gsb_prologue": (_i, [_i] + [_vp] * 10),
     "gsb_prologue_backward": (_i, [_i] + [_vp] * 15),
     "gsb_pose_grad": (_i, [_i, _vp, _vp, _vp, _vp]),
-    "gsb_adam_step": (_i, [_ll, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _ll, _vp]),
+    "gsb_adam_step": (_i, [_ll, _vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, _ll, _vp]),
+    "gsb_scale_regulariser": (_i, [_i, _vp, _f, _f, _f, _vp, _vp, _vp]),
     "gsb_loss_scratch_bytes": (_sz, [_i, _i]),
     "gsb_mapping_loss": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gsb_backproject_scratch_bytes": (_sz, [_i, _i]),
@@ -64,7 +65,7 @@ SIGNATURES = {
     "gsb_prune_rows": (_i, [_i, _vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i), _vp, _vp, _sz, _vp]),
     "gsb_exchange_sync_bytes": (_sz, [_i]),
     "gsb_exchange_allreduce": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), _ll, _i, _i, _vp]),
-    "gsb_adam_step_groups": (_i, [_i, C.POINTER(_ll), C.POINTER(_f), _vp, _vp, _vp, _vp, _f, _f, _f, _ll, _vp]),
+    "gsb_adam_step_groups": (_i, [_i, C.POINTER(_ll), C.POINTER(_f), _vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_double, _ll, _vp]),
     "gsb_host_scratch_bytes": (_sz, [_i, _i, _i, _i, _ll]),
     "gsb_forward_backward_host": (_ll, [C.POINTER(RasterArgs), _ll, _vp, _vp, _vp, _vp, C.POINTER(GradOutputs), _vp, _sz, _vp]),
     "gsb_forward_backward_host_async": (_i, [C.POINTER(RasterArgs), _ll, _vp, _vp, _vp, _vp, C.POINTER(GradOutputs), _vp, _sz, _vp, _vp]),

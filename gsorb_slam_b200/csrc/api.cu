@@ -390,8 +390,8 @@ int gsb_pose_grad(int P, const float* means_world, const float* dL_dmeans_cam, f
                                     nullptr, nullptr, nullptr, nullptr, dL_dTcw, (cudaStream_t)stream);
 }
 
-int gsb_adam_step(long long n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
-                  float beta2, float eps, long long step, gsb_stream_t stream)
+int gsb_adam_step(long long n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, double lr, double beta1,
+                  double beta2, double eps, long long step, gsb_stream_t stream)
 {
     if (n < 0 || step < 1 || (n > 0 && (!param || !grad || !exp_avg || !exp_avg_sq)))
         return fail(GSB_ERR_INVALID_ARGUMENT, "adam_step: bad arguments");
@@ -399,7 +399,7 @@ int gsb_adam_step(long long n, float* param, const float* grad, float* exp_avg, 
 }
 
 int gsb_adam_step_groups(int ngroups, const long long* group_sizes_host, const float* lrs_host, float* param, const float* grad,
-                         float* exp_avg, float* exp_avg_sq, float beta1, float beta2, float eps, long long step, gsb_stream_t stream)
+                         float* exp_avg, float* exp_avg_sq, double beta1, double beta2, double eps, long long step, gsb_stream_t stream)
 {
     if (ngroups < 0 || ngroups > 8 || step < 1 || (ngroups > 0 && (!group_sizes_host || !lrs_host || !param || !grad || !exp_avg || !exp_avg_sq)))
         return fail(GSB_ERR_INVALID_ARGUMENT, "adam_step_groups: need 0 <= ngroups <= 8, step >= 1 and all arrays");
@@ -407,6 +407,14 @@ int gsb_adam_step_groups(int ngroups, const long long* group_sizes_host, const f
         if (group_sizes_host[g] < 0) return fail(GSB_ERR_INVALID_ARGUMENT, "adam_step_groups: negative group size");
     return launch_adam_groups(ngroups, group_sizes_host, lrs_host, param, grad, exp_avg, exp_avg_sq, beta1, beta2, eps, step,
                               (cudaStream_t)stream);
+}
+
+int gsb_scale_regulariser(int P, const float* log_scales, float max_scalar, float w_scalar, float w_long, float* dL_dlog_scales,
+                          float* terms, gsb_stream_t stream)
+{
+    if (P < 0 || !terms || (P > 0 && !log_scales)) return fail(GSB_ERR_INVALID_ARGUMENT, "scale_regulariser: bad arguments");
+    // terms[4..7] of the caller's 8-float block double as the reduction scratch
+    return launch_scale_regulariser(P, log_scales, max_scalar, w_scalar, w_long, dL_dlog_scales, terms, terms + 4, (cudaStream_t)stream);
 }
 
 // ---- host-buffer convenience ----------------------------------------------------------------

@@ -380,10 +380,12 @@ int launch_prologue_backward(int P, const float* Tcw, const float* means_world, 
                              const float* log_scales, const float* g_means, const float* g_opac, const float* g_rot,
                              const float* g_scales, float* d_means, float* d_logit, float* d_quats, float* d_log_scales,
                              float* dTcw, cudaStream_t s);
-int launch_adam(long long n, float* param, const float* grad, float* m, float* v, float lr, float beta1, float beta2,
-                float eps, long long step, cudaStream_t s);
+int launch_adam(long long n, float* param, const float* grad, float* m, float* v, double lr, double beta1, double beta2,
+                double eps, long long step, cudaStream_t s);
 int launch_adam_groups(int ngroups, const long long* sizes, const float* lrs, float* param, const float* grad, float* m, float* v,
-                       float beta1, float beta2, float eps, long long step, cudaStream_t s);
+                       double beta1, double beta2, double eps, long long step, cudaStream_t s);
+int launch_scale_regulariser(int P, const float* log_scales, float max_scalar, float w_scalar, float w_long, float* d_log_scales,
+                             float* terms, float* acc, cudaStream_t s);
 size_t knn_workspace_bytes(int P);
 int launch_knn(int P, const float* points, float* mean_dist2, char* ws, cudaStream_t s);
 

@@ -110,12 +110,12 @@ prologue_backward_kernel(int P, const float* __restrict__ Tcw, const float* __re
 
 __global__ void __launch_bounds__(EX_THREADS)
 adam_kernel(long long n, float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
-            float* __restrict__ v, float beta1, float beta2, float eps, float step_size, float inv_sqrt_bc2)
+            float* __restrict__ v, float omb1, float beta2, float omb2, float eps, float step_size, float inv_sqrt_bc2)
 {
     for (long long i = (long long)blockIdx.x * EX_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * EX_THREADS) {
         const float g = grad[i];
-        const float mi = m[i] + (g - m[i]) * (1.0f - beta1);            // exp_avg.lerp_(grad, 1 - beta1)
-        const float vi = v[i] * beta2 + (1.0f - beta2) * g * g;         // mul_(beta2).addcmul_(g, g, 1 - beta2)
+        const float mi = m[i] + (g - m[i]) * omb1;                      // exp_avg.lerp_(grad, 1 - beta1)
+        const float vi = v[i] * beta2 + omb2 * g * g;                   // mul_(beta2).addcmul_(g, g, 1 - beta2)
         m[i] = mi;
         v[i] = vi;
         const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;             // (sqrt(v) / sqrt(bc2)).add_(eps)
@@ -132,7 +132,7 @@ struct AdamGroups {
 };
 __global__ void __launch_bounds__(EX_THREADS)
 adam_groups_kernel(long long total, float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
-                   float* __restrict__ v, float beta1, float beta2, float eps, float inv_sqrt_bc2, AdamGroups G)
+                   float* __restrict__ v, float omb1, float beta2, float omb2, float eps, float inv_sqrt_bc2, AdamGroups G)
 {
     for (long long i = (long long)blockIdx.x * EX_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * EX_THREADS) {
         float step_size = G.step_size[0];
@@ -140,12 +140,72 @@ adam_groups_kernel(long long total, float* __restrict__ param, const float* __re
         for (int g = 1; g < 8; g++)
             if (g < G.n && i >= G.bound[g - 1]) step_size = G.step_size[g];
         const float gr = grad[i];
-        const float mi = m[i] + (gr - m[i]) * (1.0f - beta1);
-        const float vi = v[i] * beta2 + (1.0f - beta2) * gr * gr;
+        const float mi = m[i] + (gr - m[i]) * omb1;
+        const float vi = v[i] * beta2 + omb2 * gr * gr;
         m[i] = mi;
         v[i] = vi;
         const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
         param[i] = param[i] - step_size * (mi / denom);
+    }
+}
+
+// ---- scale regularisers of the mapping loss (src/Render.cc:462-469) --------------------------------------------------
+//   big   = where(exp(log_scales) > maxScalar)[0]      row index once per AXIS that exceeds (a row can appear 1-3 times)
+//   reg_scalar = sum_big (max_axis exp(ls) - maxScalar),   reg_long = mean_big (max_axis exp(ls) - min_axis exp(ls))
+// acc[0] = number of selected (row, axis) pairs C, acc[1] = reg_scalar, acc[2] = sum of (max - min) over the selection.
+__global__ void __launch_bounds__(EX_THREADS)
+scale_reg_sum_kernel(int P, const float* __restrict__ log_scales, float max_scalar, float* __restrict__ acc)
+{
+    float c = 0.f, a = 0.f, b = 0.f;
+    for (int i = blockIdx.x * EX_THREADS + threadIdx.x; i < P; i += gridDim.x * EX_THREADS) {
+        const float s0 = expf(log_scales[3 * (size_t)i]), s1 = expf(log_scales[3 * (size_t)i + 1]), s2 = expf(log_scales[3 * (size_t)i + 2]);
+        const float n = (s0 > max_scalar ? 1.f : 0.f) + (s1 > max_scalar ? 1.f : 0.f) + (s2 > max_scalar ? 1.f : 0.f);
+        if (n > 0.f) {
+            const float mx = fmaxf(s0, fmaxf(s1, s2)), mn = fminf(s0, fminf(s1, s2));
+            c += n;
+            a += n * (mx - max_scalar);
+            b += n * (mx - mn);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane_id() == 0 && c > 0.f) {
+        atomicAdd(acc, c);
+        atomicAdd(acc + 1, a);
+        atomicAdd(acc + 2, b);
+    }
+}
+
+// d(w_scalar reg_scalar + w_long reg_long) / d(log_scales), ADDED to d_log_scales; terms = {reg_scalar, reg_long, C, 0}
+__global__ void __launch_bounds__(EX_THREADS)
+scale_reg_apply_kernel(int P, const float* __restrict__ log_scales, float max_scalar, float w_scalar, float w_long,
+                       const float* __restrict__ acc, float* __restrict__ d_log_scales, float* __restrict__ terms)
+{
+    const float C = acc[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && terms) {
+        terms[0] = acc[1];
+        terms[1] = acc[2] / C;   // mean over an empty selection is NaN in the reference too (the gradients are unaffected)
+        terms[2] = C;
+        terms[3] = 0.f;
+    }
+    if (!(C > 0.f) || !d_log_scales) return;
+    const float wl = w_long / C;
+    for (int i = blockIdx.x * EX_THREADS + threadIdx.x; i < P; i += gridDim.x * EX_THREADS) {
+        const float s[3] = {expf(log_scales[3 * (size_t)i]), expf(log_scales[3 * (size_t)i + 1]), expf(log_scales[3 * (size_t)i + 2])};
+        const float n = (s[0] > max_scalar ? 1.f : 0.f) + (s[1] > max_scalar ? 1.f : 0.f) + (s[2] > max_scalar ? 1.f : 0.f);
+        if (n > 0.f) {
+            int imax = 0, imin = 0;   // first maximum / first minimum, as torch.max / torch.min report them
+            if (s[1] > s[imax]) imax = 1;
+            if (s[2] > s[imax]) imax = 2;
+            if (s[1] < s[imin]) imin = 1;
+            if (s[2] < s[imin]) imin = 2;
+            d_log_scales[3 * (size_t)i + imax] += n * (w_scalar + wl) * s[imax];   // d exp(ls) / d ls = exp(ls)
+            d_log_scales[3 * (size_t)i + imin] -= n * wl * s[imin];
+        }
     }
 }
 
@@ -179,26 +239,28 @@ int launch_prologue_backward(int P, const float* Tcw, const float* means_world, 
     return GSB_OK;
 }
 
-int launch_adam(long long n, float* param, const float* grad, float* m, float* v, float lr, float beta1, float beta2,
-                float eps, long long step, cudaStream_t s)
+int launch_adam(long long n, float* param, const float* grad, float* m, float* v, double lr, double beta1, double beta2,
+                double eps, long long step, cudaStream_t s)
 {
     if (n <= 0) return GSB_OK;
-    const double bc1 = 1.0 - pow((double)beta1, (double)step);
-    const double bc2 = 1.0 - pow((double)beta2, (double)step);
-    const float step_size = (float)((double)lr / bc1);
+    // torch keeps the hyper-parameters as doubles and rounds each derived scalar once (1 - beta, lr / bias_correction1, ...)
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
+    const float step_size = (float)(lr / bc1);
     const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
-    adam_kernel<<<grid_for(n), EX_THREADS, 0, s>>>(n, param, grad, m, v, beta1, beta2, eps, step_size, inv_sqrt_bc2);
+    adam_kernel<<<grid_for(n), EX_THREADS, 0, s>>>(n, param, grad, m, v, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+                                                   (float)eps, step_size, inv_sqrt_bc2);
     GSB_LAUNCH_CHECK();
     return GSB_OK;
 }
 
 int launch_adam_groups(int ngroups, const long long* sizes, const float* lrs, float* param, const float* grad, float* m, float* v,
-                       float beta1, float beta2, float eps, long long step, cudaStream_t s)
+                       double beta1, double beta2, double eps, long long step, cudaStream_t s)
 {
     AdamGroups G;
     G.n = ngroups;
     long long total = 0;
-    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
     for (int g = 0; g < 8; g++) {
         if (g < ngroups) total += sizes[g];
         G.bound[g] = total;
@@ -206,7 +268,21 @@ int launch_adam_groups(int ngroups, const long long* sizes, const float* lrs, fl
     }
     if (total == 0) return GSB_OK;
     StageTimer _t(ST_OTHER, s);
-    adam_groups_kernel<<<grid_for(total), EX_THREADS, 0, s>>>(total, param, grad, m, v, beta1, beta2, eps, (float)(1.0 / sqrt(bc2)), G);
+    adam_groups_kernel<<<grid_for(total), EX_THREADS, 0, s>>>(total, param, grad, m, v, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+                                                              (float)eps, (float)(1.0 / sqrt(bc2)), G);
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+
+int launch_scale_regulariser(int P, const float* log_scales, float max_scalar, float w_scalar, float w_long, float* d_log_scales,
+                             float* terms, float* acc, cudaStream_t s)
+{
+    GSB_CUDA_CHECK(cudaMemsetAsync(acc, 0, 4 * sizeof(float), s));
+    if (P <= 0) return GSB_OK;
+    StageTimer _t(ST_OTHER, s);
+    scale_reg_sum_kernel<<<grid_for(P), EX_THREADS, 0, s>>>(P, log_scales, max_scalar, acc);
+    GSB_LAUNCH_CHECK();
+    scale_reg_apply_kernel<<<grid_for(P), EX_THREADS, 0, s>>>(P, log_scales, max_scalar, w_scalar, w_long, acc, d_log_scales, terms);
     GSB_LAUNCH_CHECK();
     return GSB_OK;
 }

@@ -31,21 +31,53 @@ BLOCK_ROWS = sum(w for _, w in GROUPS)  # 14
 
 
 class GradBlock:
-    """One contiguous ``[14 * P]`` fp32 buffer with a ``[P, w]`` view per parameter group.
-    ``storage`` lets the caller place it in a symmetric allocation (``SymmetricExchange.alloc``)."""
+    """One contiguous fp32 buffer holding the five parameter groups, group-major, with a ``[P, w]`` view per group.
 
-    def __init__(self, P: int, device, dtype=torch.float32, storage: Optional[torch.Tensor] = None):
+    ``capacity`` (rows, >= P) makes it an ARENA: group g starts at ``offset_g * capacity`` and only its first ``P`` rows are
+    in use, so Gaussians can be appended in place (``resize``) until the capacity is exhausted -- the capacity-doubling
+    replacement of the ``torch::cat`` per tensor and per Adam moment of ``Gaussian::CatTensorToOptimizer``
+    (src/Gaussian.cc:241-258).  With ``capacity == P`` (default) the layout is the packed ``[14, P]`` block.  ``flat`` always
+    spans the whole arena: the padding rows are zero in every block (parameters, gradients, moments), so Adam and the
+    all-reduce can run over ``flat`` unchanged.  ``storage`` lets the caller place it in a symmetric allocation
+    (``SymmetricExchange.alloc``)."""
+
+    def __init__(self, P: int, device, dtype=torch.float32, storage: Optional[torch.Tensor] = None, capacity: Optional[int] = None):
         self.P = int(P)
+        self.capacity = int(capacity) if capacity is not None else self.P
+        if self.capacity < self.P:
+            raise ValueError("capacity smaller than P")
+        n = BLOCK_ROWS * self.capacity
         if storage is None:
-            storage = torch.zeros(BLOCK_ROWS * self.P, dtype=dtype, device=device)
-        if storage.numel() < BLOCK_ROWS * self.P or storage.dtype != dtype:
+            storage = torch.zeros(n, dtype=dtype, device=device)
+        if storage.numel() < n or storage.dtype != dtype:
             raise ValueError("storage too small for the gradient block")
-        self.flat = storage[:BLOCK_ROWS * self.P]
+        self.flat = storage[:n]
+        self._make_views()
+
+    def _make_views(self):
         self.views: Dict[str, torch.Tensor] = {}
         off = 0
         for name, w in GROUPS:
-            self.views[name] = self.flat[off:off + w * self.P].view(self.P, w)
-            off += w * self.P
+            self.views[name] = self.flat[off * self.capacity:off * self.capacity + w * self.P].view(self.P, w)
+            off += w
+
+    def resize(self, P: int) -> None:
+        """Change the number of rows in use (<= capacity); the views are rebuilt, the data stays where it is."""
+        if P > self.capacity or P < 0:
+            raise ValueError("resize beyond the arena's capacity")
+        self.P = int(P)
+        self._make_views()
+
+    def grown(self, capacity: int) -> "GradBlock":
+        """A new arena of ``capacity`` rows holding this one's rows (padding zero)."""
+        nb = GradBlock(self.P, self.flat.device, self.flat.dtype, capacity=capacity)
+        for name, _ in GROUPS:
+            nb.views[name].copy_(self.views[name])
+        return nb
+
+    def group_sizes(self):
+        """Elements per group over the WHOLE arena (what gsb_adam_step_groups walks)."""
+        return [w * self.capacity for _, w in GROUPS]
 
     def __getitem__(self, name: str) -> torch.Tensor:
         return self.views[name]

@@ -26,16 +26,23 @@ DEFAULT_LR = {"means": 1e-4, "rgb": 2.5e-3, "quats": 1e-3, "opacity": 0.05, "sca
 
 
 class MapOptimizer:
+    """The Gaussian map of one rank and its optimiser state, resident on the GPU as ARENAS (``GradBlock`` with a capacity):
+    parameters, gradients and both Adam moments can grow in place (``add_gaussians``, ``densify``) and shrink
+    (``prune_low_opacity``) without a ``torch::cat`` / ``index_select`` per tensor (src/Gaussian.cc:209-258)."""
+
     def __init__(self, means, rgb, logit_opacities, log_scales, unnorm_quats, *, width, height, tanfovx, tanfovy,
                  projmatrix, background=None, lr: Optional[Dict[str, float]] = None, betas=(0.9, 0.999), eps=1e-15,
-                 device="cuda:0", max_rendered: Optional[int] = None):
+                 device="cuda:0", max_rendered: Optional[int] = None, capacity: Optional[int] = None, scene_radius: float = 0.0,
+                 w_reg_scalar: float = 10.0, w_reg_long: float = 5.0):
         self.L = _lib.lib()
         self.dev = torch.device(device)
         d = self.dev
         t = lambda a: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(d, torch.float32)
         self.P = int(t(means).shape[0])
         P = self.P
-        self.params = GradBlock(P, d)   # same packed layout as the gradient block
+        self.capacity = max(int(capacity) if capacity else P, P)
+        cap = self.capacity
+        self.params = GradBlock(P, d, capacity=cap)   # same layout as the gradient block
         self.params["means"].copy_(t(means)); self.params["rgb"].copy_(t(rgb))
         self.params["opacity"].copy_(t(logit_opacities).reshape(P, 1)); self.params["scales"].copy_(t(log_scales))
         self.params["quats"].copy_(t(unnorm_quats))
@@ -44,11 +51,11 @@ class MapOptimizer:
         self.exchange = None
         if world()[1] > 1 and self.dev.type == "cuda":
             try:
-                self.exchange = SymmetricExchange(BLOCK_ROWS * P, d)
+                self.exchange = SymmetricExchange(BLOCK_ROWS * cap, d)
             except Exception:
                 self.exchange = None
-        self.grads = GradBlock(P, d, storage=self.exchange.alloc(BLOCK_ROWS * P) if self.exchange else None)
-        self.exp_avg, self.exp_avg_sq = GradBlock(P, d), GradBlock(P, d)
+        self.grads = GradBlock(P, d, storage=self.exchange.alloc(BLOCK_ROWS * cap) if self.exchange else None, capacity=cap)
+        self.exp_avg, self.exp_avg_sq = GradBlock(P, d, capacity=cap), GradBlock(P, d, capacity=cap)
         self.lr = dict(DEFAULT_LR if lr is None else lr)
         self.betas, self.eps, self.t = betas, float(eps), 0
         self.W, self.H = int(width), int(height)
@@ -58,19 +65,38 @@ class MapOptimizer:
         self.view = torch.eye(4, device=d).reshape(16).contiguous()
         self.campos = torch.zeros(3, device=d)
         self.bg = t(background if background is not None else np.zeros(3, np.float32))
-        # activated temporaries + their gradients
+        # scale regularisers of the mapping loss (src/Render.cc:418, :462-469): maxScalar = 0.1 * scene radius
+        # (Render::mMaxZ / sceneRaduisDepthRatio, :661); weights Examples/RGB-D/replica.yaml:93-94.  0 = regularisers off
+        self.scene_radius, self.w_reg_scalar, self.w_reg_long = float(scene_radius), float(w_reg_scalar), float(w_reg_long)
+        self.dTcw = torch.empty((3, 4), dtype=torch.float32, device=d)
+        self.color = torch.empty((3, self.H, self.W), dtype=torch.float32, device=d)
+        self.depth = torch.empty((1, self.H, self.W), dtype=torch.float32, device=d)
+        self.reg_terms = torch.zeros(8, dtype=torch.float32, device=d)
+        self.max_rendered = int(max_rendered) if max_rendered else 4 * cap + 4096
+        self.img = torch.empty(int(self.L.gsb_image_bytes(self.W, self.H)), dtype=torch.uint8, device=d)
+        self.binning = torch.empty(int(self.L.gsb_binning_bytes(self.max_rendered)), dtype=torch.uint8, device=d)
+        # forward status (GeomHeader words: magic, P, num_rendered, binned, overflow latch, ...) polled once per step
+        self._status = torch.zeros(8, dtype=torch.int32).pin_memory() if d.type == "cuda" else torch.zeros(8, dtype=torch.int32)
+        self._status_ev = torch.cuda.Event() if d.type == "cuda" else None
+        self.overflow_retries = 0
+        self._alloc_rows()
+
+    # ---- per-row temporaries and the C-ABI argument blocks: rebuilt when the arena grows, re-pointed when P changes ----
+    def _alloc_rows(self):
+        d, cap = self.dev, self.capacity
         e = lambda *s: torch.empty(s, dtype=torch.float32, device=d)
-        self.means_cam, self.opac, self.rot, self.scales = e(P, 3), e(P), e(P, 4), e(P, 3)
-        self.g_means_cam, self.g_opac, self.g_rot, self.g_scales = e(P, 3), e(P), e(P, 4), e(P, 3)
-        self.g_side = e(P, 13)   # mean2D 3 | conic 4 | cov3D 6: reference outputs nobody consumes here
-        self.dTcw = e(3, 4)
-        self.color, self.depth = e(3, self.H, self.W), e(1, self.H, self.W)
-        self.radii = torch.empty(P, dtype=torch.int32, device=d)
-        self.max_rendered = int(max_rendered) if max_rendered else 4 * P + 4096
-        L = self.L
-        u8 = lambda n: torch.empty(int(n), dtype=torch.uint8, device=d)
-        self.geom, self.img = u8(L.gsb_geometry_bytes(P)), u8(L.gsb_image_bytes(self.W, self.H))
-        self.binning = u8(L.gsb_binning_bytes(self.max_rendered))
+        # activated temporaries + their gradients
+        self.means_cam, self.opac, self.rot, self.scales = e(cap, 3), e(cap), e(cap, 4), e(cap, 3)
+        self.g_means_cam, self.g_opac, self.g_rot, self.g_scales = e(cap, 3), e(cap), e(cap, 4), e(cap, 3)
+        self.g_side = e(cap, 13)   # mean2D 3 | conic 4 | cov3D 6: reference outputs nobody consumes here
+        self.radii = torch.empty(cap, dtype=torch.int32, device=d)
+        self.geom = torch.empty(int(self.L.gsb_geometry_bytes(cap)), dtype=torch.uint8, device=d)
+        if hasattr(self, "g_z"):
+            self.g_z = e(cap)
+        self._point_args()
+
+    def _point_args(self):
+        P, cap = self.P, self.capacity
         a = RasterArgs()
         a.P, a.D, a.M, a.width, a.height = P, 0, 0, self.W, self.H
         a.background, a.means3D, a.colors_precomp = self.bg.data_ptr(), self.means_cam.data_ptr(), self.params.ptr("rgb")
@@ -79,9 +105,145 @@ class MapOptimizer:
         a.tan_fovx, a.tan_fovy = self.tanfovx, self.tanfovy
         self.args = a
         sp = self.g_side.data_ptr()
-        self.gout = GradOutputs(dL_dmean2D=sp, dL_dconic=sp + 12 * P, dL_dcov3D=sp + 28 * P, dL_dopacity=self.g_opac.data_ptr(),
+        self.gout = GradOutputs(dL_dmean2D=sp, dL_dconic=sp + 12 * cap, dL_dcov3D=sp + 28 * cap, dL_dopacity=self.g_opac.data_ptr(),
                                 dL_dcolor=self.grads.ptr("rgb"), dL_dmean3D=self.g_means_cam.data_ptr(), dL_dsh=None,
                                 dL_dscale=self.g_scales.data_ptr(), dL_drot=self.g_rot.data_ptr())
+        self._adam_sizes = (C.c_longlong * len(GROUPS))(*self.params.group_sizes())
+
+    # ---- growing and shrinking the map --------------------------------------------------------------------------------
+    def reserve(self, capacity: int) -> None:
+        """Grow the arenas to ``capacity`` rows (parameters, gradients, Adam moments, per-row temporaries)."""
+        if capacity <= self.capacity:
+            return
+        if self.exchange is not None:
+            raise RuntimeError("the gradient block of a multi-GPU map lives in a symmetric allocation: create the MapOptimizer "
+                               "with capacity=... large enough for the session")
+        self.params, self.exp_avg, self.exp_avg_sq = self.params.grown(capacity), self.exp_avg.grown(capacity), self.exp_avg_sq.grown(capacity)
+        self.grads = GradBlock(self.P, self.dev, capacity=capacity)
+        self.capacity = int(capacity)
+        self._alloc_rows()
+
+    def add_gaussians(self, means, rgb, logit_opacities, log_scales, unnorm_quats) -> int:
+        """``Gaussian::AddGaussianPoints`` -> ``UpdateOptimizerParams`` -> ``CatTensorToOptimizer`` (src/Gaussian.cc:50-95,
+        241-258): K new rows behind the existing ones, zero Adam moments, the step counter is shared.  In place while the
+        arena has room; otherwise the arena grows by half (at least to fit)."""
+        K = int(means.shape[0])
+        if K == 0:
+            return 0
+        P = self.P
+        if P + K > self.capacity:
+            self.reserve(max(P + K, self.capacity + self.capacity // 2))
+        for blk in (self.params, self.grads, self.exp_avg, self.exp_avg_sq):
+            blk.resize(P + K)
+        new = dict(means=means, rgb=rgb, opacity=logit_opacities.reshape(K, 1), scales=log_scales, quats=unnorm_quats)
+        for name, _ in GROUPS:
+            self.params[name][P:].copy_(new[name].to(self.dev, torch.float32).reshape(self.params[name][P:].shape))
+            self.exp_avg[name][P:].zero_()
+            self.exp_avg_sq[name][P:].zero_()
+            self.grads[name][P:].zero_()
+        self.P = P + K
+        if 4 * self.P + 4096 > self.max_rendered:
+            self._grow_binning(4 * self.capacity + 4096)
+        self._point_args()
+        return K
+
+    def add_mask(self, color, depth_sil, gt_depth, median_mul: float = 0.5):
+        """The densification mask of ``Render::AddGaussian`` (src/Render.cc:557-583) on the device: pixels that are dark, not
+        yet opaque and off in depth by more than an adaptive threshold (mean + median_mul * median of the small depth errors,
+        at least 1 cm), or whose silhouette is below 0.8.  Returns a uint8 [H, W] mask (255 = add), as ``ImshowDepth`` hands
+        it to ``ProjectPixel`` (which keeps values >= 250)."""
+        gray = (color[0] * 299 + color[1] * 587 + color[2] * 114) / 1000
+        black = gray < 50 / 255.0
+        diff = (gt_depth - depth_sil[0]).abs()
+        small = (diff < 0.05) & (gt_depth > 0) & (depth_sil[0] > 0)
+        sel = diff[small]
+        th = float(sel.sum() / small.sum() + median_mul * sel.median()) if sel.numel() else float("nan")
+        if not th >= 0.01:   # also NaN (empty selection)
+            th = 0.01
+        c1 = ~(depth_sil[1] > 0.99) & black & (diff > th)
+        c2 = depth_sil[1] < 0.8
+        return ((c1 | c2).to(torch.uint8) * 255).contiguous()
+
+    def densify(self, Tcw, gt_color, gt_depth, fx: float, fy: float, cx: float, cy: float, color=None, depth_sil=None,
+                median_mul: float = 0.5, mask=None) -> int:
+        """``Render::AddGaussian`` for one keyframe: densification mask (from the last ``render_fused`` outputs unless given)
+        -> GPU back-projection of the selected pixels (``gsb_backproject`` = ProjectPixel + the SinglePixel initialisation of
+        AddGaussianPoints) -> append.  Returns the number of Gaussians added; updates ``scene_radius`` bookkeeping input
+        ``max_z``."""
+        L, d = self.L, self.dev
+        color = self.color if color is None else color
+        depth_sil = self.depth_sil if depth_sil is None else depth_sil
+        gtc = gt_color.to(d, torch.float32).contiguous()
+        gtd = gt_depth.to(d, torch.float32).contiguous()
+        if mask is None:
+            mask = self.add_mask(color, depth_sil, gtd, median_mul)
+        Twc = torch.linalg.inv(Tcw.detach().to("cpu", torch.float64)).to(torch.float32).contiguous()
+        cap = int(mask.numel())
+        e = lambda *s: torch.empty(s, dtype=torch.float32, device=d)
+        means, rgb, ls, quat, op = e(cap, 3), e(cap, 3), e(cap, 3), e(cap, 4), e(cap)
+        count = torch.zeros(1, dtype=torch.int32, device=d)
+        if not hasattr(self, "max_z"):
+            self.max_z = torch.zeros(1, dtype=torch.float32, device=d)
+        nb = int(L.gsb_backproject_scratch_bytes(self.W, self.H))
+        scratch = torch.empty(nb, dtype=torch.uint8, device=d)
+        Th = (C.c_float * 16)(*Twc.reshape(-1).tolist())
+        with torch.cuda.device(d):
+            _lib.check(L.gsb_backproject(self.W, self.H, mask.data_ptr(), gtd.data_ptr(), gtc.data_ptr(), float(fx), float(fy), float(cx),
+                                         float(cy), Th, cap, means.data_ptr(), rgb.data_ptr(), ls.data_ptr(), quat.data_ptr(), op.data_ptr(),
+                                         count.data_ptr(), self.max_z.data_ptr(), scratch.data_ptr(), nb, self._s()))
+        K = int(count.item())
+        return self.add_gaussians(means[:K], rgb[:K], op[:K], ls[:K], quat[:K])
+
+    def prune_low_opacity(self, threshold: float = 0.005) -> int:
+        """``Render::RemoveGaussian`` (src/Render.cc:598-616; Gaussian.cc:193-239, pruneOpcities 0.005): rows whose
+        sigmoid(logit opacity) is below the threshold leave the parameters and both Adam moments, order preserved --
+        one flag kernel and ONE compaction pass over the 15 tensors (gsb_low_opacity_keep + gsb_prune_rows)."""
+        L, d, P = self.L, self.dev, self.P
+        keep = torch.empty(P, dtype=torch.uint8, device=d)
+        src_blocks = (self.params, self.exp_avg, self.exp_avg_sq)
+        dst_blocks = tuple(GradBlock(P, d, capacity=self.capacity) for _ in src_blocks)
+        n = 3 * len(GROUPS)
+        src = (C.c_void_p * n)(*[blk.ptr(name) for blk in src_blocks for name, _ in GROUPS])
+        dst = (C.c_void_p * n)(*[blk.ptr(name) for blk in dst_blocks for name, _ in GROUPS])
+        widths = (C.c_int * n)(*[w for _ in src_blocks for _, w in GROUPS])
+        count = torch.zeros(1, dtype=torch.int32, device=d)
+        nb = int(L.gsb_prune_scratch_bytes(P))
+        scratch = torch.empty(nb, dtype=torch.uint8, device=d)
+        with torch.cuda.device(d):
+            _lib.check(L.gsb_low_opacity_keep(P, self.params.ptr("opacity"), float(threshold), keep.data_ptr(), self._s()))
+            _lib.check(L.gsb_prune_rows(P, keep.data_ptr(), n, src, dst, widths, count.data_ptr(), scratch.data_ptr(), nb, self._s()))
+        K = int(count.item())
+        if K == P:
+            return 0
+        self.params, self.exp_avg, self.exp_avg_sq = dst_blocks
+        for blk in (self.params, self.exp_avg, self.exp_avg_sq, self.grads):
+            blk.resize(K)
+        if self.exchange is None:
+            self.grads.flat.zero_()
+        self.P = K
+        self._point_args()
+        return P - K
+
+    def _grow_binning(self, max_rendered: int) -> None:
+        self.max_rendered = int(max_rendered)
+        self.binning = torch.empty(int(self.L.gsb_binning_bytes(self.max_rendered)), dtype=torch.uint8, device=self.dev)
+
+    # ---- the forward's overflow latch: polled once per step, never ignored ---------------------------------------------
+    def _poll_forward(self):
+        """Stream-ordered copy of the forward's status words to pinned host memory (no synchronisation here)."""
+        self._status.copy_(self.geom[:32].view(torch.int32), non_blocking=True)
+        self._status_ev.record(torch.cuda.current_stream(self.dev))
+
+    def _overflowed(self) -> bool:
+        """True if the last forward found more tile instances than ``max_rendered``: the binning blob is grown and the caller
+        renders again (what adapter/Rasterizer.cc does for the drop-in path).  Waits for the FORWARD only."""
+        self._status_ev.synchronize()
+        if int(self._status[4]) == 0:
+            return False
+        need = int(self._status[2]) & 0xffffffff
+        self._grow_binning(max(need + need // 4 + 4096, 2 * self.max_rendered))
+        self.overflow_retries += 1
+        return True
 
     def save_ply(self, path: str) -> None:
         """Write the map as the reference's GaussianModel.ply (src/Utils.cc:182-280; read by scripts/replay.py)."""
@@ -100,16 +262,22 @@ class MapOptimizer:
         return torch.cuda.current_stream(self.dev).cuda_stream
 
     def render(self, Tcw: torch.Tensor):
-        """Forward only: prologue + rasterizer.  Returns (color [3,H,W], depth [1,H,W], radii [P])."""
-        L, p, s = self.L, self.params, self._s()
+        """Forward only: prologue + rasterizer.  Returns (color [3,H,W], depth [1,H,W], radii [P]).  A frame with more tile
+        instances than the binning blob holds is rendered again with a larger blob (never silently truncated)."""
+        L, p = self.L, self.params
         self._Tcw = Tcw.to(self.dev, torch.float32).contiguous()
-        with torch.cuda.device(self.dev):
-            _lib.check(L.gsb_prologue(self.P, self._Tcw.data_ptr(), p.ptr("means"), p.ptr("opacity"), p.ptr("quats"), p.ptr("scales"),
-                                      self.means_cam.data_ptr(), self.opac.data_ptr(), self.rot.data_ptr(), self.scales.data_ptr(), s))
-            _lib.check(L.gsb_forward_ws(C.byref(self.args), self.geom.data_ptr(), self.geom.numel(), self.binning.data_ptr(),
-                                        self.binning.numel(), self.max_rendered, self.img.data_ptr(), self.img.numel(),
-                                        self.color.data_ptr(), self.depth.data_ptr(), self.radii.data_ptr(), s))
-        return self.color, self.depth, self.radii
+        while True:
+            s = self._s()
+            with torch.cuda.device(self.dev):
+                _lib.check(L.gsb_prologue(self.P, self._Tcw.data_ptr(), p.ptr("means"), p.ptr("opacity"), p.ptr("quats"), p.ptr("scales"),
+                                          self.means_cam.data_ptr(), self.opac.data_ptr(), self.rot.data_ptr(), self.scales.data_ptr(), s))
+                _lib.check(L.gsb_forward_ws(C.byref(self.args), self.geom.data_ptr(), self.geom.numel(), self.binning.data_ptr(),
+                                            self.binning.numel(), self.max_rendered, self.img.data_ptr(), self.img.numel(),
+                                            self.color.data_ptr(), self.depth.data_ptr(), self.radii.data_ptr(), s))
+                self._poll_forward()
+            if not self._overflowed():
+                break
+        return self.color, self.depth, self.radii[:self.P]
 
     def backward(self, dL_dpix: torch.Tensor):
         """Rasterizer backward + prologue backward into the packed gradient block (and dL/dTcw)."""
@@ -124,14 +292,11 @@ class MapOptimizer:
                                                g.ptr("quats"), g.ptr("scales"), self.dTcw.data_ptr(), s))
         return g
 
-    def render_fused(self, Tcw: torch.Tensor):
-        """Prologue + ONE five-channel rasterization: (color [3,H,W], depth_sil [2,H,W], median_depth [1,H,W], radii)
-        -- what Render::RenderForFrame gets from its depth pass and its RGB pass (src/Render.cc:445-448)."""
+    def _forward_fused(self):
         L, p, s = self.L, self.params, self._s()
-        self._Tcw = Tcw.to(self.dev, torch.float32).contiguous()
         if not hasattr(self, "depth_sil"):
             self.depth_sil = torch.empty((2, self.H, self.W), dtype=torch.float32, device=self.dev)
-            self.g_z = torch.empty(self.P, dtype=torch.float32, device=self.dev)
+            self.g_z = torch.empty(self.capacity, dtype=torch.float32, device=self.dev)
         with torch.cuda.device(self.dev):
             _lib.check(L.gsb_prologue(self.P, self._Tcw.data_ptr(), p.ptr("means"), p.ptr("opacity"), p.ptr("quats"), p.ptr("scales"),
                                       self.means_cam.data_ptr(), self.opac.data_ptr(), self.rot.data_ptr(), self.scales.data_ptr(), s))
@@ -139,7 +304,18 @@ class MapOptimizer:
                                               self.binning.numel(), self.max_rendered, self.img.data_ptr(), self.img.numel(),
                                               self.color.data_ptr(), self.depth_sil.data_ptr(), self.depth.data_ptr(),
                                               self.radii.data_ptr(), s))
-        return self.color, self.depth_sil, self.depth, self.radii
+            self._poll_forward()
+
+    def render_fused(self, Tcw: torch.Tensor):
+        """Prologue + ONE five-channel rasterization: (color [3,H,W], depth_sil [2,H,W], median_depth [1,H,W], radii)
+        -- what Render::RenderForFrame gets from its depth pass and its RGB pass (src/Render.cc:445-448).  Stand-alone use:
+        an overflowing frame is rendered again with a larger binning blob before this returns."""
+        self._Tcw = Tcw.to(self.dev, torch.float32).contiguous()
+        while True:
+            self._forward_fused()
+            if not self._overflowed():
+                break
+        return self.color, self.depth_sil, self.depth, self.radii[:self.P]
 
     def backward_fused(self, dL_dcolor: torch.Tensor, dL_ddepth_sil: torch.Tensor, z_attached: bool = True):
         """Backward of ``render_fused`` into the packed gradient block.  ``z_attached``: the depth pass' z_cam colour is a
@@ -157,13 +333,20 @@ class MapOptimizer:
                                                g.ptr("quats"), g.ptr("scales"), self.dTcw.data_ptr(), s))
         return g
 
+    def add_scale_regularisers(self):
+        """reg_scalar / reg_long of the mapping loss (src/Render.cc:462-469) added to the log-scale gradients; no-op while
+        ``scene_radius`` is 0.  ``reg_terms`` (device) = {reg_scalar, reg_long, selected (row, axis) pairs, 0}."""
+        if not self.scene_radius > 0.0:
+            return
+        with torch.cuda.device(self.dev):
+            _lib.check(self.L.gsb_scale_regulariser(self.P, self.params.ptr("scales"), 0.1 * self.scene_radius, self.w_reg_scalar,
+                                                    self.w_reg_long, self.grads.ptr("scales"), self.reg_terms.data_ptr(), self._s()))
+
     def adam(self):
         """torch::optim::Adam step on every group, reading the (all-reduced) gradient block in place: ONE launch over the
-        packed [14, P] block with a learning rate per group (gsb_adam_step_groups)."""
+        whole arena with a learning rate per group (gsb_adam_step_groups; padding rows are zero and stay zero)."""
         self.t += 1
         L, s = self.L, self._s()
-        if not hasattr(self, "_adam_sizes"):
-            self._adam_sizes = (C.c_longlong * len(GROUPS))(*[w * self.P for _, w in GROUPS])
         lrs = (C.c_float * len(GROUPS))(*[float(self.lr[name]) for name, _ in GROUPS])
         with torch.cuda.device(self.dev):
             _lib.check(L.gsb_adam_step_groups(len(GROUPS), self._adam_sizes, lrs, self.params.flat.data_ptr(), self.grads.flat.data_ptr(),
@@ -185,6 +368,7 @@ class MapOptimizer:
         color, depth_sil, median, _ = self.render_fused(Tcw)
         dC, dD = loss_grad(color, depth_sil, median)
         self.backward_fused(dC, dD, z_attached=z_attached)
+        self.add_scale_regularisers()
         self._exchange_and_adam(average)
         return color, depth_sil
 
@@ -192,11 +376,13 @@ class MapOptimizer:
                   w_image: float = 1.0, w_depth: float = 0.7, w_surdepth: float = 0.35, average: bool = False):
         """One complete mapping iteration of Render::RenderForFrame (src/Render.cc:420-476) without a single torch op on the
         hot path: prologue -> ONE five-channel rasterization -> fused L1 + SSIM + depth loss and its gradient
-        (gsb_mapping_loss) -> summed backward -> prologue backward -> exchange -> Adam.  Weights default to
-        Examples/RGB-D/replica.yaml:89-94.  Returns the 8 loss terms (device tensor: l1, ssim, depth_l1, surdepth_l1, total,
-        n_valid, n_valid_sur, 0); the scale regularisers (Render.cc:462-467) are the caller's."""
-        L, s = self.L, self._s()
-        color, depth_sil, median, _ = self.render_fused(Tcw)
+        (gsb_mapping_loss) -> summed backward -> prologue backward -> scale regularisers (:462-469, when ``scene_radius`` is
+        set) -> exchange -> Adam.  Weights default to Examples/RGB-D/replica.yaml:89-94.  Returns the 8 loss terms (device
+        tensor: l1, ssim, depth_l1, surdepth_l1, total of the pixel terms, n_valid, n_valid_sur, 0); ``reg_terms`` holds the
+        regularisers.  The forward's overflow latch is read once (the host waits for the FORWARD only, with the loss and the
+        backward already queued behind it): an overflowing frame is redone with a larger binning blob before Adam."""
+        L = self.L
+        self._Tcw = Tcw.to(self.dev, torch.float32).contiguous()
         if not hasattr(self, "_loss_scratch"):
             nb = int(L.gsb_loss_scratch_bytes(self.W, self.H))
             self._loss_scratch = torch.empty(nb, dtype=torch.uint8, device=self.dev)
@@ -205,12 +391,17 @@ class MapOptimizer:
             self.loss_terms = torch.empty(8, dtype=torch.float32, device=self.dev)
         gtc = gt_color.to(self.dev, torch.float32).contiguous()
         gtd = gt_depth.to(self.dev, torch.float32).contiguous()
-        with torch.cuda.device(self.dev):
-            _lib.check(L.gsb_mapping_loss(self.W, self.H, color.data_ptr(), depth_sil.data_ptr(), median.data_ptr(), gtc.data_ptr(),
-                                          gtd.data_ptr(), float(lambda_), float(w_image), float(w_depth), float(w_surdepth),
-                                          self._gC.data_ptr(), self._gD.data_ptr(), self.loss_terms.data_ptr(),
-                                          self._loss_scratch.data_ptr(), self._loss_scratch.numel(), s))
-        self.backward_fused(self._gC, self._gD, z_attached=True)
+        while True:
+            self._forward_fused()
+            with torch.cuda.device(self.dev):
+                _lib.check(L.gsb_mapping_loss(self.W, self.H, self.color.data_ptr(), self.depth_sil.data_ptr(), self.depth.data_ptr(),
+                                              gtc.data_ptr(), gtd.data_ptr(), float(lambda_), float(w_image), float(w_depth),
+                                              float(w_surdepth), self._gC.data_ptr(), self._gD.data_ptr(), self.loss_terms.data_ptr(),
+                                              self._loss_scratch.data_ptr(), self._loss_scratch.numel(), self._s()))
+            self.backward_fused(self._gC, self._gD, z_attached=True)
+            if not self._overflowed():
+                break
+        self.add_scale_regularisers()
         self._exchange_and_adam(average)
         return self.loss_terms
 
@@ -218,5 +409,6 @@ class MapOptimizer:
         """One optimisation step on this rank's keyframe.  ``loss_grad(color, depth) -> dL/dcolor``."""
         color, depth, _ = self.render(Tcw)
         self.backward(loss_grad(color, depth))
+        self.add_scale_regularisers()
         self._exchange_and_adam(average)
         return color

@@ -229,9 +229,10 @@ int gsb_pose_grad(int P, const float* means_world, const float* dL_dmeans_cam, f
 /* Fused multi-tensor Adam (torch::optim::Adam semantics: bias-corrected, eps outside the
  * sqrt, no weight decay / amsgrad; src/Gaussian.cc:131-175).  One launch updates n
  * contiguous fp32 values: p -= lr * mhat / (sqrt(vhat) + eps).  `step` is the 1-based step
- * count AFTER this update. */
+ * count AFTER this update.  The hyper-parameters are doubles, as torch holds them: 1 - beta and lr / bias_correction are
+ * formed in double and rounded once (1.0f - 0.999f is off by 1.3e-5 relative). */
 int gsb_adam_step(long long n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
-                  float lr, float beta1, float beta2, float eps, long long step,
+                  double lr, double beta1, double beta2, double eps, long long step,
                   gsb_stream_t stream);
 
 /* ---- fused loss of one mapping iteration (extension) ------------------------
@@ -250,6 +251,15 @@ int gsb_mapping_loss(int width, int height, const float* color, const float* dep
                      float lambda_, float w_image, float w_depth, float w_surdepth,
                      float* dL_dcolor, float* dL_ddepth_sil, float* loss_terms,
                      void* scratch, size_t scratch_bytes, gsb_stream_t stream);
+
+/* The two scale regularisers of the mapping loss (src/Render.cc:462-469), which act on the parameters, not on pixels:
+ *   big = where(exp(log_scales) > max_scalar)[0]   (a row appears once per axis that exceeds),
+ *   reg_scalar = sum_big (max_axis exp(ls) - max_scalar),  reg_long = mean_big (max_axis exp(ls) - min_axis exp(ls)),
+ * max_scalar = 0.1 * scene radius (:418).  ADDS d(w_scalar reg_scalar + w_long reg_long)/d(log_scales) to dL_dlog_scales
+ * [P,3] (may be NULL) and writes terms[0..3] = {reg_scalar, reg_long (NaN when nothing is selected, as in the reference),
+ * number of selected (row, axis) pairs, 0}; `terms` is 8 floats of DEVICE memory (4..7 are scratch). */
+int gsb_scale_regulariser(int P, const float* log_scales, float max_scalar, float w_scalar, float w_long,
+                          float* dL_dlog_scales, float* terms, gsb_stream_t stream);
 
 /* ---- densification: back-projection of selected pixels (extension) ------
  * GPU twin of the host loops Render::ProjectPixel / Render::InitGaussianPoint (src/Render.cc:617-655, :666-707) and of the
@@ -301,7 +311,7 @@ int gsb_exchange_allreduce(void* multicast_ptr, void* const* peer_ptrs, void* co
  * param / grad / exp_avg / exp_avg_sq hold sum(group_sizes) values. */
 int gsb_adam_step_groups(int ngroups, const long long* group_sizes_host, const float* lrs_host,
                          float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
-                         float beta1, float beta2, float eps, long long step, gsb_stream_t stream);
+                         double beta1, double beta2, double eps, long long step, gsb_stream_t stream);
 
 /* ---- host-buffer convenience (bench "e2e" leg and quick integration tests) -------------
  * One forward + backward with every array in HOST memory (pinned recommended): copies the

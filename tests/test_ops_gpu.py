@@ -742,3 +742,165 @@ def test_pose_refinement_recovers_a_perturbed_camera():
     losses = [po.step(gt_c, gt_d) for _ in range(80)]
     assert np.isfinite(losses).all() and losses[-1] < 0.5 * losses[0], (losses[0], losses[-1])
     assert err() < 0.5 * e0, (e0, err())
+
+
+def test_scale_regularisers_match_torch_autograd():
+    """gsb_scale_regulariser against the literal torch expressions of src/Render.cc:462-469 (where / index_select / max / min /
+    mean over the rows selected once per exceeding axis) and their autograd."""
+    import torch
+    from gsorb_slam_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(3)
+    P = 50_000
+    ls = (torch.randn(P, 3, generator=g) * 0.8 - 2.5).to(dev).requires_grad_(True)
+    max_scalar, w_scalar, w_long = 0.2, 10.0, 5.0
+    big = torch.where(torch.exp(ls) > max_scalar)[0]
+    assert 100 < big.numel() < P
+    sel = torch.exp(ls.index_select(0, big))
+    reg_scalar = (sel.max(1)[0] - max_scalar).sum()
+    reg_long = (sel.max(1)[0] - sel.min(1)[0]).mean()
+    (w_long * reg_long + w_scalar * reg_scalar).backward()
+    grad = torch.full((P, 3), 0.25, device=dev)          # the kernel ADDS to what the rasterizer wrote
+    terms = torch.zeros(8, device=dev)
+    _lib.check(L.gsb_scale_regulariser(P, ls.data_ptr(), max_scalar, w_scalar, w_long, grad.data_ptr(), terms.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream))
+    t = to_np(terms)
+    assert abs(t[0] - float(reg_scalar.detach())) <= 1e-4 * abs(float(reg_scalar.detach()))
+    assert abs(t[1] - float(reg_long.detach())) <= 1e-4 * abs(float(reg_long.detach()))
+    assert int(t[2]) == big.numel()
+    assert rel_to_scale(to_np(grad) - 0.25, to_np(ls.grad)) <= 1e-5
+    # nothing selected: gradients untouched, reg_long is NaN exactly as torch's mean over an empty selection
+    grad.fill_(0.25)
+    _lib.check(L.gsb_scale_regulariser(P, ls.data_ptr(), 1e9, w_scalar, w_long, grad.data_ptr(), terms.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream))
+    assert float(grad.min()) == 0.25 and float(grad.max()) == 0.25 and np.isnan(to_np(terms)[1]) and to_np(terms)[0] == 0.0
+
+
+def _torch_adam(p, g, m, v, lr, t, betas=(0.9, 0.999), eps=1e-15):
+    """torch.optim.Adam's update (no amsgrad / weight decay), on explicit state tensors."""
+    m.lerp_(g, 1 - betas[0])
+    v.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+    bc1, bc2 = 1 - betas[0] ** t, 1 - betas[1] ** t
+    p.addcdiv_(m, (v.sqrt() / bc2 ** 0.5).add_(eps), value=-lr / bc1)
+
+
+def test_map_grows_and_shrinks_like_cat_and_index_select():
+    """A map that grows across keyframes (Render::AddGaussian -> Gaussian::AddGaussianPoints -> CatTensorToOptimizer,
+    src/Render.cc:557-594, src/Gaussian.cc:50-95, 241-258) and is pruned (RemoveLowOpcitiesGaussian / RemovePoints, :193-239):
+    MapOptimizer's arenas against a torch restatement that cats / index_selects every parameter tensor and Adam moment and
+    shares ONE step counter (new rows start with zero moments at the current step), fed the same gradients."""
+    import torch
+    from gsorb_slam_b200.distributed import GROUPS
+    from gsorb_slam_b200.mapping import DEFAULT_LR, MapOptimizer
+    from gsorb_slam_b200.scene import make_scene
+    dev = torch.device("cuda:0")
+    W, H, fx, fy = 160, 120, 130.0, 128.0
+    sc = make_scene(6000, (W, H, fx, fy), seed=21, scale_mul=2.0)
+    cam = sc.cam
+    sc.means3D[sc.means3D[:, 0] > 0.15 * np.abs(sc.means3D[:, 2]), 2] = -1.0   # nothing maps the right part of the view yet
+    mo = MapOptimizer(sc.means3D, sc.colors, sc.logit_opacities, sc.log_scales, sc.unnorm_quats, width=W, height=H,
+                      tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, projmatrix=cam.projmatrix, device=dev)   # capacity = P: must grow
+    key = {"means": "means", "rgb": "rgb", "opacity": "opacity", "scales": "scales", "quats": "quats"}
+    shadow = {n: mo.params[n].clone() for n, _ in GROUPS}
+    sm = {n: torch.zeros_like(shadow[n]) for n in shadow}
+    sv = {n: torch.zeros_like(shadow[n]) for n in shadow}
+    t = 0
+    Tcw = torch.eye(4, device=dev)
+    dL = torch.from_numpy(sc.dL_dpix).to(dev)
+
+    def one_step():
+        nonlocal t
+        mo.render(Tcw)
+        mo.backward(dL)
+        grads = {n: mo.grads[n].clone() for n, _ in GROUPS}
+        mo.adam()
+        t += 1
+        for n, _ in GROUPS:
+            _torch_adam(shadow[n], grads[n], sm[n], sv[n], DEFAULT_LR[n], t)
+
+    def check():
+        assert mo.P == shadow["means"].shape[0]
+        for n, _ in GROUPS:
+            assert rel_to_scale(to_np(mo.params[n]), to_np(shadow[n])) <= 2e-6, n
+            assert rel_to_scale(to_np(mo.exp_avg[n]), to_np(sm[n])) <= 2e-6, n
+            assert rel_to_scale(to_np(mo.exp_avg_sq[n]), to_np(sv[n])) <= 2e-6, n
+
+    for _ in range(3):
+        one_step()
+    check()
+    # ---- keyframe 1: densify where the silhouette is weak (a synthetic "sensor" frame) ----
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    gt_depth = (torch.rand(H, W, generator=gen) * 3 + 1).to(dev)
+    gt_depth[::7, ::5] = 0.0                                                   # invalid sensor pixels are never back-projected
+    gt_color = torch.rand(3, H, W, generator=gen).to(dev)
+    color, depth_sil, _, _ = mo.render_fused(Tcw)
+    mask = mo.add_mask(color, depth_sil, gt_depth)
+    # numpy restatement of Render.cc:557-583
+    c, ds, gd = to_np(color), to_np(depth_sil), to_np(gt_depth)
+    gray = (c[0] * 299 + c[1] * 587 + c[2] * 114) / 1000
+    diff = np.abs(gd - ds[0])
+    small = (diff < 0.05) & (gd > 0) & (ds[0] > 0)
+    th = max(0.01, float(diff[small].sum() / small.sum() + 0.5 * np.sort(diff[small])[(small.sum() - 1) // 2])) if small.any() else 0.01
+    want = ((~(ds[1] > 0.99)) & (gray < 50 / 255.0) & (diff > th)) | (ds[1] < 0.8)
+    np.testing.assert_array_equal(to_np(mask) >= 250, want)
+    P0 = mo.P
+    added = mo.densify(Tcw, gt_color, gt_depth, fx, fy, (W - 1) / 2.0, (H - 1) / 2.0, mask=mask)
+    assert added == int((want & (gd > 0)).sum()) and added > 100 and mo.P == P0 + added and mo.capacity >= mo.P
+    new = {n: mo.params[n][P0:].clone() for n, _ in GROUPS}
+    assert float(new["opacity"].min()) == 1.0 and float(new["quats"][:, 0].min()) == 1.0 and float(new["quats"][:, 1:].abs().max()) == 0.0
+    for n, _ in GROUPS:   # CatTensorToOptimizer: parameters cat'ed, moments cat'ed with zeros
+        shadow[n] = torch.cat([shadow[n], new[n]], 0)
+        sm[n] = torch.cat([sm[n], torch.zeros_like(new[n])], 0)
+        sv[n] = torch.cat([sv[n], torch.zeros_like(new[n])], 0)
+    check()
+    for _ in range(3):
+        one_step()
+    check()
+    # ---- prune: sigmoid(logit) < 0.005 (force a few hundred rows below it) ----
+    mo.params["opacity"][::17] = -9.0
+    shadow["opacity"][::17] = -9.0
+    keep = ~(torch.sigmoid(shadow["opacity"][:, 0]) < 0.005)
+    removed = mo.prune_low_opacity(0.005)
+    assert removed == int((~keep).sum()) and removed > 100
+    idx = keep.nonzero().squeeze(1)
+    for n, _ in GROUPS:
+        shadow[n], sm[n], sv[n] = shadow[n].index_select(0, idx), sm[n].index_select(0, idx), sv[n].index_select(0, idx)
+    check()
+    for _ in range(2):
+        one_step()
+    check()
+    # a second densification fits the arena that the first one grew (no reallocation)
+    cap = mo.capacity
+    mo.add_gaussians(new["means"][:50], new["rgb"][:50], new["opacity"][:50], new["scales"][:50], new["quats"][:50])
+    assert mo.capacity == cap
+    one_step_ok = mo.render(Tcw)[0]
+    assert bool(torch.isfinite(one_step_ok).all())
+
+
+def test_map_optimizer_grows_the_binning_blob_instead_of_truncating():
+    """a frame with more tile instances than the binning capacity must not be rendered truncated.  Large splats
+    (about 20 instances per Gaussian) against the default 4 P + 4096 capacity: every entry point notices the overflow latch,
+    grows the blob and renders again; results equal those of an optimizer sized generously from the start."""
+    import torch
+    from gsorb_slam_b200.mapping import MapOptimizer
+    from gsorb_slam_b200.scene import make_scene
+    dev = torch.device("cuda:0")
+    W, H = 160, 120
+    sc = make_scene(3000, (W, H, 130.0, 128.0), seed=31, scale_mul=8.0)
+    cam = sc.cam
+    mk = lambda mr: MapOptimizer(sc.means3D, sc.colors, sc.logit_opacities, sc.log_scales, sc.unnorm_quats, width=W, height=H,
+                                 tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, projmatrix=cam.projmatrix, device=dev, max_rendered=mr,
+                                 scene_radius=1.0)
+    small, big = mk(None), mk(1 << 20)
+    Tcw = torch.eye(4, device=dev)
+    gt_c = torch.rand(3, H, W, device=dev)
+    gt_d = torch.rand(H, W, device=dev) * 4 + 0.5
+    for _ in range(2):
+        la = small.step_slam(Tcw, gt_c, gt_d)
+        lb = big.step_slam(Tcw, gt_c, gt_d)
+    assert small.overflow_retries >= 1 and big.overflow_retries == 0
+    assert rel_to_scale(to_np(la), to_np(lb)) <= 1e-5
+    assert rel_to_scale(to_np(small.params.flat), to_np(big.params.flat)) <= 1e-6
+    # the regularisers were active (scale_mul 8 puts many scales above 0.1 * scene_radius)
+    assert float(small.reg_terms[2]) > 0
