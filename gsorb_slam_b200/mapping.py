@@ -25,6 +25,16 @@ from .distributed import BLOCK_ROWS, GROUPS, GradBlock, SymmetricExchange, allre
 DEFAULT_LR = {"means": 1e-4, "rgb": 2.5e-3, "quats": 1e-3, "opacity": 0.05, "scales": 1e-3}
 
 
+def keyframe_batch_hyperparameters(G: int, lr: Optional[Dict[str, float]] = None, betas=(0.9, 0.999)):
+    """Optimiser settings for the G-rank keyframe-batch shard (one G-view minibatch Adam step instead of G single-view steps,
+    SURVEY.md 8e): gradients AVERAGED over the ranks, learning rates x G / 2, betas -> betas ** G (the moment averages then
+    forget over the same number of FRAMES).  Measured by tools/minibatch_parity.py (profiles/r02_minibatch_parity.json, 200 k
+    Gaussians, 16 training / 4 held-out views, 480 frames): held-out PSNR +0.014 dB against the reference's sequential
+    schedule at G = 8 (x G instead of x G / 2: +0.19 dB); unscaled settings lose 4.1 dB."""
+    lr = dict(DEFAULT_LR if lr is None else lr)
+    return {k: v * max(1.0, G / 2.0) for k, v in lr.items()}, (betas[0] ** G, betas[1] ** G)
+
+
 class MapOptimizer:
     """The Gaussian map of one rank and its optimiser state, resident on the GPU as ARENAS (``GradBlock`` with a capacity):
     parameters, gradients and both Adam moments can grow in place (``add_gaussians``, ``densify``) and shrink
@@ -372,15 +382,14 @@ class MapOptimizer:
         self._exchange_and_adam(average)
         return color, depth_sil
 
-    def step_slam(self, Tcw: torch.Tensor, gt_color: torch.Tensor, gt_depth: torch.Tensor, lambda_: float = 0.8,
-                  w_image: float = 1.0, w_depth: float = 0.7, w_surdepth: float = 0.35, average: bool = False):
-        """One complete mapping iteration of Render::RenderForFrame (src/Render.cc:420-476) without a single torch op on the
-        hot path: prologue -> ONE five-channel rasterization -> fused L1 + SSIM + depth loss and its gradient
-        (gsb_mapping_loss) -> summed backward -> prologue backward -> scale regularisers (:462-469, when ``scene_radius`` is
-        set) -> exchange -> Adam.  Weights default to Examples/RGB-D/replica.yaml:89-94.  Returns the 8 loss terms (device
-        tensor: l1, ssim, depth_l1, surdepth_l1, total of the pixel terms, n_valid, n_valid_sur, 0); ``reg_terms`` holds the
-        regularisers.  The forward's overflow latch is read once (the host waits for the FORWARD only, with the loss and the
-        backward already queued behind it): an overflowing frame is redone with a larger binning blob before Adam."""
+    def slam_gradients(self, Tcw: torch.Tensor, gt_color: torch.Tensor, gt_depth: torch.Tensor, lambda_: float = 0.8,
+                       w_image: float = 1.0, w_depth: float = 0.7, w_surdepth: float = 0.35):
+        """The gradient half of a mapping iteration (src/Render.cc:420-470) without a single torch op on the hot path:
+        prologue -> ONE five-channel rasterization -> fused L1 + SSIM + depth loss and its gradient (gsb_mapping_loss) ->
+        summed backward -> prologue backward, into ``grads``.  The forward's overflow latch is read once (the host waits for
+        the FORWARD only, with the loss and the backward already queued behind it): an overflowing frame is redone with a
+        larger binning blob.  Returns the 8 loss terms (device tensor: l1, ssim, depth_l1, surdepth_l1, total of the pixel
+        terms, n_valid, n_valid_sur, 0)."""
         L = self.L
         self._Tcw = Tcw.to(self.dev, torch.float32).contiguous()
         if not hasattr(self, "_loss_scratch"):
@@ -401,9 +410,17 @@ class MapOptimizer:
             self.backward_fused(self._gC, self._gD, z_attached=True)
             if not self._overflowed():
                 break
+        return self.loss_terms
+
+    def step_slam(self, Tcw: torch.Tensor, gt_color: torch.Tensor, gt_depth: torch.Tensor, lambda_: float = 0.8,
+                  w_image: float = 1.0, w_depth: float = 0.7, w_surdepth: float = 0.35, average: bool = False):
+        """One complete mapping iteration of Render::RenderForFrame (src/Render.cc:420-476): ``slam_gradients`` -> scale
+        regularisers (:462-469, when ``scene_radius`` is set; ``reg_terms``) -> exchange -> Adam.  Weights default to
+        Examples/RGB-D/replica.yaml:89-94."""
+        terms = self.slam_gradients(Tcw, gt_color, gt_depth, lambda_, w_image, w_depth, w_surdepth)
         self.add_scale_regularisers()
         self._exchange_and_adam(average)
-        return self.loss_terms
+        return terms
 
     def step(self, Tcw: torch.Tensor, loss_grad: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], average: bool = False):
         """One optimisation step on this rank's keyframe.  ``loss_grad(color, depth) -> dL/dcolor``."""
