@@ -133,6 +133,115 @@ def algorithmic_bytes(P, V, R, HW):
     }
 
 
+SECONDARY = ["tum_100000", "cfg2_500k_pose", "cfg3_2m", "cfg4_5m", "dense_1m", "culled_1m", "headline_1m_raster", "quantised_1m"]
+SECONDARY_WHAT = {"tum_100000": "BASELINE config #1: 100 k @640x480", "cfg2_500k_pose": "config #2: 500 k @640x480, camera-pose backward (gsb_pose_grad) in the step",
+                  "cfg3_2m": "config #3: 2 M @1200x680 (one GPU's share of the keyframe-batch shard)", "cfg4_5m": "config #4: 5 M @1296x968 (whole frame on one GPU)",
+                  "dense_1m": "headline map, 3x larger splats", "culled_1m": "headline map, 35 % outside the frustum",
+                  "headline_1m_raster": "headline map in raster (creation) order", "quantised_1m": "InitWorld-like map: quantised depths, raster order"}
+
+
+def secondary_workloads(L, dev, flush, steps):
+    """ms per device-resident fwd+bwd frame of every other workload (CUDA events per step, L2 flushed between steps), ours."""
+    import torch
+    from gsorb_slam_b200 import _lib
+    from gsorb_slam_b200.lowlevel import frame_from_scene
+    from gsorb_slam_b200.scene import CONFIGS, make_config, make_large_case
+    out = {}
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    for name in SECONDARY:
+        sc, extra = (make_config(name), {}) if (name in CONFIGS or name.endswith("_raster")) else make_large_case(name)
+        P = sc.P
+        R0 = frame_from_scene(sc, device=dev).rendered()
+        mr = max(4 * P + 4096, R0 + 4096)
+        fr = frame_from_scene(sc, device=dev, sync_free=True, max_rendered=mr)
+        g = fr.alloc_grads()
+        go = fr._grads[1]
+        dL = torch.from_numpy(sc.dL_dpix).to(dev)
+        mw = torch.from_numpy(extra["means_world"]).to(dev) if "means_world" in extra else None
+        dT = torch.empty((3, 4), dtype=torch.float32, device=dev)
+
+        def step():
+            _lib.check(L.gsb_forward_ws(C.byref(fr._args), fr.geom.data_ptr(), fr.geom.numel(), fr.binning.data_ptr(), fr.binning.numel(),
+                                        mr, fr.img.data_ptr(), fr.img.numel(), fr.color.data_ptr(), fr.depth.data_ptr(), fr.radii.data_ptr(), stream))
+            _lib.check(L.gsb_backward(C.byref(fr._args), -1, fr.radii.data_ptr(), fr.geom.data_ptr(), fr.binning.data_ptr(),
+                                      fr.img.data_ptr(), dL.data_ptr(), C.byref(go), stream))
+            if mw is not None:
+                _lib.check(L.gsb_pose_grad(P, mw.data_ptr(), g["dL_dmean3D"].data_ptr(), dT.data_ptr(), stream))
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); step(); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ms = float(np.median([a.elapsed_time(b) for a, b in evs]))
+        out[name] = {"what": SECONDARY_WHAT[name], "gaussians": P, "image": f"{sc.cam.width}x{sc.cam.height}", "num_rendered": int(R0),
+                     "visible": int((fr.radii > 0).sum().item()), "ms_per_frame": ms, "frames_per_s": 1000.0 / ms, "steps": steps}
+        del fr, g, go, dL, mw
+        torch.cuda.empty_cache()
+    # simple_knn (distCUDA2, src/spatial.cu:15-27) on one point per pixel of a 640x480 frame -- what InitWorld hands it
+    from gsorb_slam_b200.scene import make_scene
+    pts = torch.from_numpy(make_scene(307_200, "tum", seed=7).means3D).to(dev)
+    outk = torch.empty(pts.shape[0], dtype=torch.float32, device=dev)
+    nb = int(L.gsb_knn_workspace_bytes(pts.shape[0]))
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    knn = lambda: _lib.check(L.gsb_knn_mean_dist2(pts.shape[0], pts.data_ptr(), outk.data_ptr(), ws.data_ptr(), nb, stream))
+    for _ in range(3):
+        knn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        knn()
+    b.record()
+    torch.cuda.synchronize()
+    out["knn_307200"] = {"what": "gsb_knn_mean_dist2 (SimpleKNN::knn behind distCUDA2), 307 200 points", "ms_per_call": a.elapsed_time(b) / steps}
+    return out
+
+
+def secondary_workloads_reference(steps):
+    """The same table through the UNMODIFIED reference kernels (its adapter's call pattern), for the reference arm."""
+    import torch
+    from gsorb_slam_b200.scene import CONFIGS, make_config, make_large_case, make_scene
+    from oracle import gs_ref
+    out = {}
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    for name in SECONDARY:
+        sc, _ = (make_config(name), {}) if (name in CONFIGS or name.endswith("_raster")) else make_large_case(name)
+        fr = gs_ref.frame_from_scene(sc, run=False)
+        dL = torch.from_numpy(sc.dL_dpix).cuda()
+        for _ in range(5):
+            fr.forward(); fr.backward(dL)
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fr.forward(); fr.backward(dL); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ms = float(np.median([a.elapsed_time(b) for a, b in evs]))
+        out[name] = {"what": SECONDARY_WHAT[name].replace(" (gsb_pose_grad) in the step", " left to autograd (not in this number)"),
+                     "gaussians": sc.P, "image": f"{sc.cam.width}x{sc.cam.height}", "num_rendered": int(fr.num_rendered),
+                     "ms_per_frame": ms, "frames_per_s": 1000.0 / ms, "steps": steps}
+        del fr, dL
+        torch.cuda.empty_cache()
+    pts = make_scene(307_200, "tum", seed=7).means3D
+    for _ in range(2):
+        gs_ref.knn_mean_dist2(pts)
+    p = torch.from_numpy(pts).cuda()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        gs_ref.knn_mean_dist2(p)
+    b.record()
+    torch.cuda.synchronize()
+    out["knn_307200"] = {"what": "SimpleKNN::knn, 307 200 points (its own allocations and synchronisations included)", "ms_per_call": a.elapsed_time(b) / steps}
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -519,6 +628,10 @@ def run_ours(args):
                      "two_pass_ms": ms_two, "fused_five_channel_ms": ms_fused, "iterations_per_s_two_pass": 1000.0 / ms_two,
                      "iterations_per_s_fused": 1000.0 / ms_fused, "steps": it_steps}
 
+    # ---- the other BASELINE.json configs and the stress variants of the headline map: device-resident fwd+bwd per frame ----
+    workloads = None
+    if world == 1 and not args.no_workloads:
+        workloads = secondary_workloads(L, dev, flush, min(args.steps, 10))
     clk.__exit__(None, None, None)
     # ---- cpu baseline (rank 0, N = 1 only) ----
     cpu = None
@@ -563,6 +676,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if iteration is not None:
             line["mapping_iteration"] = iteration
+        if workloads is not None:
+            line["workloads"] = workloads
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -795,6 +910,7 @@ def run_reference(args):
                          "api": "reference call pattern of src/Rasterizer.cu:136-297 fed from pinned host tensors, one frame at a time "
                                 "(its forward blocks on num_rendered)"},
                     clocks=clk.summary(),
+                    workloads=None if args.no_workloads else secondary_workloads_reference(min(args.steps, 10)),
                     cpu_baseline={"value": 1000.0 / ms, "unit": UNIT, "cores": 1, "kind": "reference",
                                   "sample": "unmodified reference CUDA kernels (oracle/_ref/libgsref.so, sm_100a build) on the same GPU, "
                                             "driven like src/Rasterizer.cu:136-297; 1 host thread"})
@@ -832,6 +948,7 @@ def main():
                     help="N > 1: keyframe-batch shard (weak scaling, the default metric) or tile-row shard of ONE frame (strong scaling)")
     ap.add_argument("--pose-only", action="store_true", help="--shard tile_row: exchange dL/dTcw only (tracking iteration)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the table of the other BASELINE configs / stress variants")
     ap.add_argument("--max-rendered", type=int, default=0, help="binning capacity in tile instances (default 4 P + 4096)")
     ap.add_argument("--graph", action="store_true", help="N = 1: capture the frame into a CUDA graph and time replays")
     ap.add_argument("--quick", action="store_true", help="developer mode: value + per-stage times only (no e2e / cpu legs)")
