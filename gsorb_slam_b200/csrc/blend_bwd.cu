@@ -248,6 +248,10 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
                           cudaStream_t s)
 {
     if (p.W <= 0 || p.H <= 0 || p.P <= 0) return GSB_OK;
+#ifdef GSB_TUNING   // developer builds only: the two-phase experiment (blend_bwd_twophase.cu)
+    static const bool twophase = [] { const char* e = getenv("GSB_BLEND_BWD"); return e && e[0] == 't'; }();
+    if (twophase) return launch_blend_backward_twophase(p, geom, GL, binning, image, IL, dL_dpix, dL_ddepth_sil, s);
+#endif
     GSB_CUDA_CHECK(cudaMemsetAsync(geom + GL.acc, 0, (size_t)p.P * sizeof(GradAcc), s));
     if (p.band_y1 <= p.band_y0) return GSB_OK;   // empty tile-row band: all-zero accumulators
     // tuning knobs: CTA shape (whole tile / half tile), resident CTAs per SM the compiler must allow (the register

@@ -372,6 +372,9 @@ int launch_blend_forward(const FwdParams& p, char* geom, const GeomLayout& GL, c
 int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, const char* binning,
                           const char* image, const ImageLayout& IL, const float* dL_dpix, const float* dL_ddepth_sil,
                           cudaStream_t s);
+int launch_blend_backward_twophase(const FwdParams& p, char* geom, const GeomLayout& GL, const char* binning,
+                                   const char* image, const ImageLayout& IL, const float* dL_dpix, const float* dL_ddepth_sil,
+                                   cudaStream_t s);   // tuning builds only
 int launch_gauss_backward(const FwdParams& p, const char* geom, const GeomLayout& GL, const int* radii,
                           const gsb_grad_outputs& g, float* dL_dzcolor, int z_attached, cudaStream_t s);
 int launch_prologue(int P, const float* Tcw, const float* means_world, const float* logit, const float* quats,
