@@ -744,6 +744,52 @@ def test_pose_refinement_recovers_a_perturbed_camera():
     assert err() < 0.5 * e0, (e0, err())
 
 
+def test_tracking_loop_with_orb_term_gate_and_early_exit():
+    """Render::RenderStartTraking's loop (src/Render.cc:1052-1127) through PoseOptimizer.run: photometric + depth terms from
+    the rasterizer, the ORB reprojection term with outlier matches that the chi-square gate (5.991) must drop at half the
+    budget, best pose kept, early exit on a flat loss.  The reprojection term is checked against a numpy restatement."""
+    import torch
+    from gsorb_slam_b200.mapping import MapOptimizer
+    from gsorb_slam_b200.scene import make_scene
+    from gsorb_slam_b200.tracking import PoseOptimizer, rt2T
+    W, H, fx, fy = 320, 240, 260.0, 258.0
+    sc = make_scene(60_000, (W, H, fx, fy), seed=61, scale_mul=1.6)
+    dev = torch.device("cuda:0")
+    gm = MapOptimizer(sc.means3D, sc.colors, sc.logit_opacities + 2.0, sc.log_scales, sc.unnorm_quats, width=W, height=H,
+                      tanfovx=sc.cam.tanfovx, tanfovy=sc.cam.tanfovy, projmatrix=sc.cam.projmatrix, device=dev, max_rendered=1 << 21)
+    q_true, t_true = torch.tensor([1.0, 0.0, 0.0, 0.0], device=dev), torch.zeros(3, device=dev)
+    T_true = rt2T(q_true, t_true)
+    color, depth_sil, median, _ = gm.render_fused(T_true)
+    gt_c, gt_d = color.clone(), median[0].clone()
+    # ORB matches: 300 map points in front of the camera, observed at their true projections (+ 0.3 px noise); 30 gross outliers
+    rng = np.random.default_rng(4)
+    K = np.array([[fx, 0, (W - 1) / 2.0], [0, fy, (H - 1) / 2.0], [0, 0, 1]], np.float32)
+    Xw = np.stack([rng.uniform(-1.5, 1.5, 300), rng.uniform(-1.0, 1.0, 300), rng.uniform(1.5, 5.0, 300)], 1).astype(np.float32)
+    obs = (Xw / Xw[:, 2:3]) @ K.T
+    obs = (obs[:, :2] + rng.normal(0, 0.3, (300, 2))).astype(np.float32)
+    obs[:30] += rng.uniform(20, 60, (30, 2)).astype(np.float32)
+    inv_sigma2 = (1.0 / 1.2 ** (2 * rng.integers(0, 4, 300))).astype(np.float32)
+    po = PoseOptimizer(gm, [1.0, 0.004, -0.006, 0.003], [0.02, -0.015, 0.01], lr_quat=1e-3)
+    po.set_features(K, Xw, obs, inv_sigma2)
+    # the term itself, against numpy, at the starting pose
+    T0 = po.pose().detach()
+    Xc = Xw @ to_np(T0)[:3, :3].T + to_np(T0)[:3, 3]
+    e = ((Xc / Xc[:, 2:3]) @ K.T)[:, :2] - obs
+    want = (e * e).sum(1) * inv_sigma2
+    assert rel_to_scale(to_np(po.reprojection(T0)), want) <= 1e-5
+    err = lambda T: float((T - T_true).abs().max())
+    e0 = err(T0)
+    T_best, best_loss, n = po.run(gt_c, gt_d, iters=80, w_image=0.7, w_depth=1.0, w_feature=0.1)
+    assert 1 <= n <= 80 and np.isfinite(best_loss)
+    inl = to_np(po.features["inlier"])
+    assert n <= 40 or (not inl[:30].any() and inl[30:].mean() > 0.9), "the gate drops the gross outliers and keeps the good matches"
+    assert err(T_best) < 0.6 * e0, (e0, err(T_best))
+    # early exit: a pose that already explains the frame stops at once and is not moved
+    po2 = PoseOptimizer(gm, to_np(q_true), to_np(t_true), lr_quat=1e-3)
+    _, _, n2 = po2.run(gt_c, gt_d, iters=50, w_feature=0.0, tol=1e9)
+    assert n2 == 1 and torch.equal(po2.q.detach(), q_true) and torch.equal(po2.t.detach(), t_true)
+
+
 def test_scale_regularisers_match_torch_autograd():
     """gsb_scale_regulariser against the literal torch expressions of src/Render.cc:462-469 (where / index_select / max / min /
     mean over the rows selected once per exceeding axis) and their autograd."""
