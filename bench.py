@@ -255,6 +255,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     sc = make_rank_scene(args.workload, rank)
@@ -432,11 +433,12 @@ def run_ours(args):
     else:
         class _Slot:
             pass
-        xs = torch.cuda.Stream(device=dev)   # exchange stream
+        # one stream per DIRECTION (a stream that alternates uploads and downloads gets little of the link's duplex bandwidth:
+        # tools/pcie_pipe_probe.py), one for the kernels, one for the exchange; events chain a frame through them
+        s_up, s_k, xs, s_dn = (torch.cuda.Stream(device=dev) for _ in range(4))
         slots = []
         for k in range(E2E_DEPTH):
             sl = _Slot()
-            sl.stream = torch.cuda.Stream(device=dev)
             sl.fr = frame_from_scene(sc, device=dev, sync_free=True, max_rendered=max_rendered, run=False)
             sl.fr._alloc_ws()
             sl.dL = torch.empty_like(dL)
@@ -447,46 +449,56 @@ def run_ours(args):
             sl.g.dL_dmean2D, sl.g.dL_dconic, sl.g.dL_dcov3D, sl.g.dL_dsh = sp, sp + 12 * P, sp + 28 * P, None
             sl.out = dict(color=torch.empty((3, H, W)).pin_memory(), depth=torch.empty((1, H, W)).pin_memory(),
                           radii=torch.empty(P, dtype=torch.int32).pin_memory(), block=torch.empty(14 * P).pin_memory())
-            sl.e1, sl.e2 = torch.cuda.Event(), torch.cuda.Event()
+            sl.e_up, sl.e_k, sl.e_x, sl.e_dn = (torch.cuda.Event() for _ in range(4))
+            sl.busy = False
             slots.append(sl)
-        slot_streams = [sl.stream for sl in slots] + [xs]
+        slot_streams = [s_up, s_k, xs, s_dn]
         up_pairs = lambda f: ((f.means3D, h["means"]), (f.colors, h["colors"]), (f.opacities, h["opac"]), (f.scales, h["scales"]),
                               (f.rotations, h["rots"]), (f.bg, h["bg"]), (f.view, h["view"]), (f.proj, h["proj"]), (f.campos, h["campos"]))
 
         def e2e_submit(i):
             sl = slots[i % E2E_DEPTH]
             f = sl.fr
-            sl.stream.synchronize()   # the slot's previous frame has landed in its host buffers
-            with torch.cuda.stream(sl.stream):
+            if sl.busy:
+                sl.e_dn.synchronize()   # the slot's previous frame has landed in its host buffers
+            with torch.cuda.stream(s_up):
                 for dst, src in up_pairs(f):
                     dst.copy_(src.view(dst.shape), non_blocking=True)
                 sl.dL.copy_(h["dL"], non_blocking=True)
-                st = sl.stream.cuda_stream
+                sl.e_up.record(s_up)
+            s_k.wait_event(sl.e_up)
+            with torch.cuda.stream(s_k):
+                st = s_k.cuda_stream
                 _lib.check(L.gsb_forward_ws(C.byref(f._args), f.geom.data_ptr(), f.geom.numel(), f.binning.data_ptr(), f.binning.numel(),
                                             max_rendered, f.img.data_ptr(), f.img.numel(), f.color.data_ptr(), f.depth.data_ptr(),
                                             f.radii.data_ptr(), st))
                 _lib.check(L.gsb_backward(C.byref(f._args), -1, f.radii.data_ptr(), f.geom.data_ptr(), f.binning.data_ptr(),
                                           f.img.data_ptr(), sl.dL.data_ptr(), C.byref(sl.g), st))
-                sl.e1.record(sl.stream)
-                sl.out["color"].copy_(f.color, non_blocking=True)
-                sl.out["depth"].copy_(f.depth, non_blocking=True)
-                sl.out["radii"].copy_(f.radii, non_blocking=True)
-            xs.wait_event(sl.e1)
+                sl.e_k.record(s_k)
+            xs.wait_event(sl.e_k)
             with torch.cuda.stream(xs):
                 if xch is not None:
                     xch.allreduce(sl.block, use_multicast=use_mc)
                 else:
                     dist.all_reduce(sl.block)
-                sl.e2.record(xs)
-            sl.stream.wait_event(sl.e2)
-            with torch.cuda.stream(sl.stream):
+                sl.e_x.record(xs)
+            s_dn.wait_event(sl.e_k)
+            with torch.cuda.stream(s_dn):
+                sl.out["color"].copy_(f.color, non_blocking=True)
+                sl.out["depth"].copy_(f.depth, non_blocking=True)
+                sl.out["radii"].copy_(f.radii, non_blocking=True)
+                s_dn.wait_event(sl.e_x)
                 sl.out["block"].copy_(sl.block, non_blocking=True)
+                sl.e_dn.record(s_dn)
+            sl.busy = True
 
         def e2e_drain():
             for sl in slots:
-                sl.stream.synchronize()
+                if sl.busy:
+                    sl.e_dn.synchronize()
+                    sl.busy = False
         e2e_api = (f"pinned host buffers -> gsb_forward_ws + gsb_backward -> exchange ({xch_kind}) -> download of the reduced block; "
-                   f"{E2E_DEPTH} frames in flight per rank")
+                   f"{E2E_DEPTH} frames in flight per rank, one stream per copy direction")
         e2e_probe = lambda: (slots[0].out["color"], slots[0].out["block"])
 
     def e2e_run(steps):
@@ -698,6 +710,7 @@ def run_tile_row(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     sc = make_rank_scene(args.workload, 0)      # the same keyframe on every rank

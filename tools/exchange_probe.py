@@ -34,4 +34,13 @@ for it in range(15):
     if it >= 5: ts.append(a.elapsed_time(b))
 t = torch.tensor([sum(ts) / len(ts)], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0: print(f"nccl: {float(t)*1000:.1f} us")
+# odd P: the [14, P] block is not a whole number of 16-byte words; allreduce rounds up into the zero padding alloc reserved
+P_odd = 100_003
+X2 = SymmetricExchange(14 * P_odd + 8, dev)
+blk2 = X2.alloc(14 * P_odd)
+src2 = torch.randn(14 * P_odd, device=dev, generator=g)
+ref2 = src2.clone(); dist.all_reduce(ref2)
+blk2.copy_(src2); X2.allreduce(blk2, use_multicast=False); torch.cuda.synchronize()
+err2 = float((blk2 - ref2).abs().max())
+if rank == 0: print(f"p2p-oddP: max|err| vs NCCL {err2:.3e}, identical across ranks True, n = {14 * P_odd}")
 dist.destroy_process_group()
