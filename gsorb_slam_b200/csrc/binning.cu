@@ -793,24 +793,31 @@ int launch_binning(const FwdParams& p, char* geom, const GeomLayout& GL, char* b
     {
         StageTimer _t(ST_TILE_SORT, s);
         // per-tile sort engine: comparator network; the shared-memory radix sort on the same 32-bit keys is a developer option
-        bool radix = GSB_DEFAULT_TILE_RADIX;
 #ifdef GSB_TUNING
-        static const bool radix_env = [] { const char* e = getenv("GSB_TILE_SORT"); return e ? e[0] == 'r' : GSB_DEFAULT_TILE_RADIX; }();
-        radix = radix_env;
+        static const bool radix = [] { const char* e = getenv("GSB_TILE_SORT"); return e ? e[0] == 'r' : GSB_DEFAULT_TILE_RADIX; }();
+#else
+        constexpr bool radix = false;
 #endif
-        if (radix) tile_sort_small_kernel<true><<<tiles, TSORT_THREADS, 0, s>>>(ranges, pairs, point_list);
-        else tile_sort_small_kernel<false><<<tiles, TSORT_THREADS, 0, s>>>(ranges, pairs, point_list);
-        GSB_LAUNCH_CHECK();
-        if (grid_instances > TSORT_SMALL) {   // a longer tile list is only possible then
-            const int g = tiles < NUM_SMS ? tiles : NUM_SMS;
-            if (radix) {
+        const int g = tiles < NUM_SMS ? tiles : NUM_SMS;
+#ifdef GSB_TUNING
+        if (radix) {
+            tile_sort_small_kernel<true><<<tiles, TSORT_THREADS, 0, s>>>(ranges, pairs, point_list);
+            GSB_LAUNCH_CHECK();
+            if (grid_instances > TSORT_SMALL) {
                 GSB_SET_ATTR_ONCE(tile_sort_mid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSORT_MID * 4);
                 tile_sort_mid_kernel<true><<<g, 1024, TSORT_MID * 4, s>>>(ranges, pairs, point_list, tiles, hdr);
-            } else {
+                GSB_LAUNCH_CHECK();
+            }
+        }
+#endif
+        if (!radix) {
+            tile_sort_small_kernel<false><<<tiles, TSORT_THREADS, 0, s>>>(ranges, pairs, point_list);
+            GSB_LAUNCH_CHECK();
+            if (grid_instances > TSORT_SMALL) {   // a longer tile list is only possible then
                 GSB_SET_ATTR_ONCE(tile_sort_mid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSORT_MID * 4);
                 tile_sort_mid_kernel<false><<<g, 1024, TSORT_MID * 4, s>>>(ranges, pairs, point_list, tiles, hdr);
+                GSB_LAUNCH_CHECK();
             }
-            GSB_LAUNCH_CHECK();
         }
     }
     return GSB_OK;

@@ -17,12 +17,11 @@
 //     into one 48-byte packed accumulator per Gaussian, and only for splats that touched at
 //     least one pixel of the block; the four quarters of a warp work on four different splats
 //     at once;
-//   * no cull pass at all: the forward pass records, per window of 32 list entries and per 4x2
-//     block, the bit mask of the entries that were blended into at least one pixel of the block
-//     ("hit words", BinningLayout::hits).  The backward stages the 256 hit words of a batch with
-//     the records (one 4-byte cp.async per thread) and every quarter-warp walks exactly the
-//     entries that hit ITS block, back to front -- 25 % fewer (block, splat) visits than the
-//     conservative footprint test and no per-batch ballots;
+//   * no cull pass at all: the forward pass records, per window of 32 list entries and per PIXEL, the bit mask of the
+//     entries that were blended into the pixel ("hit words", BinningLayout::hits).  The backward ORs the eight words of a
+//     4x2 block into the block's word while it stages a batch (two LDG.128 per thread) and every quarter-warp walks
+//     exactly the entries that hit ITS block, back to front -- 25 % fewer (block, splat) visits than the conservative
+//     footprint test and no per-batch ballots;
 //   * the walk starts at the tile's highest n_contrib (recorded by the forward pass), not at
 //     the end of the tile's list;
 //   * records are gathered with cp.async into a ring of shared-memory buffers with one CTA
@@ -254,25 +253,12 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
 #endif
     GSB_CUDA_CHECK(cudaMemsetAsync(geom + GL.acc, 0, (size_t)p.P * sizeof(GradAcc), s));
     if (p.band_y1 <= p.band_y0) return GSB_OK;   // empty tile-row band: all-zero accumulators
-    // tuning knobs: CTA shape (whole tile / half tile), resident CTAs per SM the compiler must allow (the register
-    // budget), depth of the staging ring
-#ifdef GSB_TUNING   // developer builds only (make tune)
-    static const int halves = [] { const char* e = getenv("GSB_BLEND_BWD_HALVES"); return e ? atoi(e) : 1; }();
-    static const int minb = [] { const char* e = getenv("GSB_BLEND_BWD_MINB"); return e ? atoi(e) : 0; }();
-    static const int stages = [] { const char* e = getenv("GSB_BLEND_BWD_STAGES"); return e ? atoi(e) : 3; }();
-#else
-    constexpr int halves = 1, minb = 0, stages = 3;
-#endif
     {
         StageTimer _t(ST_BLEND_BWD, s);
 #define GSB_BWD_LAUNCH(MB, NS, HV) GSB_BWD_LAUNCH_CH(MB, NS, HV, 3, false)
 #define GSB_BWD_LAUNCH_CH(MB, NS, HV, CH, BK)                                                                                          \
     do {                                                                                                                    \
-        static const bool attr_set = [] {                                                                                   \
-            cudaFuncSetAttribute(blend_backward_kernel<MB, NS, HV, CH, BK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
-            return true;                                                                                                    \
-        }();                                                                                                                \
-        (void)attr_set;                                                                                                     \
+        GSB_SET_ATTR_ONCE((blend_backward_kernel<MB, NS, HV, CH, BK>), cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
         blend_backward_kernel<MB, NS, HV, CH, BK><<<dim3(IL.tiles_x, (p.band_y1 - p.band_y0) * HV), 256 / HV, 0, s>>>(                       \
             reinterpret_cast<const uint2*>(image + IL.ranges), binning, reinterpret_cast<const SplatRec*>(geom + GL.rec), p.W, \
             p.H, p.background, reinterpret_cast<const float*>(image + IL.final_T),                                          \
@@ -281,11 +267,11 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
             reinterpret_cast<const uint32_t*>(image + IL.hits_tail),                                                        \
             reinterpret_cast<const GeomHeader*>(geom + GL.header), (uint32_t)p.band_y0);                                                       \
     } while (0)
-#ifdef GSB_TUNING
+#ifdef GSB_TUNING   // developer builds only (make tune): CTA shape (whole / half tile), register budget, staging depth, staging engine
+        static const int halves = [] { const char* e = getenv("GSB_BLEND_BWD_HALVES"); return e ? atoi(e) : 1; }();
+        static const int minb = [] { const char* e = getenv("GSB_BLEND_BWD_MINB"); return e ? atoi(e) : 0; }();
+        static const int stages = [] { const char* e = getenv("GSB_BLEND_BWD_STAGES"); return e ? atoi(e) : 3; }();
         static const bool bulk = [] { const char* e = getenv("GSB_BLEND_STAGE"); return e ? e[0] == 'b' : GSB_DEFAULT_BULK; }();
-#else
-        constexpr bool bulk = GSB_DEFAULT_BULK;
-#endif
         if (dL_ddepth_sil) {
             if (bulk) GSB_BWD_LAUNCH_CH(4, 3, 1, 5, true); else GSB_BWD_LAUNCH_CH(4, 3, 1, 5, false);
         } else if (bulk && halves == 1 && stages != 2 && minb != 3) {
@@ -297,6 +283,11 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
             if (stages == 2) { if (minb == 3) GSB_BWD_LAUNCH(3, 2, 1); else GSB_BWD_LAUNCH(4, 2, 1); }
             else { if (minb == 3) GSB_BWD_LAUNCH(3, 3, 1); else GSB_BWD_LAUNCH(4, 3, 1); }
         }
+#else
+        // whole-tile CTAs, 4 resident per SM, three-deep cp.async (LDGSTS) staging ring: the measured best
+        if (dL_ddepth_sil) GSB_BWD_LAUNCH_CH(4, 3, 1, 5, false);
+        else GSB_BWD_LAUNCH_CH(4, 3, 1, 3, false);
+#endif
 #undef GSB_BWD_LAUNCH
 #undef GSB_BWD_LAUNCH_CH
         GSB_LAUNCH_CHECK();

@@ -22,14 +22,15 @@
 // NVLink traffic per rank and direction: n * 4 bytes (+ 1/world) with multicast -- every rank's copy
 // travels to the switch once and the reduced block comes back once (56 + 7 MB at 1 M Gaussians on
 // 8 GPUs) -- against 2 * (world-1)/world * n * 4 for a ring or P2P all-reduce (98 MB).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace gsb {
 
 constexpr int XCH_MAX_WORLD = 16;
-constexpr int XCH_CTAS = 2 * NUM_SMS;   // all co-resident (a CTA spins on its peers)
+constexpr int XCH_MAX_CTAS = 8 * NUM_SMS;   // handshake slots (all CTAs of a launch are co-resident: a CTA spins on its peers)
+constexpr int XCH_CTAS = 2 * NUM_SMS;
 constexpr int XCH_THREADS = 256;
-constexpr int XCH_UNROLL = 4;
 
 struct XchPtrs {
     float* peer[XCH_MAX_WORLD];      // this rank's mapping of every rank's block (own included)
@@ -74,7 +75,7 @@ __device__ __forceinline__ void pairwise_barrier(const XchPtrs& X, int rank, int
     __syncthreads();
 }
 
-template <bool MULTIMEM>
+template <bool MULTIMEM, int XCH_UNROLL>
 __global__ void __launch_bounds__(XCH_THREADS)
 exchange_allreduce_kernel(XchPtrs X, float* __restrict__ mc, long long n4, int rank, int world)
 {
@@ -137,7 +138,7 @@ extern "C" {
 size_t gsb_exchange_sync_bytes(int world)
 {
     (void)world;
-    return (size_t)XCH_CTAS * XCH_MAX_WORLD * sizeof(uint32_t);
+    return (size_t)XCH_MAX_CTAS * XCH_MAX_WORLD * sizeof(uint32_t);
 }
 
 int gsb_exchange_allreduce(void* multicast_ptr, void* const* peer_ptrs, void* const* sync_ptrs, long long n, int rank,
@@ -165,10 +166,22 @@ int gsb_exchange_allreduce(void* multicast_ptr, void* const* peer_ptrs, void* co
     cudaStream_t s = (cudaStream_t)stream;
     {
         StageTimer _t(ST_OTHER, s);
-        if (multicast_ptr)
-            exchange_allreduce_kernel<true><<<XCH_CTAS, XCH_THREADS, 0, s>>>(X, static_cast<float*>(multicast_ptr), n / 4, rank, world);
-        else
-            exchange_allreduce_kernel<false><<<XCH_CTAS, XCH_THREADS, 0, s>>>(X, nullptr, n / 4, rank, world);
+        int ctas = XCH_CTAS, unroll = 4;
+#ifdef GSB_TUNING   // developer builds only
+        const char* e1 = getenv("GSB_XCH_CTAS_PER_SM");   // read on every call: a probe sweeps them inside one process
+        const char* e2 = getenv("GSB_XCH_UNROLL");
+        const int ctas_env = e1 ? atoi(e1) : 2, unroll_env = e2 ? atoi(e2) : 4;
+        ctas = (ctas_env < 1 ? 1 : ctas_env > 8 ? 8 : ctas_env) * NUM_SMS;
+        unroll = unroll_env;
+#endif
+        float* mc = static_cast<float*>(multicast_ptr);
+#define GSB_XCH(MM, U) exchange_allreduce_kernel<MM, U><<<ctas, XCH_THREADS, 0, s>>>(X, mc, n / 4, rank, world)
+        if (multicast_ptr) {
+            if (unroll == 2) GSB_XCH(true, 2); else if (unroll == 8) GSB_XCH(true, 8); else GSB_XCH(true, 4);
+        } else {
+            if (unroll == 2) GSB_XCH(false, 2); else if (unroll == 8) GSB_XCH(false, 8); else GSB_XCH(false, 4);
+        }
+#undef GSB_XCH
         GSB_LAUNCH_CHECK();
     }
     return GSB_OK;

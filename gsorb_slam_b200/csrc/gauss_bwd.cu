@@ -278,14 +278,13 @@ int launch_gauss_backward(const FwdParams& p, const char* geom, const GeomLayout
     {
         StageTimer _t(ST_GAUSS_BWD, s);
         // 4 resident CTAs (64 registers, small spill) hide more memory latency than 3 (80 registers): measured, round 1
-        int minb = 4;
 #ifdef GSB_TUNING
-        static const int minb_env = [] { const char* e = getenv("GSB_GAUSS_BWD_MINB"); return e ? atoi(e) : 4; }();
-        minb = minb_env;
-#endif
+        static const int minb = [] { const char* e = getenv("GSB_GAUSS_BWD_MINB"); return e ? atoi(e) : 4; }();
         if (minb == 3) gauss_backward_kernel<3><<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(q);
         else if (minb == 5) gauss_backward_kernel<5><<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(q);
-        else gauss_backward_kernel<4><<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(q);
+        else
+#endif
+        gauss_backward_kernel<4><<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(q);
         GSB_LAUNCH_CHECK();
     }
     return GSB_OK;

@@ -251,10 +251,8 @@ int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, char
     {
         StageTimer _t(ST_PREPROCESS, s);
         // resident CTAs per SM the compiler must allow (the kernel is latency bound: occupancy against registers): 8, measured
-        int minb = 8;
 #ifdef GSB_TUNING
-        static const int minb_env = [] { const char* e = getenv("GSB_PREPROCESS_MINB"); return e ? atoi(e) : 8; }();
-        minb = minb_env;
+        static const int minb = [] { const char* e = getenv("GSB_PREPROCESS_MINB"); return e ? atoi(e) : 8; }();
 #endif
 #define GSB_PRE_LAUNCH(MB)                                                                                                \
     preprocess_kernel<MB><<<GL.num_blocks, PRE_THREADS, 0, s>>>(                                                          \
@@ -263,7 +261,10 @@ int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, char
         reinterpret_cast<uint32_t*>(image + IL.tile_count), reinterpret_cast<uint8_t*>(geom + GL.clamped),                \
         al(p.means3D), al(p.scales), al(p.colors_precomp), reinterpret_cast<uint2*>(image + IL.ranges),                 \
         reinterpret_cast<uint32_t*>(image + IL.tile_cursor), reinterpret_cast<GeomHeader*>(geom + GL.header), capacity)
-        if (minb == 6) GSB_PRE_LAUNCH(6); else if (minb == 5) GSB_PRE_LAUNCH(5); else GSB_PRE_LAUNCH(8);
+#ifdef GSB_TUNING
+        if (minb == 6) GSB_PRE_LAUNCH(6); else if (minb == 5) GSB_PRE_LAUNCH(5); else
+#endif
+        GSB_PRE_LAUNCH(8);
 #undef GSB_PRE_LAUNCH
         GSB_LAUNCH_CHECK();
     }
