@@ -83,12 +83,14 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
     }
     float bg_dot_dpixel = __ldg(bg) * d0 + __ldg(bg + 1) * d1 + __ldg(bg + 2) * d2;
     if (CH == 5) bg_dot_dpixel += __ldg(bg) * d3 + __ldg(bg + 1) * d4;   // the depth pass blends over the same background tensor
-    float ar3 = 0.f, ar4 = 0.f, lc3 = 0.f, lc4 = 0.f;
     const float d8k = (CH == 5 && (l8 & 4)) ? d3 : d2, d8s = (l8 & 4) ? d2 : d3;   // keep / send factors of sums 8 and 9
     const float dk = (l8 & 4) ? d1 : d0, ds = (l8 & 4) ? d0 : d1;   // stage-1 keep / send factors of the colour sums
     // accumulator slot of the sum lane l8 ends up with (GradAcc layout: {Su dx, Su dy, Su dx^2, Su dxdy, Su dy^2, Su, Sw dr, Sw dg, Sw db})
     const int acc_slot = l8 == 0 ? 0 : l8 == 1 ? 2 : l8 == 2 ? 3 : l8 == 3 ? 6 : l8 == 4 ? 1 : l8 == 5 ? 4 : l8 == 6 ? 5 : 7;
-    float ar0 = 0.f, ar1 = 0.f, ar2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
+    // Colour seen behind the current splat, as ONE scalar: s = dL/dpix . (sum of c_j alpha_j T_j over the splats j already walked)
+    // + T_final bg . dL/dpix.  With T_k(1 - alpha_k) = T_after the reference's T_k (c_k - accum_rec) . dL/dpix - T_final/(1 - alpha_k) bg . dL/dpix
+    // (backward.cu:505-535: per-channel accum_rec / last_color recurrences) equals (T_k c_k . dL/dpix - s) / (1 - alpha_k).
+    float s_behind = T_final * bg_dot_dpixel;
     // last window (of 32 list entries) in which this quarter-warp's 4x2 block blended anything: the forward
     // pass wrote hit words for every window up to it
     int qmax = last_contributor;
@@ -142,6 +144,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
         // own last hit window (wq_last); negative = nothing for this quarter in the batch
         const int wtop = min(min(BLEND_BATCH / 32 - 1, (n - 1 - kb * BLEND_BATCH) >> 5), wq_last - kb * (BLEND_BATCH / 32));
         auto fetch = [&](int wv) -> uint32_t { return s_hits[buf][wv * BLOCKS + lwarp * 4 + q]; };
+        const int e_last = last_contributor - kb * BLEND_BATCH;   // slots [0, e_last) of this batch are at or before this pixel's last contributor
         int wi = max(wtop, 0);
         uint32_t mask = wtop >= 0 ? fetch(wi) : 0u;
         {
@@ -149,10 +152,11 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
                 if (mask == 0u && wi > wi_lo) mask = fetch(--wi);   // this quarter moves on to its next window (one per iteration)
                 if (!__any_sync(0xffffffffu, mask != 0u || wi > wi_lo)) break;   // nothing queued and no window left, in any quarter
                 const bool act = mask != 0;
-                const int eb = act ? 31 - __clz(mask) : 0;
+                uint32_t eb;                                   // highest queued entry; FLO yields 0xffffffff for an empty mask -> entry 31 (read, not used)
+                asm("bfind.u32 %0, %1;" : "=r"(eb) : "r"(mask));
+                eb &= 31u;
                 mask &= ~(1u << eb);
-                const int e = wi * 32 + eb;
-                const int pos = kb * BLEND_BATCH + e + 1;  // 1-based list position
+                const int e = wi * 32 + (int)eb;           // slot of the batch; 1-based list position = kb * BLEND_BATCH + e + 1
                 const float4 A = S.A(buf, e);
                 const float4 B = S.B(buf, e);
                 const float4 Cc = S.C(buf, e);
@@ -161,38 +165,23 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
                 // Branch-free body: a lane that does not contribute carries u = wc = 0 through the sums and
                 // leaves its recurrences untouched (with exact hit words nearly every visit has contributors,
                 // so skipping the arithmetic for an all-idle warp is not worth the divergence bookkeeping).
-                const float G = expf(fminf(power, 0.0f));
+                // exp by one FMUL + MUFU.EX2 (relative error < 1e-6; gradients carry a 1e-3 tolerance).  No alpha >= 1/255 test: the record's
+                // power threshold A.w is exact (preprocess.cu), so `power >= A.w` IS the forward's decision -- it must be repeated exactly,
+                // one flipped pair shifts T by 0.4 % for every splat in front of it at that pixel -- whatever the exponential's rounding.
+                const float G = ex2_approx(power * 1.4426950408889634f);
                 const float alpha = fminf(0.99f, __fmul_rn(B.w, G));
-                const bool contrib = act && pos <= last_contributor && !(power > 0.0f) && !(power < A.w) && !(alpha < 1.0f / 255.0f);
+                const bool contrib = act && e < e_last && !(power > 0.0f) && !(power < A.w);
                 const float inv = rcp_approx(1.0f - alpha);                 // 1 / (1 - alpha), one MUFU.RCP
                 const float Tn = T * inv;                                   // T_before = T_after / (1 - alpha)
-                const float om = 1.f - last_alpha;
-                const float a0 = fmaf(last_alpha, lc0, om * ar0);           // colour accumulated behind this splat
-                const float a1 = fmaf(last_alpha, lc1, om * ar1);
-                const float a2 = fmaf(last_alpha, lc2, om * ar2);
-                float chan = fmaf(Cc.x - a0, d0, fmaf(Cc.y - a1, d1, (Cc.z - a2) * d2));
-                float a3 = 0.f, a4 = 0.f;
-                if (CH == 5) {
-                    a3 = fmaf(last_alpha, lc3, om * ar3);
-                    a4 = fmaf(last_alpha, lc4, om * ar4);
-                    chan = fmaf(Cc.w - a3, d3, fmaf(1.0f - a4, d4, chan));
-                }
-                float dL_dalpha = Tn * chan;
-                dL_dalpha = fmaf(-T_final * inv, bg_dot_dpixel, dL_dalpha);
+                float cd = fmaf(Cc.x, d0, fmaf(Cc.y, d1, Cc.z * d2));       // c_k . dL/dpix
+                if (CH == 5) cd = fmaf(Cc.w, d3, cd + d4);                  // colours z_cam and 1 of the depth / silhouette pass
+                const float dL_dalpha = fmaf(T, cd, -s_behind) * inv;
                 // raw moments of u = G * dL/dalpha; the conic / opacity / 0.5 W factors are per-Gaussian
                 // constants and are applied once, in gauss_bwd.cu
                 const float u = contrib ? G * dL_dalpha : 0.f;
                 const float wc = contrib ? alpha * Tn : 0.f;                // d colour_out / d colour_splat
-                if (contrib) {
-                    T = Tn;
-                    ar0 = a0; ar1 = a1; ar2 = a2;
-                    lc0 = Cc.x; lc1 = Cc.y; lc2 = Cc.z;
-                    if (CH == 5) {
-                        ar3 = a3; ar4 = a4;
-                        lc3 = Cc.w; lc4 = 1.0f;
-                    }
-                    last_alpha = alpha;
-                }
+                s_behind = contrib ? fmaf(cd, wc, s_behind) : s_behind;   // a select, not wc = 0: an idle lane may have read a stale (non-finite) record
+                T = contrib ? Tn : T;
                 const uint32_t cb = __ballot_sync(0xffffffffu, contrib);
                 if (cb == 0) continue;
                 // Reduce-scatter of the 8 sums {S u dx, S u dx^2, S u dx dy, S w d_r | S u dy, S u dy^2, S u, S w d_g}
@@ -281,7 +270,7 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
             else { if (minb == 8) GSB_BWD_LAUNCH(8, 3, 2); else if (minb == 10) GSB_BWD_LAUNCH(10, 3, 2); else GSB_BWD_LAUNCH(6, 3, 2); }
         } else {
             if (stages == 2) { if (minb == 3) GSB_BWD_LAUNCH(3, 2, 1); else GSB_BWD_LAUNCH(4, 2, 1); }
-            else { if (minb == 3) GSB_BWD_LAUNCH(3, 3, 1); else GSB_BWD_LAUNCH(4, 3, 1); }
+            else { if (minb == 3) GSB_BWD_LAUNCH(3, 3, 1); else if (minb == 5) GSB_BWD_LAUNCH(5, 3, 1); else GSB_BWD_LAUNCH(4, 3, 1); }
         }
 #else
         // whole-tile CTAs, 4 resident per SM, three-deep cp.async (LDGSTS) staging ring: the measured best

@@ -25,6 +25,7 @@
 //     cp.async per record; one CTA barrier per batch, ids prefetched one batch ahead of the copies);
 //   * CH = 5 blends the depth / silhouette pass of the same iteration in the same walk.
 #include <cstdlib>
+#include <cstddef>
 #include "common.cuh"
 #include "stage.cuh"
 
@@ -69,15 +70,28 @@ __device__ __forceinline__ uint32_t bit_mask(int pos, int width)
     return d;
 }
 
-// The CTA's shared memory, in ONE struct so that the order is fixed: the walk forms record addresses from
-// "entry = 32 window + ffs(mask) - 1", which is -1 for a lane that has nothing to pop -- a[0][-1] must be mapped memory
-// (the value is never used).
+// The CTA's shared memory, in ONE struct so that the order is fixed: a lane with nothing to pop forms the address of "entry 32" of
+// its window (FLO of an empty mask is -1), i.e. the first record of the next window or, past the last buffer, the start of the
+// next array of the struct -- mapped memory either way (the value is never used).
 template <int NS>
 struct FwdSmem {
-    uint32_t guard[4];   // a[0][-1]
     StageRing<NS, BLEND_THREADS, false> ring;
+    uint32_t box[NS][BLEND_THREADS];   // per staged entry: 16-bit column mask | 16-bit row mask << 16 of its footprint box inside the tile
     uint32_t max_contrib;
 };
+
+__device__ __forceinline__ float4 lds128(uint32_t addr)   // 32-bit shared-window address: register + immediate, no generic-address arithmetic
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 
 // CH = 3: the reference pass.  CH = 5: the RGB pass and the depth / silhouette pass of one mapping iteration
 // (src/Render.cc:445-448: colours [r, g, b] and [z_cam, 1, 0] over the SAME geometry) blended together; channel 3
@@ -106,8 +120,7 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     const int px = bx0 + (int)(lane & 7), py = by0 + (int)(lane >> 3);
     const bool inside = px < W && py < H;
     float pxf = (float)px, pyf = (float)py;
-    int rx0 = bx0, ry0 = by0;
-    asm volatile("" : "+f"(pxf), "+f"(pyf), "+r"(rx0), "+r"(ry0));   // stay in registers (not re-derived from the thread id per window)
+    asm volatile("" : "+f"(pxf), "+f"(pyf));   // stay in registers (not re-derived from the thread id per window)
     if (tid == 0) {
         SM.max_contrib = 0;
         if (blockIdx.x == 0 && blockIdx.y == 0) hdr->layout_capacity = layout_capacity;  // the backward pass locates the hit words with it
@@ -131,9 +144,30 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     uint32_t id_next = NS - 1 < batches ? load_id(NS - 1) : 0xffffffffu;
     bool warp_done = __all_sync(0xffffffffu, done != 0);
     const TransposeConsts transpose(lane);
+    // 32-bit shared-window addresses of the ring (a[0][0]) and of the box words; b[] and c[] sit NS * BATCH * 16 bytes apart
+    const uint32_t sa0 = (uint32_t)__cvta_generic_to_shared(&S.a[0][0]), sbox0 = (uint32_t)__cvta_generic_to_shared(&SM.box[0][0]);
+    constexpr uint32_t OFF_B = NS * BATCH * 16, OFF_C = 2 * NS * BATCH * 16;
+    static_assert(offsetof(FwdSmem<NS>, box) == sizeof(StageRing<NS, BLEND_THREADS, false>), "box[] must follow the ring (see FwdSmem)");
+    const int tile_x0 = blockIdx.x * TILE_X, tile_y0 = tile_y * TILE_Y;
+    uint32_t cshift = (warp & 1) * 8, rshift = 16 + (warp >> 1) * 4;   // this warp's 8 columns / 4 rows inside the box word
+    asm volatile("" : "+r"(cshift), "+r"(rshift));
     int buf = 0;
     for (int b = 0; b < batches; b++) {
         stage_wait(S, buf, b);  // this thread's copies of batch b have landed
+        // ---- cull, part 1 (thread = entry, once per CTA instead of once per warp): the entry's footprint box (preprocess.cu: conservative
+        // alpha >= 1/255 extents) against the tile's pixel centres -> columns [c0, c1] and rows [r0, r1] of the tile's 16 x 16 as two bit masks.
+        // Pixel column tile_x0 + c is a candidate iff A.x - e.x <= tile_x0 + c <= A.x + e.x (rows alike); an empty range gives a zero mask.
+        {
+            uint32_t bw = 0;
+            if (b * BATCH + (int)tid < n) {   // else: the slot holds a stale record of an earlier batch
+                const float4 A = S.a[buf][tid];
+                const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&A.z));
+                const int c0 = max(__float2int_ru(A.x - e.x) - tile_x0, 0), c1 = min(__float2int_rd(A.x + e.x) - tile_x0, 15);
+                const int r0 = max(__float2int_ru(A.y - e.y) - tile_y0, 0), r1 = min(__float2int_rd(A.y + e.y) - tile_y0, 15);
+                bw = bit_mask(c0, max(c1 - c0 + 1, 0)) | (bit_mask(r0, max(r1 - r0 + 1, 0)) << 16);
+            }
+            SM.box[buf][tid] = bw;
+        }
         // one barrier per batch: publishes batch b, and everyone is finished with batch b-1 (whose buffer is reused below)
         if (__syncthreads_count(warp_done) == BATCH) break;  // every pixel of the tile is saturated
         {
@@ -148,36 +182,36 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
             // hit words of the batch: rows of 256 words, window after window; the list's last, partial window has its own row
             uint32_t* hp = hits_full + ((size_t)(range.x >> 5) + (size_t)(b * WINS)) * HIT_PIXELS + tid;
             const int wtail = (n >> 5) - b * WINS;   // first window of this batch that is not a full one
-            for (int w = 0; w < nwin; w++, hp += HIT_PIXELS) {
-                const float4* const ra = &S.a[buf][w * 32];   // the window's records: a at ra[], b at ra[NS * BATCH], c at ra[2 * NS * BATCH]
-                // ---- cull: lane = splat builds the coverage word of its splat over the warp's 32 pixels; transpose ----
+            uint32_t ra = sa0 + (uint32_t)buf * (BATCH * 16);          // the window's records: a at ra, b at ra + OFF_B, c at ra + OFF_C
+            uint32_t rb = sbox0 + (uint32_t)buf * (BATCH * 4) + (31 - lane) * 4;   // lane L culls entry 31 - L (see the walk)
+            for (int w = 0; w < nwin; w++, hp += HIT_PIXELS, ra += 32 * 16, rb += 32 * 4) {
+                // ---- cull, part 2: lane = splat cuts its box word down to the warp's 8 x 4 region, multiplies the 8 column bits and 4 row bits
+                // out into the coverage word over the warp's 32 pixels, and the warp transposes the 32 x 32 bit matrix ----
                 uint32_t mask;
                 {
-                    const float4 A = ra[lane];
-                    const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&A.z));
-                    // pixel column bx0 + c is a candidate iff A.x - e.x <= bx0 + c <= A.x + e.x (rows alike): the footprint box of
-                    // preprocess.cu against pixel centres, as the round-1 block test, but per pixel.  Columns [clo, chi] of the
-                    // region's 8, rows [rlo, rhi] of its 4; an empty range gives width 0.
-                    const int clo = max(__float2int_ru(A.x - e.x) - rx0, 0), chi = min(__float2int_rd(A.x + e.x) - rx0, 7);
-                    const int rlo = max(__float2int_ru(A.y - e.y) - ry0, 0), rhi = min(__float2int_rd(A.y + e.y) - ry0, 3);
-                    const uint32_t colm = bit_mask(clo, max(chi - clo + 1, 0));
-                    const uint32_t rowm = bit_mask(rlo, max(rhi - rlo + 1, 0));
-                    uint32_t pm = ((rowm * 0x00204081u) & 0x01010101u) * colm;   // row bits spread to bytes, each byte = the column bits
-                    if (w * 32 + (int)lane >= cnt) pm = 0;   // the slot holds a stale record of an earlier batch
+                    const uint32_t bw = lds32(rb);
+                    const uint32_t colm = (bw >> cshift) & 0xffu, rowm = (bw >> rshift) & 0xfu;
+                    const uint32_t pm = ((rowm * 0x00204081u) & 0x01010101u) * colm;   // row bits spread to bytes, each byte = the column bits
                     mask = transpose(pm);
                     if (done) mask = 0;
                 }
                 // ---- walk: every lane pops ITS candidates of the window, in list order ----
                 uint32_t hits = 0;
-                const uint32_t pos0 = (uint32_t)(b * BATCH + w * 32) + 1u;
+                const uint32_t pos31 = (uint32_t)(b * BATCH + w * 32) + 32u;   // 1-based list position of the window's entry 31
+                const uint32_t ra31 = ra + 31 * 16;
+                // (the masks are bit-REVERSED: lane L took entry 31 - L of the window in the cull, so entry f is bit 31 - f and the next entry
+                // in list order is the HIGHEST set bit: one FLO instead of BREV + FLO)
                 while (__any_sync(0xffffffffu, mask != 0)) {
-                    const int f = __ffs(mask) - 1;                 // -1 for a lane with nothing to pop: reads a mapped, unused record
-                    uint32_t bit;                                  // 1 << f, 0 when f = -1 (PTX shl clamps the amount; C++ << would be undefined)
-                    asm("shl.b32 %0, 1, %1;" : "=r"(bit) : "r"(f));
+                    uint32_t h;                                    // 31 - f; 0xffffffff for a lane with nothing to pop: reads a mapped, unused record
+                    asm("bfind.u32 %0, %1;" : "=r"(h) : "r"(mask));
+                    uint32_t rbit, bit;                            // PTX shifts clamp the amount: both are 0 when h = 0xffffffff
+                    asm("shl.b32 %0, 1, %1;" : "=r"(rbit) : "r"(h));
+                    asm("shr.b32 %0, 0x80000000, %1;" : "=r"(bit) : "r"(h));   // 1 << f: the hit words keep list order
                     const bool act = mask != 0;
-                    mask ^= bit;
-                    const float4 A = ra[f];
-                    const float4 B = ra[f + NS * BATCH];           // S.b[buf][w * 32 + f]
+                    mask ^= rbit;
+                    const uint32_t re = ra31 - h * 16u;            // ra + f * 16
+                    const float4 A = lds128(re);
+                    const float4 B = lds128(re + OFF_B);
                     const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
                     const float power = splat_power(dx, dy, B.x, B.y, B.z);
                     if (act && !(power > 0.0f) && !(power < A.w)) {
@@ -189,7 +223,7 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                                 mask = 0;
                                 done = 1u;
                             } else {
-                                const float4 Cc = ra[f + 2 * NS * BATCH];   // S.c[buf][w * 32 + f]
+                                const float4 Cc = lds128(re + OFF_C);
                                 C0 = fmaf(__fmul_rn(Cc.x, alpha), T, C0);
                                 C1 = fmaf(__fmul_rn(Cc.y, alpha), T, C1);
                                 C2 = fmaf(__fmul_rn(Cc.z, alpha), T, C2);
@@ -199,7 +233,7 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                                 }
                                 if (T > 0.5f) D = Cc.w;
                                 T = test_T;
-                                last = pos0 + (uint32_t)f;
+                                last = pos31 - h;
                                 hits |= bit;
                             }
                         }

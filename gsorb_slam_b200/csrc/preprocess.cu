@@ -193,17 +193,31 @@ preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ rad
                 clamped_out[idx] = (uint8_t)cl;
             }
             const float opacity = __ldg(p.opacities + idx);
-            // Conservative cull data (never changes a result: the exact tests of forward.cu:346-356
-            // are still applied to everything that survives).
-            //   alpha >= 1/255 needs power >= -ln(255*opacity); keep a safety margin.
+            // Cull data.  The footprint extents are conservative (they never change a result: the exact tests of forward.cu:346-356 are
+            // still applied to everything that survives).  The power threshold is EXACT: thr = the smallest float p <= 0 with
+            // fmul_rn(opacity, expf(p)) >= 1/255, i.e. the reference's `alpha < 1/255 -> continue` (forward.cu:357-359) restated in
+            // power space with the very expf the blend kernels evaluate.  alpha(p) grows by >= 4 ulp per ulp of p near the threshold
+            // and expf is good to 2 ulp, so the boundary is found by stepping a few ulps from -ln(255 * opacity); the four values
+            // below it are checked as well, and should one of them pass (expf not monotonic there) the threshold moves down to it.
+            // The forward kernel keeps the alpha test (thr only saves it the exponential); the backward kernel decides by thr alone.
             const float lim = logf(255.0f * opacity);             // > 0 iff the splat can ever contribute
             float thr, ex, ey;
             if (!(lim > 0.f)) {
                 thr = 1.0f;  // power <= 0 < thr always: never contributes
                 ex = ey = 0.f;
             } else {
-                const float t2 = 2.0f * (lim * 1.002f + 0.01f);   // 2 * (-thr)
-                thr = -0.5f * t2;
+                const float t2 = 2.0f * (lim * 1.002f + 0.01f);   // 2 * (-conservative threshold)
+                auto passes = [&](uint32_t bits) { return !(__fmul_rn(opacity, expf(__uint_as_float(bits))) < 1.0f / 255.0f); };
+                uint32_t pb = __float_as_uint(-lim);              // negative floats: bits + 1 = one ulp further from zero
+                int steps = 0;
+                if (passes(pb)) {
+                    while (steps++ < 24 && passes(pb + 1)) pb++;
+                } else {
+                    do pb--; while (steps++ < 24 && !passes(pb) && (pb << 1) != 0u);
+                }
+                for (uint32_t k = 2; k <= 5 && steps <= 24; k++)
+                    if (passes(pb + k)) { pb += k; k = 1; steps++; }
+                thr = steps > 24 ? -0.5f * t2 : __uint_as_float(pb);   // search did not settle (never observed): conservative threshold
                 // bbox of {d : d^T Q d <= t2} is sqrt(t2 * (Q^-1)_ii); Q^-1 = cov2D up to fp32 rounding
                 // of the conic, hence the 2 % + 0.05 px slack.
                 ex = sqrtf(t2 * o.cov_xx) * 1.02f + 0.05f;

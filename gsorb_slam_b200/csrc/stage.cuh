@@ -137,6 +137,13 @@ __device__ __forceinline__ float rcp_approx(float x)
     return r;
 }
 
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // Row of HIT_PIXELS hit words of window w of a tile whose list is [start, start + len)
 // (see BinningLayout::hits / ImageLayout::hits_tail).
 __device__ __forceinline__ uint32_t* hit_words(uint32_t* hits_full, uint32_t* hits_tail, uint32_t tile, uint32_t start,
