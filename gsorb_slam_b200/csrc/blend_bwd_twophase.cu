@@ -303,8 +303,8 @@ blend_backward_twophase_kernel(const uint2* __restrict__ ranges, const char* __r
                 }
                 if (any) {
                     float* dst = acc + (size_t)S.ids[tid] * 12;
-                    red_add_v4(dst, m_dx, m_dy, m_dx2, m_dxdy);
-                    red_add_v4(dst + 4, m_dy2, m_u, c0, c1);
+                    red_add_v4(dst, m_dx, m_dx2, m_dxdy, c0);       // slot order of blend_bwd.cu / gauss_bwd.cu
+                    red_add_v4(dst + 4, m_dy, m_dy2, m_u, c1);
                     if (CH == 5) red_add_v4(dst + 8, c2, c3, 0.f, 0.f);
                     else atomicAdd(dst + 8, c2);
                 }

@@ -110,14 +110,15 @@ gauss_backward_kernel(GaussBwdParams q)
     //   dL/dmean2D = -0.5 W o (A X + B Y), -0.5 H o (C Y + B X);  dL/dconic = -0.5 o (XX, XY, YY);  dL/dopacity = U
     float a[9];
     if (rendered) {
-        const float X = a0.x, Y = a0.y, XX = a0.z, XY = a0.w, YY = a1.x, U = a1.y;
+        // slots (blend_bwd.cu): 0 S u dx, 1 S u dx^2, 2 S u dxdy, 3 S w d_r, 4 S u dy, 5 S u dy^2, 6 S u, 7 S w d_g, 8 S w d_b, 9 S w d_z
+        const float X = a0.x, XX = a0.y, XY = a0.z, Y = a1.x, YY = a1.y, U = a1.z;
         a[0] = -0.5f * p.W * rb.w * (rb.x * X + rb.y * Y);
         a[1] = -0.5f * p.H * rb.w * (rb.z * Y + rb.y * X);
         a[2] = -0.5f * rb.w * XX;
         a[3] = -0.5f * rb.w * XY;
         a[4] = -0.5f * rb.w * YY;
         a[5] = U;
-        a[6] = a1.z; a[7] = a1.w;
+        a[6] = a0.w; a[7] = a1.w;
         a[8] = a8;
     } else {
 #pragma unroll

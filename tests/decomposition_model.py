@@ -107,6 +107,14 @@ for t in tiles:
         cwp = np.zeros((nwin * 32, 32), bool); cwp[:wd] = cw
         lw = cwp.reshape(nwin, 32, 32).sum(1)        # [win, lane]
         tot['B'] += int(lw.max(1).sum())
+        # B with exact masks (only the pairs that pass the power test reach the walk), and B over 64-entry double windows
+        bwp0 = np.zeros((nwin * 32, 32), bool); bwp0[:wd] = (valid & alive)[:wd][:, pm]
+        tot['B_exact'] = tot.get('B_exact', 0) + int(bwp0.reshape(nwin, 32, 32).sum(1).max(1).sum())
+        n2 = (nwin + 1) // 2
+        z = np.zeros((n2 * 64, 32), bool); z[:wd] = cw
+        tot['B64'] = tot.get('B64', 0) + int(z.reshape(n2, 64, 32).sum(1).max(1).sum())
+        z = np.zeros((n2 * 64, 32), bool); z[:wd] = (valid & alive)[:wd][:, pm]
+        tot['B64_exact'] = tot.get('B64_exact', 0) + int(z.reshape(n2, 64, 32).sum(1).max(1).sum())
         lb = np.zeros((nbw * 8, 32), int); lb[:nwin] = lw
         tot['C'] += int(lb.reshape(nbw, 8, 32).sum(1).max(1).sum())
         for BS in (512, 1024, 1 << 20):
@@ -133,6 +141,18 @@ for t in tiles:
         qhb = np.zeros((nbw * 256, 4), bool); qhb[:nwin * 32] = qh
         tot['bwd_q'] += int(qhb.reshape(nbw, 256, 4).sum(1).max(1).sum())
         tot['bwd_useful'] += int(bw.sum())
+        # other lane-group shapes for the backward: (bw x bh)-pixel blocks, one block per group of bw*bh lanes, free-running per batch
+        lxw = lx[pm] % 8; lyw = ly[pm] % 4
+        for bw_, bh_ in ((2, 2), (4, 1), (2, 1), (8, 1), (4, 4), (8, 2)):
+            gid = (lyw // bh_) * (8 // bw_) + (lxw // bw_)
+            ng = (8 // bw_) * (4 // bh_)
+            gh = np.stack([bwp[:, gid == g_].any(1) for g_ in range(ng)], 1)
+            ghb = np.zeros((nbw * 256, ng), bool); ghb[:nwin * 32] = gh
+            k = 'bwd_%dx%d' % (bw_, bh_)
+            tot[k] = tot.get(k, 0) + int(ghb.reshape(nbw, 256, ng).sum(1).max(1).sum())
+            tot[k + '_visits'] = tot.get(k + '_visits', 0) + int(gh.sum())
+        tot['bwd_q_mean'] = tot.get('bwd_q_mean', 0) + qh.sum() / 4.0          # perfectly balanced quarters
+        tot['bwd_q_tile'] = tot.get('bwd_q_tile', 0) + int(qh.sum(0).max())   # free-running through the whole tile list
 nt = len(tiles)
 w = tot['warps']
 print({k: v / nt for k, v in tot.items()})
