@@ -682,6 +682,24 @@ def run_ours(args):
                         "single_frame_latency_ms": ms_e2e_single,
                         "l2": "every step's inputs arrive from host memory (no flush needed)"},
                 "gpu_launches": launches_timed, "clocks": clk.summary(), "roofline": roofline}
+        # Issue-slot view of the blend kernels (they are instruction-issue bound, not byte bound): warp instructions per launch from the
+        # committed ncu capture (profiles/ncu_inst_executed.json, smsp__inst_executed.sum) over the LIVE stage time x the SMs' issue rate
+        # (148 SMs x 4 schedulers x 1 warp instruction per clock at the clock sampled during this run), and per blended (pixel, splat) pair.
+        ip = os.path.join(ROOT, "profiles", "ncu_inst_executed.json")
+        if os.path.exists(ip) and args.workload == "headline_1m":
+            try:
+                inst = json.load(open(ip))
+                mhz = (line["clocks"] or {}).get("sm_mhz") or 1965.0
+                issue_rate = 148 * 4 * mhz * 1e6
+                blended = fr.blended_pairs()
+                roofline["issue"] = {"blended_pairs": blended, "issue_peak_warp_inst_per_s": issue_rate,
+                                     "source": "profiles/ncu_inst_executed.json (ncu smsp__inst_executed.sum per launch) / live CUDA-event stage times"}
+                for k in ("blend_forward", "blend_backward"):
+                    if k in inst and k in stages:
+                        roofline["issue"][k] = {"warp_inst": inst[k], "issue_frac": inst[k] / (stages[k]["ms_per_step"] * 1e-3 * issue_rate),
+                                                "warp_inst_per_blended_pair": inst[k] / max(1, blended)}
+            except Exception as e:   # a stale or missing capture must not void the bench line
+                roofline["issue"] = {"error": repr(e)}
         if exchange_checked is not None:
             line["exchange_checked"] = exchange_checked
         if cpu is not None:

@@ -70,6 +70,7 @@ SIGNATURES = {
     "gsb_forward_backward_host": (_ll, [C.POINTER(RasterArgs), _ll, _vp, _vp, _vp, _vp, C.POINTER(GradOutputs), _vp, _sz, _vp]),
     "gsb_forward_backward_host_async": (_i, [C.POINTER(RasterArgs), _ll, _vp, _vp, _vp, _vp, C.POINTER(GradOutputs), _vp, _sz, _vp, _vp]),
     "gsb_debug_image_state": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "gsb_debug_blended_pairs": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "gsb_debug_binning_state": (_i, [_vp, _vp, _ll, _vp, _vp]),
     "gsb_debug_geometry_state": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "gsb_launch_count_reset": (_ll, []),

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <vector>
 #include "common.cuh"
+#include "stage.cuh"
 
 namespace gsb {
 
@@ -139,6 +140,27 @@ static int forward_stage2(const FwdParams& p, char* geom, const GeomLayout& GL, 
 {
     if (int rc = launch_binning(p, geom, GL, binning, BL, image, IL, grid_instances, s)) return rc;
     return launch_blend_forward(p, geom, GL, binning, BL, image, IL, out_color, out_depth, out_depth_sil, s);
+}
+
+// one CTA per tile, one thread per pixel in the blend kernels' pixel order (warp = 8x4 region, lane = row-major pixel of the region):
+// set bits of the pixel's hit words over the windows up to its last contributor
+__global__ void __launch_bounds__(BLEND_THREADS)
+count_blended_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ hits_tail,
+                     const char* __restrict__ binning, const GeomHeader* __restrict__ hdr, int W, int H, unsigned long long* __restrict__ count)
+{
+    const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int px = blockIdx.x * TILE_X + (warp & 1) * 8 + (lane & 7), py = blockIdx.y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
+    const uint2 range = ranges[tile];
+    const BinningLayout BL = BinningLayout::make((long long)hdr->layout_capacity);
+    uint32_t* hits_full = reinterpret_cast<uint32_t*>(const_cast<char*>(binning) + BL.hits);
+    unsigned long long c = 0;
+    if (px < W && py < H) {
+        const uint32_t last = n_contrib[(size_t)py * W + px];
+        for (uint32_t w = 0; w * 32 < last; w++)
+            c += __popc(hit_words(hits_full, const_cast<uint32_t*>(hits_tail), tile, range.x, range.y - range.x, w)[tid]);
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0 && c) atomicAdd(count, c);
 }
 
 __global__ void unpack_geometry_kernel(int P, const SplatRec* __restrict__ rec, const int* __restrict__ radii,
@@ -587,6 +609,23 @@ int gsb_debug_image_state(const void* image, int width, int height, float* final
     if (final_T) GSB_CUDA_CHECK(cudaMemcpyAsync(final_T, im + IL.final_T, HW * 4, cudaMemcpyDeviceToDevice, s));
     if (n_contrib) GSB_CUDA_CHECK(cudaMemcpyAsync(n_contrib, im + IL.n_contrib, HW * 4, cudaMemcpyDeviceToDevice, s));
     if (ranges) GSB_CUDA_CHECK(cudaMemcpyAsync(ranges, im + IL.ranges, T * 8, cudaMemcpyDeviceToDevice, s));
+    return GSB_OK;
+}
+
+int gsb_debug_blended_pairs(const void* geometry, const void* binning, const void* image, int width, int height,
+                            unsigned long long* count, gsb_stream_t stream)
+{
+    if (!geometry || !binning || !image || !count || width <= 0 || height <= 0)
+        return fail(GSB_ERR_INVALID_ARGUMENT, "debug_blended_pairs: bad arguments");
+    const ImageLayout IL = ImageLayout::make(width, height);
+    cudaStream_t s = (cudaStream_t)stream;
+    GSB_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(unsigned long long), s));
+    const char* im = (const char*)image;
+    count_blended_kernel<<<dim3(IL.tiles_x, IL.tiles_y), BLEND_THREADS, 0, s>>>(
+        reinterpret_cast<const uint2*>(im + IL.ranges), reinterpret_cast<const uint32_t*>(im + IL.n_contrib),
+        reinterpret_cast<const uint32_t*>(im + IL.hits_tail), (const char*)binning, reinterpret_cast<const GeomHeader*>(geometry),
+        width, height, count);
+    GSB_LAUNCH_CHECK();
     return GSB_OK;
 }
 

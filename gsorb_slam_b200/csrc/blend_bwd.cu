@@ -46,7 +46,7 @@ __device__ __forceinline__ void red_add_v4(float* dst, float x, float y, float z
 }
 
 template <int NS, int GL, bool BULK>
-struct BwdSmem {
+struct BwdShared {
     StageRing<NS, 256, BULK> ring;
     uint32_t ids[NS][256];
     alignas(8) uint32_t hits[NS][8 * 8 * (32 / GL)];   // [window of the batch][lane group of the tile]
@@ -70,7 +70,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
     constexpr int GROUPS = 8 * GPW;     // lane groups per tile
     // dynamic shared memory (three stages of the 2-lane variant exceed the 48 KB static limit)
     extern __shared__ __align__(16) unsigned char bwd_smem_raw[];
-    using Smem = BwdSmem<NS, GL, BULK>;
+    using Smem = BwdShared<NS, GL, BULK>;
     Smem& SM = *reinterpret_cast<Smem*>(bwd_smem_raw);
     StageRing<NS, BLEND_BATCH, BULK>& S = SM.ring;
     uint32_t (&s_ids)[NS][BLEND_BATCH] = SM.ids;
@@ -278,8 +278,8 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
 #define GSB_BWD_LAUNCH_CH(MB, NS, GLN, CH, BK)                                                                                          \
     do {                                                                                                                    \
         GSB_SET_ATTR_ONCE((blend_backward_kernel<MB, NS, GLN, CH, BK>), cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
-        GSB_SET_ATTR_ONCE((blend_backward_kernel<MB, NS, GLN, CH, BK>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem<NS, GLN, BK>)); \
-        blend_backward_kernel<MB, NS, GLN, CH, BK><<<dim3(IL.tiles_x, p.band_y1 - p.band_y0), 256, sizeof(BwdSmem<NS, GLN, BK>), s>>>(                       \
+        GSB_SET_ATTR_ONCE((blend_backward_kernel<MB, NS, GLN, CH, BK>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdShared<NS, GLN, BK>)); \
+        blend_backward_kernel<MB, NS, GLN, CH, BK><<<dim3(IL.tiles_x, p.band_y1 - p.band_y0), 256, sizeof(BwdShared<NS, GLN, BK>), s>>>(                       \
             reinterpret_cast<const uint2*>(image + IL.ranges), binning, reinterpret_cast<const SplatRec*>(geom + GL.rec), p.W, \
             p.H, p.background, reinterpret_cast<const float*>(image + IL.final_T),                                          \
             reinterpret_cast<const uint32_t*>(image + IL.n_contrib), reinterpret_cast<const uint32_t*>(image + IL.tile_max_contrib), \

@@ -179,6 +179,14 @@ class Frame:
                                                     rg.data_ptr(), self._stream()))
         return dict(final_T=fT, n_contrib=nc, ranges=rg)
 
+    def blended_pairs(self) -> int:
+        """(pixel, splat) pairs the forward pass blended (set bits of its hit words): the blend kernels' unit of work."""
+        c = torch.zeros(1, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.gsb_debug_blended_pairs(self.geom.data_ptr(), self.binning.data_ptr(), self.img.data_ptr(), self.W, self.H,
+                                                      c.data_ptr(), self._stream()))
+        return int(c.item())
+
     def binning_state(self):
         R = self.rendered()
         pl = torch.empty((R,), dtype=torch.int32, device=self.device)

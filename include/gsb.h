@@ -347,6 +347,11 @@ int gsb_forward_backward_host_async(const gsb_raster_args* host_args, long long 
 int gsb_debug_image_state(const void* image, int width, int height,
                           float* final_T, uint32_t* n_contrib, uint32_t* ranges,
                           gsb_stream_t stream);
+/* Number of (pixel, splat) pairs the last forward pass blended = set bits of the hit words it recorded (one word per
+ * 32-entry window of a tile's list and pixel), summed over every pixel's windows up to its n_contrib; `count` is one
+ * DEVICE uint64.  The measurement unit of the blend kernels (bench.py: warp-instructions per blended pair). */
+int gsb_debug_blended_pairs(const void* geometry, const void* binning, const void* image, int width, int height,
+                            unsigned long long* count, gsb_stream_t stream);
 int gsb_debug_binning_state(const void* geometry, const void* binning, long long R,
                             uint32_t* point_list, gsb_stream_t stream);
 int gsb_debug_geometry_state(const void* geometry, int P, float* depths, float* means2D,

@@ -201,3 +201,37 @@ def test_tile_row_bands_sum_to_the_full_frame(cuts, fused):
     np.testing.assert_array_equal(depth.view(np.uint32), to_np(full.depth).view(np.uint32))
     for k in g_full:
         assert rel_to_scale(g_sum[k], g_full[k]) <= 1e-5, k
+
+
+def test_blended_pair_count_matches_a_numpy_walk_of_the_oracle_lists():
+    """gsb_debug_blended_pairs (set bits of the forward's hit words) against a numpy restatement of the blend loop
+    (forward.cu:336-388: power > 0 and alpha < 1/255 skipped, stop before T(1 - alpha) < 1e-4) over the oracle's tile lists."""
+    from gsorb_slam_b200.lowlevel import frame_from_scene
+    from gsorb_slam_b200.scene import make_scene
+    from oracle import gs_oracle
+    sc = make_scene(20_000, (96, 64, 80.0, 80.0), seed=5)
+    fr = frame_from_scene(sc)
+    orc = gs_oracle.frame_from_scene(sc)
+    g, b = orc.geometry(), orc.binning()
+    W, H = sc.cam.width, sc.cam.height
+    tx = (W + 15) // 16
+    m2, co = g["means2D"], g["conic_opacity"]
+    want = 0
+    for t, (s, e) in enumerate(b["ranges"]):
+        ids = b["point_list"][s:e]
+        if len(ids) == 0:
+            continue
+        px = ((t % tx) * 16 + np.arange(16))[None, :].repeat(16, 0).reshape(-1).astype(np.float32)
+        py = ((t // tx) * 16 + np.arange(16))[:, None].repeat(16, 1).reshape(-1).astype(np.float32)
+        inside = (px < W) & (py < H)
+        dx = m2[ids, 0][:, None] - px[None]; dy = m2[ids, 1][:, None] - py[None]
+        a_, b_, c_, o_ = (co[ids, k][:, None] for k in range(4))
+        power = np.float32(-0.5) * (a_ * dx * dx + c_ * dy * dy) - b_ * dx * dy
+        alpha = np.minimum(np.float32(0.99), o_ * np.exp(power))
+        valid = (power <= 0) & (alpha >= np.float32(1.0 / 255.0))
+        T = np.cumprod(np.where(valid, 1 - alpha, 1.0), axis=0)
+        stop = valid & (T < 1e-4)
+        done = np.where(stop.any(0), stop.argmax(0), len(ids))
+        want += int((valid & (np.arange(len(ids))[:, None] < done[None]) & inside[None]).sum())
+    got = fr.blended_pairs()
+    assert abs(got - want) <= max(4, want // 100_000), (got, want)   # numpy's exp differs from expf in the last bit at the 1/255 threshold

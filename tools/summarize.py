@@ -48,6 +48,21 @@ def traffic(path):
         agg.setdefault(stage[n], []).append(b)
     return json.dumps({k: sum(v) / len(v) for k, v in agg.items()}, indent=1)
 
+def instructions(path):
+    """smsp__inst_executed.sum (warp instructions) per launch, keyed like traffic() -> profiles/ncu_inst_executed.json"""
+    import json
+    rows = list(csv.reader(open(path)))
+    hdr = rows[0]; idx = {h: i for i, h in enumerate(hdr)}
+    stage = {'preprocess_kernel': 'preprocess', 'duplicate_kernel': 'duplicate', 'tile_sort_small_kernel': 'tile_sort',
+             'blend_forward_kernel': 'blend_forward', 'blend_backward_kernel': 'blend_backward',
+             'gauss_backward_kernel': 'gauss_backward'}
+    agg = {}
+    for r in rows[2:]:
+        n = r[idx['Kernel Name']].split('(')[0].replace('void ', '').replace('gsb::', '').split('<')[0]
+        if n in stage:
+            agg.setdefault(stage[n], []).append(float(r[idx['smsp__inst_executed.sum']].replace(',', '')))
+    return json.dumps({k: sum(v) / len(v) for k, v in agg.items()}, indent=1)
+
 if __name__ == '__main__':
     cmd = sys.argv[1]
-    print(launches(sys.argv[2]) if cmd == 'launches' else traffic(sys.argv[2]) if cmd == 'traffic' else raw(sys.argv[2]))
+    print(launches(sys.argv[2]) if cmd == 'launches' else traffic(sys.argv[2]) if cmd == 'traffic' else instructions(sys.argv[2]) if cmd == 'instructions' else raw(sys.argv[2]))
