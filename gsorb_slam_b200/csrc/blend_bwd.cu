@@ -32,6 +32,9 @@
 
 namespace gsb {
 
+#ifndef GSB_BWD_SPLIT_BARRIER
+#define GSB_BWD_SPLIT_BARRIER false   // split (arrive / sync) batch barrier of the backward walk, see the kernel
+#endif
 #ifndef GSB_BWD_GROUP_LANES
 #define GSB_BWD_GROUP_LANES 4   // lanes per group of the backward walk: 4 = 2x2 pixels, 2 = 2x1 pixels
 #endif
@@ -55,7 +58,7 @@ struct BwdShared {
 // GL = lanes per group: 4 (a group owns 2x2 pixels) or 2 (2x1 pixels).  CH = 5: backward of the fused RGB + depth / silhouette pass
 // (see blend_fwd.cu): dL/dalpha sums over five channels, and the gradient of the z_cam colour (sum of w * dL/dpix[3]) lands in
 // accumulator slot 9.
-template <int MINB, int NS, int GL, int CH, bool BULK>
+template <int MINB, int NS, int GL, int CH, bool BULK, bool SPLIT>
 __global__ void __launch_bounds__(256, MINB)
 blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__ binning,
                       const SplatRec* __restrict__ rec, int W, int H, const float* __restrict__ bg,
@@ -153,24 +156,60 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
             }
         }
     };
+    // Pipeline.  SPLIT = false: batches k+1 .. k+NS-1 in flight while batch k is walked, ONE CTA barrier per batch (publishes batch k
+    // and proves everyone is finished with batch k-1, whose buffer is refilled right after it).
+    // SPLIT = true (three buffers, one batch in flight): the barrier of batch k+1 is split into an ARRIVE that a warp issues
+    // a few walk iterations into batch k -- its own copies of batch k+1, issued at the top of batch k, have landed by then -- and the
+    // SYNC at the top of batch k+1 (named barriers 1..3, one per buffer; 256 arrivals + 256 syncs per phase).  A warp that is
+    // ahead therefore only waits for the others to be a few iterations into the PREVIOUS batch, not to have finished it; buffer
+    // (k+1) % 3 = (k-2) % 3 is refilled at the top of batch k, which every thread reaches only after all warps left batch k-2.
+    static_assert(!SPLIT || (NS == 3 && !BULK), "the split barrier is written for the three-deep cp.async ring");
+    constexpr int ARRIVE_AT = 6;   // walk iterations into a batch after which a warp reports its copies of the next one
+    // (immediate barrier ids: a register operand makes ptxas reserve all 16 named barriers of the CTA)
+    auto bar_arrive = [](int b) {
+        if (b == 0) asm volatile("barrier.cta.arrive 1, 512;" ::: "memory");
+        else if (b == 1) asm volatile("barrier.cta.arrive 2, 512;" ::: "memory");
+        else asm volatile("barrier.cta.arrive 3, 512;" ::: "memory");
+    };
+    auto bar_sync = [](int b) {
+        if (b == 0) asm volatile("barrier.cta.sync 1, 512;" ::: "memory");
+        else if (b == 1) asm volatile("barrier.cta.sync 2, 512;" ::: "memory");
+        else asm volatile("barrier.cta.sync 3, 512;" ::: "memory");
+    };
     S.init();
-#pragma unroll
-    for (int i = 0; i < NS - 1; i++) {
-        if (i < batches) stage(i, i, load_id(i));
+    uint32_t id_next;
+    if (SPLIT) {
+        stage(0, 0, load_id(0));
         cp_async_commit();
+        id_next = load_id(1);
+        cp_async_wait<0>();
+        bar_arrive(0);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NS - 1; i++) {
+            if (i < batches) stage(i, i, load_id(i));
+            cp_async_commit();
+        }
+        id_next = load_id(NS - 1);
     }
-    uint32_t id_next = load_id(NS - 1);
 
     int buf = 0;
     for (int k = 0; k < batches; k++) {
-        stage_wait(S, buf, k);
-        __syncthreads();  // publishes batch k; everyone is finished with batch k-1, whose buffer is reused below
-        {
-            const int nbuf = buf == 0 ? NS - 1 : buf - 1;  // (k + NS - 1) % NS
+        const int nbuf = SPLIT ? (buf == NS - 1 ? 0 : buf + 1) : (buf == 0 ? NS - 1 : buf - 1);   // buffer of batch k + 1 / k + NS - 1
+        if (SPLIT) {
+            bar_sync(buf);   // batch k is complete; every warp is at least ARRIVE_AT iterations into batch k-1
+            if (k + 1 < batches) stage(k + 1, nbuf, id_next);
+            cp_async_commit();
+            id_next = load_id(k + 2);
+        } else {
+            stage_wait(S, buf, k);
+            __syncthreads();  // publishes batch k; everyone is finished with batch k-1, whose buffer is reused below
             if (k + NS - 1 < batches) stage(k + NS - 1, nbuf, id_next);
             cp_async_commit();
             id_next = load_id(k + NS);
         }
+        const bool report = SPLIT && k + 1 < batches;   // this warp owes the arrival for batch k + 1
+        int it = 0;
         const int kb = batches - 1 - k;
         // Every lane group walks the hit words of ITS pixels through the whole batch at its own pace (window after
         // window, back to front): the warp iterates max-over-groups of the BATCH's visit counts.
@@ -182,6 +221,11 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
         int wi = max(wtop, 0);
         uint32_t mask = wtop >= 0 ? hrow[wi * GROUPS] : 0u;
         while (true) {
+            if (report && it == ARRIVE_AT) {
+                cp_async_wait<0>();
+                bar_arrive(nbuf);
+            }
+            it++;
             if (mask == 0u && wi > 0) mask = hrow[--wi * GROUPS];   // this group moves on to its next window (one per iteration)
             if (!__any_sync(0xffffffffu, mask != 0u || wi > 0)) break;   // nothing queued and no window left, in any group
             const bool act = mask != 0;
@@ -257,6 +301,10 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
                 }
             }
         }
+        if (report && it <= ARRIVE_AT) {   // a short walk: report now
+            cp_async_wait<0>();
+            bar_arrive(nbuf);
+        }
         buf = buf == NS - 1 ? 0 : buf + 1;
     }
     cp_async_wait<0>();
@@ -275,11 +323,11 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
     if (p.band_y1 <= p.band_y0) return GSB_OK;   // empty tile-row band: all-zero accumulators
     {
         StageTimer _t(ST_BLEND_BWD, s);
-#define GSB_BWD_LAUNCH_CH(MB, NS, GLN, CH, BK)                                                                                          \
+#define GSB_BWD_LAUNCH_CH(MB, NS, GLN, CH, BK, SP)                                                                                          \
     do {                                                                                                                    \
-        GSB_SET_ATTR_ONCE((blend_backward_kernel<MB, NS, GLN, CH, BK>), cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
-        GSB_SET_ATTR_ONCE((blend_backward_kernel<MB, NS, GLN, CH, BK>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdShared<NS, GLN, BK>)); \
-        blend_backward_kernel<MB, NS, GLN, CH, BK><<<dim3(IL.tiles_x, p.band_y1 - p.band_y0), 256, sizeof(BwdShared<NS, GLN, BK>), s>>>(                       \
+        GSB_SET_ATTR_ONCE((blend_backward_kernel<MB, NS, GLN, CH, BK, SP>), cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
+        GSB_SET_ATTR_ONCE((blend_backward_kernel<MB, NS, GLN, CH, BK, SP>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdShared<NS, GLN, BK>)); \
+        blend_backward_kernel<MB, NS, GLN, CH, BK, SP><<<dim3(IL.tiles_x, p.band_y1 - p.band_y0), 256, sizeof(BwdShared<NS, GLN, BK>), s>>>(                       \
             reinterpret_cast<const uint2*>(image + IL.ranges), binning, reinterpret_cast<const SplatRec*>(geom + GL.rec), p.W, \
             p.H, p.background, reinterpret_cast<const float*>(image + IL.final_T),                                          \
             reinterpret_cast<const uint32_t*>(image + IL.n_contrib), reinterpret_cast<const uint32_t*>(image + IL.tile_max_contrib), \
@@ -287,18 +335,20 @@ int launch_blend_backward(const FwdParams& p, char* geom, const GeomLayout& GL, 
             reinterpret_cast<const uint32_t*>(image + IL.hits_tail),                                                        \
             reinterpret_cast<const GeomHeader*>(geom + GL.header), (uint32_t)p.band_y0);                                                       \
     } while (0)
-#define GSB_BWD_LAUNCH(MB, NS, GLN) do { if (dL_ddepth_sil) GSB_BWD_LAUNCH_CH(MB, NS, GLN, 5, false); else GSB_BWD_LAUNCH_CH(MB, NS, GLN, 3, false); } while (0)
-#ifdef GSB_TUNING   // developer builds only (make tune): lanes per group, register budget, staging depth, staging engine
+#define GSB_BWD_LAUNCH(MB, NS, GLN, SP) do { if (dL_ddepth_sil) GSB_BWD_LAUNCH_CH(MB, NS, GLN, 5, false, SP); else GSB_BWD_LAUNCH_CH(MB, NS, GLN, 3, false, SP); } while (0)
+#ifdef GSB_TUNING   // developer builds only (make tune): lanes per group, register budget, staging depth, staging engine, barrier kind
         static const int glanes = [] { const char* e = getenv("GSB_BLEND_BWD_GROUP"); return e ? atoi(e) : GSB_BWD_GROUP_LANES; }();
         static const int minb = [] { const char* e = getenv("GSB_BLEND_BWD_MINB"); return e ? atoi(e) : 4; }();
         static const int stages = [] { const char* e = getenv("GSB_BLEND_BWD_STAGES"); return e ? atoi(e) : 3; }();
         static const bool bulk = [] { const char* e = getenv("GSB_BLEND_STAGE"); return e ? e[0] == 'b' : GSB_DEFAULT_BULK; }();
-        if (bulk) { if (dL_ddepth_sil) GSB_BWD_LAUNCH_CH(4, 3, GSB_BWD_GROUP_LANES, 5, true); else GSB_BWD_LAUNCH_CH(4, 3, GSB_BWD_GROUP_LANES, 3, true); }
-        else if (glanes == 2) { if (minb == 5) GSB_BWD_LAUNCH(5, 3, 2); else if (stages == 2) GSB_BWD_LAUNCH(4, 2, 2); else GSB_BWD_LAUNCH(4, 3, 2); }
-        else { if (minb == 5) GSB_BWD_LAUNCH(5, 3, 4); else if (minb == 3) GSB_BWD_LAUNCH(3, 3, 4); else if (stages == 2) GSB_BWD_LAUNCH(4, 2, 4); else GSB_BWD_LAUNCH(4, 3, 4); }
+        static const bool split = [] { const char* e = getenv("GSB_BLEND_BWD_SPLIT"); return e ? atoi(e) != 0 : GSB_BWD_SPLIT_BARRIER; }();
+        if (bulk) { if (dL_ddepth_sil) GSB_BWD_LAUNCH_CH(4, 3, GSB_BWD_GROUP_LANES, 5, true, false); else GSB_BWD_LAUNCH_CH(4, 3, GSB_BWD_GROUP_LANES, 3, true, false); }
+        else if (glanes == 2) { if (minb == 5) GSB_BWD_LAUNCH(5, 3, 2, false); else if (stages == 2) GSB_BWD_LAUNCH(4, 2, 2, false); else GSB_BWD_LAUNCH(4, 3, 2, false); }
+        else if (split) { if (minb == 5) GSB_BWD_LAUNCH(5, 3, 4, true); else GSB_BWD_LAUNCH(4, 3, 4, true); }
+        else { if (minb == 5) GSB_BWD_LAUNCH(5, 3, 4, false); else if (minb == 3) GSB_BWD_LAUNCH(3, 3, 4, false); else if (stages == 2) GSB_BWD_LAUNCH(4, 2, 4, false); else GSB_BWD_LAUNCH(4, 3, 4, false); }
 #else
         // 4 resident CTAs per SM, three-deep cp.async (LDGSTS) staging ring: the measured best
-        GSB_BWD_LAUNCH(4, 3, GSB_BWD_GROUP_LANES);
+        GSB_BWD_LAUNCH(4, 3, GSB_BWD_GROUP_LANES, GSB_BWD_SPLIT_BARRIER);
 #endif
 #undef GSB_BWD_LAUNCH
 #undef GSB_BWD_LAUNCH_CH
