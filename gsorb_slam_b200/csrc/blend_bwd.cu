@@ -1,31 +1,33 @@
 // blend_bwd.cu -- per-tile back-to-front gradient of the alpha blend (K7) for sm_100a.
 //
 // Replaces BACKWARD::render / renderCUDA<3> (backward.cu:399-557, launch :641-656).
-// Same recurrences as the reference: start from the stored final transmittance and the
+// Same result as the reference's recurrences: start from the stored final transmittance and the
 // position of the last blended splat, walk the tile's list backwards, T <- T / (1 - alpha),
-// running "colour behind" accumulator, background term, gradients w.r.t. colour, 2D mean
+// colour accumulated behind the splat, background term, gradients w.r.t. colour, 2D mean
 // (in NDC units: x 0.5 W, x 0.5 H), conic (slots x, y, w) and opacity.  No depth gradient.
 // Per pair only u = G dL/dalpha and its first / second moments in (dx, dy) are formed; the
 // linear maps from those 6 sums to d(mean2D), d(conic), d(opacity) use per-Gaussian constants
-// and are applied once per Gaussian in gauss_bwd.cu (packed accumulator layout:
-// {S u dx, S u dy, S u dx^2, S u dx dy, S u dy^2, S u, S wc d_r, S wc d_g, S wc d_b}).
+// and are applied once per Gaussian in gauss_bwd.cu (packed accumulator layout, 12 floats:
+// {S u dx, S u dx^2, S u dx dy, S w d_r | S u dy, S u dy^2, S u, S w d_g | S w d_b, S w d_z}).
 //
 // What is different (design, not results):
-//   * the reference issues 9 global atomicAdds per contributing (pixel, splat) pair; here a
-//     QUARTER-WARP owns a 4x2 pixel block, reduces the 9 partial sums of a splat across its 8
-//     lanes with a shuffle reduce-scatter (10 SHFL) and issues two RED.ADD.F32 instructions
-//     into one 48-byte packed accumulator per Gaussian, and only for splats that touched at
-//     least one pixel of the block; the four quarters of a warp work on four different splats
-//     at once;
+//   * the reference issues 9 global atomicAdds per contributing (pixel, splat) pair; here a GROUP of 4 lanes owns a 2x2 pixel
+//     block (8 groups per warp; a 2-lane / 2x1-pixel variant is a tune-build knob), reduces the sums of a splat across its lanes
+//     with a two-stage shuffle reduce-scatter and issues one 8-byte vector RED per lane (+ one scalar RED per group) into one
+//     48-byte packed accumulator per Gaussian, and only for splats that touched at least one pixel of the block; the eight groups
+//     of a warp work on eight different splats at once (round 1 used 8-lane groups on 4x2 blocks: 128 iterations per warp and
+//     tile at the headline workload against 110 now, tests/decomposition_model.py);
+//   * the per-channel "colour behind" recurrences of the reference (accum_rec / last_color / last_alpha, 7 registers of state,
+//     ~20 instructions per pair) are ONE scalar: s = dL/dpix . (sum of c_j alpha_j T_j over the splats behind) + T_final bg . dL/dpix,
+//     with dL/dalpha_k = (T_after c_k . dL/dpix - s) / (1 - alpha_k);
 //   * no cull pass at all: the forward pass records, per window of 32 list entries and per PIXEL, the bit mask of the
-//     entries that were blended into the pixel ("hit words", BinningLayout::hits).  The backward ORs the eight words of a
-//     4x2 block into the block's word while it stages a batch (two LDG.128 per thread) and every quarter-warp walks
-//     exactly the entries that hit ITS block, back to front -- 25 % fewer (block, splat) visits than the conservative
-//     footprint test and no per-batch ballots;
-//   * the walk starts at the tile's highest n_contrib (recorded by the forward pass), not at
-//     the end of the tile's list;
-//   * records are gathered with cp.async into a ring of shared-memory buffers with one CTA
-//     barrier per batch (stage.cuh).
+//     entries that were blended into the pixel ("hit words", BinningLayout::hits).  The backward ORs the words of a group's pixels
+//     while it stages a batch (two LDG.128 per thread) and every group walks exactly the entries that hit ITS block, back to
+//     front, through the whole batch at its own pace;
+//   * the alpha >= 1/255 decision is `power >= A.w`: preprocess.cu stores the EXACT power threshold of each Gaussian, so the
+//     exponential here can be one FMUL + MUFU.EX2 without ever disagreeing with the forward pass about which pairs were blended;
+//   * the walk starts at the tile's highest n_contrib (recorded by the forward pass), not at the end of the tile's list;
+//   * records are gathered with cp.async into a ring of shared-memory buffers with one CTA barrier per batch (stage.cuh).
 #include <cstdlib>
 #include "common.cuh"
 #include "stage.cuh"

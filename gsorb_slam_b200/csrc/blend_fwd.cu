@@ -9,15 +9,17 @@
 // Work decomposition (round 2; the round-1 kernel walked the tile list per 4x2 pixel block, four blocks in lock step
 // per warp, and issued 9.6 warp-instructions per blended pair -- 27 % of its lane slots did useful work):
 //   * one CTA per 16x16 tile, a warp owns an 8x4 pixel region, a LANE owns ONE pixel and pops ITS OWN candidates;
-//   * per window of 32 staged splats a warp builds the 32 x 32 bit matrix "splat j's conservative alpha >= 1/255
-//     footprint box covers pixel p" with lane = splat (two float->int conversions per axis, the 8-column and 4-row
-//     coverage bits multiplied out into a 32-pixel word) and TRANSPOSES it across the warp with a five-stage shuffle
-//     butterfly (two byte permutes, three rotate + bit-select stages), so that lane = pixel holds the bit mask of its
-//     own candidates in a register;
+//   * the cull is split: ONCE per CTA and batch, thread = entry turns the entry's conservative alpha >= 1/255 footprint box
+//     (preprocess.cu) into a 16-bit column mask and a 16-bit row mask over the tile (four float->int conversions per entry instead
+//     of per entry and warp); per window of 32 staged splats a warp then cuts its 8 columns / 4 rows out of the box words with
+//     lane = splat, multiplies them out into the 32 x 32 bit matrix "splat j's box covers pixel p" and TRANSPOSES it across the
+//     warp with a five-stage shuffle butterfly (two byte permutes, three rotate + bit-select stages), so that lane = pixel holds
+//     the bit mask of its own candidates in a register (bit-reversed, so that the next entry in list order is one FLO away);
 //   * every lane then pops its candidates of the window in list order; the warp iterates max-over-lanes of the
-//     per-PIXEL candidate counts (157 iterations per warp at the headline workload instead of 191 with per-block
+//     per-PIXEL candidate counts (159 iterations per warp at the headline workload instead of 195 with per-block
 //     lists; tests/decomposition_model.py).  The exact tests of forward.cu:346-362 are applied to every candidate, so
-//     results are unchanged;
+//     results are unchanged; the record's power threshold is exact (preprocess.cu), so the exponential is only evaluated
+//     for pairs that are blended (or that saturate the pixel);
 //   * the bits a lane actually blended are its hit word of the window: one word per (window, pixel), written
 //     coalesced (BinningLayout::hits / ImageLayout::hits_tail); the backward pass replays exactly those pairs and needs
 //     no alpha test;

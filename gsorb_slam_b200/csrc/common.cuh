@@ -30,8 +30,9 @@ constexpr int HIT_WINDOW = 32;                   // list entries covered by one 
 //   a = { x_pix, y_pix, half2(extent_x, extent_y), power_threshold }   <- all the cull pass reads
 //   b = { conic.x, conic.y, conic.z, opacity }
 //   c = { r, g, b, depth }
-// power_threshold: conservative lower bound on `power` below which alpha < 1/255 is
-// certain (the exact test is still applied to everything that passes).
+// power_threshold: the EXACT boundary of the alpha >= 1/255 test in power space: the smallest float p with
+// fmul_rn(opacity, expf(p)) >= 1/255 (found per Gaussian in preprocess.cu).  The forward kernel still applies the
+// reference's alpha test (the threshold only saves it the exponential); the backward kernel decides by it alone.
 // extent_x/y: conservative half-extents (pixels) of the alpha >= 1/255 footprint's bbox.
 // ---------------------------------------------------------------------------------------
 struct alignas(16) SplatRec {
@@ -39,10 +40,11 @@ struct alignas(16) SplatRec {
 };
 static_assert(sizeof(SplatRec) == 48, "record must be 48 bytes");
 
-// Packed backward accumulators (one per Gaussian, 48 bytes, fp32 atomics / vector reds):
-//   a = { dL_dmean2D.x, dL_dmean2D.y, dL_dconic.x, dL_dconic.y }
-//   b = { dL_dconic.w, dL_dopacity, dL_dcolor.r, dL_dcolor.g }
-//   c = { dL_dcolor.b, dL_dzcolor (fused 5-channel pass only), -, - }
+// Packed backward accumulators (one per Gaussian, 48 bytes, fp32 vector REDs): raw moments of u = G dL/dalpha and the
+// colour sums of w = alpha T (blend_bwd.cu); gauss_bwd.cu turns them into dL/dmean2D, dL/dconic, dL/dopacity, dL/dcolor
+//   a = { S u dx, S u dx^2, S u dx dy, S w d_r }
+//   b = { S u dy, S u dy^2, S u,       S w d_g }
+//   c = { S w d_b, S w d_z (fused 5-channel pass only), -, - }
 struct alignas(16) GradAcc {
     float4 a, b, c;
 };

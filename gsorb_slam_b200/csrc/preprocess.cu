@@ -142,6 +142,13 @@ preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ rad
     stage_float3(p.means3D, s_mean, p.P, base, aligned_means);
     if (p.scales) stage_float3(p.scales, s_scale, p.P, base, aligned_scales);
     if (p.colors_precomp) stage_float3(p.colors_precomp, s_col, p.P, base, aligned_colors);
+    // per-Gaussian loads that depend only on idx are issued before the staging barrier (the kernel is bound by memory latency)
+    float4 q_ld = make_float4(0.f, 0.f, 0.f, 1.f);
+    float opacity_ld = 0.f;
+    if (idx < p.P) {
+        if (!p.cov3D_precomp) q_ld = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+        opacity_ld = __ldg(p.opacities + idx);
+    }
     __syncthreads();
 
     uint32_t touched = 0;
@@ -153,7 +160,7 @@ preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ rad
             const float2 a = __ldg(c2), b = __ldg(c2 + 1), c = __ldg(c2 + 2);
             cov3D[0] = a.x; cov3D[1] = a.y; cov3D[2] = b.x; cov3D[3] = b.y; cov3D[4] = c.x; cov3D[5] = c.y;
         } else {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+            const float4 q = q_ld;
             compute_cov3d(s_scale[3 * threadIdx.x], s_scale[3 * threadIdx.x + 1], s_scale[3 * threadIdx.x + 2],
                           p.scale_modifier, q.x, q.y, q.z, q.w, cov3D);
         }
@@ -192,7 +199,7 @@ preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ rad
                 sh_to_rgb(p.D, p.shs + (size_t)idx * p.M * 3, mx, my, mz, p.cam_pos, rgb, cl);
                 clamped_out[idx] = (uint8_t)cl;
             }
-            const float opacity = __ldg(p.opacities + idx);
+            const float opacity = opacity_ld;
             // Cull data.  The footprint extents are conservative (they never change a result: the exact tests of forward.cu:346-356 are
             // still applied to everything that survives).  The power threshold is EXACT: thr = the smallest float p <= 0 with
             // fmul_rn(opacity, expf(p)) >= 1/255, i.e. the reference's `alpha < 1/255 -> continue` (forward.cu:357-359) restated in
