@@ -4,6 +4,7 @@
 // the fused fast path -- against the ctypes path and the reference fixtures.
 #include <torch/extension.h>
 
+#include "Exchange.h"
 #include "Rasterizer.cuh"
 
 using namespace ORB_SLAM2;
@@ -46,4 +47,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
         return GaussianRasterizer(rs).mark_visible(positions);
     });
     m.def("dist_cuda2", [](torch::Tensor points) { return distCUDA2(points, points.device()); });
+    // the C++ host of the exchange step (adapter/Exchange.h); driven by tools/exchange_probe.py under torchrun
+    py::class_<GradientExchange>(m, "GradientExchange")
+        .def(py::init([](int64_t capacity_floats, torch::Tensor like, const std::string& group_name) {
+            return new GradientExchange(capacity_floats, like.device(), group_name);
+        }))
+        .def("alloc", &GradientExchange::alloc)
+        .def("allreduce", &GradientExchange::allreduce, py::arg("t"), py::arg("use_multicast") = true)
+        .def("rank", &GradientExchange::rank)
+        .def("world_size", &GradientExchange::world_size)
+        .def("has_multicast", &GradientExchange::has_multicast);
 }

@@ -123,7 +123,7 @@ def test_libtorch_adapter_builds_and_exposes_the_reference_surface():
         pytest.skip("adapter not built (run __graft_entry__.build())")
     sys.path.insert(0, os.path.join(root, "adapter"))
     A = importlib.import_module("gsb_adapter")
-    for name in ("forward", "forward_fused", "visable", "mark_visible", "dist_cuda2"):
+    for name in ("forward", "forward_fused", "visable", "mark_visible", "dist_cuda2", "GradientExchange"):
         assert hasattr(A, name)
     src = open(os.path.join(root, "adapter", "Rasterizer.cuh")).read()
     for name in ("GaussianRasterizationSettings", "GaussianRasterizer", "_RasterizeGaussians", "rasterize_gaussians", "filter_radii",

@@ -43,4 +43,25 @@ ref2 = src2.clone(); dist.all_reduce(ref2)
 blk2.copy_(src2); X2.allreduce(blk2, use_multicast=False); torch.cuda.synchronize()
 err2 = float((blk2 - ref2).abs().max())
 if rank == 0: print(f"p2p-oddP: max|err| vs NCCL {err2:.3e}, identical across ranks True, n = {14 * P_odd}")
+# the C++ (libtorch) host of the same kernel: adapter/Exchange.{h,cc} through the pybind test harness
+try:
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "adapter"))
+    import gsb_adapter
+except Exception as e:   # the adapter is optional on a box without the built .so
+    gsb_adapter = None
+    if rank == 0: print("cpp host not available:", repr(e)[:120])
+if gsb_adapter is not None:
+    n3 = 14 * 250_001   # an odd P as well
+    Xc = gsb_adapter.GradientExchange(n3 + 8, torch.empty(1, device=dev), dist.group.WORLD.group_name)
+    blk3 = Xc.alloc(n3)
+    src3 = torch.randn(n3, device=dev, generator=g)
+    ref3 = src3.clone(); dist.all_reduce(ref3)
+    for name, mc in (("cpp-multimem", True), ("cpp-p2p", False)):
+        if mc and not Xc.has_multicast():
+            continue
+        blk3.copy_(src3); Xc.allreduce(blk3, mc); torch.cuda.synchronize()
+        err3 = float((blk3 - ref3).abs().max())
+        chk = blk3.double().sum().reshape(1); lst = [torch.empty_like(chk) for _ in range(world)]; dist.all_gather(lst, chk)
+        ident = all(float(x) == float(lst[0]) for x in lst)
+        if rank == 0: print(f"{name}: max|err| vs NCCL {err3:.3e}, identical across ranks {ident}, n = {n3}, world {Xc.world_size()}")
 dist.destroy_process_group()
