@@ -27,6 +27,12 @@ for mc in ((True, False) if X.multicast_ptr else (False,)):
             us = timed(lambda: X.allreduce(blk, use_multicast=mc))
             err = float((blk - ref).abs().max())
             if rank == 0: print(f"{'multimem' if mc else 'p2p'} ctas/sm {c} unroll {u}: {us:.1f} us, max|err| {err:.2e}", flush=True)
+# fixed cost of a launch: the two cross-rank handshakes + fence, on a 16 KB block
+small = X.buf[:4096]
+for mc in ((True, False) if X.multicast_ptr else (False,)):
+    os.environ["GSB_XCH_CTAS_PER_SM"] = "2"; os.environ["GSB_XCH_UNROLL"] = "4"
+    us = timed(lambda: X.allreduce(small, use_multicast=mc))
+    if rank == 0: print(f"{'multimem' if mc else 'p2p'} 16 KB block (handshakes + fence only): {us:.1f} us", flush=True)
 blk_n = src.clone()
 us = timed(lambda: dist.all_reduce(blk))
 if rank == 0: print(f"nccl: {us:.1f} us")
