@@ -46,43 +46,29 @@ tile_scan_kernel(const uint32_t* __restrict__ tile_count, uint2* __restrict__ ra
     tile_scan_body<SCAN_THREADS, 16>(tile_count, ranges, cursor, tiles, hdr, capacity, P);
 }
 
-// ---- K3: one thread per Gaussian writes its instances into the tile segments ---------------------
-// Slots of Gaussians touching <= 4 tiles were fixed by the counting atomics of preprocess
-// (GeomLayout::ranks): no atomics here.  Larger Gaussians claim slots in the tail of each segment.
+// ---- K3 (fallback): one thread per Gaussian writes its instances into the tile segments -----------
+// Normally there is no K3: preprocess writes every record into its tile's bucket (ImageLayout::buckets) and the tile sort reads
+// it there.  Only a frame whose longest tile list exceeds BUCKET_CAP takes this pass: every thread returns at once otherwise.
+// All instances claim their slots with cursor atomics (the segment starts come from the scan).
 __global__ void __launch_bounds__(DUP_THREADS)
-duplicate_kernel(int P, const SplatRec* __restrict__ rec, const int* __restrict__ radii, const uint4* __restrict__ ranks,
-                 const uint2* __restrict__ ranges, uint32_t* __restrict__ cursor, const GeomHeader* __restrict__ hdr,
+duplicate_kernel(int P, const SplatRec* __restrict__ rec, const int* __restrict__ radii,
+                 uint32_t* __restrict__ cursor, const GeomHeader* __restrict__ hdr,
                  uint64_t* __restrict__ pairs, int tiles_x, int tiles_y, int band_y0, int band_y1)
 {
-    const int idx = blockIdx.x * DUP_THREADS + threadIdx.x;
-    if (idx >= P) return;
-    // every load that depends only on idx is issued before the first use (the kernel is one long latency chain otherwise);
-    // records / ranks of culled Gaussians are stale bytes inside the blob: harmless to read, never used
-    const int radius = radii[idx];
-    const float4 a = rec[idx].a;
-    const float depth = rec[idx].c.w;
-    const uint4 rk4 = ranks[idx];
+    if (hdr->max_tile_len <= (uint32_t)BUCKET_CAP) return;   // grid-uniform: the normal case costs one small launch
     const uint32_t cap = hdr->num_rendered_clamped;
-    if (radius <= 0) return;
-    const uint64_t record = ((uint64_t)__float_as_uint(depth) << 32) | (uint32_t)idx;
-    uint32_t minx, miny, maxx, maxy;
-    get_rect(a.x, a.y, radius, tiles_x, tiles_y, minx, miny, maxx, maxy);
-    miny = max(miny, (uint32_t)band_y0);   // the same band clamp as preprocess (tile-row shard)
-    maxy = min(maxy, (uint32_t)band_y1);
-    if (maxy <= miny) return;
-    const uint32_t touched = (maxx - minx) * (maxy - miny);
-    if (touched <= 4) {
-        const uint32_t rk[4] = {rk4.x, rk4.y, rk4.z, rk4.w};
-        uint32_t tx = minx, ty = miny;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if ((uint32_t)k < touched) {
-                const uint32_t pos = ranges[ty * (uint32_t)tiles_x + tx].x + rk[k];
-                if (pos < cap) pairs[pos] = record;
-                if (++tx == maxx) { tx = minx; ty++; }
-            }
-        }
-    } else {
+    for (int idx = blockIdx.x * DUP_THREADS + threadIdx.x; idx < P; idx += gridDim.x * DUP_THREADS) {   // a few CTAs per SM, grid-stride
+        // records of culled Gaussians are stale bytes inside the blob: harmless to read, never used
+        const int radius = radii[idx];
+        if (radius <= 0) continue;
+        const float4 a = rec[idx].a;
+        const float depth = rec[idx].c.w;
+        const uint64_t record = ((uint64_t)__float_as_uint(depth) << 32) | (uint32_t)idx;
+        uint32_t minx, miny, maxx, maxy;
+        get_rect(a.x, a.y, radius, tiles_x, tiles_y, minx, miny, maxx, maxy);
+        miny = max(miny, (uint32_t)band_y0);   // the same band clamp as preprocess (tile-row shard)
+        maxy = min(maxy, (uint32_t)band_y1);
+        if (maxy <= miny) continue;
         for (uint32_t y = miny; y < maxy; y++)
             for (uint32_t x = minx; x < maxx; x++) {
                 const uint32_t pos = atomicAdd(&cursor[(size_t)(y * (uint32_t)tiles_x + x) * TILE_CTR_STRIDE], 1u);
@@ -392,7 +378,7 @@ __device__ __noinline__ void tile_sort_long_runs(uint64_t* __restrict__ seg, uin
 constexpr int TIE_ROUNDS = 8;   // odd-even rounds spent on neighbours whose quantised depths collide before the exact sort takes over
 
 template <int E, int THREADS, bool RADIX>
-__device__ __forceinline__ void tile_sort_class32(const uint2 r, uint64_t* __restrict__ pairs,
+__device__ __forceinline__ void tile_sort_class32(const uint2 r, uint64_t* __restrict__ seg,
                                                   uint32_t* __restrict__ point_list, uint32_t* __restrict__ s,
                                                   uint32_t* __restrict__ s_red, uint32_t* __restrict__ s_cnt)
 {
@@ -400,8 +386,7 @@ __device__ __forceinline__ void tile_sort_class32(const uint2 r, uint64_t* __res
     constexpr int IDX_BITS = (THREADS == 1024 ? 10 : 8) + LOG_E;
     constexpr int DEPTH_BITS = RADIX ? (32 - IDX_BITS < TR_QBITS ? 32 - IDX_BITS : TR_QBITS) : 32 - IDX_BITS;
     constexpr uint32_t IDX_MASK = (1u << IDX_BITS) - 1u;
-    const uint32_t n = r.y - r.x, t = threadIdx.x;
-    uint64_t* seg = pairs + r.x;
+    const uint32_t n = r.y - r.x, t = threadIdx.x;   // seg: the tile's n unsorted records (its bucket, or its segment of `pairs`)
     // depth bits of this thread's E consecutive records, tile-wide minimum and maximum
     uint32_t dep[E];
     uint32_t mn = 0xffffffffu, mx = 0u;
@@ -515,7 +500,8 @@ __device__ __forceinline__ void tile_sort_class32(const uint2 r, uint64_t* __res
 
 template <bool RADIX>
 __global__ void __launch_bounds__(TSORT_THREADS, 5)
-tile_sort_small_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list)
+tile_sort_small_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list,
+                       uint64_t* __restrict__ buckets, const GeomHeader* __restrict__ hdr)
 {
     __shared__ __align__(16) uint32_t s[TSORT_SMALL];
     __shared__ uint32_t s_red[128];
@@ -523,13 +509,15 @@ tile_sort_small_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ 
     const uint2 r = ranges[blockIdx.x];
     const uint32_t n = r.y - r.x;
     if (n == 0 || n > (uint32_t)TSORT_SMALL) return;   // longer lists: the 128 KB / global classes
+    // the tile's unsorted records: its bucket (written by preprocess) unless some list of the frame overflowed its bucket
+    uint64_t* seg = hdr->max_tile_len <= (uint32_t)BUCKET_CAP ? buckets + (size_t)blockIdx.x * BUCKET_CAP : pairs + r.x;
     const uint32_t npad = n <= 256 ? 256u : next_pow2(n);
     switch (npad) {
-        case 256: tile_sort_class32<1, TSORT_THREADS, false>(r, pairs, point_list, s, s_red, s_cnt); break;
-        case 512: tile_sort_class32<2, TSORT_THREADS, false>(r, pairs, point_list, s, s_red, s_cnt); break;
-        case 1024: tile_sort_class32<4, TSORT_THREADS, RADIX>(r, pairs, point_list, s, s_red, s_cnt); break;
-        case 2048: tile_sort_class32<8, TSORT_THREADS, RADIX>(r, pairs, point_list, s, s_red, s_cnt); break;
-        default: tile_sort_class32<16, TSORT_THREADS, RADIX>(r, pairs, point_list, s, s_red, s_cnt); break;
+        case 256: tile_sort_class32<1, TSORT_THREADS, false>(r, seg, point_list, s, s_red, s_cnt); break;
+        case 512: tile_sort_class32<2, TSORT_THREADS, false>(r, seg, point_list, s, s_red, s_cnt); break;
+        case 1024: tile_sort_class32<4, TSORT_THREADS, RADIX>(r, seg, point_list, s, s_red, s_cnt); break;
+        case 2048: tile_sort_class32<8, TSORT_THREADS, RADIX>(r, seg, point_list, s, s_red, s_cnt); break;
+        default: tile_sort_class32<16, TSORT_THREADS, RADIX>(r, seg, point_list, s, s_red, s_cnt); break;
     }
 }
 
@@ -538,7 +526,7 @@ tile_sort_small_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ 
 // the class (the launch exits at once when the frame's longest list fits the 256-thread kernel).
 template <bool RADIX>
 __global__ void __launch_bounds__(1024, 1)
-tile_sort_mid_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list,
+tile_sort_mid_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list, uint64_t* __restrict__ buckets,
                      int tiles, const GeomHeader* __restrict__ hdr)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -551,8 +539,9 @@ tile_sort_mid_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ pa
         const uint32_t n = r.y - r.x;
         if (n <= (uint32_t)TSORT_SMALL) continue;                             // the 256-thread kernel handles this tile
         __syncthreads();                                                      // previous tile's readers are done with s[]
-        if (n <= 8192u) tile_sort_class32<8, 1024, RADIX>(r, pairs, point_list, s, s_red, s_cnt);
-        else if (n <= (uint32_t)TSORT_MID) tile_sort_class32<16, 1024, RADIX>(r, pairs, point_list, s, s_red, s_cnt);
+        uint64_t* seg = hdr->max_tile_len <= (uint32_t)BUCKET_CAP ? buckets + (size_t)tile * BUCKET_CAP : pairs + r.x;
+        if (n <= 8192u) tile_sort_class32<8, 1024, RADIX>(r, seg, point_list, s, s_red, s_cnt);
+        else if (n <= (uint32_t)TSORT_MID) tile_sort_class32<16, 1024, RADIX>(r, seg, point_list, s, s_red, s_cnt);
         else {
             // more than 16384 entries in one tile (pathological inputs): the 64-bit network in place, in global memory
             tile_sort_exact64<1024>(pairs + r.x, n, point_list + r.x);
@@ -781,13 +770,13 @@ int launch_binning(const FwdParams& p, char* geom, const GeomLayout& GL, char* b
     uint64_t* pairs = reinterpret_cast<uint64_t*>(binning + BL.pairs);
     uint32_t* point_list = reinterpret_cast<uint32_t*>(binning + BL.point_list);
     const uint2* ranges = reinterpret_cast<const uint2*>(image + IL.ranges);
+    uint64_t* buckets = reinterpret_cast<uint64_t*>(image + IL.buckets);
     const int tiles = p.tiles_x * p.tiles_y;
     {
         StageTimer _t(ST_DUPLICATE, s);
-        duplicate_kernel<<<GL.num_blocks, DUP_THREADS, 0, s>>>(
+        duplicate_kernel<<<GL.num_blocks < 8 * NUM_SMS ? GL.num_blocks : 8 * NUM_SMS, DUP_THREADS, 0, s>>>(
             p.P, reinterpret_cast<const SplatRec*>(geom + GL.rec), reinterpret_cast<const int*>(geom + GL.radii),
-            reinterpret_cast<const uint4*>(geom + GL.ranks), ranges, reinterpret_cast<uint32_t*>(image + IL.tile_cursor), hdr,
-            pairs, p.tiles_x, p.tiles_y, p.band_y0, p.band_y1);
+            reinterpret_cast<uint32_t*>(image + IL.tile_cursor), hdr, pairs, p.tiles_x, p.tiles_y, p.band_y0, p.band_y1);
         GSB_LAUNCH_CHECK();
     }
     {
@@ -801,21 +790,21 @@ int launch_binning(const FwdParams& p, char* geom, const GeomLayout& GL, char* b
         const int g = tiles < NUM_SMS ? tiles : NUM_SMS;
 #ifdef GSB_TUNING
         if (radix) {
-            tile_sort_small_kernel<true><<<tiles, TSORT_THREADS, 0, s>>>(ranges, pairs, point_list);
+            tile_sort_small_kernel<true><<<tiles, TSORT_THREADS, 0, s>>>(ranges, pairs, point_list, buckets, hdr);
             GSB_LAUNCH_CHECK();
             if (grid_instances > TSORT_SMALL) {
                 GSB_SET_ATTR_ONCE(tile_sort_mid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSORT_MID * 4);
-                tile_sort_mid_kernel<true><<<g, 1024, TSORT_MID * 4, s>>>(ranges, pairs, point_list, tiles, hdr);
+                tile_sort_mid_kernel<true><<<g, 1024, TSORT_MID * 4, s>>>(ranges, pairs, point_list, buckets, tiles, hdr);
                 GSB_LAUNCH_CHECK();
             }
         }
 #endif
         if (!radix) {
-            tile_sort_small_kernel<false><<<tiles, TSORT_THREADS, 0, s>>>(ranges, pairs, point_list);
+            tile_sort_small_kernel<false><<<tiles, TSORT_THREADS, 0, s>>>(ranges, pairs, point_list, buckets, hdr);
             GSB_LAUNCH_CHECK();
             if (grid_instances > TSORT_SMALL) {   // a longer tile list is only possible then
                 GSB_SET_ATTR_ONCE(tile_sort_mid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSORT_MID * 4);
-                tile_sort_mid_kernel<false><<<g, 1024, TSORT_MID * 4, s>>>(ranges, pairs, point_list, tiles, hdr);
+                tile_sort_mid_kernel<false><<<g, 1024, TSORT_MID * 4, s>>>(ranges, pairs, point_list, buckets, tiles, hdr);
                 GSB_LAUNCH_CHECK();
             }
         }

@@ -23,6 +23,7 @@ constexpr int TILE_CTR_STRIDE = 64;  // words between per-tile atomic counters (
 constexpr int BLEND_THREADS = TILE_X * TILE_Y;   // one blend CTA per tile, one thread per pixel
 constexpr int HIT_PIXELS = TILE_X * TILE_Y;      // hit words per window of a tile's list: one per pixel
 constexpr int HIT_WINDOW = 32;                   // list entries covered by one hit word
+constexpr int BUCKET_CAP = 8192;                 // records per tile that preprocess writes straight into the tile's bucket (ImageLayout::buckets)
 
 // ---------------------------------------------------------------------------------------
 // Packed per-Gaussian splat record: 48 bytes, 16-byte aligned, gathered by the blend
@@ -71,7 +72,7 @@ static_assert(sizeof(GeomHeader) == 256, "header is 256 bytes");
 inline __host__ __device__ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct GeomLayout {            // offsets inside the geometry blob
-    size_t header, rec, radii, tiles_touched, ranks, clamped, acc, total;
+    size_t header, rec, radii, tiles_touched, clamped, acc, total;
     int num_blocks;            // preprocess blocks of 256 Gaussians
     __host__ __device__ static GeomLayout make(int P)
     {
@@ -84,7 +85,6 @@ struct GeomLayout {            // offsets inside the geometry blob
         L.rec = take(Pz * sizeof(SplatRec));
         L.radii = take(Pz * 4);
         L.tiles_touched = take(Pz * 4);
-        L.ranks = take(Pz * 16);   // slot of the Gaussian inside each of the (at most 4) tile segments it joins
         L.clamped = take(Pz);
         L.acc = take(Pz * sizeof(GradAcc));
         L.total = off;
@@ -93,7 +93,7 @@ struct GeomLayout {            // offsets inside the geometry blob
 };
 
 struct ImageLayout {
-    size_t final_T, n_contrib, ranges, tile_max_contrib, tile_count, tile_cursor, hits_tail, total;
+    size_t final_T, n_contrib, ranges, tile_max_contrib, tile_count, tile_cursor, hits_tail, buckets, total;
     int tiles_x, tiles_y;
     __host__ __device__ static ImageLayout make(int W, int H)
     {
@@ -109,11 +109,14 @@ struct ImageLayout {
         L.tile_max_contrib = take(T * 8);   // highest n_contrib of each tile (both words)
         // one counter per TILE_CTR_STRIDE words: adjacent tiles land in different L2 slices, so the
         // ~2 M atomics of a frame are not funnelled through the few slices a dense array maps to
-        // word 0: instances of Gaussians touching <= 4 tiles (their atomics return the slot, kept in GeomLayout::ranks);
-        // word 1: instances of larger Gaussians (slots claimed by `duplicate` through tile_cursor)
+        // (word 0 of a slot: the tile's instance count; the counting atomic of preprocess returns the record's slot in the tile's bucket)
         L.tile_count = take((T + 1) * 4 * TILE_CTR_STRIDE);   // + one slot: completion counter of the preprocess CTAs
-        L.tile_cursor = take(T * 4 * TILE_CTR_STRIDE);   // next free slot for the larger Gaussians of each tile
+        L.tile_cursor = take(T * 4 * TILE_CTR_STRIDE);   // next free slot of each tile's segment (only the fallback `duplicate` pass uses it)
         L.hits_tail = take(T * HIT_PIXELS * 4);          // hit words of each tile's last, partial window (blend kernels)
+        // Per-tile buckets of BUCKET_CAP unsorted (depth bits << 32 | id) records, written by preprocess at the slot its counting atomic
+        // returned; the tile sort reads a tile's records from here whenever the frame's longest list fits (GeomHeader::max_tile_len <=
+        // BUCKET_CAP: no `duplicate` pass at all).  Never cleared: only the first `count` records of a bucket are read.  64 KB per tile.
+        L.buckets = take(T * (size_t)BUCKET_CAP * 8);
         L.total = off;
         return L;
     }

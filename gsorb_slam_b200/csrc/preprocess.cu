@@ -130,7 +130,7 @@ __device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh,
 template <int MINB>
 __global__ void __launch_bounds__(PRE_THREADS, MINB)
 preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ radii_blob, int* __restrict__ radii_out,
-                  uint32_t* __restrict__ tiles_touched, uint4* __restrict__ ranks, uint32_t* __restrict__ tile_count,
+                  uint32_t* __restrict__ tiles_touched, uint64_t* __restrict__ buckets, uint32_t* __restrict__ tile_count,
                   uint8_t* __restrict__ clamped_out, int aligned_means, int aligned_scales, int aligned_colors,
                   uint2* __restrict__ ranges, uint32_t* __restrict__ cursor, GeomHeader* __restrict__ hdr, uint32_t capacity)
 {
@@ -172,24 +172,33 @@ preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ rad
             const uint32_t by0 = max(o.miny, (uint32_t)p.band_y0), by1 = min(o.maxy, (uint32_t)p.band_y1);
             const uint32_t rows = by1 > by0 ? by1 - by0 : 0u;
             touched = rows * (o.maxx - o.minx);
-            // First half of the binning: per-tile instance counts.  A Gaussian that joins at most four tile
-            // lists (nearly all of them at SLAM splat sizes) keeps the slot each atomic returns, so `duplicate`
-            // places its instances without a second round of atomics; larger ones are only counted here.
-            if (touched <= 4) {
-                uint32_t rk[4] = {0u, 0u, 0u, 0u};
+            // Binning: one counting atomic per (Gaussian, tile) instance; the slot it returns is the record's place in the tile's
+            // bucket, so the (depth bits << 32 | id) record is written right here and the tile sort picks it up -- no second pass over
+            // the Gaussians.  Slots past the bucket's capacity are only counted: the scan sees the longest list and the per-tile
+            // kernels fall back to the `duplicate` pass for such a frame (binning.cu).
+            const uint64_t record = ((uint64_t)__float_as_uint(o.depth) << 32) | (uint32_t)idx;
+            if (touched <= 4) {   // nearly all of them at SLAM splat sizes: the atomics are issued back to back, then the stores
+                uint32_t slot[4], tl[4];
                 uint32_t tx = o.minx, ty = by0;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
+                    slot[k] = 0xffffffffu;
+                    tl[k] = ty * (uint32_t)p.tiles_x + tx;
                     if ((uint32_t)k < touched) {
-                        rk[k] = atomicAdd(&tile_count[(size_t)(ty * (uint32_t)p.tiles_x + tx) * TILE_CTR_STRIDE], 1u);
+                        slot[k] = atomicAdd(&tile_count[(size_t)tl[k] * TILE_CTR_STRIDE], 1u);
                         if (++tx == o.maxx) { tx = o.minx; ty++; }
                     }
                 }
-                ranks[idx] = make_uint4(rk[0], rk[1], rk[2], rk[3]);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (slot[k] < (uint32_t)BUCKET_CAP) buckets[(size_t)tl[k] * BUCKET_CAP + slot[k]] = record;
             } else {
                 for (uint32_t ty = by0; ty < by1; ty++)
-                    for (uint32_t tx = o.minx; tx < o.maxx; tx++)
-                        atomicAdd(&tile_count[(size_t)(ty * (uint32_t)p.tiles_x + tx) * TILE_CTR_STRIDE + 1], 1u);
+                    for (uint32_t tx = o.minx; tx < o.maxx; tx++) {
+                        const uint32_t tile = ty * (uint32_t)p.tiles_x + tx;
+                        const uint32_t slot = atomicAdd(&tile_count[(size_t)tile * TILE_CTR_STRIDE], 1u);
+                        if (slot < (uint32_t)BUCKET_CAP) buckets[(size_t)tile * BUCKET_CAP + slot] = record;
+                    }
             }
             float rgb[3];
             uint32_t cl = 0;
@@ -253,7 +262,9 @@ preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ rad
     __shared__ bool s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();   // this CTA's counting atomics are performed before it reports
+        // No fence here: every counting atomic of this CTA has RETURNED its slot to the issuing thread (the bucket store's address
+        // depends on it), i.e. it has been performed at the L2, before that thread reached the barrier above -- and the counts are
+        // all the scan reads.  (A __threadfence() here also waited for the CTA's scattered bucket stores: 15 us per frame.)
         const int tiles = p.tiles_x * p.tiles_y;
         s_last = atomicAdd(&tile_count[(size_t)tiles * TILE_CTR_STRIDE], 1u) == gridDim.x - 1;
     }
@@ -278,7 +289,7 @@ int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, char
 #define GSB_PRE_LAUNCH(MB)                                                                                                \
     preprocess_kernel<MB><<<GL.num_blocks, PRE_THREADS, 0, s>>>(                                                          \
         p, reinterpret_cast<SplatRec*>(geom + GL.rec), reinterpret_cast<int*>(geom + GL.radii), radii_out,                \
-        reinterpret_cast<uint32_t*>(geom + GL.tiles_touched), reinterpret_cast<uint4*>(geom + GL.ranks),                  \
+        reinterpret_cast<uint32_t*>(geom + GL.tiles_touched), reinterpret_cast<uint64_t*>(image + IL.buckets),             \
         reinterpret_cast<uint32_t*>(image + IL.tile_count), reinterpret_cast<uint8_t*>(geom + GL.clamped),                \
         al(p.means3D), al(p.scales), al(p.colors_precomp), reinterpret_cast<uint2*>(image + IL.ranges),                 \
         reinterpret_cast<uint32_t*>(image + IL.tile_cursor), reinterpret_cast<GeomHeader*>(geom + GL.header), capacity)

@@ -29,7 +29,7 @@ __device__ __forceinline__ void tile_scan_body(const uint32_t* __restrict__ tile
         for (int k = 0; k < SCAN_MAX_PER; k++) cnt[k] = (k < per && t0 + k < tiles) ? load(t0 + k) : make_uint2(0u, 0u);
 #pragma unroll
         for (int k = 0; k < SCAN_MAX_PER; k++) {
-            const uint32_t x = cnt[k].x + cnt[k].y;   // instances of small (slot known) + large (slot claimed later) Gaussians
+            const uint32_t x = cnt[k].x + cnt[k].y;   // the tile's instance count (word 1 is unused)
             sum += x;
             maxlen = max(maxlen, x);
         }
@@ -65,7 +65,7 @@ __device__ __forceinline__ void tile_scan_body(const uint32_t* __restrict__ tile
         const uint32_t x = c.x + c.y;
         // a too-small binning capacity truncates the tail of the tile-major list (overflow is latched below)
         ranges[i] = make_uint2(min(start, capacity), min(start + x, capacity));
-        cursor[(size_t)i * TILE_CTR_STRIDE] = start + c.x;   // large Gaussians fill the tail of the segment
+        cursor[(size_t)i * TILE_CTR_STRIDE] = start;   // the fallback `duplicate` pass claims the segment's slots from its start
         start += x;
     };
     if (per <= SCAN_MAX_PER) {
