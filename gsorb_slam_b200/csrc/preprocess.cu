@@ -233,7 +233,20 @@ preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ rad
                 }
                 for (uint32_t k = 2; k <= 5 && steps <= 24; k++)
                     if (passes(pb + k)) { pb += k; k = 1; steps++; }
-                thr = steps > 24 ? -0.5f * t2 : __uint_as_float(pb);   // search did not settle (never observed): conservative threshold
+                if (steps > 24) {
+                    // the ulp walk did not settle (a threshold within a few 1e-7 of zero: opacity barely above 1/255): bisect the bit
+                    // patterns between -0.0 (passes: lim > 0) and the conservative bound (fails) -- the backward kernel has no alpha test
+                    // to fall back on, so the threshold must be exact here too
+                    uint32_t lo = 0x80000000u, hi = __float_as_uint(-0.5f * t2);
+                    if (!passes(lo)) lo = hi = __float_as_uint(1.0f);          // cannot contribute at all
+                    else if (passes(hi)) lo = hi;                               // (not expected) keep the conservative bound
+                    while (hi - lo > 1u) {
+                        const uint32_t mid = lo + ((hi - lo) >> 1);
+                        if (passes(mid)) lo = mid; else hi = mid;
+                    }
+                    pb = lo;
+                }
+                thr = __uint_as_float(pb);
                 // bbox of {d : d^T Q d <= t2} is sqrt(t2 * (Q^-1)_ii); Q^-1 = cov2D up to fp32 rounding
                 // of the conic, hence the 2 % + 0.05 px slack.
                 ex = sqrtf(t2 * o.cov_xx) * 1.02f + 0.05f;

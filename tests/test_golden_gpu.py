@@ -235,3 +235,34 @@ def test_blended_pair_count_matches_a_numpy_walk_of_the_oracle_lists():
         want += int((valid & (np.arange(len(ids))[:, None] < done[None]) & inside[None]).sum())
     got = fr.blended_pairs()
     assert abs(got - want) <= max(4, want // 100_000), (got, want)   # numpy's exp differs from expf in the last bit at the 1/255 threshold
+
+
+def test_backward_repeats_the_forward_alpha_decisions_at_the_threshold():
+    """The backward decides "alpha >= 1/255" by the record's exact power threshold (preprocess.cu) and evaluates the exponential
+    with MUFU.EX2; the forward applies the reference's alpha test with expf.  Opacities within a few ulps of 1/255 (where the
+    threshold search walks to zero or bisects) and ordinary ones: image bit-identical to the live reference kernels, gradients
+    within 1e-3 of them elementwise -- one disagreement about a blended pair shifts T by 0.4 % for every splat in front of it."""
+    from oracle import gs_ref
+    if not gs_ref.available():
+        pytest.skip("oracle/_ref/libgsref.so not on this box (the CPU oracle's exp differs from expf in the last bit)")
+    from gsorb_slam_b200.lowlevel import frame_from_scene
+    from gsorb_slam_b200.scene import make_scene
+    sc = make_scene(30_000, (160, 120, 130.0, 128.0), seed=21, scale_mul=1.5)
+    rng = np.random.default_rng(4)
+    t = np.float32(1.0 / 255.0)
+    ulps = rng.integers(-3, 400, sc.P // 2)
+    vals = (t.view(np.uint32) + ulps).astype(np.uint32).view(np.float32)       # 1/255 - 3 ulp ... 1/255 + 400 ulp
+    sc.opacities[: sc.P // 2] = vals
+    sc.opacities[sc.P // 2: sc.P // 2 + 2000] = rng.uniform(0.0039, 0.0045, 2000).astype(np.float32)
+    fr = frame_from_scene(sc)
+    g = fr.backward(sc.dL_dpix)
+    rf = gs_ref.frame_from_scene(sc)
+    gr = rf.backward(sc.dL_dpix)
+    np.testing.assert_array_equal(to_np(fr.color).view(np.uint32), to_np(rf.color).view(np.uint32))
+    np.testing.assert_array_equal(to_np(fr.image_state()["n_contrib"]).astype(np.uint32), to_np(rf.image_state()["n_contrib"]).astype(np.uint32))
+    for k in ("dL_dmean3D", "dL_dscale", "dL_drot", "dL_dopacity", "dL_dcolor"):
+        a, b = to_np(g[k]).astype(np.float64).reshape(sc.P, -1), to_np(gr[k]).astype(np.float64).reshape(sc.P, -1)
+        assert rel_to_scale(a, b) <= TOL_GRAD, k
+        big = np.abs(b) > 1e-4 * np.abs(b).max()
+        rel = np.abs(a - b)[big] / np.abs(b)[big]
+        assert (rel > 1e-3).mean() <= 1e-3, (k, float(rel.max()), float((rel > 1e-3).mean()))
