@@ -222,13 +222,22 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
         const int e_last = last_contributor - kb * BLEND_BATCH;   // slots [0, e_last) of this batch are at or before this pixel's last contributor
         int wi = max(wtop, 0);
         uint32_t mask = wtop >= 0 ? hrow[wi * GROUPS] : 0u;
+        uint32_t nmask = wi > 0 ? hrow[(wi - 1) * GROUPS] : 0u;   // hit word of the group's NEXT window, fetched one window ahead
+        float* const acc_l = acc + 2 * l * (GL == 4 ? 1 : 2);     // this lane's pair / quad of accumulator slots
         while (true) {
             if (report && it == ARRIVE_AT) {
                 cp_async_wait<0>();
                 bar_arrive(nbuf);
             }
             it++;
-            if (mask == 0u && wi > 0) mask = hrow[--wi * GROUPS];   // this group moves on to its next window (one per iteration)
+            {   // a group whose window is exhausted moves on to its next one (one per iteration); written with selects: no divergence
+                const bool adv = mask == 0u && wi > 0;
+                mask = adv ? nmask : mask;
+                wi -= adv ? 1 : 0;
+                const uint32_t* nxt = hrow + (wi > 0 ? wi - 1 : 0) * GROUPS;   // always a mapped word
+                const uint32_t fetched = *nxt;
+                nmask = adv ? fetched : nmask;
+            }
             if (!__any_sync(0xffffffffu, mask != 0u || wi > 0)) break;   // nothing queued and no window left, in any group
             const bool act = mask != 0;
             uint32_t eb;                                   // highest queued entry; FLO yields 0xffffffff for an empty mask -> entry 31 (read, not used)
@@ -239,6 +248,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
             const float4 A = S.A(buf, e);
             const float4 B = S.B(buf, e);
             const float4 Cc = S.C(buf, e);
+            const uint32_t gid = s_ids[buf][e];        // the Gaussian's id, needed by the REDs at the end of the iteration
             const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
             const float power = splat_power(dx, dy, B.x, B.y, B.z);
             // Branch-free body: a lane that does not contribute carries u = wc = 0 through the sums and
@@ -262,44 +272,45 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
             s_behind = contrib ? fmaf(cd, wc, s_behind) : s_behind;   // a select, not wc = 0: an idle lane may have read a stale (non-finite) record
             T = contrib ? Tn : T;
             const uint32_t cb = __ballot_sync(0xffffffffu, contrib);
-            if (cb == 0) continue;
-            // Reduce-scatter of the 8 sums {S u dx, S u dx^2, S u dx dy, S w d_r | S u dy, S u dy^2, S u, S w d_g} over the group's
-            // lanes.  Stage 1 pairs sums whose summands differ only in a lane-selectable factor, so "keep" and "send" are formed
-            // directly (4 selects instead of 8):  m_k = hi ? dy : dx, m_s = hi ? dx : dy:  keep {u m_k, u m_k^2}, send {u m_s, u m_s^2}
-            const float mk = hi ? dy : dx, ms = hi ? dx : dy;
-            const float k0 = u * mk, s0 = u * ms;
-            const float k1 = k0 * mk, s1 = s0 * ms;
-            const float uxy = k0 * ms;                                  // u dx dy (symmetric)
-            const float k2 = hi ? u : uxy, s2 = hi ? uxy : u;
-            const float k3 = wc * dk, s3 = wc * ds;                     // dk / ds: d_r, d_g pre-swapped per lane
-            float r0 = k0 + __shfl_xor_sync(0xffffffffu, s0, GL / 2);
-            float r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, GL / 2);
-            float r2 = k2 + __shfl_xor_sync(0xffffffffu, s2, GL / 2);
-            float r3 = k3 + __shfl_xor_sync(0xffffffffu, s3, GL / 2);
-            // sums 8 (S w d_b) and, with five channels, 9 (S w d_z): the lo lanes end up with 8, the hi lanes with 9
-            float v8 = wc * d8k;
-            v8 += __shfl_xor_sync(0xffffffffu, CH == 5 ? wc * d8s : v8, GL / 2);
-            const bool touched = (cb >> gshift) & ((1u << GL) - 1u);   // this group blended the splat into at least one of its pixels
-            // accumulator slots (GradAcc, read by gauss_bwd.cu): 0 S u dx, 1 S u dx^2, 2 S u dxdy, 3 S w d_r, 4 S u dy, 5 S u dy^2, 6 S u,
-            // 7 S w d_g, 8 S w d_b, 9 S w d_z
-            if (GL == 4) {
-                const bool b1 = l & 1;   // second stage: the even lane keeps (r0, r1), the odd lane (r2, r3)
-                const float sa = b1 ? r0 : r2, ka = b1 ? r2 : r0;
-                const float sb = b1 ? r1 : r3, kb2 = b1 ? r3 : r1;
-                r0 = ka + __shfl_xor_sync(0xffffffffu, sa, 1);
-                r1 = kb2 + __shfl_xor_sync(0xffffffffu, sb, 1);
-                v8 += __shfl_xor_sync(0xffffffffu, v8, 1);
-                if (touched) {
-                    float* dst = acc + (size_t)s_ids[buf][e] * 12;
-                    red_add_v2(dst + 2 * l, r0, r1);
-                    if (l == 0) atomicAdd(dst + 8, v8);
-                    if (CH == 5 && l == 2) atomicAdd(dst + 9, v8);
-                }
-            } else {
-                if (touched) {
-                    float* dst = acc + (size_t)s_ids[buf][e] * 12;
-                    red_add_v4(dst + 4 * l, r0, r1, r2, r3);
-                    if (CH == 5 || l == 0) atomicAdd(dst + 8 + l, v8);
+            if (cb != 0) {   // some lane of the warp blended the splat it visited
+                // Reduce-scatter of the 8 sums {S u dx, S u dx^2, S u dx dy, S w d_r | S u dy, S u dy^2, S u, S w d_g} over the group's
+                // lanes.  Stage 1 pairs sums whose summands differ only in a lane-selectable factor, so "keep" and "send" are formed
+                // directly (4 selects instead of 8):  m_k = hi ? dy : dx, m_s = hi ? dx : dy:  keep {u m_k, u m_k^2}, send {u m_s, u m_s^2}
+                const float mk = hi ? dy : dx, ms = hi ? dx : dy;
+                const float k0 = u * mk, s0 = u * ms;
+                const float k1 = k0 * mk, s1 = s0 * ms;
+                const float uxy = k0 * ms;                                  // u dx dy (symmetric)
+                const float k2 = hi ? u : uxy, s2 = hi ? uxy : u;
+                const float k3 = wc * dk, s3 = wc * ds;                     // dk / ds: d_r, d_g pre-swapped per lane
+                float r0 = k0 + __shfl_xor_sync(0xffffffffu, s0, GL / 2);
+                float r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, GL / 2);
+                float r2 = k2 + __shfl_xor_sync(0xffffffffu, s2, GL / 2);
+                float r3 = k3 + __shfl_xor_sync(0xffffffffu, s3, GL / 2);
+                // sums 8 (S w d_b) and, with five channels, 9 (S w d_z): the lo lanes end up with 8, the hi lanes with 9
+                float v8 = wc * d8k;
+                v8 += __shfl_xor_sync(0xffffffffu, CH == 5 ? wc * d8s : v8, GL / 2);
+                const bool touched = (cb >> gshift) & ((1u << GL) - 1u);   // this group blended the splat into at least one of its pixels
+                // accumulator slots (GradAcc, read by gauss_bwd.cu): 0 S u dx, 1 S u dx^2, 2 S u dxdy, 3 S w d_r, 4 S u dy, 5 S u dy^2, 6 S u,
+                // 7 S w d_g, 8 S w d_b, 9 S w d_z
+                if (GL == 4) {
+                    const bool b1 = l & 1;   // second stage: the even lane keeps (r0, r1), the odd lane (r2, r3)
+                    const float sa = b1 ? r0 : r2, ka = b1 ? r2 : r0;
+                    const float sb = b1 ? r1 : r3, kb2 = b1 ? r3 : r1;
+                    r0 = ka + __shfl_xor_sync(0xffffffffu, sa, 1);
+                    r1 = kb2 + __shfl_xor_sync(0xffffffffu, sb, 1);
+                    v8 += __shfl_xor_sync(0xffffffffu, v8, 1);
+                    if (touched) {
+                        float* dst = acc_l + (size_t)gid * 12;   // slots 2 l, 2 l + 1 of the Gaussian's accumulator
+                        red_add_v2(dst, r0, r1);
+                        if (l == 0) atomicAdd(dst + 8, v8);             // slot 8
+                        if (CH == 5 && l == 2) atomicAdd(dst + 5, v8);  // slot 9 = 2 l + 5
+                    }
+                } else {
+                    if (touched) {
+                        float* dst = acc_l + (size_t)gid * 12;   // slots 4 l .. 4 l + 3
+                        red_add_v4(dst, r0, r1, r2, r3);
+                        if (CH == 5 || l == 0) atomicAdd(dst + 8 - 3 * l, v8);   // slot 8 + l
+                    }
                 }
             }
         }
