@@ -583,7 +583,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "frac_of_nominal_8TBs": achieved / 8000.0, "frame_frac_of_nominal_8TBs": ab["frame"] / (ms_per_step * 1e-3) / 1e9 / 8000.0,
                 "pairs_per_pass": pairs, "pairs_per_s_blend_forward": (pairs / (fwd_ms * 1e-3)) if fwd_ms else None,
-                "diagnosis": "blend kernels are instruction-issue bound (ncu: ~74 % issue-active, DRAM 3-5 %); see DESIGN.md section 3",
+                "diagnosis": "blend kernels are instruction-issue bound (ncu: 68-71 % issue-active, DRAM 6-11 %): see roofline.issue and DESIGN.md section 3",
                 "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": ab[dom], "kernel_ms": dom_ms,
                 "frame_alg_bytes": ab["frame"], "frame_frac_of_peak": ab["frame"] / (ms_per_step * 1e-3) / 1e9 / peak,
                 "stages": stages}
