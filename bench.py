@@ -633,9 +633,17 @@ def run_ours(args):
         gt_c = fr.color.clone().clamp(0, 1)
         gt_d = torch.rand(H, W, device=dev) * 5 + 0.5
         ms_full = timed(lambda: mo.step_slam(Tcw_id, gt_c, gt_d), it_steps, 3) / it_steps
+        # one tracking iteration (Render::RenderStartTraking, src/Render.cc:1052-1127): fixed Gaussians, Rt2T -> five-channel pass with
+        # detached depth colours -> fused masked-L1 loss (gsb_tracking_loss) -> backward -> dL/dTcw on the device -> pose Adam; the
+        # loss is read back every iteration, as the reference's loss.item() does
+        from gsorb_slam_b200.tracking import PoseOptimizer
+        po = PoseOptimizer(mo, [1.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0])
+        ms_track = timed(lambda: po.step(gt_c, gt_d, 0.7, 1.0, True), it_steps, 3) / it_steps
+        del po
         del mo
         iteration = {"what": "RGB pass + depth/silhouette pass of one mapping iteration, fwd+bwd, device-resident",
-                     "complete_iteration_ms": ms_full,
+                     "complete_iteration_ms": ms_full, "tracking_iteration_ms": ms_track,
+                     "tracking_iteration": "PoseOptimizer.step: Rt2T + fused pass + gsb_tracking_loss + backward + pose gradient + pose Adam, one host sync (loss)",
                      "complete_iteration": "MapOptimizer.step_slam: prologue + fused pass + fused L1/SSIM/depth loss + backward + pose gradient + Adam, no torch op",
                      "two_pass_ms": ms_two, "fused_five_channel_ms": ms_fused, "iterations_per_s_two_pass": 1000.0 / ms_two,
                      "iterations_per_s_fused": 1000.0 / ms_fused, "steps": it_steps}

@@ -57,6 +57,7 @@ SIGNATURES = {
     "gsb_adam_step": (_i, [_ll, _vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, _ll, _vp]),
     "gsb_scale_regulariser": (_i, [_i, _vp, _f, _f, _f, _vp, _vp, _vp]),
     "gsb_loss_scratch_bytes": (_sz, [_i, _i]),
+    "gsb_tracking_loss": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp]),
     "gsb_mapping_loss": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gsb_backproject_scratch_bytes": (_sz, [_i, _i]),
     "gsb_backproject": (_i, [_i, _i, _vp, _vp, _vp, _f, _f, _f, _f, C.POINTER(_f), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -202,6 +202,60 @@ loss_grad_kernel(LossParams q)
     }
 }
 
+
+// ---- tracking iteration (src/Render.cc:1075-1093; L1LossForTracking, src/Utils.cc:45-52) ----------------------------------------
+// mask = silhouette > 0.99 and gt depth is not NaN ("uncertainDepth"); image term = sum over the mask of |I - G| (three channels),
+// depth term = sum over the mask of |D - G_d| with D the median depth (no gradient: include/Rasterizer.cuh:210) or the blended depth.
+// One pass: per-pixel gradients sign(.) * weight * mask, block sums, one atomicAdd per block and term; the last block to finish
+// forms the loss.  terms = {image_l1, depth_l1, loss, n_mask, -, -, -, completion counter (bits)}.
+constexpr int TRK_THREADS = 256;
+__global__ void __launch_bounds__(TRK_THREADS)
+tracking_loss_kernel(int HW, const float* __restrict__ color, const float* __restrict__ depth_sil, const float* __restrict__ median,
+                     const float* __restrict__ gt_color, const float* __restrict__ gt_depth, float w_image, float w_depth,
+                     int use_sur, float* __restrict__ dC, float* __restrict__ dD, float* __restrict__ terms)
+{
+    float s_img = 0.f, s_dep = 0.f, s_n = 0.f;
+    for (int i = blockIdx.x * TRK_THREADS + threadIdx.x; i < HW; i += gridDim.x * TRK_THREADS) {
+        const float gd = gt_depth[i];
+        const bool m = depth_sil[HW + i] > 0.99f && !(gd != gd);
+        float dsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float d = color[c * HW + i] - gt_color[c * HW + i];
+            dC[c * HW + i] = m ? w_image * ((d > 0.f) - (d < 0.f)) : 0.f;
+            dsum += fabsf(d);
+        }
+        const float dd = (use_sur ? median[i] : depth_sil[i]) - gd;
+        if (dD) {
+            dD[i] = (m && !use_sur) ? w_depth * ((dd > 0.f) - (dd < 0.f)) : 0.f;
+            dD[HW + i] = 0.f;
+        }
+        if (m) { s_img += dsum; s_dep += fabsf(dd); s_n += 1.f; }
+    }
+    __shared__ float red[3][TRK_THREADS / 32];
+    __shared__ bool last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s_img += __shfl_xor_sync(0xffffffffu, s_img, o);
+        s_dep += __shfl_xor_sync(0xffffffffu, s_dep, o);
+        s_n += __shfl_xor_sync(0xffffffffu, s_n, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s_img; red[1][threadIdx.x >> 5] = s_dep; red[2][threadIdx.x >> 5] = s_n; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f, c = 0.f;
+        for (int w = 0; w < TRK_THREADS / 32; w++) { a += red[0][w]; b += red[1][w]; c += red[2][w]; }
+        atomicAdd(terms + 0, a); atomicAdd(terms + 1, b); atomicAdd(terms + 3, c);
+        __threadfence();
+        last = atomicAdd(reinterpret_cast<unsigned int*>(terms + 7), 1u) == gridDim.x - 1;
+        if (last) {
+            __threadfence();
+            const float img = __ldcg(terms + 0), dep = __ldcg(terms + 1);
+            terms[2] = w_image * img + w_depth * dep;
+        }
+    }
+}
+
 }  // namespace gsb
 
 using namespace gsb;
@@ -250,6 +304,28 @@ int gsb_mapping_loss(int width, int height, const float* color, const float* dep
         loss_stats_kernel<<<grid, LT * LT, 0, s>>>(q);
         GSB_LAUNCH_CHECK();
         loss_grad_kernel<<<grid, LT * LT, 0, s>>>(q);
+        GSB_LAUNCH_CHECK();
+    }
+    return GSB_OK;
+}
+
+
+int gsb_tracking_loss(int width, int height, const float* color, const float* depth_sil, const float* median_depth,
+                      const float* gt_color, const float* gt_depth, float w_image, float w_depth, int use_surdepth,
+                      float* dL_dcolor, float* dL_ddepth_sil, float* loss_terms, gsb_stream_t stream)
+{
+    if (width <= 0 || height <= 0 || !color || !depth_sil || !gt_color || !gt_depth || !dL_dcolor || !loss_terms || (use_surdepth && !median_depth)) {
+        set_error("tracking_loss: image size, color, depth_sil, gt_color, gt_depth, dL_dcolor, loss_terms (and median_depth with use_surdepth) are required");
+        return GSB_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int HW = width * height;
+    GSB_CUDA_CHECK(cudaMemsetAsync(loss_terms, 0, 8 * sizeof(float), s));
+    {
+        StageTimer _t(ST_OTHER, s);
+        const int blocks = (HW + TRK_THREADS - 1) / TRK_THREADS;
+        tracking_loss_kernel<<<blocks < 2 * NUM_SMS ? blocks : 2 * NUM_SMS, TRK_THREADS, 0, s>>>(
+            HW, color, depth_sil, median_depth, gt_color, gt_depth, w_image, w_depth, use_surdepth ? 1 : 0, dL_dcolor, dL_ddepth_sil, loss_terms);
         GSB_LAUNCH_CHECK();
     }
     return GSB_OK;

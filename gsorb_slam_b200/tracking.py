@@ -5,17 +5,20 @@ src/Gaussian.cc:98-128) follow the gradient of a masked L1 image / depth loss.
 Per iteration: ``Tcw = Rt2T(q, t)`` (src/Utils.cc:170-179, ``ToRotation`` include/Utils.h:56-77) -> ONE five-channel
 rasterization with the depth colours detached (tracking mode, src/Render.cc:957) -> masked L1 sums over the pixels whose
 silhouette exceeds 0.99 (:1075-1092) -> rasterizer backward -> ``gsb_prologue_backward`` reduces ``dL/dTcw = sum_i g_i [p_i;1]^T``
-on the device (the reference materialises an N x 4 x 4 repeat + bmm for it) -> the 12 numbers are chained to (q, t) by autograd
-on a 4x4 matrix -> Adam with the reference's learning rates (both groups use the quaternion rate, src/Gaussian.cc:149-150).
+on the device (the reference materialises an N x 4 x 4 repeat + bmm for it) -> the 12 numbers are chained to (q, t) in closed form
+on the host -> Adam with the reference's learning rates (both groups use the quaternion rate, src/Gaussian.cc:149-150).
 The ORB reprojection term (:1012-1065): matched map points X_w, undistorted keypoints and their inverse level variances come
 from the ORB front end (host data, ``set_features``); the term sum_inliers e^T diag(1/sigma^2) e, e = K X_c / X_c.z - obs, is a
-few hundred points and is differentiated by torch autograd on the same 4x4 matrix; the chi-square gate (5.991, two degrees of
+few hundred points and is differentiated in closed form on the host; the chi-square gate (5.991, two degrees of
 freedom) is applied once, at half the iteration budget (:1081-1085); ``run`` stops early when the loss moves by less than 1e-3
 (:1109-1110) and returns the best pose seen (:1101-1108).
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
+
+from . import _lib
 
 from .mapping import MapOptimizer
 
@@ -31,36 +34,100 @@ def rt2T(q: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
     return torch.cat([top, torch.tensor([[0.0, 0.0, 0.0, 1.0]], device=q.device, dtype=q.dtype)], 0)
 
 
+def rt2T_np(q: np.ndarray, t: np.ndarray) -> np.ndarray:
+    """``rt2T`` on the host, float32."""
+    qn = (q / np.sqrt((q * q).sum(dtype=np.float32))).astype(np.float32)
+    w, x, y, z = (np.float32(v) for v in qn)
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                          [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                          [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]], dtype=np.float32)
+    T[:3, 3] = t
+    return T
+
+
+def rt2T_backward_np(q: np.ndarray, G: np.ndarray):
+    """dL/dq [4], dL/dt [3] from G = dL/dTcw (rows 0..2 of the 4x4 matrix, [3,4]): the autograd of ``rt2T`` in closed form."""
+    n = float(np.sqrt((q.astype(np.float64) ** 2).sum()))
+    w, x, y, z = (q.astype(np.float64) / n)
+    dR = np.array([[[0, -z, y], [z, 0, -x], [-y, x, 0]],
+                   [[0, y, z], [y, -2 * x, -w], [z, w, -2 * x]],
+                   [[-2 * y, x, w], [x, 0, z], [-w, z, -2 * y]],
+                   [[-2 * z, -w, x], [w, -2 * z, y], [x, y, 0]]], dtype=np.float64) * 2.0
+    gqn = (dR * G[None, :3, :3].astype(np.float64)).sum((1, 2))
+    qn = np.array([w, x, y, z])
+    gq = (gqn - qn * (qn @ gqn)) / n          # through q / |q|
+    return gq.astype(np.float32), G[:3, 3].astype(np.float32)
+
+
 class PoseOptimizer:
+    """State on the HOST: the seven pose parameters, their Adam moments and the ORB matches are a few hundred floats, and the
+    loop reads the loss back every iteration anyway (the reference's ``loss.item()``), so the chain rule through ``Rt2T``, the
+    reprojection term and the Adam update are closed-form numpy (about 0.1 ms) instead of ~100 small torch kernels per iteration
+    (1.4 ms of launch overhead); the rasterizer, the masked L1 loss and dL/dTcw stay on the device."""
+
     def __init__(self, gaussians: MapOptimizer, quat, trans, lr_quat: float = 2e-3, betas=(0.9, 0.999), eps: float = 1e-15):
         self.g = gaussians
-        dev = gaussians.dev
-        self.q = torch.as_tensor(quat, dtype=torch.float32, device=dev).clone().requires_grad_(True)
-        self.t = torch.as_tensor(trans, dtype=torch.float32, device=dev).clone().requires_grad_(True)
+        as_np = lambda a: (a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)).astype(np.float32).copy()
+        self._q, self._t = as_np(quat).reshape(4), as_np(trans).reshape(3)
         # CreateOptimizerForPose: the translation group is created with the QUATERNION learning rate (src/Gaussian.cc:150)
-        self.adam = torch.optim.Adam([{"params": [self.q], "lr": lr_quat}, {"params": [self.t], "lr": lr_quat}], betas=betas, eps=eps)
-        self.best = (self.q.detach().clone(), self.t.detach().clone(), float("inf"))
+        self.lr, self.betas, self.eps = float(lr_quat), (float(betas[0]), float(betas[1])), float(eps)
+        self._adam = dict(step=0, m=np.zeros(7, np.float32), v=np.zeros(7, np.float32))
+        self.best = (self._q.copy(), self._t.copy(), float("inf"))
         self.features = None
         self.last_terms = {}
 
+    # torch views of the state (tests, callers that hand the pose on)
+    @property
+    def q(self) -> torch.Tensor:
+        return torch.from_numpy(self._q.copy()).to(self.g.dev)
+
+    @property
+    def t(self) -> torch.Tensor:
+        return torch.from_numpy(self._t.copy()).to(self.g.dev)
+
     def pose(self) -> torch.Tensor:
-        return rt2T(self.q, self.t)
+        return torch.from_numpy(rt2T_np(self._q, self._t)).to(self.g.dev)
 
     def set_features(self, K, Xw, obs, inv_sigma2) -> None:
         """ORB matches of the frame (src/Render.cc:1012-1047): ``K`` [3,3] intrinsics, ``Xw`` [M,3] matched map points,
         ``obs`` [M,2] undistorted keypoints, ``inv_sigma2`` [M] inverse variance of each keypoint's pyramid level."""
-        dev = self.g.dev
-        f32 = lambda a: torch.as_tensor(a, dtype=torch.float32, device=dev)
+        f32 = lambda a: (a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)).astype(np.float32)
         self.features = dict(K=f32(K), Xw=f32(Xw), obs=f32(obs), w=f32(inv_sigma2).reshape(-1),
-                             inlier=torch.ones(f32(Xw).shape[0], dtype=torch.bool, device=dev))
+                             inlier=np.ones(f32(Xw).shape[0], dtype=bool))
+
+    def _reprojection_np(self, T: np.ndarray, with_grad: bool = False):
+        f = self.features
+        Xc = f["Xw"] @ T[:3, :3].T + T[:3, 3]
+        iz = 1.0 / Xc[:, 2:3]
+        u = Xc * iz
+        e = (u @ f["K"].T)[:, :2] - f["obs"]
+        err = (e * e).sum(1) * f["w"]
+        if not with_grad:
+            return err
+        ge = 2.0 * f["w"][:, None] * e * f["inlier"][:, None]                     # d(sum of inlier errors) / d e
+        gu = ge @ f["K"][:2, :]                                                   # [M,3]; u_z is constant
+        gXc = np.stack([gu[:, 0] * iz[:, 0], gu[:, 1] * iz[:, 0], -(gu[:, 0] * u[:, 0] + gu[:, 1] * u[:, 1]) * iz[:, 0]], 1)
+        G = np.zeros((3, 4), np.float32)
+        G[:, :3] = gXc.T @ f["Xw"]
+        G[:, 3] = gXc.sum(0)
+        return err, G
 
     def reprojection(self, Tcw: torch.Tensor):
         """Weighted squared reprojection error of every match, [M] (src/Render.cc:1058-1065)."""
-        f = self.features
-        Xc = f["Xw"] @ Tcw[:3, :3].T + Tcw[:3, 3]
-        uv = (Xc / Xc[:, 2:3]) @ f["K"].T
-        e = uv[:, :2] - f["obs"]
-        return (e * e).sum(1) * f["w"]
+        return torch.from_numpy(self._reprojection_np(Tcw.detach().cpu().numpy().astype(np.float32))).to(self.g.dev)
+
+    def _adam_step(self, grad: np.ndarray) -> None:
+        """torch::optim::Adam on the 7 parameters (bias-corrected, eps outside the square root; src/Gaussian.cc:145-175)."""
+        a = self._adam
+        a["step"] += 1
+        b1, b2 = self.betas
+        a["m"] = (b1 * a["m"] + (1 - b1) * grad).astype(np.float32)
+        a["v"] = (b2 * a["v"] + (1 - b2) * grad * grad).astype(np.float32)
+        c1, c2 = 1.0 - b1 ** a["step"], 1.0 - b2 ** a["step"]
+        upd = (self.lr / c1) * a["m"] / (np.sqrt(a["v"]) / np.sqrt(c2) + self.eps)
+        self._q = (self._q - upd[:4]).astype(np.float32)
+        self._t = (self._t - upd[4:]).astype(np.float32)
 
     def step(self, gt_color: torch.Tensor, gt_depth: torch.Tensor, w_image: float = 1.0, w_depth: float = 1.0,
              use_surdepth: bool = True, w_feature: float = 0.0, gate_features: bool = False) -> float:
@@ -69,37 +136,40 @@ class PoseOptimizer:
         ``w_feature`` > 0 (and ``set_features`` called) adds the ORB reprojection term; ``gate_features`` re-selects the
         inliers (chi-square 5.991) before it is summed -- the reference does that once, at half its iteration budget."""
         g = self.g
-        Tcw = self.pose()
-        color, depth_sil, median, _ = g.render_fused(Tcw.detach())
-        mask = (depth_sil[1] > 0.99) & ~torch.isnan(gt_depth)                      # "uncertainDepth", src/Render.cc:1075
-        dI = color - gt_color
-        dC = (w_image * torch.sign(dI) * mask).contiguous()
-        dD = torch.zeros_like(depth_sil)
-        if use_surdepth:
-            depth_term = (median[0] - gt_depth).abs()[mask].sum()
-        else:
-            dd = depth_sil[0] - gt_depth
-            dD[0] = w_depth * torch.sign(dd) * mask
-            depth_term = dd.abs()[mask].sum()
-        image_term = dI.abs()[mask.expand_as(dI)].sum()
-        feat = None
-        if w_feature > 0.0 and self.features is not None and self.features["Xw"].shape[0] > 0:
-            err = self.reprojection(Tcw)
-            if gate_features:
-                self.features["inlier"] = (err < 5.991).detach()                   # src/Render.cc:1081-1084
-            feat = err[self.features["inlier"]].sum()
-        loss = float(w_image * image_term + w_depth * depth_term + (w_feature * feat.detach() if feat is not None else 0.0))
-        self.last_terms = dict(image=float(image_term), depth=float(depth_term), feature=float(feat.detach()) if feat is not None else 0.0)
+        T = rt2T_np(self._q, self._t)
+        color, depth_sil, median, _ = g.render_fused(torch.from_numpy(T))
+        # masked L1 terms and their gradients in ONE kernel (gsb_tracking_loss): mask = "uncertainDepth" (src/Render.cc:1075),
+        # sums over the mask (L1LossForTracking, src/Utils.cc:45-52), dL/dcolor and dL/d(depth, silhouette)
+        if not hasattr(self, "_dC"):
+            self._dC, self._dD = torch.empty_like(color), torch.empty_like(depth_sil)
+            self._out = torch.zeros(20, dtype=torch.float32, device=g.dev)        # loss terms [8] | dL/dTcw [12]
+            self._host = torch.empty(20, dtype=torch.float32).pin_memory()
+        dC, dD, terms = self._dC, self._dD, self._out[:8]
+        gtc, gtd = gt_color.contiguous(), gt_depth.contiguous()
+        with torch.cuda.device(g.dev):
+            _lib.check(g.L.gsb_tracking_loss(g.W, g.H, color.data_ptr(), depth_sil.data_ptr(), median.data_ptr(), gtc.data_ptr(),
+                                             gtd.data_ptr(), float(w_image), float(w_depth), 1 if use_surdepth else 0,
+                                             dC.data_ptr(), dD.data_ptr(), terms.data_ptr(), torch.cuda.current_stream(g.dev).cuda_stream))
         g.backward_fused(dC, dD, z_attached=False)                                 # -> g.dTcw [3,4] on the device
-        self.adam.zero_grad()
-        grad = torch.zeros(4, 4, device=g.dev)
-        grad[:3] = g.dTcw
-        Tcw.backward(gradient=grad, retain_graph=feat is not None)
-        if feat is not None:
-            (w_feature * feat).backward()
+        self._out[8:].copy_(g.dTcw.reshape(-1))
+        self._host.copy_(self._out, non_blocking=True)
+        torch.cuda.current_stream(g.dev).synchronize()                             # the reference's loss.item(): one sync per iteration
+        h = self._host.numpy()
+        image_term, depth_term, loss = float(h[0]), float(h[1]), float(h[2])
+        G = h[8:].reshape(3, 4).astype(np.float32).copy()
+        feat = 0.0
+        if w_feature > 0.0 and self.features is not None and self.features["Xw"].shape[0] > 0:
+            if gate_features:
+                self.features["inlier"] = self._reprojection_np(T) < 5.991        # src/Render.cc:1081-1084
+            err, Gf = self._reprojection_np(T, with_grad=True)
+            feat = float(err[self.features["inlier"]].sum())
+            loss += w_feature * feat
+            G += np.float32(w_feature) * Gf
+        self.last_terms = dict(image=image_term, depth=depth_term, feature=feat)
         if loss == loss and loss < self.best[2]:                                   # best-so-far bookkeeping, :1101-1108
-            self.best = (self.q.detach().clone(), self.t.detach().clone(), loss)
-        self.adam.step()
+            self.best = (self._q.copy(), self._t.copy(), loss)
+        gq, gt = rt2T_backward_np(self._q, G)
+        self._adam_step(np.concatenate([gq, gt]))
         return loss
 
     def run(self, gt_color: torch.Tensor, gt_depth: torch.Tensor, iters: int = 200, w_image: float = 0.7, w_depth: float = 1.0,
@@ -112,19 +182,14 @@ class PoseOptimizer:
         last = 0.0
         n = 0
         for it in range(iters):
-            q0, t0 = self.q.detach().clone(), self.t.detach().clone()
-            state = {k: {kk: (vv.clone() if torch.is_tensor(vv) else vv) for kk, vv in v.items()} for k, v in self.adam.state.items()}
+            q0, t0 = self._q.copy(), self._t.copy()
+            state = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in self._adam.items()}
             loss = self.step(gt_color, gt_depth, w_image, w_depth, use_surdepth, w_feature, gate_features=(it == gate_at))
             n = it + 1
             if abs(last - loss) < tol:
                 # the reference breaks BEFORE StepUpdataForPose (:1109-1110): undo this iteration's Adam step
-                with torch.no_grad():
-                    self.q.copy_(q0); self.t.copy_(t0)
-                for k, v in state.items():
-                    self.adam.state[k] = v
+                self._q, self._t, self._adam = q0, t0, state
                 break
             last = loss
         bq, bt, bl = self.best
-        with torch.no_grad():
-            T = rt2T(bq, bt)
-        return T, bl, n
+        return torch.from_numpy(rt2T_np(bq, bt)).to(self.g.dev), bl, n

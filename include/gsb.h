@@ -252,6 +252,18 @@ int gsb_mapping_loss(int width, int height, const float* color, const float* dep
                      float* dL_dcolor, float* dL_ddepth_sil, float* loss_terms,
                      void* scratch, size_t scratch_bytes, gsb_stream_t stream);
 
+/* ---- fused loss of one tracking iteration (extension) -------------------------
+ * The producer of dL/dpixel in Render::RenderStartTraking (src/Render.cc:1075-1093; L1LossForTracking, src/Utils.cc:45-52) and its
+ * autograd, in one kernel:  mask = silhouette > 0.99 and gt_depth is not NaN ("uncertainDepth");
+ *   loss = w_image * sum_mask |I - G| (three channels) + w_depth * sum_mask |D - G_d|,
+ * D = median_depth [H,W] when use_surdepth (it carries no gradient: include/Rasterizer.cuh:210), else depth_sil[0].
+ * Outputs: dL_dcolor [3,H,W] = w_image sign(I - G) mask, dL_ddepth_sil [2,H,W] (may be NULL; channel 0 = w_depth sign(D - G_d) mask
+ * without use_surdepth, zero otherwise) and loss_terms[8] on the DEVICE = {image_l1, depth_l1, loss, n_mask, 0, 0, 0, internal}.
+ * The ORB reprojection term of the same loop acts on the pose, not on pixels, and stays with the caller. */
+int gsb_tracking_loss(int width, int height, const float* color, const float* depth_sil, const float* median_depth,
+                      const float* gt_color, const float* gt_depth, float w_image, float w_depth, int use_surdepth,
+                      float* dL_dcolor, float* dL_ddepth_sil, float* loss_terms, gsb_stream_t stream);
+
 /* The two scale regularisers of the mapping loss (src/Render.cc:462-469), which act on the parameters, not on pixels:
  *   big = where(exp(log_scales) > max_scalar)[0]   (a row appears once per axis that exceeds),
  *   reg_scalar = sum_big (max_axis exp(ls) - max_scalar),  reg_long = mean_big (max_axis exp(ls) - min_axis exp(ls)),

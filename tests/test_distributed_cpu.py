@@ -77,3 +77,34 @@ def test_tile_row_bands_cover_and_balance():
     assert b == [(0, 1), (1, 8)]
     with pytest.raises(ValueError):
         tile_row_bands(4, 0)
+
+
+def test_pose_chain_rule_and_reprojection_gradient_match_torch_autograd():
+    """The host-side closed forms of gsorb_slam_b200/tracking.py (Rt2T and its backward, the ORB reprojection term and its
+    gradient w.r.t. Tcw; src/Utils.cc:170-179, src/Render.cc:1058-1065) against torch autograd of the literal expressions."""
+    import numpy as np
+    import torch
+    from gsorb_slam_b200.tracking import PoseOptimizer, rt2T, rt2T_backward_np, rt2T_np
+    rng = np.random.default_rng(0)
+    q, t, G = rng.normal(size=4).astype(np.float32), rng.normal(size=3).astype(np.float32), rng.normal(size=(3, 4)).astype(np.float32)
+    qt, tt = torch.tensor(q, requires_grad=True), torch.tensor(t, requires_grad=True)
+    T = rt2T(qt, tt)
+    (T[:3] * torch.tensor(G)).sum().backward()
+    gq, gt = rt2T_backward_np(q, G)
+    assert np.abs(rt2T_np(q, t) - T.detach().numpy()).max() <= 1e-6
+    assert np.abs(gq - qt.grad.numpy()).max() <= 1e-5 and np.abs(gt - tt.grad.numpy()).max() <= 1e-6
+    po = PoseOptimizer.__new__(PoseOptimizer)   # the reprojection term needs no rasterizer
+    M = 64
+    K = np.array([[260, 0, 159.5], [0, 258, 119.5], [0, 0, 1]], np.float32)
+    Xw = np.stack([rng.uniform(-1, 1, M), rng.uniform(-1, 1, M), rng.uniform(2, 5, M)], 1).astype(np.float32)
+    obs, w = rng.uniform(0, 300, (M, 2)).astype(np.float32), rng.uniform(0.3, 1, M).astype(np.float32)
+    po.features = dict(K=K, Xw=Xw, obs=obs, w=w, inlier=rng.random(M) < 0.8)
+    Tn = rt2T_np(np.array([1, 0.01, -0.02, 0.03], np.float32), np.array([0.1, -0.05, 0.02], np.float32))
+    err, Gf = po._reprojection_np(Tn, with_grad=True)
+    Tt = torch.tensor(Tn, requires_grad=True)
+    Xc = torch.tensor(Xw) @ Tt[:3, :3].T + Tt[:3, 3]
+    e = ((Xc / Xc[:, 2:3]) @ torch.tensor(K).T)[:, :2] - torch.tensor(obs)
+    er = (e * e).sum(1) * torch.tensor(w)
+    er[torch.tensor(po.features["inlier"])].sum().backward()
+    assert np.abs(err - er.detach().numpy()).max() <= 1e-6 * np.abs(err).max()
+    assert np.abs(Gf - Tt.grad.numpy()[:3]).max() <= 1e-5 * np.abs(Gf).max()

@@ -744,6 +744,42 @@ def test_pose_refinement_recovers_a_perturbed_camera():
     assert err() < 0.5 * e0, (e0, err())
 
 
+@pytest.mark.parametrize("use_sur", [True, False])
+def test_fused_tracking_loss_matches_torch(use_sur):
+    """gsb_tracking_loss against a torch restatement of src/Render.cc:1075-1093 (L1LossForTracking over the "uncertainDepth"
+    mask, src/Utils.cc:45-52) and its autograd: terms within 1e-5 relative, gradients exactly sign(.) * weight * mask."""
+    import torch
+    from gsorb_slam_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda:0")
+    H, W = 97, 131
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    color = torch.rand(3, H, W, device=dev, generator=g)
+    gt_color = torch.rand(3, H, W, device=dev, generator=g)
+    gt_color[:, 5, 7] = color[:, 5, 7]                                  # zero residuals: sign(0) = 0
+    depth_sil = torch.stack([torch.rand(H, W, device=dev, generator=g) * 5, 0.9 + 0.12 * torch.rand(H, W, device=dev, generator=g)])
+    median = (torch.rand(1, H, W, device=dev, generator=g) * 5).contiguous()
+    gt_depth = torch.rand(H, W, device=dev, generator=g) * 5
+    gt_depth[torch.rand(H, W, device=dev, generator=g) < 0.1] = float("nan")
+    w_i, w_d = 0.7, 1.3
+    c = color.clone().requires_grad_(True); ds = depth_sil.clone().requires_grad_(True)
+    mask = (ds[1] > 0.99) & ~torch.isnan(gt_depth)
+    img = (c - gt_color).abs()[mask.expand(3, H, W)].sum()
+    dep = ((median[0] if use_sur else ds[0]) - gt_depth).abs()[mask].sum()
+    (w_i * img + w_d * dep).backward()
+    dC, dD, terms = torch.empty_like(color), torch.empty_like(depth_sil), torch.empty(8, device=dev)
+    _lib.check(L.gsb_tracking_loss(W, H, color.data_ptr(), depth_sil.data_ptr(), median.data_ptr(), gt_color.data_ptr(), gt_depth.data_ptr(),
+                                   w_i, w_d, 1 if use_sur else 0, dC.data_ptr(), dD.data_ptr(), terms.data_ptr(),
+                                   torch.cuda.current_stream(dev).cuda_stream))
+    t = terms.tolist()
+    img, dep = img.detach(), dep.detach()
+    assert abs(t[0] - float(img)) <= 1e-5 * float(img) and abs(t[1] - float(dep)) <= 1e-5 * float(dep)
+    assert abs(t[2] - (w_i * float(img) + w_d * float(dep))) <= 1e-5 * abs(t[2]) and t[3] == float(mask.sum())
+    torch.testing.assert_close(dC, c.grad, rtol=0, atol=1e-7)
+    want_dD = ds.grad if ds.grad is not None else torch.zeros_like(depth_sil)
+    torch.testing.assert_close(dD, want_dD, rtol=0, atol=1e-7)
+
+
 def test_tracking_loop_with_orb_term_gate_and_early_exit():
     """Render::RenderStartTraking's loop (src/Render.cc:1052-1127) through PoseOptimizer.run: photometric + depth terms from
     the rasterizer, the ORB reprojection term with outlier matches that the chi-square gate (5.991) must drop at half the
