@@ -295,9 +295,11 @@ int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, char
     auto al = [](const void* q) { return q && (reinterpret_cast<uintptr_t>(q) & 15) == 0 ? 1 : 0; };
     {
         StageTimer _t(ST_PREPROCESS, s);
-        // resident CTAs per SM the compiler must allow (the kernel is latency bound: occupancy against registers): 8, measured
+        // resident CTAs per SM the compiler must allow (the kernel is latency bound: occupancy against registers).  Measured with the
+        // bucket stores in the kernel: 8 (32 registers, 44 B of spills) 67.6 us, 6 (40 registers) 64.0 us, 5 (48) 65.9 us.  (Deferring
+        // the bucket stores to the end of the thread, under the atomics' round trip, costs registers: 66.7 us at 6.)
 #ifdef GSB_TUNING
-        static const int minb = [] { const char* e = getenv("GSB_PREPROCESS_MINB"); return e ? atoi(e) : 8; }();
+        static const int minb = [] { const char* e = getenv("GSB_PREPROCESS_MINB"); return e ? atoi(e) : 6; }();
 #endif
 #define GSB_PRE_LAUNCH(MB)                                                                                                \
     preprocess_kernel<MB><<<GL.num_blocks, PRE_THREADS, 0, s>>>(                                                          \
@@ -307,9 +309,9 @@ int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, char
         al(p.means3D), al(p.scales), al(p.colors_precomp), reinterpret_cast<uint2*>(image + IL.ranges),                 \
         reinterpret_cast<uint32_t*>(image + IL.tile_cursor), reinterpret_cast<GeomHeader*>(geom + GL.header), capacity)
 #ifdef GSB_TUNING
-        if (minb == 6) GSB_PRE_LAUNCH(6); else if (minb == 5) GSB_PRE_LAUNCH(5); else
+        if (minb == 8) GSB_PRE_LAUNCH(8); else if (minb == 5) GSB_PRE_LAUNCH(5); else
 #endif
-        GSB_PRE_LAUNCH(8);
+        GSB_PRE_LAUNCH(6);
 #undef GSB_PRE_LAUNCH
         GSB_LAUNCH_CHECK();
     }
