@@ -11,7 +11,7 @@ ncu -i gpurun_out/${TAG}_prof.ncu-rep --page raw --csv > gpurun_out/${TAG}_prof_
 # staging engine A/B on the backward (tune build): LDGSTS ring (default) vs one 48-byte cp.async.bulk (UBLKCP) per record
 for v in ldgsts bulk; do echo "== GSB_BLEND_STAGE=$v" >> gpurun_out/${TAG}_stage_ab.txt; GSB_LIB=$PWD/gsorb_slam_b200/libgsb_tune.so GSB_BLEND_STAGE=$v python bench.py --quick --steps 30 2>/dev/null | cut -c1-330 >> gpurun_out/${TAG}_stage_ab.txt; done
 # sanitizers over the small parity cases (every kernel of the frame, all staging / barrier / atomic paths)
-timeout 900 compute-sanitizer --tool memcheck --print-limit 10 python -m pytest tests/test_golden_gpu.py -m gpu -x -q -k "small_case and tiny_default or ragged or ties and 6000 or tile_sort and one_plane" > gpurun_out/${TAG}_memcheck.log 2>&1
+timeout 900 compute-sanitizer --tool memcheck --print-limit 10 python -m pytest tests/test_golden_gpu.py -m gpu -x -q -k "small_case and tiny_default or ragged or ties and 6000 or tile_sort and one_plane or blended_pair or alpha_decisions" > gpurun_out/${TAG}_memcheck.log 2>&1
 timeout 900 compute-sanitizer --tool racecheck --print-limit 10 python -m pytest tests/test_golden_gpu.py -m gpu -x -q -k "small_case and tiny_default and True" > gpurun_out/${TAG}_racecheck.log 2>&1
 tail -3 gpurun_out/${TAG}_pytest.log; cut -c1-300 gpurun_out/${TAG}_bench_ref.json gpurun_out/${TAG}_bench.json gpurun_out/${TAG}_quick.json; cat gpurun_out/${TAG}_stage_ab.txt | cut -c1-250
 grep -E "ERROR SUMMARY|passed|failed" gpurun_out/${TAG}_memcheck.log gpurun_out/${TAG}_racecheck.log
