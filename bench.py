@@ -8,7 +8,9 @@ supplied) over one synthetic frame per rank.  Default workload: the headline con
 1 M Gaussians at 640x480 (gsorb_slam_b200/scene.py CONFIGS["headline_1m"], seed 0).
 
 * ``value``   : whole-job frames/s with every input resident in HBM (gsb_forward_ws + gsb_backward,
-                sync-free), timed with CUDA events around each step, L2 flushed between steps.
+                sync-free), timed with CUDA events around each step, L2 flushed between steps.  N = 1: the
+                step is a CUDA-graph replay of the frame captured from those two calls; the plain-launch
+                time of the same loop is printed as ``plain_launches`` (--no-graph times only that).
 * ``e2e``     : same metric through the host-buffer C-ABI call (gsb_forward_backward_host): pinned host
                 inputs copied H2D and image + gradients copied D2H inside the timed region.
 * ``roofline``: dominant kernel's algorithmic bytes / its CUDA-event duration (gsb_profile_*), against
@@ -16,8 +18,9 @@ supplied) over one synthetic frame per rank.  Default workload: the headline con
 * ``cpu_baseline``: the oracle's naive per-pixel C++ loop (oracle/gs_oracle.cpp, OpenMP) on the box's
                 host cores, a bounded sample of the same workload (rank 0, N = 1 only).
 * N > 1       : keyframe-batch shard -- every rank rasterizes a different camera over replicated
-                Gaussians, then ONE NCCL all-reduce of the packed per-Gaussian gradient block [14, P]
-                (SURVEY.md 8e); weak scaling, value = N frames / max-over-ranks step time.
+                Gaussians, then ONE sum all-reduce of the packed per-Gaussian gradient block [14, P] by the libgsb
+                exchange kernel (checked against NCCL on a warm-up step: ``exchange_checked``; SURVEY.md 8e);
+                weak scaling, value = N frames / max-over-ranks step time.
 * ``--impl reference``: the UNMODIFIED reference CUDA kernels (oracle/_ref/libgsref.so, built from
                 /root/reference by oracle/Makefile) driven as src/Rasterizer.cu drives them, same workload.
                 (The reference's implementation of this path is CUDA, not CPU, so this arm runs on the
@@ -369,15 +372,20 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    if args.graph and world == 1:
-        # the sync-free entry points only enqueue kernels and memsets: capture one frame, replay it every step
+    # N = 1: the timed step is a CUDA-graph replay of the frame (the sync-free entry points only enqueue kernels and memsets, so one
+    # frame is captured once and replayed every step: no launch gaps between its 7 kernels, 18 us per frame at the headline
+    # workload); the same loop with plain launches is timed beside it (`plain_launches`).  --no-graph: plain launches only.
+    eager_step, use_graph, launches_per_frame = step, (world == 1 and not args.no_graph), None
+    if use_graph:
         for _ in range(3):
             step()
         torch.cuda.synchronize()
         cg = torch.cuda.CUDAGraph()
+        L.gsb_launch_count_reset()
         with torch.cuda.graph(cg):
             step()
-        eager_step, step = step, cg.replay
+        launches_per_frame = int(L.gsb_launch_count_reset())   # kernel nodes of the graph (the library counts its launches)
+        step = cg.replay
 
     # clocks / throttle reasons are sampled from here until the last GPU leg of this function (main timed region, e2e,
     # per-stage profile, mapping iteration): all of them are timed regions of the line that gets printed
@@ -389,13 +397,22 @@ def run_ours(args):
     launches_timed = launches * args.steps // (args.steps + args.warmup)
     ms_per_step = ms_total / args.steps
     value = world * FPR * 1000.0 / ms_per_step
+    plain = None
+    if use_graph:
+        launches_timed = launches_per_frame * args.steps      # the graph's kernel nodes, replayed once per timed step
+        step = eager_step                                      # every later leg (stage profile, e2e, iteration) uses plain launches
+        ms_plain = timed(step, args.steps, args.warmup) / args.steps
+        plain = {"value": world * FPR * 1000.0 / ms_plain, "ms_per_step": ms_plain}
 
     if args.quick:
         clk.__exit__(None, None, None)
     if args.quick and args.graph:
         if rank == 0:
-            print(json.dumps({"quick": True, "graph": True, "workload": args.workload, "value": value, "ms_per_step": ms_per_step}), flush=True)
+            print(json.dumps({"quick": True, "graph": use_graph, "workload": args.workload, "value": value, "ms_per_step": ms_per_step,
+                              "plain_launches": plain}), flush=True)
         return
+    if args.quick and plain is not None:   # the developer loop compares stage sums with the plain-launch frame
+        value, ms_per_step = plain["value"], plain["ms_per_step"]
     if args.quick:
         L.gsb_profile_begin()
         for _ in range(args.steps):
@@ -704,6 +721,10 @@ def run_ours(args):
                         "single_frame_latency_ms": ms_e2e_single,
                         "l2": "every step's inputs arrive from host memory (no flush needed)"},
                 "gpu_launches": launches_timed, "clocks": clk.summary(), "roofline": roofline}
+        line["launch"] = ("CUDA-graph replay of the frame (7 kernels + 2 memsets captured once from the sync-free C ABI calls)" if use_graph
+                          else "plain stream launches")
+        if plain is not None:
+            line["plain_launches"] = plain
         # Issue-slot view of the blend kernels (they are instruction-issue bound, not byte bound): warp instructions per launch from the
         # committed ncu capture (profiles/ncu_inst_executed.json, smsp__inst_executed.sum) over the LIVE stage time x the SMs' issue rate
         # (148 SMs x 4 schedulers x 1 warp instruction per clock at the clock sampled during this run), and per blended (pixel, splat) pair.
@@ -1003,7 +1024,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-workloads", action="store_true", help="skip the table of the other BASELINE configs / stress variants")
     ap.add_argument("--max-rendered", type=int, default=0, help="binning capacity in tile instances (default 4 P + 4096)")
-    ap.add_argument("--graph", action="store_true", help="N = 1: capture the frame into a CUDA graph and time replays")
+    ap.add_argument("--graph", action="store_true", help="--quick: print the graph-replay and plain-launch frame times only")
+    ap.add_argument("--no-graph", action="store_true", help="N = 1: time plain launches instead of CUDA-graph replays of the frame")
     ap.add_argument("--quick", action="store_true", help="developer mode: value + per-stage times only (no e2e / cpu legs)")
     ap.add_argument("--frames-per-rank", type=int, default=1,
                     help="keyframes every rank renders per step (their gradients are summed locally before the ONE exchange of the step): "
