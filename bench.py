@@ -8,8 +8,8 @@ supplied) over one synthetic frame per rank.  Default workload: the headline con
 1 M Gaussians at 640x480 (gsorb_slam_b200/scene.py CONFIGS["headline_1m"], seed 0).
 
 * ``value``   : whole-job frames/s with every input resident in HBM (gsb_forward_ws + gsb_backward,
-                sync-free), timed with CUDA events around each step, L2 flushed between steps.  N = 1: the
-                step is a CUDA-graph replay of the frame captured from those two calls; the plain-launch
+                sync-free), timed with CUDA events around each step, L2 flushed between steps.  The frame of a
+                step is a CUDA-graph replay captured from those two calls (N > 1: followed by the exchange kernel); the plain-launch
                 time of the same loop is printed as ``plain_launches`` (--no-graph times only that).
 * ``e2e``     : same metric through the host-buffer C-ABI call (gsb_forward_backward_host): pinned host
                 inputs copied H2D and image + gradients copied D2H inside the timed region.
@@ -258,7 +258,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # (NCCL_DEBUG is left as the caller set it: unset prints nothing; WARN or higher prints the version banner on stdout before the JSON line)
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     sc = make_rank_scene(args.workload, rank)
@@ -306,7 +306,7 @@ def run_ours(args):
         g2.dL_dmean3D, g2.dL_dcolor, g2.dL_dopacity, g2.dL_dscale, g2.dL_drot = b2, b2 + 12 * P, b2 + 24 * P, b2 + 28 * P, b2 + 40 * P
         g2.dL_dmean2D, g2.dL_dconic, g2.dL_dcov3D, g2.dL_dsh = sp, sp + 12 * P, sp + 28 * P, None
 
-    def step():
+    def frames():   # this rank's forward + backward passes of the step (what the CUDA graph captures)
         stream = torch.cuda.current_stream(dev).cuda_stream   # looked up per call: a CUDA-graph capture runs on its own stream
         for j in range(FPR):
             _lib.check(L.gsb_forward_ws(C.byref(fr._args), fr.geom.data_ptr(), fr.geom.numel(), fr.binning.data_ptr(),
@@ -316,11 +316,17 @@ def run_ours(args):
                                       fr.img.data_ptr(), dL.data_ptr(), C.byref(g if j == 0 else g2), stream))
             if j:
                 block.add_(block2)
+
+    def exchange():
         if world > 1:
             if xch is not None:
                 xch.allreduce(block, use_multicast=use_mc)
             else:
                 dist.all_reduce(block)
+
+    def step():
+        frames()
+        exchange()
 
     # N > 1: the exchange kernel is CHECKED here, on this box, against NCCL's all-reduce of the same per-rank blocks
     exchange_checked = None
@@ -372,20 +378,29 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    # N = 1: the timed step is a CUDA-graph replay of the frame (the sync-free entry points only enqueue kernels and memsets, so one
+    # The timed step is a CUDA-graph replay of the frame (the sync-free entry points only enqueue kernels and memsets, so one
     # frame is captured once and replayed every step: no launch gaps between its 7 kernels, 18 us per frame at the headline
     # workload); the same loop with plain launches is timed beside it (`plain_launches`).  --no-graph: plain launches only.
-    eager_step, use_graph, launches_per_frame = step, (world == 1 and not args.no_graph), None
+    eager_step, use_graph, launches_per_frame = step, not args.no_graph, None
     if use_graph:
         for _ in range(3):
             step()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         cg = torch.cuda.CUDAGraph()
         L.gsb_launch_count_reset()
         with torch.cuda.graph(cg):
-            step()
+            frames()
         launches_per_frame = int(L.gsb_launch_count_reset())   # kernel nodes of the graph (the library counts its launches)
-        step = cg.replay
+        if world == 1:
+            step = cg.replay
+        else:   # N > 1: the exchange kernel follows the replayed frame on the same stream (one more launch per step)
+            launches_per_frame += 1 if xch is not None else 0
+
+            def step():
+                cg.replay()
+                exchange()
 
     # clocks / throttle reasons are sampled from here until the last GPU leg of this function (main timed region, e2e,
     # per-stage profile, mapping iteration): all of them are timed regions of the line that gets printed
@@ -721,8 +736,8 @@ def run_ours(args):
                         "single_frame_latency_ms": ms_e2e_single,
                         "l2": "every step's inputs arrive from host memory (no flush needed)"},
                 "gpu_launches": launches_timed, "clocks": clk.summary(), "roofline": roofline}
-        line["launch"] = ("CUDA-graph replay of the frame (7 kernels + 2 memsets captured once from the sync-free C ABI calls)" if use_graph
-                          else "plain stream launches")
+        line["launch"] = ("CUDA-graph replay of the frame (7 kernels + 2 memsets captured once from the sync-free C ABI calls)"
+                          + (", then the exchange kernel" if world > 1 else "") if use_graph else "plain stream launches")
         if plain is not None:
             line["plain_launches"] = plain
         # Issue-slot view of the blend kernels (they are instruction-issue bound, not byte bound): warp instructions per launch from the
@@ -771,7 +786,7 @@ def run_tile_row(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # (NCCL_DEBUG is left as the caller set it: unset prints nothing; WARN or higher prints the version banner on stdout before the JSON line)
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     sc = make_rank_scene(args.workload, 0)      # the same keyframe on every rank
@@ -1025,7 +1040,7 @@ def main():
     ap.add_argument("--no-workloads", action="store_true", help="skip the table of the other BASELINE configs / stress variants")
     ap.add_argument("--max-rendered", type=int, default=0, help="binning capacity in tile instances (default 4 P + 4096)")
     ap.add_argument("--graph", action="store_true", help="--quick: print the graph-replay and plain-launch frame times only")
-    ap.add_argument("--no-graph", action="store_true", help="N = 1: time plain launches instead of CUDA-graph replays of the frame")
+    ap.add_argument("--no-graph", action="store_true", help="time plain launches instead of CUDA-graph replays of the frame")
     ap.add_argument("--quick", action="store_true", help="developer mode: value + per-stage times only (no e2e / cpu legs)")
     ap.add_argument("--frames-per-rank", type=int, default=1,
                     help="keyframes every rank renders per step (their gradients are summed locally before the ONE exchange of the step): "
