@@ -108,21 +108,6 @@ prologue_backward_kernel(int P, const float* __restrict__ Tcw, const float* __re
     if (dTcw) reduce12_and_add(part, dTcw);
 }
 
-__global__ void __launch_bounds__(EX_THREADS)
-adam_kernel(long long n, float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
-            float* __restrict__ v, float omb1, float beta2, float omb2, float eps, float step_size, float inv_sqrt_bc2)
-{
-    for (long long i = (long long)blockIdx.x * EX_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * EX_THREADS) {
-        const float g = grad[i];
-        const float mi = m[i] + (g - m[i]) * omb1;                      // exp_avg.lerp_(grad, 1 - beta1)
-        const float vi = v[i] * beta2 + omb2 * g * g;                   // mul_(beta2).addcmul_(g, g, 1 - beta2)
-        m[i] = mi;
-        v[i] = vi;
-        const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;             // (sqrt(v) / sqrt(bc2)).add_(eps)
-        param[i] = param[i] - step_size * (mi / denom);                 // addcdiv_(m, denom, -step_size)
-    }
-}
-
 // The whole packed block in ONE launch: group g covers [bound[g-1], bound[g]) and has its own learning rate
 // (torch::optim::Adam with one param group per tensor, src/Gaussian.cc:158-175).
 struct AdamGroups {
@@ -282,8 +267,17 @@ int launch_adam(long long n, float* param, const float* grad, float* m, float* v
     const double bc2 = 1.0 - pow(beta2, (double)step);
     const float step_size = (float)(lr / bc1);
     const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
-    adam_kernel<<<grid_for(n), EX_THREADS, 0, s>>>(n, param, grad, m, v, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
-                                                   (float)eps, step_size, inv_sqrt_bc2);
+    AdamGroups G;   // one group: the same (vectorised) kernel as the packed block
+    G.n = 1;
+    for (int g = 0; g < 8; g++) { G.bound[g] = n; G.step_size[g] = step_size; }
+    const bool vec = ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(m) |
+                       reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+    if (vec)
+        adam_groups_kernel<true><<<grid_for((n + 3) / 4), EX_THREADS, 0, s>>>(n, param, grad, m, v, (float)(1.0 - beta1), (float)beta2,
+                                                                            (float)(1.0 - beta2), (float)eps, inv_sqrt_bc2, G);
+    else
+        adam_groups_kernel<false><<<grid_for(n), EX_THREADS, 0, s>>>(n, param, grad, m, v, (float)(1.0 - beta1), (float)beta2,
+                                                                   (float)(1.0 - beta2), (float)eps, inv_sqrt_bc2, G);
     GSB_LAUNCH_CHECK();
     return GSB_OK;
 }
