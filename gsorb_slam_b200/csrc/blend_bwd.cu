@@ -299,11 +299,15 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
                     r0 = ka + __shfl_xor_sync(0xffffffffu, sa, 1);
                     r1 = kb2 + __shfl_xor_sync(0xffffffffu, sb, 1);
                     v8 += __shfl_xor_sync(0xffffffffu, v8, 1);
+                    // five channels: lane 0 fetches sum 9 from the hi pair, so that slots 8 and 9 leave in ONE 8-byte RED
+                    const float v9 = CH == 5 ? __shfl_xor_sync(0xffffffffu, v8, 2) : 0.f;
                     if (touched) {
                         float* dst = acc_l + (size_t)gid * 12;   // slots 2 l, 2 l + 1 of the Gaussian's accumulator
                         red_add_v2(dst, r0, r1);
-                        if (l == 0) atomicAdd(dst + 8, v8);             // slot 8
-                        if (CH == 5 && l == 2) atomicAdd(dst + 5, v8);  // slot 9 = 2 l + 5
+                        if (l == 0) {
+                            if (CH == 5) red_add_v2(dst + 8, v8, v9);   // slots 8, 9
+                            else atomicAdd(dst + 8, v8);                // slot 8
+                        }
                     }
                 } else {
                     if (touched) {
