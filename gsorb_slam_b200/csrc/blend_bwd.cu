@@ -66,7 +66,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
                       const SplatRec* __restrict__ rec, int W, int H, const float* __restrict__ bg,
                       const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                       const uint32_t* __restrict__ tile_max_contrib, const float* __restrict__ dL_dpix,
-                      const float* __restrict__ dL_ddepth_sil, float* __restrict__ acc /* [P][12] */, const uint32_t* __restrict__ hits_tail,
+                      const float* __restrict__ dL_ddepth_sil, float* __restrict__ acc /* [P][16] */, const uint32_t* __restrict__ hits_tail,
                       const GeomHeader* __restrict__ hdr, uint32_t band_y0)
 {
     static_assert(GL == 4 || GL == 2, "lane groups of 4 (2x2 pixels) or 2 (2x1 pixels)");
@@ -223,7 +223,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
         int wi = max(wtop, 0);
         uint32_t mask = wtop >= 0 ? hrow[wi * GROUPS] : 0u;
         uint32_t nmask = wi > 0 ? hrow[(wi - 1) * GROUPS] : 0u;   // hit word of the group's NEXT window, fetched one window ahead
-        float* const acc_l = acc + 2 * l * (GL == 4 ? 1 : 2);     // this lane's pair / quad of accumulator slots
+        float* const acc_l = acc + (GL == 4 ? 4 * l : 8 * l);     // this lane's float4 of the accumulator record (GL = 2: its two float4)
         while (true) {
             if (report && it == ARRIVE_AT) {
                 cp_async_wait<0>();
@@ -290,8 +290,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
                 float v8 = wc * d8k;
                 v8 += __shfl_xor_sync(0xffffffffu, CH == 5 ? wc * d8s : v8, GL / 2);
                 const bool touched = (cb >> gshift) & ((1u << GL) - 1u);   // this group blended the splat into at least one of its pixels
-                // accumulator slots (GradAcc, read by gauss_bwd.cu): 0 S u dx, 1 S u dx^2, 2 S u dxdy, 3 S w d_r, 4 S u dy, 5 S u dy^2, 6 S u,
-                // 7 S w d_g, 8 S w d_b, 9 S w d_z
+                // accumulator record (GradAcc, 16 floats, read by gauss_bwd.cu): lane l of a 4-lane group owns floats 4 l .. 4 l + 3
                 if (GL == 4) {
                     const bool b1 = l & 1;   // second stage: the even lane keeps (r0, r1), the odd lane (r2, r3)
                     const float sa = b1 ? r0 : r2, ka = b1 ? r2 : r0;
@@ -299,21 +298,16 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const char* __restrict__
                     r0 = ka + __shfl_xor_sync(0xffffffffu, sa, 1);
                     r1 = kb2 + __shfl_xor_sync(0xffffffffu, sb, 1);
                     v8 += __shfl_xor_sync(0xffffffffu, v8, 1);
-                    // five channels: lane 0 fetches sum 9 from the hi pair, so that slots 8 and 9 leave in ONE 8-byte RED
-                    const float v9 = CH == 5 ? __shfl_xor_sync(0xffffffffu, v8, 2) : 0.f;
-                    if (touched) {
-                        float* dst = acc_l + (size_t)gid * 12;   // slots 2 l, 2 l + 1 of the Gaussian's accumulator
-                        red_add_v2(dst, r0, r1);
-                        if (l == 0) {
-                            if (CH == 5) red_add_v2(dst + 8, v8, v9);   // slots 8, 9
-                            else atomicAdd(dst + 8, v8);                // slot 8
-                        }
-                    }
+                    // lane 0: {S u dx, S u dx^2, S w d_b, 0}  lane 1: {S u dxdy, S w d_r, 0, 0}  lane 2: {S u dy, S u dy^2, S w d_z | 0, 0}
+                    // lane 3: {S u, S w d_g, 0, 0} -- ONE 16-byte RED per lane and visit
+                    const float third = (l == 0 || (CH == 5 && l == 2)) ? v8 : 0.f;
+                    if (touched) red_add_v4(acc_l + (size_t)gid * ACC_FLOATS, r0, r1, third, 0.f);
                 } else {
-                    if (touched) {
-                        float* dst = acc_l + (size_t)gid * 12;   // slots 4 l .. 4 l + 3
-                        red_add_v4(dst, r0, r1, r2, r3);
-                        if (CH == 5 || l == 0) atomicAdd(dst + 8 - 3 * l, v8);   // slot 8 + l
+                    if (touched) {   // lo lane: floats 0, 1 | 4, 5 (+ 2);  hi lane: floats 8, 9 | 12, 13 (+ 10 with five channels)
+                        float* dst = acc_l + (size_t)gid * ACC_FLOATS;
+                        red_add_v2(dst, r0, r1);
+                        red_add_v2(dst + 4, r2, r3);
+                        if (CH == 5 || l == 0) atomicAdd(dst + 2, v8);
                     }
                 }
             }

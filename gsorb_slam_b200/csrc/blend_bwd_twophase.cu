@@ -87,7 +87,7 @@ blend_backward_twophase_kernel(const uint2* __restrict__ ranges, const char* __r
                       const SplatRec* __restrict__ rec, int W, int H, const float* __restrict__ bg,
                       const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                       const uint32_t* __restrict__ tile_max_contrib, const float* __restrict__ dL_dpix,
-                      const float* __restrict__ dL_ddepth_sil, float* __restrict__ acc /* [P][12] */, const uint32_t* __restrict__ hits_tail,
+                      const float* __restrict__ dL_ddepth_sil, float* __restrict__ acc /* [P][16] */, const uint32_t* __restrict__ hits_tail,
                       const GeomHeader* __restrict__ hdr, uint32_t band_y0)
 {
     extern __shared__ __align__(16) unsigned char bwd_smem_raw[];
@@ -302,11 +302,11 @@ blend_backward_twophase_kernel(const uint2* __restrict__ ranges, const char* __r
                     }
                 }
                 if (any) {
-                    float* dst = acc + (size_t)S.ids[tid] * 12;
-                    red_add_v4(dst, m_dx, m_dx2, m_dxdy, c0);       // slot order of blend_bwd.cu / gauss_bwd.cu
-                    red_add_v4(dst + 4, m_dy, m_dy2, m_u, c1);
-                    if (CH == 5) red_add_v4(dst + 8, c2, c3, 0.f, 0.f);
-                    else atomicAdd(dst + 8, c2);
+                    float* dst = acc + (size_t)S.ids[tid] * ACC_FLOATS;   // GradAcc layout (common.cuh)
+                    red_add_v4(dst, m_dx, m_dx2, c2, 0.f);
+                    red_add_v4(dst + 4, m_dxdy, c0, 0.f, 0.f);
+                    red_add_v4(dst + 8, m_dy, m_dy2, CH == 5 ? c3 : 0.f, 0.f);
+                    red_add_v4(dst + 12, m_u, c1, 0.f, 0.f);
                 }
             }
             hw_hi = hw_lo - 1;

@@ -41,14 +41,18 @@ struct alignas(16) SplatRec {
 };
 static_assert(sizeof(SplatRec) == 48, "record must be 48 bytes");
 
-// Packed backward accumulators (one per Gaussian, 48 bytes, fp32 vector REDs): raw moments of u = G dL/dalpha and the
-// colour sums of w = alpha T (blend_bwd.cu); gauss_bwd.cu turns them into dL/dmean2D, dL/dconic, dL/dopacity, dL/dcolor
-//   a = { S u dx, S u dx^2, S u dx dy, S w d_r }
-//   b = { S u dy, S u dy^2, S u,       S w d_g }
-//   c = { S w d_b, S w d_z (fused 5-channel pass only), -, - }
+// Packed backward accumulators (one per Gaussian, 64 bytes = two aligned sectors, fp32 vector REDs): raw moments of u = G dL/dalpha
+// and the colour sums of w = alpha T (blend_bwd.cu); gauss_bwd.cu turns them into dL/dmean2D, dL/dconic, dL/dopacity, dL/dcolor.
+// One float4 per lane of a 4-lane group, so that every lane issues ONE 16-byte RED per visit (slots marked - stay zero):
+//   a = { S u dx,    S u dx^2, S w d_b, - }
+//   b = { S u dx dy, S w d_r,  -,       - }
+//   c = { S u dy,    S u dy^2, S w d_z (fused 5-channel pass only), - }
+//   d = { S u,       S w d_g,  -,       - }
+constexpr int ACC_FLOATS = 16;
 struct alignas(16) GradAcc {
-    float4 a, b, c;
+    float4 a, b, c, d;
 };
+static_assert(sizeof(GradAcc) == ACC_FLOATS * 4, "accumulator record is 64 bytes");
 
 // ---- opaque state blobs -------------------------------------------------------------------
 constexpr uint32_t GEOM_MAGIC = 0x67736231u;  // "gsb1"

@@ -16,7 +16,7 @@ constexpr int GB_THREADS = 256;
 struct GaussBwdParams {
     FwdParams f;
     const int* radii;
-    const float* acc;          // [P][12] packed blend-backward sums (raw moments, see blend_bwd.cu)
+    const float* acc;          // [P][16] packed blend-backward sums (raw moments, GradAcc in common.cuh)
     const SplatRec* rec;       // conic + opacity for the moment -> gradient maps
     const uint8_t* clamped;    // SH clamp bits
     gsb_grad_outputs g;
@@ -94,9 +94,8 @@ gauss_backward_kernel(GaussBwdParams q)
     // every load that depends only on idx is issued up front, whether or not the Gaussian was rendered: the
     // kernel is bound by memory latency, and a dependent chain radii -> accumulators -> parameters triples it
     const int radius_ld = q.radii[idx];
-    const float4* ap = reinterpret_cast<const float4*>(q.acc + i * 12);
-    const float4 a0 = ap[0], a1 = ap[1];
-    const float a8 = q.acc[i * 12 + 8];
+    const float4* ap = reinterpret_cast<const float4*>(q.acc + i * ACC_FLOATS);
+    const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];
     const float4 rb = q.rec[i].b;  // conic.x, conic.y, conic.z, opacity (stale bytes when not rendered: never used then)
     const float mx = p.means3D[3 * i], my = p.means3D[3 * i + 1], mz = p.means3D[3 * i + 2];
     float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -110,16 +109,16 @@ gauss_backward_kernel(GaussBwdParams q)
     //   dL/dmean2D = -0.5 W o (A X + B Y), -0.5 H o (C Y + B X);  dL/dconic = -0.5 o (XX, XY, YY);  dL/dopacity = U
     float a[9];
     if (rendered) {
-        // slots (blend_bwd.cu): 0 S u dx, 1 S u dx^2, 2 S u dxdy, 3 S w d_r, 4 S u dy, 5 S u dy^2, 6 S u, 7 S w d_g, 8 S w d_b, 9 S w d_z
-        const float X = a0.x, XX = a0.y, XY = a0.z, Y = a1.x, YY = a1.y, U = a1.z;
+        // GradAcc: a = {S u dx, S u dx^2, S w d_b, -}, b = {S u dxdy, S w d_r, -, -}, c = {S u dy, S u dy^2, S w d_z, -}, d = {S u, S w d_g, -, -}
+        const float X = a0.x, XX = a0.y, XY = a1.x, Y = a2.x, YY = a2.y, U = a3.x;
         a[0] = -0.5f * p.W * rb.w * (rb.x * X + rb.y * Y);
         a[1] = -0.5f * p.H * rb.w * (rb.z * Y + rb.y * X);
         a[2] = -0.5f * rb.w * XX;
         a[3] = -0.5f * rb.w * XY;
         a[4] = -0.5f * rb.w * YY;
         a[5] = U;
-        a[6] = a0.w; a[7] = a1.w;
-        a[8] = a8;
+        a[6] = a1.y; a[7] = a3.y;
+        a[8] = a0.z;
     } else {
 #pragma unroll
         for (int k = 0; k < 9; k++) a[k] = 0.f;
@@ -127,7 +126,7 @@ gauss_backward_kernel(GaussBwdParams q)
     if (g.dL_dmean2D) { g.dL_dmean2D[3 * i] = a[0]; g.dL_dmean2D[3 * i + 1] = a[1]; g.dL_dmean2D[3 * i + 2] = 0.f; }
     if (g.dL_dconic) { g.dL_dconic[4 * i] = a[2]; g.dL_dconic[4 * i + 1] = a[3]; g.dL_dconic[4 * i + 2] = 0.f; g.dL_dconic[4 * i + 3] = a[4]; }
     if (g.dL_dopacity) g.dL_dopacity[i] = a[5];
-    if (q.dL_dzcolor) q.dL_dzcolor[i] = rendered ? q.acc[i * 12 + 9] : 0.f;
+    if (q.dL_dzcolor) q.dL_dzcolor[i] = rendered ? a2.z : 0.f;
     if (g.dL_dcolor) { g.dL_dcolor[3 * i] = a[6]; g.dL_dcolor[3 * i + 1] = a[7]; g.dL_dcolor[3 * i + 2] = a[8]; }
 
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -253,7 +252,7 @@ gauss_backward_kernel(GaussBwdParams q)
     } else if (p.shs && g.dL_dsh) {
         for (int k = 0; k < p.M * 3; k++) g.dL_dsh[i * p.M * 3 + k] = 0.f;
     }
-    if (q.z_attached && rendered) dmz += q.acc[i * 12 + 9];
+    if (q.z_attached && rendered) dmz += a2.z;
     if (g.dL_dmean3D) { g.dL_dmean3D[3 * i] = dmx; g.dL_dmean3D[3 * i + 1] = dmy; g.dL_dmean3D[3 * i + 2] = dmz; }
     if (g.dL_dcov3D) {
 #pragma unroll
