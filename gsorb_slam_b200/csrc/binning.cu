@@ -51,7 +51,7 @@ tile_scan_kernel(const uint32_t* __restrict__ tile_count, uint2* __restrict__ ra
 // it there.  Only a frame whose longest tile list exceeds BUCKET_CAP takes this pass: every thread returns at once otherwise.
 // All instances claim their slots with cursor atomics (the segment starts come from the scan).
 __global__ void __launch_bounds__(DUP_THREADS)
-duplicate_kernel(int P, const SplatRec* __restrict__ rec, const int* __restrict__ radii,
+duplicate_kernel(int P, const SplatRec* __restrict__ rec, const int* __restrict__ radii, const uint32_t* __restrict__ tiles_touched,
                  uint32_t* __restrict__ cursor, const GeomHeader* __restrict__ hdr,
                  uint64_t* __restrict__ pairs, int tiles_x, int tiles_y, int band_y0, int band_y1)
 {
@@ -60,7 +60,7 @@ duplicate_kernel(int P, const SplatRec* __restrict__ rec, const int* __restrict_
     for (int idx = blockIdx.x * DUP_THREADS + threadIdx.x; idx < P; idx += gridDim.x * DUP_THREADS) {   // a few CTAs per SM, grid-stride
         // records of culled Gaussians are stale bytes inside the blob: harmless to read, never used
         const int radius = radii[idx];
-        if (radius <= 0) continue;
+        if (radius <= 0 || tiles_touched[idx] == 0) continue;   // (outside this rank's band: no record was written)
         const float4 a = rec[idx].a;
         const float depth = rec[idx].c.w;
         const uint64_t record = ((uint64_t)__float_as_uint(depth) << 32) | (uint32_t)idx;
@@ -776,7 +776,7 @@ int launch_binning(const FwdParams& p, char* geom, const GeomLayout& GL, char* b
         StageTimer _t(ST_DUPLICATE, s);
         duplicate_kernel<<<GL.num_blocks < 8 * NUM_SMS ? GL.num_blocks : 8 * NUM_SMS, DUP_THREADS, 0, s>>>(
             p.P, reinterpret_cast<const SplatRec*>(geom + GL.rec), reinterpret_cast<const int*>(geom + GL.radii),
-            reinterpret_cast<uint32_t*>(image + IL.tile_cursor), hdr, pairs, p.tiles_x, p.tiles_y, p.band_y0, p.band_y1);
+            reinterpret_cast<const uint32_t*>(geom + GL.tiles_touched), reinterpret_cast<uint32_t*>(image + IL.tile_cursor), hdr, pairs, p.tiles_x, p.tiles_y, p.band_y0, p.band_y1);
         GSB_LAUNCH_CHECK();
     }
     {

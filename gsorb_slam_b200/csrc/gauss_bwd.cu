@@ -16,6 +16,7 @@ constexpr int GB_THREADS = 256;
 struct GaussBwdParams {
     FwdParams f;
     const int* radii;
+    const uint32_t* tiles_touched;   // tiles of THIS band the Gaussian joined (preprocess): 0 = nothing to back-propagate
     const float* acc;          // [P][16] packed blend-backward sums (raw moments, GradAcc in common.cuh)
     const SplatRec* rec;       // conic + opacity for the moment -> gradient maps
     const uint8_t* clamped;    // SH clamp bits
@@ -82,7 +83,7 @@ __device__ __forceinline__ void sh_backward(int deg, int M, const float* __restr
     dmz += (-ox * oz * ddir[0] - oy * oz * ddir[1] + (sum2 - oz * oz) * ddir[2]) * invsum32;
 }
 
-template <int MINB>
+template <int MINB, bool BAND>
 __global__ void __launch_bounds__(GB_THREADS, MINB)
 gauss_backward_kernel(GaussBwdParams q)
 {
@@ -93,16 +94,25 @@ gauss_backward_kernel(GaussBwdParams q)
     const gsb_grad_outputs& g = q.g;
     // every load that depends only on idx is issued up front, whether or not the Gaussian was rendered: the
     // kernel is bound by memory latency, and a dependent chain radii -> accumulators -> parameters triples it
-    const int radius_ld = q.radii[idx];
+    // (tile-row shard: most Gaussians lie outside this rank's band -- there the dependent load pays: radius and band-local tile count
+    // first, everything else only for the Gaussians the band rendered; their gradients are written as zeros)
+    // BAND = false (the whole image): every load that depends only on idx is issued up front, as before
+    int radius_ld = q.radii[idx];
+    if (BAND && radius_ld > 0 && q.tiles_touched[idx] == 0) radius_ld = 0;
+    const bool fetch = !BAND || radius_ld > 0;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* ap = reinterpret_cast<const float4*>(q.acc + i * ACC_FLOATS);
-    const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];
-    const float4 rb = q.rec[i].b;  // conic.x, conic.y, conic.z, opacity (stale bytes when not rendered: never used then)
-    const float mx = p.means3D[3 * i], my = p.means3D[3 * i + 1], mz = p.means3D[3 * i + 2];
+    const float4 a0 = fetch ? ap[0] : z4, a1 = fetch ? ap[1] : z4, a2 = fetch ? ap[2] : z4, a3 = fetch ? ap[3] : z4;
+    const float4 rb = fetch ? q.rec[i].b : z4;  // conic.x, conic.y, conic.z, opacity (stale bytes when not rendered: never used then)
+    float mx = 0.f, my = 0.f, mz = 0.f;
     float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    if (!p.cov3D_precomp) {
-        qv = *reinterpret_cast<const float4*>(p.rotations + 4 * i);
-        s0 = p.scales[3 * i]; s1 = p.scales[3 * i + 1]; s2 = p.scales[3 * i + 2];
+    if (fetch) {
+        mx = p.means3D[3 * i]; my = p.means3D[3 * i + 1]; mz = p.means3D[3 * i + 2];
+        if (!p.cov3D_precomp) {
+            qv = *reinterpret_cast<const float4*>(p.rotations + 4 * i);
+            s0 = p.scales[3 * i]; s1 = p.scales[3 * i + 1]; s2 = p.scales[3 * i + 2];
+        }
     }
     const bool rendered = radius_ld > 0;
     // packed sums from the blend backward -> reference-layout 2D gradients (backward.cu:536-554):
@@ -269,6 +279,7 @@ int launch_gauss_backward(const FwdParams& p, const char* geom, const GeomLayout
     GaussBwdParams q;
     q.f = p;
     q.radii = radii ? radii : reinterpret_cast<const int*>(geom + GL.radii);
+    q.tiles_touched = reinterpret_cast<const uint32_t*>(geom + GL.tiles_touched);
     q.acc = reinterpret_cast<const float*>(geom + GL.acc);
     q.rec = reinterpret_cast<const SplatRec*>(geom + GL.rec);
     q.clamped = reinterpret_cast<const uint8_t*>(geom + GL.clamped);
@@ -280,11 +291,12 @@ int launch_gauss_backward(const FwdParams& p, const char* geom, const GeomLayout
         // 4 resident CTAs (64 registers, small spill) hide more memory latency than 3 (80 registers): measured, round 1
 #ifdef GSB_TUNING
         static const int minb = [] { const char* e = getenv("GSB_GAUSS_BWD_MINB"); return e ? atoi(e) : 4; }();
-        if (minb == 3) gauss_backward_kernel<3><<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(q);
-        else if (minb == 5) gauss_backward_kernel<5><<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(q);
+        if (minb == 3) gauss_backward_kernel<3, false><<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(q);
+        else if (minb == 5) gauss_backward_kernel<5, false><<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(q);
         else
 #endif
-        gauss_backward_kernel<4><<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(q);
+        if (p.band_y0 > 0 || p.band_y1 < p.tiles_y) gauss_backward_kernel<4, true><<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(q);
+        else gauss_backward_kernel<4, false><<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(q);
         GSB_LAUNCH_CHECK();
     }
     return GSB_OK;

@@ -127,7 +127,7 @@ __device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh,
 
 // One thread per Gaussian, 256 per CTA.  Emits the packed record, radii, tiles_touched and
 // the CTA's tile-count sum (first level of the two-level scan).
-template <int MINB>
+template <int MINB, bool BAND>
 __global__ void __launch_bounds__(PRE_THREADS, MINB)
 preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ radii_blob, int* __restrict__ radii_out,
                   uint32_t* __restrict__ tiles_touched, uint64_t* __restrict__ buckets, uint32_t* __restrict__ tile_count,
@@ -172,6 +172,11 @@ preprocess_kernel(FwdParams p, SplatRec* __restrict__ rec, int* __restrict__ rad
             const uint32_t by0 = max(o.miny, (uint32_t)p.band_y0), by1 = min(o.maxy, (uint32_t)p.band_y1);
             const uint32_t rows = by1 > by0 ? by1 - by0 : 0u;
             touched = rows * (o.maxx - o.minx);
+        }
+        // tile-row shard: a Gaussian that is visible but touches no tile of this rank's band keeps its radius and writes nothing
+        // else -- no record, no colour, no threshold search (tiles_touched = 0 tells the per-Gaussian backward to skip it)
+        if (o.visible && (!BAND || touched > 0)) {   // BAND = false (the whole image): a visible Gaussian always touches a tile
+            const uint32_t by0 = max(o.miny, (uint32_t)p.band_y0), by1 = min(o.maxy, (uint32_t)p.band_y1);
             // Binning: one counting atomic per (Gaussian, tile) instance; the slot it returns is the record's place in the tile's
             // bucket, so the (depth bits << 32 | id) record is written right here and the tile sort picks it up -- no second pass over
             // the Gaussians.  Slots past the bucket's capacity are only counted: the scan sees the longest list and the per-tile
@@ -301,18 +306,21 @@ int launch_preprocess(const FwdParams& p, char* geom, const GeomLayout& GL, char
 #ifdef GSB_TUNING
         static const int minb = [] { const char* e = getenv("GSB_PREPROCESS_MINB"); return e ? atoi(e) : 6; }();
 #endif
-#define GSB_PRE_LAUNCH(MB)                                                                                                \
-    preprocess_kernel<MB><<<GL.num_blocks, PRE_THREADS, 0, s>>>(                                                          \
+#define GSB_PRE_LAUNCH_BD(MB, BD)                                                                                         \
+    preprocess_kernel<MB, BD><<<GL.num_blocks, PRE_THREADS, 0, s>>>(                                                          \
         p, reinterpret_cast<SplatRec*>(geom + GL.rec), reinterpret_cast<int*>(geom + GL.radii), radii_out,                \
         reinterpret_cast<uint32_t*>(geom + GL.tiles_touched), reinterpret_cast<uint64_t*>(image + IL.buckets),             \
         reinterpret_cast<uint32_t*>(image + IL.tile_count), reinterpret_cast<uint8_t*>(geom + GL.clamped),                \
         al(p.means3D), al(p.scales), al(p.colors_precomp), reinterpret_cast<uint2*>(image + IL.ranges),                 \
         reinterpret_cast<uint32_t*>(image + IL.tile_cursor), reinterpret_cast<GeomHeader*>(geom + GL.header), capacity)
+        const bool band_mode = p.band_y0 > 0 || p.band_y1 < p.tiles_y;   // tile-row shard: Gaussians outside the band write no record
+#define GSB_PRE_LAUNCH(MB) do { if (band_mode) GSB_PRE_LAUNCH_BD(MB, true); else GSB_PRE_LAUNCH_BD(MB, false); } while (0)
 #ifdef GSB_TUNING
         if (minb == 8) GSB_PRE_LAUNCH(8); else if (minb == 5) GSB_PRE_LAUNCH(5); else
 #endif
         GSB_PRE_LAUNCH(6);
 #undef GSB_PRE_LAUNCH
+#undef GSB_PRE_LAUNCH_BD
         GSB_LAUNCH_CHECK();
     }
     return GSB_OK;
