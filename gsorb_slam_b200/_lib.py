@@ -33,6 +33,13 @@ class GradOutputs(C.Structure):
                                    "dL_dsh", "dL_dscale", "dL_drot")]
 
 
+class MapUpdate(C.Structure):
+    """gsb_map_update (groups: means, rgb, logit opacities, log scales, unnormalised quaternions)"""
+    _fields_ = [("Tcw", _vp), ("params", _vp * 5), ("exp_avg", _vp * 5), ("exp_avg_sq", _vp * 5), ("grads", _vp * 5),
+                ("lr", C.c_float * 5), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("step", _ll),
+                ("dL_dTcw", _vp), ("max_scalar", C.c_float), ("w_scalar", C.c_float), ("w_long", C.c_float), ("reg_terms", _vp)]
+
+
 # name -> (restype, argtypes); every symbol include/gsb.h declares
 SIGNATURES = {
     "gsb_version": (_i, []),
@@ -47,6 +54,7 @@ SIGNATURES = {
     "gsb_backward": (_i, [C.POINTER(RasterArgs), _ll, _vp, _vp, _vp, _vp, _vp, C.POINTER(GradOutputs), _vp]),
     "gsb_forward_fused_ws": (_i, [C.POINTER(RasterArgs), _vp, _sz, _vp, _sz, _ll, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "gsb_backward_fused": (_i, [C.POINTER(RasterArgs), _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(GradOutputs), _vp, _i, _vp]),
+    "gsb_backward_fused_update": (_i, [C.POINTER(RasterArgs), _vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(MapUpdate), _vp]),
     "gsb_visible_filter": (_i, [C.POINTER(RasterArgs), _vp, _vp]),
     "gsb_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
     "gsb_knn_workspace_bytes": (_sz, [_i]),

@@ -352,6 +352,36 @@ int gsb_backward_fused(const gsb_raster_args* args, const int* radii, const void
     return backward_impl(args, radii, geometry, binning, image, dL_dcolor, dL_ddepth_sil, grads, dL_dzcolor, z_attached, stream);
 }
 
+int gsb_backward_fused_update(const gsb_raster_args* args, const int* radii, const void* geometry, const void* binning,
+                              const void* image, const float* dL_dcolor, const float* dL_ddepth_sil, int z_attached,
+                              const gsb_map_update* u, gsb_stream_t stream)
+{
+    if (int rc = validate(args, true, false)) return rc;
+    if (!geometry || !binning || !image) return fail(GSB_ERR_INVALID_ARGUMENT, "forward state blobs are required");
+    if (!dL_dcolor || !u) return fail(GSB_ERR_INVALID_ARGUMENT, "dL_dcolor / update are required");
+    if (args->shs || args->cov3D_precomp || !args->colors_precomp)
+        return fail(GSB_ERR_INVALID_ARGUMENT, "backward_fused_update: precomputed colours, scales and rotations only");
+    const FwdParams p = make_params(args);
+    if (p.band_y0 > 0 || p.band_y1 < p.tiles_y) return fail(GSB_ERR_INVALID_ARGUMENT, "backward_fused_update: whole image only");
+    int ngrads = 0;
+    for (int g = 0; g < 5; g++) {
+        if (p.P > 0 && (!u->params[g] || !u->exp_avg[g] || !u->exp_avg_sq[g]))
+            return fail(GSB_ERR_INVALID_ARGUMENT, "backward_fused_update: parameters and both Adam moments are required");
+        ngrads += u->grads[g] ? 1 : 0;
+    }
+    if (ngrads != 0 && ngrads != 5) return fail(GSB_ERR_INVALID_ARGUMENT, "backward_fused_update: grads are all NULL or all set");
+    if (p.P > 0 && args->colors_precomp != u->params[1])
+        return fail(GSB_ERR_INVALID_ARGUMENT, "backward_fused_update: colors_precomp must be the rgb parameter group");
+    if (!u->Tcw || u->step < 1 || (u->max_scalar > 0.f && !u->reg_terms))
+        return fail(GSB_ERR_INVALID_ARGUMENT, "backward_fused_update: Tcw, step >= 1 and (with regularisers) reg_terms are required");
+    cudaStream_t s = (cudaStream_t)stream;
+    const GeomLayout GL = GeomLayout::make(p.P);
+    const ImageLayout IL = ImageLayout::make(p.W, p.H);
+    char* geom = (char*)const_cast<void*>(geometry);
+    if (int rc = launch_blend_backward(p, geom, GL, (const char*)binning, (const char*)image, IL, dL_dcolor, dL_ddepth_sil, s)) return rc;
+    return launch_map_update(p, geom, GL, radii, z_attached, *u, s);
+}
+
 int gsb_visible_filter(const gsb_raster_args* args, int* radii, gsb_stream_t stream)
 {
     if (int rc = validate(args, false)) return rc;

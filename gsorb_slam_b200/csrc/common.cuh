@@ -398,6 +398,9 @@ int launch_adam_groups(int ngroups, const long long* sizes, const float* lrs, fl
                        double beta1, double beta2, double eps, long long step, cudaStream_t s);
 int launch_scale_regulariser(int P, const float* log_scales, float max_scalar, float w_scalar, float w_long, float* d_log_scales,
                              float* terms, float* acc, cudaStream_t s);
+int launch_scale_regulariser_sum(int P, const float* log_scales, float max_scalar, float* acc, cudaStream_t s);
+int launch_map_update(const FwdParams& p, const char* geom, const GeomLayout& GL, const int* radii, int z_attached,
+                      const gsb_map_update& u, cudaStream_t s);
 size_t knn_workspace_bytes(int P);
 int launch_knn(int P, const float* points, float* mean_dist2, char* ws, cudaStream_t s);
 

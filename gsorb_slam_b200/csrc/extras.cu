@@ -8,6 +8,7 @@
 //   pose_grad          that reduction alone.
 //   adam_step          torch::optim::Adam step of src/Gaussian.cc:131-175 over a flat block.
 #include "common.cuh"
+#include "map_math.cuh"
 
 namespace gsb {
 
@@ -24,38 +25,17 @@ prologue_kernel(int P, const float* __restrict__ Tcw, const float* __restrict__ 
     if (means_cam) {
         const float x = means_world[3 * i], y = means_world[3 * i + 1], z = means_world[3 * i + 2];
 #pragma unroll
-        for (int r = 0; r < 3; r++)
-            means_cam[3 * i + r] = fmaf(Tcw[4 * r + 2], z, fmaf(Tcw[4 * r + 1], y, Tcw[4 * r] * x)) + Tcw[4 * r + 3];
+        for (int r = 0; r < 3; r++) means_cam[3 * i + r] = to_camera(Tcw, r, x, y, z);
     }
-    if (opac) opac[i] = 1.0f / (1.0f + expf(-logit[i]));
+    if (opac) opac[i] = sigmoid_act(logit[i]);
     if (rot) {
         const float a = quats[4 * i], b = quats[4 * i + 1], c = quats[4 * i + 2], d = quats[4 * i + 3];
-        const float nrm = fmaxf(sqrtf(a * a + b * b + c * c + d * d), 1e-12f);  // F::normalize eps
+        const float nrm = quat_norm(a, b, c, d);
         rot[4 * i] = a / nrm; rot[4 * i + 1] = b / nrm; rot[4 * i + 2] = c / nrm; rot[4 * i + 3] = d / nrm;
     }
     if (scales) {
 #pragma unroll
         for (int k = 0; k < 3; k++) scales[3 * i + k] = expf(log_scales[3 * i + k]);
-    }
-}
-
-// Block-reduce 12 partial sums and add them to out[12] with one atomic per value per CTA.
-__device__ __forceinline__ void reduce12_and_add(float* v, float* __restrict__ out)
-{
-    __shared__ float s_part[EX_THREADS / 32][12];
-#pragma unroll
-    for (int k = 0; k < 12; k++) {
-        float x = v[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane_id() == 0) s_part[threadIdx.x >> 5][k] = x;
-    }
-    __syncthreads();
-    if (threadIdx.x < 12) {
-        float x = 0.f;
-#pragma unroll
-        for (int w = 0; w < EX_THREADS / 32; w++) x += s_part[w][threadIdx.x];
-        atomicAdd(out + threadIdx.x, x);
     }
 }
 
@@ -86,12 +66,12 @@ prologue_backward_kernel(int P, const float* __restrict__ Tcw, const float* __re
             }
         }
         if (d_logit && g_opac) {
-            const float s = 1.0f / (1.0f + expf(-logit[i]));
+            const float s = sigmoid_act(logit[i]);
             d_logit[i] = g_opac[i] * s * (1.0f - s);
         }
         if (d_quats && g_rot) {
             const float a = quats[4 * i], b = quats[4 * i + 1], c = quats[4 * i + 2], d = quats[4 * i + 3];
-            const float nrm = fmaxf(sqrtf(a * a + b * b + c * c + d * d), 1e-12f);
+            const float nrm = quat_norm(a, b, c, d);
             const float na = a / nrm, nb = b / nrm, nc = c / nrm, nd = d / nrm;
             const float ga = g_rot[4 * i], gb = g_rot[4 * i + 1], gc = g_rot[4 * i + 2], gd = g_rot[4 * i + 3];
             const float dot = na * ga + nb * gb + nc * gc + nd * gd;
@@ -105,7 +85,7 @@ prologue_backward_kernel(int P, const float* __restrict__ Tcw, const float* __re
             for (int k = 0; k < 3; k++) d_log_scales[3 * i + k] = g_scales[3 * i + k] * expf(log_scales[3 * i + k]);
         }
     }
-    if (dTcw) reduce12_and_add(part, dTcw);
+    if (dTcw) reduce12_and_add<EX_THREADS>(part, dTcw);
 }
 
 // The whole packed block in ONE launch: group g covers [bound[g-1], bound[g]) and has its own learning rate
@@ -122,14 +102,6 @@ __device__ __forceinline__ float adam_group_step(const AdamGroups& G, long long 
     for (int g = 1; g < 8; g++)
         if (g < G.n && i >= G.bound[g - 1]) step_size = G.step_size[g];
     return step_size;
-}
-__device__ __forceinline__ void adam_update(float& p, float gr, float& mi, float& vi, float step_size, float omb1, float beta2, float omb2,
-                                            float eps, float inv_sqrt_bc2)
-{
-    mi = mi + (gr - mi) * omb1;
-    vi = vi * beta2 + omb2 * gr * gr;
-    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
-    p = p - step_size * (mi / denom);
 }
 // VEC = true: 16-byte accesses, four elements per thread and iteration (the kernel moves 7 x 4 bytes per element and nothing else:
 // 392 MB per step at 1 M Gaussians); the group of a quad is looked up once unless a group boundary falls inside it.  total4 quads,
@@ -308,14 +280,23 @@ int launch_adam_groups(int ngroups, const long long* sizes, const float* lrs, fl
     return GSB_OK;
 }
 
-int launch_scale_regulariser(int P, const float* log_scales, float max_scalar, float w_scalar, float w_long, float* d_log_scales,
-                             float* terms, float* acc, cudaStream_t s)
+// the reduction pass alone: acc[0..2] = {C, reg_scalar, sum of (max - min)} (map_update.cu folds the apply pass into its own kernel)
+int launch_scale_regulariser_sum(int P, const float* log_scales, float max_scalar, float* acc, cudaStream_t s)
 {
     GSB_CUDA_CHECK(cudaMemsetAsync(acc, 0, 4 * sizeof(float), s));
     if (P <= 0) return GSB_OK;
     StageTimer _t(ST_OTHER, s);
     scale_reg_sum_kernel<<<grid_for(P), EX_THREADS, 0, s>>>(P, log_scales, max_scalar, acc);
     GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+
+int launch_scale_regulariser(int P, const float* log_scales, float max_scalar, float w_scalar, float w_long, float* d_log_scales,
+                             float* terms, float* acc, cudaStream_t s)
+{
+    if (int rc = launch_scale_regulariser_sum(P, log_scales, max_scalar, acc, s)) return rc;
+    if (P <= 0) return GSB_OK;
+    StageTimer _t(ST_OTHER, s);
     scale_reg_apply_kernel<<<grid_for(P), EX_THREADS, 0, s>>>(P, log_scales, max_scalar, w_scalar, w_long, acc, d_log_scales, terms);
     GSB_LAUNCH_CHECK();
     return GSB_OK;

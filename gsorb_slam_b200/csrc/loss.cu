@@ -70,10 +70,10 @@ loss_stats_kernel(LossParams q)
     const bool inside = px < q.W && py < q.H;
     const size_t HW = (size_t)q.W * q.H, pix = (size_t)py * q.W + px;
     float l1 = 0.f, ssim_acc = 0.f;
-    for (int ch = 0; ch < 3; ch++) {
+    const int ch = blockIdx.z;   // one CTA per (tile, channel): 3 x 1200 short CTAs fill the 148 x 8 slots better than 1200 long ones
+    {
         const float* I = q.color + ch * HW;
         const float* G = q.gt_color + ch * HW;
-        __syncthreads();   // previous channel's readers are done with the buffers
         for (int i = threadIdx.x; i < LH * LH; i += LT * LT) {   // zero-padded halo (conv2d padding 5)
             const int hx = i % LH, hy = i / LH, gx = x0 + hx - LW / 2, gy = y0 + hy - LW / 2;
             const bool in = gx >= 0 && gx < q.W && gy >= 0 && gy < q.H;
@@ -114,7 +114,7 @@ loss_stats_kernel(LossParams q)
         }
     }
     float dsum = 0.f, ssum = 0.f, nv = 0.f, nvs = 0.f;
-    if (inside && q.gt_depth && q.depth_sil) {
+    if (ch == 0 && inside && q.gt_depth && q.depth_sil) {
         const float gd = q.gt_depth[pix];
         if (gd > 0.f) {
             nv = 1.f;
@@ -125,11 +125,14 @@ loss_stats_kernel(LossParams q)
             }
         }
     }
-    const float t0 = block_sum_256(l1, s_red), t1 = block_sum_256(ssim_acc, s_red), t2 = block_sum_256(dsum, s_red);
-    const float t3 = block_sum_256(ssum, s_red), t4 = block_sum_256(nv, s_red), t5 = block_sum_256(nvs, s_red);
-    if (threadIdx.x == 0) {
-        atomicAdd(&q.totals->l1_sum, t0); atomicAdd(&q.totals->ssim_sum, t1); atomicAdd(&q.totals->depth_sum, t2);
-        atomicAdd(&q.totals->sur_sum, t3); atomicAdd(&q.totals->n_valid, t4); atomicAdd(&q.totals->n_valid_sur, t5);
+    const float t0 = block_sum_256(l1, s_red), t1 = block_sum_256(ssim_acc, s_red);
+    if (threadIdx.x == 0) { atomicAdd(&q.totals->l1_sum, t0); atomicAdd(&q.totals->ssim_sum, t1); }
+    if (ch == 0) {   // the depth terms travel with channel 0
+        const float t2 = block_sum_256(dsum, s_red), t3 = block_sum_256(ssum, s_red), t4 = block_sum_256(nv, s_red), t5 = block_sum_256(nvs, s_red);
+        if (threadIdx.x == 0) {
+            atomicAdd(&q.totals->depth_sum, t2); atomicAdd(&q.totals->sur_sum, t3); atomicAdd(&q.totals->n_valid, t4);
+            atomicAdd(&q.totals->n_valid_sur, t5);
+        }
     }
 }
 
@@ -146,8 +149,8 @@ loss_grad_kernel(LossParams q)
     const float n_all = 3.f * (float)HW;
     const float g_ssim = -(1.f - q.lambda_) * q.w_image / n_all;   // dL / d ssim_p
     const float g_l1 = q.lambda_ * q.w_image / n_all;
-    for (int ch = 0; ch < 3; ch++) {
-        __syncthreads();
+    const int ch = blockIdx.z;
+    {
         // d mu_p / d x_q = win[q - p + 5]: the partial maps are correlated with the FLIPPED window around q
         for (int i = threadIdx.x; i < LH * LH; i += LT * LT) {
             const int hx = i % LH, hy = i / LH, gx = x0 + hx - LW / 2, gy = y0 + hy - LW / 2;
@@ -181,7 +184,7 @@ loss_grad_kernel(LossParams q)
         }
     }
     const LossTotals t = *q.totals;
-    if (inside && q.dL_ddepth_sil) {
+    if (ch == 0 && inside && q.dL_ddepth_sil) {
         float gd0 = 0.f;
         if (q.gt_depth && q.depth_sil && t.n_valid > 0.f) {
             const float gd = q.gt_depth[pix];
@@ -193,7 +196,7 @@ loss_grad_kernel(LossParams q)
         q.dL_ddepth_sil[pix] = gd0;
         q.dL_ddepth_sil[HW + pix] = 0.f;   // the silhouette only gates a mask (detached, src/Render.cc:455)
     }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && q.loss_terms) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && ch == 0 && threadIdx.x == 0 && q.loss_terms) {
         const float l1 = t.l1_sum / n_all, ssim = t.ssim_sum / n_all;
         const float dl = t.n_valid > 0.f ? t.depth_sum / t.n_valid : 0.f, sl = t.n_valid_sur > 0.f ? t.sur_sum / t.n_valid_sur : 0.f;
         q.loss_terms[0] = l1; q.loss_terms[1] = ssim; q.loss_terms[2] = dl; q.loss_terms[3] = sl;
@@ -298,7 +301,7 @@ int gsb_mapping_loss(int width, int height, const float* color, const float* dep
     q.dL_dcolor = dL_dcolor; q.dL_ddepth_sil = dL_ddepth_sil; q.loss_terms = loss_terms;
     cudaStream_t s = (cudaStream_t)stream;
     GSB_CUDA_CHECK(cudaMemsetAsync(q.totals, 0, sizeof(LossTotals), s));
-    const dim3 grid((width + LT - 1) / LT, (height + LT - 1) / LT);
+    const dim3 grid((width + LT - 1) / LT, (height + LT - 1) / LT, 3);   // z = colour channel
     {
         StageTimer _t(ST_OTHER, s);
         loss_stats_kernel<<<grid, LT * LT, 0, s>>>(q);

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import GradOutputs, RasterArgs
+from ._lib import GradOutputs, MapUpdate, RasterArgs
 from .distributed import BLOCK_ROWS, GROUPS, GradBlock, SymmetricExchange, allreduce_gradients, world
 
 # Examples/RGB-D/replica.yaml:95-99 (Mapping.lrs*)
@@ -50,7 +50,9 @@ class MapOptimizer:
         t = lambda a: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(d, torch.float32)
         self.P = int(t(means).shape[0])
         P = self.P
-        self.capacity = max(int(capacity) if capacity else P, P)
+        # an automatic capacity is a multiple of 4 rows: every group of the arenas then starts 16-byte aligned and the fused
+        # update (gsb_backward_fused_update) stages its rows with bulk copies; an explicit capacity is taken as given
+        self.capacity = max(int(capacity), P) if capacity else (P + 3) // 4 * 4
         cap = self.capacity
         self.params = GradBlock(P, d, capacity=cap)   # same layout as the gradient block
         self.params["means"].copy_(t(means)); self.params["rgb"].copy_(t(rgb))
@@ -142,7 +144,7 @@ class MapOptimizer:
             return 0
         P = self.P
         if P + K > self.capacity:
-            self.reserve(max(P + K, self.capacity + self.capacity // 2))
+            self.reserve((max(P + K, self.capacity + self.capacity // 2) + 3) // 4 * 4)   # groups stay 16-byte aligned
         for blk in (self.params, self.grads, self.exp_avg, self.exp_avg_sq):
             blk.resize(P + K)
         new = dict(means=means, rgb=rgb, opacity=logit_opacities.reshape(K, 1), scales=log_scales, quats=unnorm_quats)
@@ -383,7 +385,8 @@ class MapOptimizer:
         return color, depth_sil
 
     def slam_gradients(self, Tcw: torch.Tensor, gt_color: torch.Tensor, gt_depth: torch.Tensor, lambda_: float = 0.8,
-                       w_image: float = 1.0, w_depth: float = 0.7, w_surdepth: float = 0.35):
+                       w_image: float = 1.0, w_depth: float = 0.7, w_surdepth: float = 0.35, _update: bool = False,
+                       _write_grads: bool = False):
         """The gradient half of a mapping iteration (src/Render.cc:420-470) without a single torch op on the hot path:
         prologue -> ONE five-channel rasterization -> fused L1 + SSIM + depth loss and its gradient (gsb_mapping_loss) ->
         summed backward -> prologue backward, into ``grads``.  The forward's overflow latch is read once (the host waits for
@@ -407,16 +410,50 @@ class MapOptimizer:
                                               gtc.data_ptr(), gtd.data_ptr(), float(lambda_), float(w_image), float(w_depth),
                                               float(w_surdepth), self._gC.data_ptr(), self._gD.data_ptr(), self.loss_terms.data_ptr(),
                                               self._loss_scratch.data_ptr(), self._loss_scratch.numel(), self._s()))
-            self.backward_fused(self._gC, self._gD, z_attached=True)
+                if _update:   # an overflowed forward leaves the map untouched (the kernel reads the latch): safe to queue
+                    _lib.check(L.gsb_backward_fused_update(C.byref(self.args), self.radii.data_ptr(), self.geom.data_ptr(),
+                                                           self.binning.data_ptr(), self.img.data_ptr(), self._gC.data_ptr(),
+                                                           self._gD.data_ptr(), 1, C.byref(self._map_update(_write_grads)), self._s()))
+            if not _update:
+                self.backward_fused(self._gC, self._gD, z_attached=True)
             if not self._overflowed():
                 break
         return self.loss_terms
 
+    def _map_update(self, write_grads: bool) -> MapUpdate:
+        """gsb_map_update for Adam step ``t + 1`` over the five arenas."""
+        u = MapUpdate()
+        u.Tcw = self._Tcw.data_ptr()
+        for g, (name, _) in enumerate(GROUPS):
+            u.params[g], u.exp_avg[g], u.exp_avg_sq[g] = self.params.ptr(name), self.exp_avg.ptr(name), self.exp_avg_sq.ptr(name)
+            u.grads[g] = self.grads.ptr(name) if write_grads else None
+            u.lr[g] = float(self.lr[name])
+        u.beta1, u.beta2, u.eps, u.step = float(self.betas[0]), float(self.betas[1]), self.eps, self.t + 1
+        u.dL_dTcw = self.dTcw.data_ptr()
+        u.max_scalar = 0.1 * self.scene_radius if self.scene_radius > 0.0 else 0.0
+        u.w_scalar, u.w_long, u.reg_terms = self.w_reg_scalar, self.w_reg_long, self.reg_terms.data_ptr()
+        return u
+
     def step_slam(self, Tcw: torch.Tensor, gt_color: torch.Tensor, gt_depth: torch.Tensor, lambda_: float = 0.8,
-                  w_image: float = 1.0, w_depth: float = 0.7, w_surdepth: float = 0.35, average: bool = False):
-        """One complete mapping iteration of Render::RenderForFrame (src/Render.cc:420-476): ``slam_gradients`` -> scale
-        regularisers (:462-469, when ``scene_radius`` is set; ``reg_terms``) -> exchange -> Adam.  Weights default to
-        Examples/RGB-D/replica.yaml:89-94."""
+                  w_image: float = 1.0, w_depth: float = 0.7, w_surdepth: float = 0.35, average: bool = False,
+                  fused_update: Optional[bool] = None, write_grads: bool = False):
+        """One complete mapping iteration of Render::RenderForFrame (src/Render.cc:420-476).  Weights default to
+        Examples/RGB-D/replica.yaml:89-94.
+        One rank (``fused_update`` None or True): everything behind the per-pixel backward -- per-Gaussian backward, chain
+        rule of the prologue, scale regularisers (when ``scene_radius`` is set; ``reg_terms``), Adam -- is ONE launch
+        (gsb_backward_fused_update) and no gradient array is written unless ``write_grads``.
+        Several ranks, or ``fused_update=False``: ``slam_gradients`` -> regularisers -> exchange -> Adam as separate passes
+        (the gradient block has to exist between them)."""
+        single = world()[1] == 1
+        if fused_update is None:
+            fused_update = single
+        if fused_update and not single:
+            raise ValueError("the fused update skips the gradient exchange: single rank only")
+        if fused_update:
+            terms = self.slam_gradients(Tcw, gt_color, gt_depth, lambda_, w_image, w_depth, w_surdepth, _update=True,
+                                        _write_grads=write_grads)
+            self.t += 1
+            return terms
         terms = self.slam_gradients(Tcw, gt_color, gt_depth, lambda_, w_image, w_depth, w_surdepth)
         self.add_scale_regularisers()
         self._exchange_and_adam(average)

@@ -186,6 +186,38 @@ int gsb_backward_fused(const gsb_raster_args* args, const int* radii,
                        const float* dL_dcolor, const float* dL_ddepth_sil,
                        const gsb_grad_outputs* grads, float* dL_dzcolor, int z_attached, gsb_stream_t stream);
 
+/* ---- the per-Gaussian tail of a mapping iteration in ONE launch (extension) ---------------------------
+ * What follows the rasterizer's per-pixel backward in Render::RenderForFrame (src/Render.cc:420-476), per Gaussian:
+ * BACKWARD::preprocess (backward.cu:560-621) -> autograd of the activation prologue (src/Render.cc:750-759: Tcw [mean;1],
+ * sigmoid, normalize, exp) -> the scale regularisers (:462-469) -> torch::optim::Adam with one learning rate per tensor
+ * (src/Gaussian.cc:131-175).  gsb_backward_fused + gsb_prologue_backward + gsb_scale_regulariser + gsb_adam_step_groups do the
+ * same in four streaming passes; here one thread carries a Gaussian from the blend-backward sums to its updated parameters and
+ * no gradient array is written (unless `grads` asks for the raw-parameter gradients as well).
+ * Group order everywhere: 0 means [P,3] (world frame), 1 rgb [P,3], 2 logit opacities [P], 3 log scales [P,3],
+ * 4 unnormalised quaternions [P,4].  The forward must have been run on the prologue's outputs of THESE parameters with
+ * colors_precomp = params[1], no SH, no precomputed covariances, over the whole image.
+ * If that forward overflowed its binning blob (the lists it blended were truncated) NOTHING is updated: the caller grows the
+ * blob, renders again and calls this again with the same `step`. */
+typedef struct gsb_map_update {
+    const float* Tcw;          /* [4,4] row-major, device: the pose the prologue used */
+    float* params[5];          /* updated in place */
+    float* exp_avg[5];         /* Adam first moments, updated in place */
+    float* exp_avg_sq[5];      /* Adam second moments, updated in place */
+    float* grads[5];           /* all NULL, or all set: dL/d(raw parameter) is written too (regularisers included) */
+    float lr[5];
+    double beta1, beta2, eps;
+    long long step;            /* 1-based count of THIS Adam step (bias corrections) */
+    float* dL_dTcw;            /* [3,4] device or NULL: sum_i g_i [mean_i; 1]^T */
+    float max_scalar;          /* scale regularisers as in gsb_scale_regulariser; <= 0: off */
+    float w_scalar, w_long;
+    float* reg_terms;          /* 8 floats, device (required when the regularisers are on): as gsb_scale_regulariser's `terms` */
+} gsb_map_update;
+/* dL_ddepth_sil NULL: the three-channel pass (gsb_forward_ws); otherwise the five-channel pass (gsb_forward_fused_ws). */
+int gsb_backward_fused_update(const gsb_raster_args* args, const int* radii,
+                              const void* geometry, const void* binning, const void* image,
+                              const float* dL_dcolor, const float* dL_ddepth_sil, int z_attached,
+                              const gsb_map_update* update, gsb_stream_t stream);
+
 /* ---- visibility helpers --------------------------------------------------------------*/
 /* Radii-only projection (Rasterizer::visible_filter): radii[P] fully written. */
 int gsb_visible_filter(const gsb_raster_args* args, int* radii, gsb_stream_t stream);

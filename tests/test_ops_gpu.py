@@ -633,6 +633,55 @@ def test_complete_slam_iteration_decreases_its_loss():
     assert bool(torch.isfinite(opt.params.flat).all())
 
 
+@pytest.mark.parametrize("scene_radius", [0.0, 1.0])
+def test_fused_map_update_matches_the_separate_passes(scene_radius):
+    """gsb_backward_fused_update (per-Gaussian backward + prologue chain rule + scale regularisers + Adam in one launch) against
+    gsb_backward_fused -> gsb_prologue_backward -> gsb_scale_regulariser -> gsb_adam_step_groups, three iterations at a pose
+    that is not the identity: same raw gradients, pose gradient, regulariser terms, parameters and Adam moments (the two
+    paths share their row-level device functions; 1e-6 of the tensor scale allows for a different FMA contraction)."""
+    import torch
+    from gsorb_slam_b200.distributed import GROUPS
+    from gsorb_slam_b200.lowlevel import frame_from_scene
+    from gsorb_slam_b200.mapping import MapOptimizer
+    from gsorb_slam_b200.scene import make_scene
+    dev = torch.device("cuda:0")
+    W, H = 160, 120
+    sc = make_scene(20_000, (W, H, 130.0, 128.0), seed=57, scale_mul=3.0 if scene_radius > 0 else 1.5)
+    tgt = frame_from_scene(sc, fused=True, max_rendered=1 << 20)
+    gt_c, gt_d = tgt.color.clone(), tgt.depth_sil[0].clone()
+    rng = np.random.default_rng(3)
+    rgb = np.clip(sc.colors + rng.normal(0, 0.1, sc.colors.shape), 0, 1).astype(np.float32)
+    # an arena capacity that is not a multiple of 4 leaves the groups unaligned: the per-thread variant of the kernel; the automatic
+    # capacity takes the bulk-copy variant (78 full CTAs and a partial one of 32 rows)
+    cap = None if scene_radius > 0 else 20_000 + 37
+    mk = lambda: MapOptimizer(sc.means3D, rgb, sc.logit_opacities, sc.log_scales, sc.unnorm_quats, width=W, height=H,
+                              tanfovx=sc.cam.tanfovx, tanfovy=sc.cam.tanfovy, projmatrix=sc.cam.projmatrix, device=dev,
+                              max_rendered=1 << 20, scene_radius=scene_radius, capacity=cap)
+    a, b = mk(), mk()
+    ang = 0.02
+    Tcw = torch.tensor([[np.cos(ang), 0, np.sin(ang), 0.01], [0, 1, 0, -0.02], [-np.sin(ang), 0, np.cos(ang), 0.03], [0, 0, 0, 1]],
+                       dtype=torch.float32, device=dev)
+    for it in range(3):
+        ta = a.step_slam(Tcw, gt_c, gt_d, fused_update=True, write_grads=True).clone()
+        tb = b.step_slam(Tcw, gt_c, gt_d, fused_update=False).clone()
+        assert a.t == b.t == it + 1
+        assert rel_to_scale(to_np(ta), to_np(tb)) <= 1e-6
+        for name, _ in GROUPS:
+            assert rel_to_scale(to_np(a.grads[name]), to_np(b.grads[name])) <= (1e-6 if it == 0 else 2e-5), (it, name)
+            assert rel_to_scale(to_np(a.params[name]), to_np(b.params[name])) <= (1e-6 if it == 0 else 2e-5), (it, name)
+            assert rel_to_scale(to_np(a.exp_avg[name]), to_np(b.exp_avg[name])) <= (1e-6 if it == 0 else 2e-5), (it, name)
+            assert rel_to_scale(to_np(a.exp_avg_sq[name]), to_np(b.exp_avg_sq[name])) <= (1e-6 if it == 0 else 2e-5), (it, name)
+        assert rel_to_scale(to_np(a.dTcw), to_np(b.dTcw)) <= 1e-4      # 20 000 terms summed in a different order
+        if scene_radius > 0:
+            assert float(b.reg_terms[2]) > 0
+            assert rel_to_scale(to_np(a.reg_terms[:3]), to_np(b.reg_terms[:3])) <= 1e-6
+    # padding rows of the arenas stay zero, and without write_grads the gradient block is not touched
+    assert float(a.params.flat.view(14, -1)[0, 0]) == float(b.params.flat.view(14, -1)[0, 0])
+    a.grads.flat.fill_(7.0)
+    a.step_slam(Tcw, gt_c, gt_d)
+    assert bool((a.grads.flat == 7.0).all())
+
+
 @pytest.mark.parametrize("W,H,use_mask", [(160, 120, True), (101, 77, False), (640, 480, True)])
 def test_backproject_matches_the_reference_host_loop(W, H, use_mask):
     """gsb_backproject against a numpy restatement of Render::ProjectPixel + Gaussian::AddGaussianPoints (SinglePixel):
