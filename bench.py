@@ -670,7 +670,9 @@ def run_ours(args):
         ms_fused = timed(fused, it_steps, 3) / it_steps
         fr._args.colors_precomp = rgbcol.data_ptr()
         # the COMPLETE iteration through the fused host-side step: prologue + five-channel pass + fused L1/SSIM/depth loss and
-        # its gradient + summed backward + prologue backward (pose gradient) + Adam on the packed [14,P] block
+        # its gradient + per-pixel backward + ONE per-Gaussian kernel for everything behind it (gsb_backward_fused_update:
+        # per-Gaussian backward, prologue chain rule with the pose gradient, Adam); "separate passes" = the same iteration with
+        # gsb_backward_fused -> gsb_prologue_backward -> gsb_adam_step_groups, what several ranks run around the exchange
         from gsorb_slam_b200.mapping import MapOptimizer
         mo = MapOptimizer(sc.means3D, sc.colors, sc.logit_opacities, sc.log_scales, sc.unnorm_quats, width=W, height=H,
                           tanfovx=sc.cam.tanfovx, tanfovy=sc.cam.tanfovy, projmatrix=sc.cam.projmatrix, device=dev,
@@ -679,6 +681,7 @@ def run_ours(args):
         gt_c = fr.color.clone().clamp(0, 1)
         gt_d = torch.rand(H, W, device=dev) * 5 + 0.5
         ms_full = timed(lambda: mo.step_slam(Tcw_id, gt_c, gt_d), it_steps, 3) / it_steps
+        ms_full_sep = timed(lambda: mo.step_slam(Tcw_id, gt_c, gt_d, fused_update=False), it_steps, 3) / it_steps
         # one tracking iteration (Render::RenderStartTraking, src/Render.cc:1052-1127): fixed Gaussians, Rt2T -> five-channel pass with
         # detached depth colours -> fused masked-L1 loss (gsb_tracking_loss) -> backward -> dL/dTcw on the device -> pose Adam; the
         # loss is read back every iteration, as the reference's loss.item() does
@@ -688,9 +691,10 @@ def run_ours(args):
         del po
         del mo
         iteration = {"what": "RGB pass + depth/silhouette pass of one mapping iteration, fwd+bwd, device-resident",
-                     "complete_iteration_ms": ms_full, "tracking_iteration_ms": ms_track,
-                     "tracking_iteration": "PoseOptimizer.step: Rt2T + fused pass + gsb_tracking_loss + backward + pose gradient + pose Adam, one host sync (loss)",
-                     "complete_iteration": "MapOptimizer.step_slam: prologue + fused pass + fused L1/SSIM/depth loss + backward + pose gradient + Adam, no torch op",
+                     "complete_iteration_ms": ms_full, "complete_iteration_separate_passes_ms": ms_full_sep,
+                     "tracking_iteration_ms": ms_track,
+                     "tracking_iteration": "PoseOptimizer.step: Rt2T + means-only prologue + fused pass + gsb_tracking_loss + gsb_backward_fused_pose (dL/dTcw only) + pose Adam, one host sync (loss)",
+                     "complete_iteration": "MapOptimizer.step_slam: prologue + fused pass + fused L1/SSIM/depth loss + gsb_backward_fused_update (per-pixel backward, then per-Gaussian backward + chain rule + pose gradient + Adam in one kernel), no torch op",
                      "two_pass_ms": ms_two, "fused_five_channel_ms": ms_fused, "iterations_per_s_two_pass": 1000.0 / ms_two,
                      "iterations_per_s_fused": 1000.0 / ms_fused, "steps": it_steps}
 

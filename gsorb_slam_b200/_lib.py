@@ -55,6 +55,7 @@ SIGNATURES = {
     "gsb_forward_fused_ws": (_i, [C.POINTER(RasterArgs), _vp, _sz, _vp, _sz, _ll, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "gsb_backward_fused": (_i, [C.POINTER(RasterArgs), _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(GradOutputs), _vp, _i, _vp]),
     "gsb_backward_fused_update": (_i, [C.POINTER(RasterArgs), _vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(MapUpdate), _vp]),
+    "gsb_backward_fused_pose": (_i, [C.POINTER(RasterArgs), _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "gsb_visible_filter": (_i, [C.POINTER(RasterArgs), _vp, _vp]),
     "gsb_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
     "gsb_knn_workspace_bytes": (_sz, [_i]),

@@ -382,6 +382,25 @@ int gsb_backward_fused_update(const gsb_raster_args* args, const int* radii, con
     return launch_map_update(p, geom, GL, radii, z_attached, *u, s);
 }
 
+int gsb_backward_fused_pose(const gsb_raster_args* args, const int* radii, const void* geometry, const void* binning,
+                            const void* image, const float* dL_dcolor, const float* dL_ddepth_sil, int z_attached,
+                            const float* means_world, float* dL_dTcw, gsb_stream_t stream)
+{
+    if (int rc = validate(args, true, false)) return rc;
+    if (!geometry || !binning || !image) return fail(GSB_ERR_INVALID_ARGUMENT, "forward state blobs are required");
+    if (!dL_dcolor || !dL_dTcw || (args->P > 0 && !means_world))
+        return fail(GSB_ERR_INVALID_ARGUMENT, "backward_fused_pose: dL_dcolor, means_world and dL_dTcw are required");
+    if (args->shs || args->cov3D_precomp)
+        return fail(GSB_ERR_INVALID_ARGUMENT, "backward_fused_pose: precomputed colours, scales and rotations only");
+    const FwdParams p = make_params(args);
+    cudaStream_t s = (cudaStream_t)stream;
+    const GeomLayout GL = GeomLayout::make(p.P);
+    const ImageLayout IL = ImageLayout::make(p.W, p.H);
+    char* geom = (char*)const_cast<void*>(geometry);
+    if (int rc = launch_blend_backward(p, geom, GL, (const char*)binning, (const char*)image, IL, dL_dcolor, dL_ddepth_sil, s)) return rc;
+    return launch_pose_gradient(p, geom, GL, radii, z_attached, means_world, dL_dTcw, s);
+}
+
 int gsb_visible_filter(const gsb_raster_args* args, int* radii, gsb_stream_t stream)
 {
     if (int rc = validate(args, false)) return rc;

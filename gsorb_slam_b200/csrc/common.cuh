@@ -401,6 +401,8 @@ int launch_scale_regulariser(int P, const float* log_scales, float max_scalar, f
 int launch_scale_regulariser_sum(int P, const float* log_scales, float max_scalar, float* acc, cudaStream_t s);
 int launch_map_update(const FwdParams& p, const char* geom, const GeomLayout& GL, const int* radii, int z_attached,
                       const gsb_map_update& u, cudaStream_t s);
+int launch_pose_gradient(const FwdParams& p, const char* geom, const GeomLayout& GL, const int* radii, int z_attached,
+                         const float* means_world, float* dTcw, cudaStream_t s);
 size_t knn_workspace_bytes(int P);
 int launch_knn(int P, const float* points, float* mean_dist2, char* ws, cudaStream_t s);
 

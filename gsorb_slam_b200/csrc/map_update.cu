@@ -297,6 +297,73 @@ map_update_bulk_kernel(MapUpdateParams q)
     if (full && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays alive until it is read
 }
 
+// ---- tracking: only the camera pose is optimised (Render::RenderStartTraking, src/Render.cc:1052-1127) -------------------------
+// dL/dTcw[0:3,:] = sum_i dL/dmean_cam_i [mean_world_i; 1]^T needs the per-Gaussian backward only as far as dL/dmean_cam: no gradient
+// array is written and the scale / rotation branch of the chain is dead code here.  Reads the activated arrays the forward saw.
+struct PoseGradParams {
+    FwdParams f;
+    const int* radii;
+    const float* acc;
+    const SplatRec* rec;
+    const uint32_t* tiles_touched;   // tile-row band only (else NULL): 0 = this band wrote no record for the Gaussian
+    const float* means_world;
+    float* dTcw;
+    int z_attached;
+};
+
+__global__ void __launch_bounds__(MU_THREADS, 4)
+pose_gradient_kernel(PoseGradParams q)
+{
+    const FwdParams& p = q.f;
+    const int idx = blockIdx.x * MU_THREADS + threadIdx.x;
+    float part[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) part[k] = 0.f;
+    if (idx < p.P) {
+        const size_t i = (size_t)idx;
+        int radius = q.radii[idx];
+        if (q.tiles_touched && q.tiles_touched[idx] == 0) radius = 0;
+        const float4* ap = reinterpret_cast<const float4*>(q.acc + i * ACC_FLOATS);
+        const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];
+        const float4 rb = q.rec[i].b;
+        const float mx = p.means3D[3 * i], my = p.means3D[3 * i + 1], mz = p.means3D[3 * i + 2];
+        const float4 qv = *reinterpret_cast<const float4*>(p.rotations + 4 * i);
+        const float s0 = p.scales[3 * i], s1 = p.scales[3 * i + 1], s2 = p.scales[3 * i + 2];
+        const float wx = q.means_world[3 * i], wy = q.means_world[3 * i + 1], wz = q.means_world[3 * i + 2];
+        if (radius > 0) {
+            float a[9], dcov[6], dscale[3], drot[4];
+            float dmx = 0.f, dmy = 0.f, dmz = 0.f;
+            gauss_moments_to_2d(p, true, a0, a1, a2, a3, rb, a);
+            gauss_backward_chain<false>(p, i, a, mx, my, mz, qv, s0, s1, s2, nullptr, 0u, dcov, dmx, dmy, dmz, dscale, drot);
+            if (q.z_attached) dmz += a2.z;
+            part[0] = dmx * wx; part[1] = dmx * wy; part[2] = dmx * wz; part[3] = dmx;
+            part[4] = dmy * wx; part[5] = dmy * wy; part[6] = dmy * wz; part[7] = dmy;
+            part[8] = dmz * wx; part[9] = dmz * wy; part[10] = dmz * wz; part[11] = dmz;
+        }
+    }
+    reduce12_scatter_and_add<MU_THREADS>(part, q.dTcw);
+}
+
+int launch_pose_gradient(const FwdParams& p, const char* geom, const GeomLayout& GL, const int* radii, int z_attached,
+                         const float* means_world, float* dTcw, cudaStream_t s)
+{
+    GSB_CUDA_CHECK(cudaMemsetAsync(dTcw, 0, 12 * sizeof(float), s));
+    if (p.P <= 0) return GSB_OK;
+    PoseGradParams q;
+    q.f = p;
+    q.radii = radii ? radii : reinterpret_cast<const int*>(geom + GL.radii);
+    q.acc = reinterpret_cast<const float*>(geom + GL.acc);
+    q.rec = reinterpret_cast<const SplatRec*>(geom + GL.rec);
+    q.tiles_touched = (p.band_y0 > 0 || p.band_y1 < p.tiles_y) ? reinterpret_cast<const uint32_t*>(geom + GL.tiles_touched) : nullptr;
+    q.means_world = means_world;
+    q.dTcw = dTcw;
+    q.z_attached = z_attached;
+    StageTimer _t(ST_GAUSS_BWD, s);
+    pose_gradient_kernel<<<(p.P + MU_THREADS - 1) / MU_THREADS, MU_THREADS, 0, s>>>(q);
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+
 int launch_map_update(const FwdParams& p, const char* geom, const GeomLayout& GL, const int* radii, int z_attached,
                       const gsb_map_update& u, cudaStream_t s)
 {

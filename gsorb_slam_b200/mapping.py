@@ -304,27 +304,31 @@ class MapOptimizer:
                                                g.ptr("quats"), g.ptr("scales"), self.dTcw.data_ptr(), s))
         return g
 
-    def _forward_fused(self):
+    def _forward_fused(self, means_only: bool = False):
+        """``means_only``: the map has not changed since the last prologue (tracking): only the camera-frame means are redone."""
         L, p, s = self.L, self.params, self._s()
         if not hasattr(self, "depth_sil"):
             self.depth_sil = torch.empty((2, self.H, self.W), dtype=torch.float32, device=self.dev)
             self.g_z = torch.empty(self.capacity, dtype=torch.float32, device=self.dev)
         with torch.cuda.device(self.dev):
+            act = (None, None, None) if means_only else (self.opac.data_ptr(), self.rot.data_ptr(), self.scales.data_ptr())
             _lib.check(L.gsb_prologue(self.P, self._Tcw.data_ptr(), p.ptr("means"), p.ptr("opacity"), p.ptr("quats"), p.ptr("scales"),
-                                      self.means_cam.data_ptr(), self.opac.data_ptr(), self.rot.data_ptr(), self.scales.data_ptr(), s))
+                                      self.means_cam.data_ptr(), *act, s))
             _lib.check(L.gsb_forward_fused_ws(C.byref(self.args), self.geom.data_ptr(), self.geom.numel(), self.binning.data_ptr(),
                                               self.binning.numel(), self.max_rendered, self.img.data_ptr(), self.img.numel(),
                                               self.color.data_ptr(), self.depth_sil.data_ptr(), self.depth.data_ptr(),
                                               self.radii.data_ptr(), s))
             self._poll_forward()
 
-    def render_fused(self, Tcw: torch.Tensor):
+    def render_fused(self, Tcw: torch.Tensor, frozen_map: bool = False):
         """Prologue + ONE five-channel rasterization: (color [3,H,W], depth_sil [2,H,W], median_depth [1,H,W], radii)
         -- what Render::RenderForFrame gets from its depth pass and its RGB pass (src/Render.cc:445-448).  Stand-alone use:
-        an overflowing frame is rendered again with a larger binning blob before this returns."""
+        an overflowing frame is rendered again with a larger binning blob before this returns.  ``frozen_map``: the caller
+        guarantees that no parameter changed since the previous render of this optimizer (the tracking loop): the activations
+        of opacity / rotation / scale are reused and only the camera-frame means are recomputed."""
         self._Tcw = Tcw.to(self.dev, torch.float32).contiguous()
         while True:
-            self._forward_fused()
+            self._forward_fused(means_only=frozen_map)
             if not self._overflowed():
                 break
         return self.color, self.depth_sil, self.depth, self.radii[:self.P]
@@ -344,6 +348,20 @@ class MapOptimizer:
                                                self.g_rot.data_ptr(), self.g_scales.data_ptr(), g.ptr("means"), g.ptr("opacity"),
                                                g.ptr("quats"), g.ptr("scales"), self.dTcw.data_ptr(), s))
         return g
+
+    def backward_pose(self, dL_dcolor: torch.Tensor, dL_ddepth_sil: torch.Tensor, z_attached: bool = False,
+                      out: Optional[torch.Tensor] = None):
+        """Backward of ``render_fused`` as far as the camera pose: ``dTcw`` [3,4] and nothing else (gsb_backward_fused_pose) --
+        the tracking loop's backward (src/Render.cc:1052-1127 optimises the pose only).  ``out``: 12 device floats that receive
+        the gradient instead of ``dTcw``."""
+        L, s = self.L, self._s()
+        dC = dL_dcolor.to(self.dev, torch.float32).contiguous()
+        dD = dL_ddepth_sil.to(self.dev, torch.float32).contiguous()
+        with torch.cuda.device(self.dev):
+            _lib.check(L.gsb_backward_fused_pose(C.byref(self.args), self.radii.data_ptr(), self.geom.data_ptr(), self.binning.data_ptr(),
+                                                 self.img.data_ptr(), dC.data_ptr(), dD.data_ptr(), 1 if z_attached else 0,
+                                                 self.params.ptr("means"), (self.dTcw if out is None else out).data_ptr(), s))
+        return self.dTcw if out is None else out
 
     def add_scale_regularisers(self):
         """reg_scalar / reg_long of the mapping loss (src/Render.cc:462-469) added to the log-scale gradients; no-op while

@@ -74,6 +74,7 @@ class PoseOptimizer:
         self.lr, self.betas, self.eps = float(lr_quat), (float(betas[0]), float(betas[1])), float(eps)
         self._adam = dict(step=0, m=np.zeros(7, np.float32), v=np.zeros(7, np.float32))
         self.best = (self._q.copy(), self._t.copy(), float("inf"))
+        self._rendered_once = False   # the first step runs the whole prologue (the map may have changed since the last frame)
         self.features = None
         self.last_terms = {}
 
@@ -137,23 +138,37 @@ class PoseOptimizer:
         inliers (chi-square 5.991) before it is summed -- the reference does that once, at half its iteration budget."""
         g = self.g
         T = rt2T_np(self._q, self._t)
-        color, depth_sil, median, _ = g.render_fused(torch.from_numpy(T))
-        # masked L1 terms and their gradients in ONE kernel (gsb_tracking_loss): mask = "uncertainDepth" (src/Render.cc:1075),
-        # sums over the mask (L1LossForTracking, src/Utils.cc:45-52), dL/dcolor and dL/d(depth, silhouette)
         if not hasattr(self, "_dC"):
-            self._dC, self._dD = torch.empty_like(color), torch.empty_like(depth_sil)
+            self._dC = torch.empty((3, g.H, g.W), dtype=torch.float32, device=g.dev)
+            self._dD = torch.empty((2, g.H, g.W), dtype=torch.float32, device=g.dev)
             self._out = torch.zeros(20, dtype=torch.float32, device=g.dev)        # loss terms [8] | dL/dTcw [12]
             self._host = torch.empty(20, dtype=torch.float32).pin_memory()
+            self._T_host = torch.empty((4, 4), dtype=torch.float32).pin_memory()
+            self._T_dev = torch.empty((4, 4), dtype=torch.float32, device=g.dev)
         dC, dD, terms = self._dC, self._dD, self._out[:8]
         gtc, gtd = gt_color.contiguous(), gt_depth.contiguous()
-        with torch.cuda.device(g.dev):
-            _lib.check(g.L.gsb_tracking_loss(g.W, g.H, color.data_ptr(), depth_sil.data_ptr(), median.data_ptr(), gtc.data_ptr(),
-                                             gtd.data_ptr(), float(w_image), float(w_depth), 1 if use_surdepth else 0,
-                                             dC.data_ptr(), dD.data_ptr(), terms.data_ptr(), torch.cuda.current_stream(g.dev).cuda_stream))
-        g.backward_fused(dC, dD, z_attached=False)                                 # -> g.dTcw [3,4] on the device
-        self._out[8:].copy_(g.dTcw.reshape(-1))
-        self._host.copy_(self._out, non_blocking=True)
-        torch.cuda.current_stream(g.dev).synchronize()                             # the reference's loss.item(): one sync per iteration
+        # The whole iteration is queued before the host waits for anything (one synchronisation per iteration, the reference's
+        # loss.item()): pose upload from pinned memory -> prologue (after this optimizer's first render only the camera-frame means:
+        # the map is frozen while the pose is tracked) -> five-channel pass -> masked L1 terms and their gradients in ONE kernel
+        # (gsb_tracking_loss: mask = "uncertainDepth", src/Render.cc:1075; sums over the mask, L1LossForTracking, src/Utils.cc:45-52)
+        # -> per-pixel backward + pose-only per-Gaussian kernel (dL/dTcw straight into the read-back block) -> D2H.  The forward's
+        # overflow latch is read after that; an overflowing frame is redone with a larger binning blob.
+        self._T_host.copy_(torch.from_numpy(T))
+        while True:
+            self._T_dev.copy_(self._T_host, non_blocking=True)
+            g._Tcw = self._T_dev
+            g._forward_fused(means_only=self._rendered_once)
+            color, depth_sil, median = g.color, g.depth_sil, g.depth
+            with torch.cuda.device(g.dev):
+                _lib.check(g.L.gsb_tracking_loss(g.W, g.H, color.data_ptr(), depth_sil.data_ptr(), median.data_ptr(), gtc.data_ptr(),
+                                                 gtd.data_ptr(), float(w_image), float(w_depth), 1 if use_surdepth else 0,
+                                                 dC.data_ptr(), dD.data_ptr(), terms.data_ptr(), torch.cuda.current_stream(g.dev).cuda_stream))
+            g.backward_pose(dC, dD, z_attached=False, out=self._out[8:])
+            self._host.copy_(self._out, non_blocking=True)
+            torch.cuda.current_stream(g.dev).synchronize()
+            self._rendered_once = True
+            if not g._overflowed():
+                break
         h = self._host.numpy()
         image_term, depth_term, loss = float(h[0]), float(h[1]), float(h[2])
         G = h[8:].reshape(3, 4).astype(np.float32).copy()

@@ -218,6 +218,16 @@ int gsb_backward_fused_update(const gsb_raster_args* args, const int* radii,
                               const float* dL_dcolor, const float* dL_ddepth_sil, int z_attached,
                               const gsb_map_update* update, gsb_stream_t stream);
 
+/* Tracking (Render::RenderStartTraking, src/Render.cc:1052-1127) optimises the camera pose only: the per-pixel backward followed by
+ * ONE per-Gaussian kernel that goes as far as dL/dmean_cam and reduces dL_dTcw [3,4] = sum_i dL/dmean_cam_i [means_world_i; 1]^T
+ * on chip -- what gsb_backward_fused + gsb_prologue_backward deliver, without writing any per-Gaussian gradient.
+ * args as for the forward (means3D = the camera-frame means the prologue wrote); a tile-row band yields that band's partial sum.
+ * dL_ddepth_sil NULL: three-channel pass. */
+int gsb_backward_fused_pose(const gsb_raster_args* args, const int* radii,
+                            const void* geometry, const void* binning, const void* image,
+                            const float* dL_dcolor, const float* dL_ddepth_sil, int z_attached,
+                            const float* means_world, float* dL_dTcw, gsb_stream_t stream);
+
 /* ---- visibility helpers --------------------------------------------------------------*/
 /* Radii-only projection (Rasterizer::visible_filter): radii[P] fully written. */
 int gsb_visible_filter(const gsb_raster_args* args, int* radii, gsb_stream_t stream);

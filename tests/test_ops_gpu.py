@@ -633,6 +633,32 @@ def test_complete_slam_iteration_decreases_its_loss():
     assert bool(torch.isfinite(opt.params.flat).all())
 
 
+def test_pose_only_backward_matches_the_full_backward():
+    """gsb_backward_fused_pose (tracking: dL/dTcw and nothing else) against gsb_backward_fused + gsb_prologue_backward, and the
+    means-only prologue of a frozen map against the full one."""
+    import torch
+    from gsorb_slam_b200.mapping import MapOptimizer
+    from gsorb_slam_b200.scene import make_scene
+    dev = torch.device("cuda:0")
+    W, H = 160, 120
+    sc = make_scene(20_000, (W, H, 130.0, 128.0), seed=58, scale_mul=1.5)
+    mo = MapOptimizer(sc.means3D, sc.colors, sc.logit_opacities, sc.log_scales, sc.unnorm_quats, width=W, height=H, tanfovx=sc.cam.tanfovx,
+                      tanfovy=sc.cam.tanfovy, projmatrix=sc.cam.projmatrix, device=dev, max_rendered=1 << 20)
+    ang = -0.03
+    Tcw = torch.tensor([[np.cos(ang), np.sin(ang), 0, 0.02], [-np.sin(ang), np.cos(ang), 0, 0.01], [0, 0, 1, -0.02], [0, 0, 0, 1]],
+                       dtype=torch.float32, device=dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    dC, dD = torch.randn(3, H, W, device=dev, generator=g), torch.randn(2, H, W, device=dev, generator=g)
+    c0, d0, m0, _ = [t.clone() for t in mo.render_fused(Tcw)]
+    for z in (False, True):
+        mo.backward_fused(dC, dD, z_attached=z)
+        want = mo.dTcw.clone()
+        got = mo.backward_pose(dC, dD, z_attached=z).clone()
+        assert float(want.abs().max()) > 0 and rel_to_scale(to_np(got), to_np(want)) <= 1e-4   # 20 000 terms, another summation order
+    c1, d1, m1, _ = mo.render_fused(Tcw, frozen_map=True)
+    assert torch.equal(c0, c1) and torch.equal(d0, d1) and torch.equal(m0, m1)
+
+
 @pytest.mark.parametrize("scene_radius", [0.0, 1.0])
 def test_fused_map_update_matches_the_separate_passes(scene_radius):
     """gsb_backward_fused_update (per-Gaussian backward + prologue chain rule + scale regularisers + Adam in one launch) against
