@@ -146,9 +146,10 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     uint32_t id_next = NS - 1 < batches ? load_id(NS - 1) : 0xffffffffu;
     bool warp_done = __all_sync(0xffffffffu, done != 0);
     const TransposeConsts transpose(lane);
-    // 32-bit shared-window addresses of the ring (a[0][0]) and of the box words; b[] and c[] sit NS * BATCH * 16 bytes apart
+    // 32-bit shared-window addresses of the ring (a[0][0]) and of the box words; a stage is BATCH + RING_PAD records, b[] and c[] sit
+    // NS stages apart
     const uint32_t sa0 = (uint32_t)__cvta_generic_to_shared(&S.a[0][0]), sbox0 = (uint32_t)__cvta_generic_to_shared(&SM.box[0][0]);
-    constexpr uint32_t OFF_B = NS * BATCH * 16, OFF_C = 2 * NS * BATCH * 16;
+    constexpr uint32_t STAGE_BYTES = (BATCH + RING_PAD) * 16, OFF_B = NS * STAGE_BYTES, OFF_C = 2 * NS * STAGE_BYTES;
     static_assert(offsetof(FwdSmem<NS>, box) == sizeof(StageRing<NS, BLEND_THREADS, false>), "box[] must follow the ring (see FwdSmem)");
     const int tile_x0 = blockIdx.x * TILE_X, tile_y0 = tile_y * TILE_Y;
     uint32_t cshift = (warp & 1) * 8, rshift = 16 + (warp >> 1) * 4;   // this warp's 8 columns / 4 rows inside the box word
@@ -184,7 +185,7 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
             // hit words of the batch: rows of 256 words, window after window; the list's last, partial window has its own row
             uint32_t* hp = hits_full + ((size_t)(range.x >> 5) + (size_t)(b * WINS)) * HIT_PIXELS + tid;
             const int wtail = (n >> 5) - b * WINS;   // first window of this batch that is not a full one
-            uint32_t ra = sa0 + (uint32_t)buf * (BATCH * 16);          // the window's records: a at ra, b at ra + OFF_B, c at ra + OFF_C
+            uint32_t ra = sa0 + (uint32_t)buf * STAGE_BYTES;           // the window's records: a at ra, b at ra + OFF_B, c at ra + OFF_C
             uint32_t rb = sbox0 + (uint32_t)buf * (BATCH * 4) + (31 - lane) * 4;   // lane L culls entry 31 - L (see the walk)
             for (int w = 0; w < nwin; w++, hp += HIT_PIXELS, ra += 32 * 16, rb += 32 * 4) {
                 // ---- cull, part 2: lane = splat cuts its box word down to the warp's 8 x 4 region, multiplies the 8 column bits and 4 row bits
@@ -204,7 +205,7 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                 // (the masks are bit-REVERSED: lane L took entry 31 - L of the window in the cull, so entry f is bit 31 - f and the next entry
                 // in list order is the HIGHEST set bit: one FLO instead of BREV + FLO)
                 while (__any_sync(0xffffffffu, mask != 0)) {
-                    uint32_t h;                                    // 31 - f; 0xffffffff for a lane with nothing to pop: reads a mapped, unused record
+                    uint32_t h;                                    // 31 - f; 0xffffffff for a lane with nothing to pop: reads "entry 32" (the next window's first record or the stage's padding) and discards it
                     asm("bfind.u32 %0, %1;" : "=r"(h) : "r"(mask));
                     uint32_t rbit, bit;                            // PTX shifts clamp the amount: both are 0 when h = 0xffffffff
                     asm("shl.b32 %0, 1, %1;" : "=r"(rbit) : "r"(h));

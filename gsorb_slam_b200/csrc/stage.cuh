@@ -35,11 +35,15 @@ namespace gsb {
 template <int NS, int BATCH, bool BULK>
 struct StageRing;
 
+// One record of padding behind every stage: the forward walk lets a lane with nothing to pop read "entry 32" of its window and
+// discard it (blend_fwd.cu); behind the last window of a stage that is this padding, not the first record of the NEXT stage,
+// which cp.async may be filling at that moment (harmless, but compute-sanitizer racecheck reports it).
+constexpr int RING_PAD = 1;
 template <int NS, int BATCH>
 struct StageRing<NS, BATCH, false> {
-    float4 a[NS][BATCH];
-    float4 b[NS][BATCH];
-    float4 c[NS][BATCH];
+    float4 a[NS][BATCH + RING_PAD];
+    float4 b[NS][BATCH + RING_PAD];
+    float4 c[NS][BATCH + RING_PAD];
     __device__ __forceinline__ void init() {}
     __device__ __forceinline__ float4 A(int buf, int e) const { return a[buf][e]; }
     __device__ __forceinline__ float4 B(int buf, int e) const { return b[buf][e]; }

@@ -14,3 +14,9 @@ gt_c = c.clone().clamp(0, 1); gt_d = torch.rand(H, W, device=dev) * 5 + 0.5
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 6):
     mo.step_slam(T, gt_c, gt_d)
 torch.cuda.synchronize()
+# tracking iterations on the same (now frozen) map
+from gsorb_slam_b200.tracking import PoseOptimizer
+po = PoseOptimizer(mo, [1.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0])
+for _ in range(int(sys.argv[2]) if len(sys.argv) > 2 else 0):
+    po.step(gt_c, gt_d, 0.7, 1.0, True)
+torch.cuda.synchronize()
