@@ -15,6 +15,8 @@ freedom) is applied once, at half the iteration budget (:1081-1085); ``run`` sto
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 import torch
 
@@ -35,29 +37,32 @@ def rt2T(q: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
 
 
 def rt2T_np(q: np.ndarray, t: np.ndarray) -> np.ndarray:
-    """``rt2T`` on the host, float32."""
-    qn = (q / np.sqrt((q * q).sum(dtype=np.float32))).astype(np.float32)
-    w, x, y, z = (np.float32(v) for v in qn)
-    T = np.eye(4, dtype=np.float32)
-    T[:3, :3] = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
-                          [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
-                          [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]], dtype=np.float32)
-    T[:3, 3] = t
-    return T
+    """``rt2T`` on the host: [4,4] float32.  Scalar double arithmetic rounded once (the tracking loop runs this, the chain rule below
+    and Adam between two GPU iterations with the device idle: plain Python floats cost about 10 us, a numpy expression of the same 23 + 37 + 25 us)."""
+    w, x, y, z = q.tolist()
+    n = math.sqrt(w * w + x * x + y * y + z * z)
+    w, x, y, z = w / n, x / n, y / n, z / n
+    t0, t1, t2 = t.tolist()
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y), t0],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x), t1],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y), t2],
+                     [0.0, 0.0, 0.0, 1.0]], dtype=np.float32)
 
 
 def rt2T_backward_np(q: np.ndarray, G: np.ndarray):
-    """dL/dq [4], dL/dt [3] from G = dL/dTcw (rows 0..2 of the 4x4 matrix, [3,4]): the autograd of ``rt2T`` in closed form."""
-    n = float(np.sqrt((q.astype(np.float64) ** 2).sum()))
-    w, x, y, z = (q.astype(np.float64) / n)
-    dR = np.array([[[0, -z, y], [z, 0, -x], [-y, x, 0]],
-                   [[0, y, z], [y, -2 * x, -w], [z, w, -2 * x]],
-                   [[-2 * y, x, w], [x, 0, z], [-w, z, -2 * y]],
-                   [[-2 * z, -w, x], [w, -2 * z, y], [x, y, 0]]], dtype=np.float64) * 2.0
-    gqn = (dR * G[None, :3, :3].astype(np.float64)).sum((1, 2))
-    qn = np.array([w, x, y, z])
-    gq = (gqn - qn * (qn @ gqn)) / n          # through q / |q|
-    return gq.astype(np.float32), G[:3, 3].astype(np.float32)
+    """dL/dq [4], dL/dt [3] from G = dL/dTcw (rows 0..2 of the 4x4 matrix, [3,4]): the autograd of ``rt2T`` in closed form
+    (dR/dw, dR/dx, dR/dy, dR/dz contracted with G[:, :3], then through q / |q|)."""
+    w, x, y, z = q.tolist()
+    n = math.sqrt(w * w + x * x + y * y + z * z)
+    w, x, y, z = w / n, x / n, y / n, z / n
+    (g00, g01, g02, g03), (g10, g11, g12, g13), (g20, g21, g22, g23) = G[:3].tolist()
+    gw = 2.0 * (-z * g01 + y * g02 + z * g10 - x * g12 - y * g20 + x * g21)
+    gx = 2.0 * (y * g01 + z * g02 + y * g10 - 2 * x * g11 - w * g12 + z * g20 + w * g21 - 2 * x * g22)
+    gy = 2.0 * (-2 * y * g00 + x * g01 + w * g02 + x * g10 + z * g12 - w * g20 + z * g21 - 2 * y * g22)
+    gz = 2.0 * (-2 * z * g00 - w * g01 + x * g02 + w * g10 - 2 * z * g11 + y * g12 + x * g20 + y * g21)
+    dot = w * gw + x * gx + y * gy + z * gz
+    gq = np.array([(gw - w * dot) / n, (gx - x * dot) / n, (gy - y * dot) / n, (gz - z * dot) / n], dtype=np.float32)
+    return gq, np.array([g03, g13, g23], dtype=np.float32)
 
 
 class PoseOptimizer:
@@ -123,12 +128,15 @@ class PoseOptimizer:
         a = self._adam
         a["step"] += 1
         b1, b2 = self.betas
-        a["m"] = (b1 * a["m"] + (1 - b1) * grad).astype(np.float32)
-        a["v"] = (b2 * a["v"] + (1 - b2) * grad * grad).astype(np.float32)
         c1, c2 = 1.0 - b1 ** a["step"], 1.0 - b2 ** a["step"]
-        upd = (self.lr / c1) * a["m"] / (np.sqrt(a["v"]) / np.sqrt(c2) + self.eps)
-        self._q = (self._q - upd[:4]).astype(np.float32)
-        self._t = (self._t - upd[4:]).astype(np.float32)
+        step_size, rc2 = self.lr / c1, 1.0 / math.sqrt(c2)
+        m, v, p = a["m"].tolist(), a["v"].tolist(), self._q.tolist() + self._t.tolist()
+        for k, g in enumerate(grad.tolist()):
+            m[k] = b1 * m[k] + (1 - b1) * g
+            v[k] = b2 * v[k] + (1 - b2) * g * g
+            p[k] -= step_size * m[k] / (math.sqrt(v[k]) * rc2 + self.eps)
+        a["m"], a["v"] = np.array(m, dtype=np.float32), np.array(v, dtype=np.float32)
+        self._q, self._t = np.array(p[:4], dtype=np.float32), np.array(p[4:], dtype=np.float32)
 
     def step(self, gt_color: torch.Tensor, gt_depth: torch.Tensor, w_image: float = 1.0, w_depth: float = 1.0,
              use_surdepth: bool = True, w_feature: float = 0.0, gate_features: bool = False) -> float:
