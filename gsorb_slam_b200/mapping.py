@@ -241,15 +241,19 @@ class MapOptimizer:
         self.binning = torch.empty(int(self.L.gsb_binning_bytes(self.max_rendered)), dtype=torch.uint8, device=self.dev)
 
     # ---- the forward's overflow latch: polled once per step, never ignored ---------------------------------------------
-    def _poll_forward(self):
-        """Stream-ordered copy of the forward's status words to pinned host memory (no synchronisation here)."""
+    def _poll_forward(self, record_event: bool = True):
+        """Stream-ordered copy of the forward's status words to pinned host memory (no synchronisation here).  Inside a CUDA
+        graph capture no event is recorded (an event recorded during capture cannot be waited for from the host)."""
         self._status.copy_(self.geom[:32].view(torch.int32), non_blocking=True)
-        self._status_ev.record(torch.cuda.current_stream(self.dev))
+        if record_event:
+            self._status_ev.record(torch.cuda.current_stream(self.dev))
 
-    def _overflowed(self) -> bool:
+    def _overflowed(self, wait: bool = True) -> bool:
         """True if the last forward found more tile instances than ``max_rendered``: the binning blob is grown and the caller
-        renders again (what adapter/Rasterizer.cc does for the drop-in path).  Waits for the FORWARD only."""
-        self._status_ev.synchronize()
+        renders again (what adapter/Rasterizer.cc does for the drop-in path).  Waits for the FORWARD only (``wait=False``: the
+        caller has synchronised the stream already)."""
+        if wait:
+            self._status_ev.synchronize()
         if int(self._status[4]) == 0:
             return False
         need = int(self._status[2]) & 0xffffffff
@@ -304,7 +308,7 @@ class MapOptimizer:
                                                g.ptr("quats"), g.ptr("scales"), self.dTcw.data_ptr(), s))
         return g
 
-    def _forward_fused(self, means_only: bool = False):
+    def _forward_fused(self, means_only: bool = False, record_event: bool = True):
         """``means_only``: the map has not changed since the last prologue (tracking): only the camera-frame means are redone."""
         L, p, s = self.L, self.params, self._s()
         if not hasattr(self, "depth_sil"):
@@ -318,7 +322,7 @@ class MapOptimizer:
                                               self.binning.numel(), self.max_rendered, self.img.data_ptr(), self.img.numel(),
                                               self.color.data_ptr(), self.depth_sil.data_ptr(), self.depth.data_ptr(),
                                               self.radii.data_ptr(), s))
-            self._poll_forward()
+            self._poll_forward(record_event)
 
     def render_fused(self, Tcw: torch.Tensor, frozen_map: bool = False):
         """Prologue + ONE five-channel rasterization: (color [3,H,W], depth_sil [2,H,W], median_depth [1,H,W], radii)

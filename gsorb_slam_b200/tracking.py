@@ -71,8 +71,10 @@ class PoseOptimizer:
     reprojection term and the Adam update are closed-form numpy (about 0.1 ms) instead of ~100 small torch kernels per iteration
     (1.4 ms of launch overhead); the rasterizer, the masked L1 loss and dL/dTcw stay on the device."""
 
-    def __init__(self, gaussians: MapOptimizer, quat, trans, lr_quat: float = 2e-3, betas=(0.9, 0.999), eps: float = 1e-15):
+    def __init__(self, gaussians: MapOptimizer, quat, trans, lr_quat: float = 2e-3, betas=(0.9, 0.999), eps: float = 1e-15,
+                 use_graph: bool = True):
         self.g = gaussians
+        self.use_graph, self._graph, self._graph_key = bool(use_graph), None, None
         as_np = lambda a: (a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)).astype(np.float32).copy()
         self._q, self._t = as_np(quat).reshape(4), as_np(trans).reshape(3)
         # CreateOptimizerForPose: the translation group is created with the QUATERNION learning rate (src/Gaussian.cc:150)
@@ -162,20 +164,41 @@ class PoseOptimizer:
         # -> per-pixel backward + pose-only per-Gaussian kernel (dL/dTcw straight into the read-back block) -> D2H.  The forward's
         # overflow latch is read after that; an overflowing frame is redone with a larger binning blob.
         self._T_host.copy_(torch.from_numpy(T))
-        while True:
+        stream = torch.cuda.current_stream(g.dev)
+
+        def enqueue(in_graph: bool):
             self._T_dev.copy_(self._T_host, non_blocking=True)
             g._Tcw = self._T_dev
-            g._forward_fused(means_only=self._rendered_once)
-            color, depth_sil, median = g.color, g.depth_sil, g.depth
+            g._forward_fused(means_only=self._rendered_once, record_event=not in_graph)
             with torch.cuda.device(g.dev):
-                _lib.check(g.L.gsb_tracking_loss(g.W, g.H, color.data_ptr(), depth_sil.data_ptr(), median.data_ptr(), gtc.data_ptr(),
+                _lib.check(g.L.gsb_tracking_loss(g.W, g.H, g.color.data_ptr(), g.depth_sil.data_ptr(), g.depth.data_ptr(), gtc.data_ptr(),
                                                  gtd.data_ptr(), float(w_image), float(w_depth), 1 if use_surdepth else 0,
                                                  dC.data_ptr(), dD.data_ptr(), terms.data_ptr(), torch.cuda.current_stream(g.dev).cuda_stream))
             g.backward_pose(dC, dD, z_attached=False, out=self._out[8:])
             self._host.copy_(self._out, non_blocking=True)
-            torch.cuda.current_stream(g.dev).synchronize()
+
+        while True:
+            # From the second iteration on the device side of the iteration is a fixed sequence over fixed buffers (only the
+            # CONTENT of the pinned pose buffer changes): it is captured once as a CUDA graph and replayed -- one launch per
+            # iteration instead of about twenty, and no gaps between the kernels.  The key covers everything that is baked in.
+            key = (gtc.data_ptr(), gtd.data_ptr(), float(w_image), float(w_depth), bool(use_surdepth), g.P, g.max_rendered,
+                   g.binning.data_ptr(), g.params.flat.data_ptr())
+            if self.use_graph and self._rendered_once:
+                if self._graph_key != key:
+                    stream.synchronize()
+                    self._graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self._graph):
+                        enqueue(True)
+                    self._graph_key = key
+                self._graph.replay()
+                stream.synchronize()
+                overflowed = g._overflowed(wait=False)
+            else:
+                enqueue(False)
+                stream.synchronize()
+                overflowed = g._overflowed()
             self._rendered_once = True
-            if not g._overflowed():
+            if not overflowed:
                 break
         h = self._host.numpy()
         image_term, depth_term, loss = float(h[0]), float(h[1]), float(h[2])
