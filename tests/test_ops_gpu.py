@@ -633,6 +633,38 @@ def test_complete_slam_iteration_decreases_its_loss():
     assert bool(torch.isfinite(opt.params.flat).all())
 
 
+@pytest.mark.parametrize("P,cap", [(1, None), (255, None), (256, None), (257, None), (1000, 1001), (1000, 1004), (4099, None)])
+def test_fused_map_update_row_counts_and_alignments(P, cap):
+    """One iteration of the fused update against the separate passes for maps that end inside / exactly on / just behind a CTA's 256
+    rows, with aligned (bulk-copy variant, partial last CTA) and unaligned (per-thread variant) arenas; the rows of the arena
+    behind P stay zero."""
+    import torch
+    from gsorb_slam_b200.distributed import GROUPS
+    from gsorb_slam_b200.mapping import MapOptimizer
+    from gsorb_slam_b200.scene import make_scene
+    dev = torch.device("cuda:0")
+    W, H = 96, 64
+    sc = make_scene(P, (W, H, 80.0, 78.0), seed=60 + P, scale_mul=6.0)
+    mk = lambda: MapOptimizer(sc.means3D, sc.colors, sc.logit_opacities, sc.log_scales, sc.unnorm_quats, width=W, height=H,
+                              tanfovx=sc.cam.tanfovx, tanfovy=sc.cam.tanfovy, projmatrix=sc.cam.projmatrix, device=dev,
+                              max_rendered=1 << 18, scene_radius=0.5, capacity=cap)
+    a, b = mk(), mk()
+    g = torch.Generator(device=dev).manual_seed(P)
+    gt_c, gt_d = torch.rand(3, H, W, device=dev, generator=g), torch.rand(H, W, device=dev, generator=g) * 4 + 0.5
+    Tcw = torch.eye(4, device=dev)
+    Tcw[0, 3], Tcw[2, 3] = 0.01, -0.02
+    a.step_slam(Tcw, gt_c, gt_d, fused_update=True, write_grads=True)
+    b.step_slam(Tcw, gt_c, gt_d, fused_update=False)
+    for name, _ in GROUPS:
+        for x, y, what in ((a.grads, b.grads, "grad"), (a.params, b.params, "param"), (a.exp_avg, b.exp_avg, "m"), (a.exp_avg_sq, b.exp_avg_sq, "v")):
+            assert rel_to_scale(to_np(x[name]), to_np(y[name])) <= 2e-6, (name, what)
+    assert rel_to_scale(to_np(a.dTcw), to_np(b.dTcw)) <= 1e-4
+    if a.capacity > P:   # padding rows: untouched
+        pad = a.params.flat.view(-1)
+        for off, (name, w) in zip((0, 3, 6, 7, 10), GROUPS):
+            assert float(pad[off * a.capacity + w * P:(off + w) * a.capacity].abs().max()) == 0.0, name
+
+
 def test_pose_only_backward_matches_the_full_backward():
     """gsb_backward_fused_pose (tracking: dL/dTcw and nothing else) against gsb_backward_fused + gsb_prologue_backward, and the
     means-only prologue of a frozen map against the full one."""
