@@ -35,6 +35,34 @@ def keyframe_batch_hyperparameters(G: int, lr: Optional[Dict[str, float]] = None
     return {k: v * max(1.0, G / 2.0) for k, v in lr.items()}, (betas[0] ** G, betas[1] ** G)
 
 
+def backproject_pixels(L, dev, W: int, H: int, mask, gt_depth, gt_color, Tcw, fx: float, fy: float, cx: float, cy: float,
+                       max_z: Optional[torch.Tensor] = None):
+    """``Render::ProjectPixel`` / ``Render::InitGaussianPoint`` + the SinglePixel initialisation of
+    ``Gaussian::AddGaussianPoints`` (src/Render.cc:617-655, 666-707; src/Gaussian.cc:50-74) on the device
+    (``gsb_backproject``): one Gaussian per pixel with ``mask >= 250`` (``mask`` None: every pixel) and depth > 0, in
+    row-major pixel order.  Returns (means [K,3], rgb [K,3], logit_opacities [K], log_scales [K,3], unnorm_quats [K,4]);
+    ``max_z`` (1 device float, the running ``Render::mMaxZ``) is raised to the largest selected depth."""
+    d = torch.device(dev)
+    gtc = gt_color.to(d, torch.float32).contiguous()
+    gtd = gt_depth.to(d, torch.float32).contiguous()
+    Twc = torch.linalg.inv(Tcw.detach().to("cpu", torch.float64)).to(torch.float32).contiguous()
+    cap = int(W) * int(H)
+    e = lambda *s: torch.empty(s, dtype=torch.float32, device=d)
+    means, rgb, ls, quat, op = e(cap, 3), e(cap, 3), e(cap, 3), e(cap, 4), e(cap)
+    count = torch.zeros(1, dtype=torch.int32, device=d)
+    nb = int(L.gsb_backproject_scratch_bytes(int(W), int(H)))
+    scratch = torch.empty(nb, dtype=torch.uint8, device=d)
+    Th = (C.c_float * 16)(*Twc.reshape(-1).tolist())
+    with torch.cuda.device(d):
+        _lib.check(L.gsb_backproject(int(W), int(H), mask.data_ptr() if mask is not None else None, gtd.data_ptr(), gtc.data_ptr(),
+                                     float(fx), float(fy), float(cx), float(cy), Th, cap, means.data_ptr(), rgb.data_ptr(),
+                                     ls.data_ptr(), quat.data_ptr(), op.data_ptr(), count.data_ptr(),
+                                     max_z.data_ptr() if max_z is not None else None, scratch.data_ptr(), nb,
+                                     torch.cuda.current_stream(d).cuda_stream))
+    K = int(count.item())
+    return means[:K], rgb[:K], op[:K], ls[:K], quat[:K]
+
+
 class MapOptimizer:
     """The Gaussian map of one rank and its optimiser state, resident on the GPU as ARENAS (``GradBlock`` with a capacity):
     parameters, gradients and both Adam moments can grow in place (``add_gaussians``, ``densify``) and shrink
@@ -182,29 +210,16 @@ class MapOptimizer:
         -> GPU back-projection of the selected pixels (``gsb_backproject`` = ProjectPixel + the SinglePixel initialisation of
         AddGaussianPoints) -> append.  Returns the number of Gaussians added; updates ``scene_radius`` bookkeeping input
         ``max_z``."""
-        L, d = self.L, self.dev
-        color = self.color if color is None else color
-        depth_sil = self.depth_sil if depth_sil is None else depth_sil
-        gtc = gt_color.to(d, torch.float32).contiguous()
+        d = self.dev
         gtd = gt_depth.to(d, torch.float32).contiguous()
         if mask is None:
+            color = self.color if color is None else color
+            depth_sil = self.depth_sil if depth_sil is None else depth_sil
             mask = self.add_mask(color, depth_sil, gtd, median_mul)
-        Twc = torch.linalg.inv(Tcw.detach().to("cpu", torch.float64)).to(torch.float32).contiguous()
-        cap = int(mask.numel())
-        e = lambda *s: torch.empty(s, dtype=torch.float32, device=d)
-        means, rgb, ls, quat, op = e(cap, 3), e(cap, 3), e(cap, 3), e(cap, 4), e(cap)
-        count = torch.zeros(1, dtype=torch.int32, device=d)
         if not hasattr(self, "max_z"):
             self.max_z = torch.zeros(1, dtype=torch.float32, device=d)
-        nb = int(L.gsb_backproject_scratch_bytes(self.W, self.H))
-        scratch = torch.empty(nb, dtype=torch.uint8, device=d)
-        Th = (C.c_float * 16)(*Twc.reshape(-1).tolist())
-        with torch.cuda.device(d):
-            _lib.check(L.gsb_backproject(self.W, self.H, mask.data_ptr(), gtd.data_ptr(), gtc.data_ptr(), float(fx), float(fy), float(cx),
-                                         float(cy), Th, cap, means.data_ptr(), rgb.data_ptr(), ls.data_ptr(), quat.data_ptr(), op.data_ptr(),
-                                         count.data_ptr(), self.max_z.data_ptr(), scratch.data_ptr(), nb, self._s()))
-        K = int(count.item())
-        return self.add_gaussians(means[:K], rgb[:K], op[:K], ls[:K], quat[:K])
+        rows = backproject_pixels(self.L, d, self.W, self.H, mask, gtd, gt_color, Tcw, fx, fy, cx, cy, self.max_z)
+        return self.add_gaussians(rows[0], rows[1], rows[2], rows[3], rows[4])
 
     def prune_low_opacity(self, threshold: float = 0.005) -> int:
         """``Render::RemoveGaussian`` (src/Render.cc:598-616; Gaussian.cc:193-239, pruneOpcities 0.005): rows whose
@@ -235,6 +250,62 @@ class MapOptimizer:
         self.P = K
         self._point_args()
         return P - K
+
+    # ---- the two loops around the iteration: Render::InitWorld and Render::RenderForFrame ------------------------------------
+    @classmethod
+    def init_world(cls, Tcw, gt_color, gt_depth, fx: float, fy: float, cx: float, cy: float, *, iters: int = 200,
+                   radius_depth_ratio: float = 3.0, lambda_: float = 0.8, w_image: float = 1.0, w_depth: float = 0.7,
+                   w_surdepth: float = 0.1, device="cuda:0", **kwargs) -> "MapOptimizer":
+        """``Render::InitWorld`` (src/Render.cc:496-553): the first RGB-D frame becomes the map -- one Gaussian per pixel with a
+        valid depth, back-projected at the frame's pose in raster order (``InitGaussianPoint``, :666-707) -- and is fitted to
+        that frame for ``iters`` iterations (200 in the reference) with the image + depth loss of :523-531: no scale
+        regulariser, the median-depth term weighted 0.1 (it carries no gradient, include/Rasterizer.cuh:210, so only the reported
+        loss depends on it).  ``scene_radius`` = max depth / ``radius_depth_ratio`` (:705, ``Mapping.raduisDepthRatio``) is set
+        on the returned optimizer for the mapping iterations that follow.  ``kwargs``: width, height, tanfovx, tanfovy,
+        projmatrix, lr ... of the constructor."""
+        d = torch.device(device)
+        L = _lib.lib()
+        W, H = int(kwargs["width"]), int(kwargs["height"])
+        max_z = torch.zeros(1, dtype=torch.float32, device=d)
+        Tcw = Tcw.to(d, torch.float32)
+        rows = backproject_pixels(L, d, W, H, None, gt_depth, gt_color, Tcw, fx, fy, cx, cy, max_z)
+        if rows[0].shape[0] == 0:
+            raise ValueError("InitWorld: the frame has no pixel with a valid depth")
+        kwargs.pop("scene_radius", None)
+        mo = cls(rows[0], rows[1], rows[2], rows[3], rows[4], device=d, scene_radius=0.0, **kwargs)
+        mo.max_z = max_z
+        gtc, gtd = gt_color.to(d, torch.float32).contiguous(), gt_depth.to(d, torch.float32).contiguous()
+        for _ in range(int(iters)):
+            mo.step_slam(Tcw, gtc, gtd, lambda_, w_image, w_depth, w_surdepth, average=world()[1] > 1)   # every rank holds the same frame
+        mo.scene_radius = float(max_z.item()) / float(radius_depth_ratio)
+        return mo
+
+    def update_scene_radius(self, radius_depth_ratio: float = 3.0) -> float:
+        """``mSceneRadius = mMaxZ / raduisDepthRatio`` (src/Render.cc:661) after a densification raised ``max_z``."""
+        if hasattr(self, "max_z"):
+            self.scene_radius = float(self.max_z.item()) / float(radius_depth_ratio)
+        return self.scene_radius
+
+    def map_keyframes(self, keyframes, iters: int = 60, rng=None, **loss_weights):
+        """The loop of ``Render::RenderForFrame`` (src/Render.cc:402-493): ``iters`` mapping iterations (``Mapping.numIters``, 60
+        in replica.yaml), each on ONE keyframe drawn uniformly from the candidate window (:423) -- ``keyframes`` is that window,
+        a sequence of (Tcw [4,4], gt_color [3,H,W], gt_depth [H,W]) which the caller selected (covisibility lives in the ORB
+        front end).  With G ranks every iteration draws G keyframes from the same generator and rank r takes the r-th: the
+        keyframe-batch shard (gradients averaged over the ranks; see ``keyframe_batch_hyperparameters``).  ``rng``: a
+        ``random.Random`` (seeded alike on every rank).  Returns the loss terms of the last iteration (device tensor)."""
+        import random
+        rng = rng if rng is not None else random.Random(0)
+        rank, G = world()
+        kf = [(T.to(self.dev, torch.float32).contiguous(), c.to(self.dev, torch.float32).contiguous(),
+               z.to(self.dev, torch.float32).contiguous()) for T, c, z in keyframes]
+        if not kf:
+            raise ValueError("map_keyframes: empty keyframe window")
+        terms = None
+        for _ in range(int(iters)):
+            draws = [rng.randrange(len(kf)) for _ in range(G)]
+            T, c, z = kf[draws[rank]]
+            terms = self.step_slam(T, c, z, average=G > 1, **loss_weights)
+        return terms
 
     def _grow_binning(self, max_rendered: int) -> None:
         self.max_rendered = int(max_rendered)

@@ -36,7 +36,11 @@ def rel_to_scale(a, b):
     assert a.shape == b.shape, (a.shape, b.shape)
     if a.size == 0:
         return 0.0
-    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+    val = float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+    if os.environ.get("GSB_REL_LOG"):   # margins of the tolerances, per test (profiles/*_rel_margins.txt)
+        with open(os.environ["GSB_REL_LOG"], "a") as f:
+            f.write(f"{os.environ.get('PYTEST_CURRENT_TEST', '')}\t{val:.3e}\n")
+    return val
 
 
 def to_np(x):

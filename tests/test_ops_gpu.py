@@ -657,7 +657,9 @@ def test_fused_map_update_row_counts_and_alignments(P, cap):
     b.step_slam(Tcw, gt_c, gt_d, fused_update=False)
     for name, _ in GROUPS:
         for x, y, what in ((a.grads, b.grads, "grad"), (a.params, b.params, "param"), (a.exp_avg, b.exp_avg, "m"), (a.exp_avg_sq, b.exp_avg_sq, "v")):
-            assert rel_to_scale(to_np(x[name]), to_np(y[name])) <= 2e-6, (name, what)
+            # the per-pixel backward sums with RED in an order that differs from run to run: a few 1e-7 relative on a sum, twice
+            # that on exp_avg_sq (P = 1 has no larger element to hide behind: 2.1e-6 was observed once on 'means' / 'v')
+            assert rel_to_scale(to_np(x[name]), to_np(y[name])) <= (2e-6 if what == "param" else 2e-5), (name, what)
     assert rel_to_scale(to_np(a.dTcw), to_np(b.dTcw)) <= 1e-4
     if a.capacity > P:   # padding rows: untouched
         pad = a.params.flat.view(-1)
@@ -696,7 +698,8 @@ def test_fused_map_update_matches_the_separate_passes(scene_radius):
     """gsb_backward_fused_update (per-Gaussian backward + prologue chain rule + scale regularisers + Adam in one launch) against
     gsb_backward_fused -> gsb_prologue_backward -> gsb_scale_regulariser -> gsb_adam_step_groups, three iterations at a pose
     that is not the identity: same raw gradients, pose gradient, regulariser terms, parameters and Adam moments (the two
-    paths share their row-level device functions; 1e-6 of the tensor scale allows for a different FMA contraction)."""
+    paths share their row-level device functions; a few 1e-6 of the tensor scale allow for a different FMA contraction and for the
+    run-to-run order of the per-pixel backward's RED sums, which exp_avg_sq sees twice)."""
     import torch
     from gsorb_slam_b200.distributed import GROUPS
     from gsorb_slam_b200.lowlevel import frame_from_scene
@@ -723,16 +726,17 @@ def test_fused_map_update_matches_the_separate_passes(scene_radius):
         ta = a.step_slam(Tcw, gt_c, gt_d, fused_update=True, write_grads=True).clone()
         tb = b.step_slam(Tcw, gt_c, gt_d, fused_update=False).clone()
         assert a.t == b.t == it + 1
-        assert rel_to_scale(to_np(ta), to_np(tb)) <= 1e-6
+        assert rel_to_scale(to_np(ta), to_np(tb)) <= 5e-6
         for name, _ in GROUPS:
-            assert rel_to_scale(to_np(a.grads[name]), to_np(b.grads[name])) <= (1e-6 if it == 0 else 2e-5), (it, name)
-            assert rel_to_scale(to_np(a.params[name]), to_np(b.params[name])) <= (1e-6 if it == 0 else 2e-5), (it, name)
-            assert rel_to_scale(to_np(a.exp_avg[name]), to_np(b.exp_avg[name])) <= (1e-6 if it == 0 else 2e-5), (it, name)
-            assert rel_to_scale(to_np(a.exp_avg_sq[name]), to_np(b.exp_avg_sq[name])) <= (1e-6 if it == 0 else 2e-5), (it, name)
+            assert rel_to_scale(to_np(a.grads[name]), to_np(b.grads[name])) <= (5e-6 if it == 0 else 2e-5), (it, name)
+            # (from the second step on Adam normalises noise-level gradients: one log-scale row sits at 1.8e-5 = 0.1 lr)
+            assert rel_to_scale(to_np(a.params[name]), to_np(b.params[name])) <= (1e-6 if it == 0 else 4e-5), (it, name)
+            assert rel_to_scale(to_np(a.exp_avg[name]), to_np(b.exp_avg[name])) <= (5e-6 if it == 0 else 2e-5), (it, name)
+            assert rel_to_scale(to_np(a.exp_avg_sq[name]), to_np(b.exp_avg_sq[name])) <= (1e-5 if it == 0 else 4e-5), (it, name)
         assert rel_to_scale(to_np(a.dTcw), to_np(b.dTcw)) <= 1e-4      # 20 000 terms summed in a different order
         if scene_radius > 0:
             assert float(b.reg_terms[2]) > 0
-            assert rel_to_scale(to_np(a.reg_terms[:3]), to_np(b.reg_terms[:3])) <= 1e-6
+            assert rel_to_scale(to_np(a.reg_terms[:3]), to_np(b.reg_terms[:3])) <= 5e-6
     # padding rows of the arenas stay zero, and without write_grads the gradient block is not touched
     assert float(a.params.flat.view(14, -1)[0, 0]) == float(b.params.flat.view(14, -1)[0, 0])
     a.grads.flat.fill_(7.0)
