@@ -108,3 +108,32 @@ def test_pose_chain_rule_and_reprojection_gradient_match_torch_autograd():
     er[torch.tensor(po.features["inlier"])].sum().backward()
     assert np.abs(err - er.detach().numpy()).max() <= 1e-6 * np.abs(err).max()
     assert np.abs(Gf - Tt.grad.numpy()[:3]).max() <= 1e-5 * np.abs(Gf).max()
+
+
+@pytest.mark.parametrize("G", [1, 2, 8])
+def test_map_keyframes_draws_one_keyframe_per_rank_and_iteration(monkeypatch, G):
+    """MapOptimizer.map_keyframes (the loop of Render::RenderForFrame, src/Render.cc:420-424): every iteration draws G keyframes
+    from ONE generator seeded alike on every rank and rank r takes the r-th, so the ranks of a step see different views of
+    the same window and a single rank reproduces the reference's one uniform draw per iteration.  Host logic only: the
+    iteration itself is replaced by a recorder."""
+    import random
+    import types
+    from gsorb_slam_b200 import mapping
+    window = [(torch.eye(4) * (k + 1), torch.full((3, 2, 2), float(k)), torch.full((2, 2), float(k))) for k in range(5)]
+    iters, seed = 12, 7
+    want = random.Random(seed)
+    draws = [[want.randrange(len(window)) for _ in range(G)] for _ in range(iters)]
+    for rank in range(G):
+        monkeypatch.setattr(mapping, "world", lambda rank=rank: (rank, G))
+        seen = []
+
+        def step_slam(T, c, z, average=False, **kw):
+            seen.append((int(T[0, 0]) - 1, average, kw))
+            return torch.zeros(8)
+        mo = types.SimpleNamespace(dev=torch.device("cpu"), step_slam=step_slam)
+        terms = mapping.MapOptimizer.map_keyframes(mo, window, iters=iters, rng=random.Random(seed), w_depth=0.5)
+        assert terms.shape == (8,)
+        assert [s[0] for s in seen] == [d[rank] for d in draws]
+        assert all(s[1] == (G > 1) and s[2] == {"w_depth": 0.5} for s in seen)   # gradients averaged over the ranks of a step
+    with pytest.raises(ValueError):
+        mapping.MapOptimizer.map_keyframes(types.SimpleNamespace(dev=torch.device("cpu"), step_slam=None), [], iters=1)
