@@ -130,3 +130,39 @@ def test_libtorch_adapter_builds_and_exposes_the_reference_surface():
                  "RasterizeGaussiansCUDA", "RasterizeGaussiansBackwardCUDA", "RasterizeGaussiansfilterCUDA", "markVisible",
                  "Visable", "mark_visible", "distCUDA2"):   # names of include/Rasterizer.cuh:28-380 + include/spatial.h
         assert name in src, name
+
+
+def test_header_is_plain_c99_and_a_c_caller_links(tmp_path):
+    """The boundary is a C ABI: include/gsb.h compiles as strict C99 (no C++-isms, no torch types), and a C program linked
+    against libgsb.so reaches the host-only entry points (version, blob sizes, argument validation with its error text)."""
+    import shutil
+    import subprocess
+    from gsorb_slam_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "caller.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "gsb.h"
+int main(void)
+{
+    gsb_raster_args a;
+    memset(&a, 0, sizeof a);                       /* P = 0, no pointers, 0 x 0 image: must be refused, not crash */
+    if (gsb_version() <= 0) return 1;
+    if (gsb_image_bytes(640, 480) == 0 || gsb_geometry_bytes(1000) == 0 || gsb_binning_bytes(4096) == 0) return 2;
+    if (gsb_forward_ws(&a, NULL, 0, NULL, 0, 0, NULL, 0, NULL, NULL, NULL, NULL) != GSB_ERR_INVALID_ARGUMENT) return 3;
+    if (strstr(gsb_last_error(), "image size") == NULL) return 4;
+    printf("%d %lu\n", gsb_version(), (unsigned long)gsb_image_bytes(640, 480));
+    return 0;
+}
+''')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-o", str(exe), "-L", libdir, "-lgsb", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    ver, nbytes = out.stdout.split()
+    L = _lib.lib()
+    assert int(ver) == L.gsb_version() and int(nbytes) == L.gsb_image_bytes(640, 480)
