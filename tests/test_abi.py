@@ -166,3 +166,34 @@ int main(void)
     ver, nbytes = out.stdout.split()
     L = _lib.lib()
     assert int(ver) == L.gsb_version() and int(nbytes) == L.gsb_image_bytes(640, 480)
+
+
+def test_no_entry_point_dereferences_null_arguments():
+    """Every entry point of include/gsb.h called with NULL for every pointer -- once with zero sizes, once with non-zero ones --
+    must come back with a status (GSB_OK for "nothing to do", GSB_ERR_INVALID_ARGUMENT otherwise; a pure size query returns its
+    size), never dereference on the host.  Run in a child process so that a crash is reported by name.  (gsb_forward takes
+    callbacks and is covered by test_validation_errors_match_reference_messages.)"""
+    import subprocess
+    import sys
+    child = r'''
+import ctypes as C, sys
+sys.path.insert(0, %r)
+from gsorb_slam_b200 import _lib
+L = _lib.lib()
+for fill in (0, 5):
+    for name in sorted(_lib.SIGNATURES):
+        if name == "gsb_forward":
+            continue
+        res, argt = _lib.SIGNATURES[name]
+        args = [fill if a in (C.c_int, C.c_longlong, C.c_size_t, C.c_uint) else (0.5 * fill if a in (C.c_float, C.c_double) else None) for a in argt]
+        print("calling", name, fill, flush=True)
+        r = getattr(L, name)(*args)
+        if res is C.c_int and name not in ("gsb_version", "gsb_num_stages"):
+            assert r in (0, -1, -2), (name, r)      # -2: a launch on all-NULL outputs found no driver (CPU box); never reached with real work
+            if r == -1:
+                assert L.gsb_last_error(), name
+print("done")
+''' % ROOT
+    p = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True)
+    last = [l for l in p.stdout.splitlines() if l.startswith("calling")][-1:] or ["(none)"]
+    assert p.returncode == 0 and p.stdout.strip().endswith("done"), (p.returncode, last, p.stderr[-600:])
